@@ -1,0 +1,164 @@
+/*
+ * b200isp.h -- C ABI of the B200-native camera-ISP hot path.
+ *
+ * Drop-in boundary for uc-vision/taichi_image's `packed`, `bayer`, `tonemap`,
+ * `interpolate` and `camera_isp` modules.  The reference has no FFI of its own:
+ * its boundary is "Python wrapper -> cached Taichi kernel object called with
+ * contiguous torch/numpy arrays" (e.g. bayer.py:202-219, packed.py:176-198).
+ * Each entry point below replaces one such kernel object; the citation names it
+ * (paths relative to /root/reference/taichi_image).
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name ends in `_host`;
+ *   - images are row-major contiguous: (H, W) CFA planes, (H, W, 3) RGB,
+ *     (H, W*3/2) bytes for packed12; sizes are in elements, never bytes;
+ *   - launches are asynchronous on `stream` (a cudaStream_t); the caller owns
+ *     all memory and keeps it alive until the stream has passed the call;
+ *   - return value 0 = success, < 0 = b200isp_status; the calls never throw
+ *     and never synchronise; b200isp_last_error() holds a thread-local message;
+ *   - `workspace` is a caller-owned device buffer of at least
+ *     b200isp_workspace_bytes() bytes, zero-initialised ONCE by the caller and
+ *     then reused across calls on the same stream (the kernels leave it zeroed);
+ *   - no global mutable state: thread-safe, multi-GPU by the caller's current
+ *     device (cudaSetDevice / torch.cuda.device).
+ */
+#ifndef B200ISP_H
+#define B200ISP_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200ISP_VERSION 100            /* 0.1.0 */
+#define B200ISP_MAX_FRAMES 64          /* frames per batched call */
+#define B200ISP_METRICS 9              /* camera_isp.py:102-115 */
+
+typedef void* b200isp_stream;          /* cudaStream_t */
+
+typedef enum {                         /* types.py:12-49 */
+  B200ISP_U8 = 0, B200ISP_U16 = 1, B200ISP_I16 = 2, B200ISP_F16 = 3, B200ISP_F32 = 4
+} b200isp_dtype;
+
+typedef enum {                         /* bayer.py:75-79 (same values) */
+  B200ISP_RGGB = 0, B200ISP_GRBG = 1, B200ISP_GBRG = 2, B200ISP_BGGR = 3
+} b200isp_pattern;
+
+typedef enum {                         /* interpolate.py:9-17 */
+  B200ISP_T_NONE = 0, B200ISP_T_ROT90 = 1, B200ISP_T_ROT180 = 2, B200ISP_T_ROT270 = 3,
+  B200ISP_T_TRANSPOSE = 4, B200ISP_T_FLIP_HORIZ = 5, B200ISP_T_FLIP_VERT = 6,
+  B200ISP_T_TRANSVERSE = 7
+} b200isp_transform_t;
+
+typedef enum { B200ISP_TM_LINEAR = 0, B200ISP_TM_REINHARD = 1, B200ISP_TM_NONE = 2 } b200isp_tonemap_t;
+
+typedef enum {
+  B200ISP_OK = 0, B200ISP_E_ARG = -1, B200ISP_E_DTYPE = -2, B200ISP_E_SHAPE = -3,
+  B200ISP_E_ALIGN = -4, B200ISP_E_CUDA = -5, B200ISP_E_FRAMES = -6, B200ISP_E_WORKSPACE = -7
+} b200isp_status;
+
+int         b200isp_version(void);
+const char* b200isp_last_error(void);
+size_t      b200isp_workspace_bytes(void);
+
+/* ---- packed.py ---------------------------------------------------------- */
+/* packed.py:59-89 encode12_kernel(in_type, scaled, ids_format)(values, encoded).
+ * n_values even; encoded has n_values*3/2 bytes. */
+int b200isp_encode12(const void* values, int in_dtype, int64_t n_values, uint8_t* encoded,
+                     int scaled, int ids_format, b200isp_stream stream);
+/* packed.py:122-131 decode12_kernel(out_type, scaled, ids_format)(encoded, out). */
+int b200isp_decode12(const uint8_t* encoded, int64_t n_values, void* out, int out_dtype,
+                     int scaled, int ids_format, b200isp_stream stream);
+/* packed.py:163-172 decode16_kernel(out_type, scaled)(encoded, out). */
+int b200isp_decode16(const uint8_t* encoded, int64_t n_values, void* out, int out_dtype,
+                     int scaled, b200isp_stream stream);
+
+/* ---- bayer.py ----------------------------------------------------------- */
+/* bayer.py:101-112 rgb_to_bayer_kernel(image, bayer, pixel_order). */
+int b200isp_rgb_to_bayer(const void* rgb, void* bayer, int dtype, int height, int width,
+                         int pattern, b200isp_stream stream);
+/* bayer.py:179-190 bayer_to_rgb_kernel(pattern, correct_colors, in_dtype, out_dtype)(bayer, out).
+ * ccm9_host: 9 row-major floats on the HOST, or NULL (no colour correction). */
+int b200isp_bayer_to_rgb(const void* bayer, int in_dtype, void* rgb, int out_dtype,
+                         int height, int width, int pattern, const float* ccm9_host,
+                         b200isp_stream stream);
+
+/* ---- util.py / tonemap.py (stand-alone, per image) ---------------------- */
+/* util.py:49-60 bounds_func: min/max over n_elems values -> bounds_out[2] (device). */
+int b200isp_bounds(const void* src, int dtype, int64_t n_elems, float* bounds_out,
+                   void* workspace, b200isp_stream stream);
+/* tonemap.py:11-17 linear_func with bounds read from device memory (bounds[0]=min,[1]=max):
+ * out = cast(clamp(((x-min)*(1/(max-min)))^(1/gamma),0,1)*scale[out_dtype]).
+ * Used by tonemap.linear_kernel (tonemap.py:26-36) after b200isp_bounds and by the ISP
+ * linear_kernel (camera_isp.py:220-227) with bounds = metrics[0:2]. */
+int b200isp_linear(const void* src, int in_dtype, void* dst, int out_dtype, int64_t n_elems,
+                   const float* bounds, float gamma, b200isp_stream stream);
+/* tonemap.py:134-168 reinhard_kernel(in,out)(image,temp,dest,gamma,intensity,la,ca):
+ * the five dependent passes of the stand-alone Reinhard operator.
+ * temp: n_pixels*3 floats (device scratch owned by the caller, as in the reference). */
+int b200isp_reinhard_standalone(const void* src, int in_dtype, float* temp, void* dst, int out_dtype,
+                                int64_t n_pixels, float gamma, float intensity, float light_adapt,
+                                float color_adapt, void* workspace, b200isp_stream stream);
+
+/* ---- interpolate.py ----------------------------------------------------- */
+/* interpolate.py:70-86 bilinear_kernel(in,out)(src,dst,scale); scale per axis (row, col). */
+int b200isp_resize_bilinear(const void* src, int in_dtype, int src_h, int src_w,
+                            void* dst, int out_dtype, int dst_h, int dst_w,
+                            float scale_row, float scale_col, b200isp_stream stream);
+/* EXTENSION (north_star "area resize"; no reference kernel): box filter over the source footprint. */
+int b200isp_resize_area(const void* src, int in_dtype, int src_h, int src_w,
+                        void* dst, int out_dtype, int dst_h, int dst_w, b200isp_stream stream);
+/* interpolate.py:93-108 transform_kernel(dtype)(src,dst,transform); src is (H,W,3). */
+int b200isp_transform(const void* src, void* dst, int dtype, int src_h, int src_w,
+                      int transform, b200isp_stream stream);
+
+/* ---- camera_isp.py (eager, per-stage; float RGB images of the ISP dtype) - */
+/* camera_isp.py:82-99 load_16u / load_32f / load_16f: element-wise convert.
+ * mode 0: out = cast(f32(u16)/65535)   (load_16u)
+ * mode 1: out = cast(f32 in)           (load_32f)
+ * mode 2: out = cast(f32(u16))         (load_16f as written) */
+int b200isp_load_convert(const void* src, void* dst, int out_dtype, int64_t n_elems, int mode,
+                         b200isp_stream stream);
+/* camera_isp.py:142-175 metering_kernel over stack([im[::stride, ::stride] for im in images]).
+ * images_host: n_images device pointers (host array) of (H,W,3) tensors of `dtype` (F16|F32).
+ * metrics: 9 floats on the device, updated in place: lerp(alpha, stats, prev). */
+int b200isp_metering_update(const void* const* images_host, int n_images, int dtype,
+                            int height, int width, int stride, float alpha, float* metrics,
+                            void* workspace, b200isp_stream stream);
+/* camera_isp.py:177-218 reinhard_kernel(image, output, metering, gamma, intensity, la, ca).
+ * Like the reference, pass 1 overwrites `image` with the un-normalised map (ISP dtype). */
+int b200isp_isp_reinhard(void* image, int dtype, void* output, int out_dtype, int64_t n_pixels,
+                         const float* metrics, float gamma, float intensity, float light_adapt,
+                         float color_adapt, void* workspace, b200isp_stream stream);
+
+/* ---- fused path: packed12 frames -> tone-mapped RGB in one sweep --------- */
+typedef struct {
+  int height, width;            /* sensor size; width % 8 == 0, height % 2 == 0 */
+  int pattern;                  /* b200isp_pattern */
+  int isp_dtype;                /* B200ISP_F16 (Camera16 rounding points) or B200ISP_F32 (Camera32) */
+  int out_dtype;                /* U8 | U16 | F16 (tone-mapped) ; F16|F32 == isp_dtype for TM_NONE */
+  int tonemap;                  /* b200isp_tonemap_t; TM_NONE = load_packed12 only (float RGB out) */
+  int has_ccm;                  /* apply ccm (= color_correction * diag(white_balance)) */
+  float ccm[9];                 /* row-major, camera_isp.py:360-369 */
+  float gamma, intensity, light_adapt, color_adapt;   /* camera_isp.py:394-396 */
+  int metering_stride;          /* camera_isp.py:251 (8) */
+  float alpha;                  /* lerp weight of the PREVIOUS metrics: 0 on the first call,
+                                   1 - moving_alpha afterwards (camera_isp.py:376-385) */
+  int update_metering;          /* 1: run the two metering phases on these frames first */
+  int rows_per_task;            /* 0 = default */
+} b200isp_fused_params;
+
+/* camera_isp.py:333-340 load_packed12 + :376-385 update_metering + :394-413 tonemap_* over a
+ * list of frames, without materialising the CFA or the float RGB.
+ * packed_host / out_host: n_frames device pointers each (host arrays).
+ * metrics: 9 floats (device), read and (if update_metering) updated in place. */
+int b200isp_process_packed12(const uint8_t* const* packed_host, void* const* out_host, int n_frames,
+                             const b200isp_fused_params* params, float* metrics,
+                             void* workspace, b200isp_stream stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200ISP_H */

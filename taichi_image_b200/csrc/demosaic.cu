@@ -1,0 +1,256 @@
+// Stand-alone CFA mosaic / Malvar-He-Cutler demosaic on typed planes
+// (reference: bayer.py:101-112 rgb_to_bayer_kernel, bayer.py:114-190 bayer_to_rgb_kernel).
+#include "stream_engine.cuh"
+#include "pixel_ops.cuh"
+
+namespace isp {
+
+// ---------------------------------------------------------------- typed row loaders
+// ALIGNED: W % 8 == 0 and 16-byte aligned base -> word/vector loads; else per-element predicated loads.
+template <typename T, bool ALIGNED> struct PlaneLoader;
+
+template <> struct PlaneLoader<uint8_t, true> {
+  const uint8_t* base;
+  struct Raw { uint32_t w[4]; };
+  __device__ __forceinline__ void fetch(int, int row, int tcol, const StreamGeom& g, Raw& raw) const {
+    if (row < 0 || row >= g.H) { raw.w[0] = raw.w[1] = raw.w[2] = raw.w[3] = 0u; return; }
+    const uint32_t* p = reinterpret_cast<const uint32_t*>(base + (size_t)row * g.W) + 2 * tcol;
+    raw.w[0] = tcol > 0 ? __ldg(p - 1) : 0u;
+    raw.w[1] = __ldg(p);
+    raw.w[2] = __ldg(p + 1);
+    raw.w[3] = tcol < g.ntcols - 1 ? __ldg(p + 2) : 0u;
+  }
+  __device__ __forceinline__ void decode(const Raw& raw, float (&v)[12]) const {
+#pragma unroll
+    for (int j = 0; j < 12; ++j) v[j] = (float)((raw.w[(j + 2) >> 2] >> (8 * ((j + 2) & 3))) & 0xFFu);
+  }
+};
+
+template <typename T> struct PlaneLoader16 {   // u16 / i16 / f16
+  const T* base;
+  struct Raw { uint32_t w[6]; };
+  __device__ __forceinline__ void fetch(int, int row, int tcol, const StreamGeom& g, Raw& raw) const {
+    if (row < 0 || row >= g.H) {
+#pragma unroll
+      for (int i = 0; i < 6; ++i) raw.w[i] = 0u;
+      return;
+    }
+    const uint32_t* p = reinterpret_cast<const uint32_t*>(base + (size_t)row * g.W) + 4 * tcol;
+    raw.w[0] = tcol > 0 ? __ldg(p - 1) : 0u;
+    const uint4 q = __ldg(reinterpret_cast<const uint4*>(p));
+    raw.w[1] = q.x; raw.w[2] = q.y; raw.w[3] = q.z; raw.w[4] = q.w;
+    raw.w[5] = tcol < g.ntcols - 1 ? __ldg(p + 4) : 0u;
+  }
+  __device__ __forceinline__ void decode(const Raw& raw, float (&v)[12]) const {
+#pragma unroll
+    for (int j = 0; j < 12; ++j) {
+      const uint16_t h = (uint16_t)(raw.w[j >> 1] >> (16 * (j & 1)));
+      if constexpr (sizeof(T) == 2 && !DT<T>::is_int) v[j] = __half2float(__ushort_as_half(h));
+      else if constexpr (std::is_same<T, int16_t>::value) v[j] = (float)(int16_t)h;
+      else v[j] = (float)h;
+    }
+  }
+};
+template <> struct PlaneLoader<uint16_t, true> : PlaneLoader16<uint16_t> {};
+template <> struct PlaneLoader<int16_t, true> : PlaneLoader16<int16_t> {};
+template <> struct PlaneLoader<__half, true> : PlaneLoader16<__half> {};
+
+template <> struct PlaneLoader<float, true> {
+  const float* base;
+  struct Raw { float v[12]; };
+  __device__ __forceinline__ void fetch(int, int row, int tcol, const StreamGeom& g, Raw& raw) const {
+    if (row < 0 || row >= g.H) {
+#pragma unroll
+      for (int i = 0; i < 12; ++i) raw.v[i] = 0.f;
+      return;
+    }
+    const float* p = base + (size_t)row * g.W + 8 * tcol;
+    float2 l = make_float2(0.f, 0.f), r = make_float2(0.f, 0.f);
+    if (tcol > 0) l = __ldg(reinterpret_cast<const float2*>(p - 2));
+    const float4 a = __ldg(reinterpret_cast<const float4*>(p));
+    const float4 b = __ldg(reinterpret_cast<const float4*>(p + 4));
+    if (tcol < g.ntcols - 1) r = __ldg(reinterpret_cast<const float2*>(p + 8));
+    raw.v[0] = l.x; raw.v[1] = l.y;
+    raw.v[2] = a.x; raw.v[3] = a.y; raw.v[4] = a.z; raw.v[5] = a.w;
+    raw.v[6] = b.x; raw.v[7] = b.y; raw.v[8] = b.z; raw.v[9] = b.w;
+    raw.v[10] = r.x; raw.v[11] = r.y;
+  }
+  __device__ __forceinline__ void decode(const Raw& raw, float (&v)[12]) const {
+#pragma unroll
+    for (int j = 0; j < 12; ++j) v[j] = raw.v[j];
+  }
+};
+
+// ---------------------------------------------------------------- 8-pixel RGB store
+template <typename OutT, bool ALIGNED>
+__device__ __forceinline__ void store_px8(OutT* dst /* at (row, 8*tcol, 0) */, const OutT (&o)[24], int ncols) {
+  if constexpr (ALIGNED) {
+    constexpr int kBytes = 24 * (int)sizeof(OutT);
+    if constexpr (kBytes % 16 == 0) {
+      const uint4* s = reinterpret_cast<const uint4*>(o);
+      uint4* d = reinterpret_cast<uint4*>(dst);
+#pragma unroll
+      for (int i = 0; i < kBytes / 16; ++i) d[i] = s[i];
+    } else {
+      const uint2* s = reinterpret_cast<const uint2*>(o);
+      uint2* d = reinterpret_cast<uint2*>(dst);
+#pragma unroll
+      for (int i = 0; i < kBytes / 8; ++i) d[i] = s[i];
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      if (j < ncols) {
+        dst[3 * j] = o[3 * j]; dst[3 * j + 1] = o[3 * j + 1]; dst[3 * j + 2] = o[3 * j + 2];
+      }
+  }
+}
+
+// ---------------------------------------------------------------- demosaic epilogue
+// bayer.py:150-155, :132-134:  c = sum / (in_scale * 16); [c = M c]; clamp(c,0,1); cast(c*out_scale).
+// Integer planes without CCM take clamp(floor(sum/16), 0, scale), which equals the float chain for
+// every reachable sum (exhaustively checked in tests/test_oracle.py).
+template <typename T>
+struct EpiDemosaic {
+  T* out;
+  int W;
+  int ccm;          // runtime (warp-uniform) flag
+  float m[9];
+  struct State {};
+  __device__ __forceinline__ void init(State&, int) const {}
+  __device__ __forceinline__ void finish(State&, int, int, bool) const {}
+
+  __device__ __forceinline__ void finish_px(float cr, float cg, float cb, T* o) const {
+    if (ccm) ccm_apply(m, cr, cg, cb);
+    constexpr float os = DT<T>::scale;
+    o[0] = cast_from_f32<T>(__fmul_rn(clamp01(cr), os));
+    o[1] = cast_from_f32<T>(__fmul_rn(clamp01(cg), os));
+    o[2] = cast_from_f32<T>(__fmul_rn(clamp01(cb), os));
+  }
+
+  __device__ __forceinline__ void emit(State&, int, int row, int tcol,
+                                       const float (&R)[8], const float (&G)[8], const float (&B)[8]) const {
+    constexpr float is = DT<T>::scale;
+    alignas(16) T o[24];
+    if (DT<T>::is_int && !ccm) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        o[3 * j]     = (T)(int)(fminf(fmaxf(R[j], 0.f), 16.f * is) * 0.0625f);
+        o[3 * j + 1] = (T)(int)(fminf(fmaxf(G[j], 0.f), 16.f * is) * 0.0625f);
+        o[3 * j + 2] = (T)(int)(fminf(fmaxf(B[j], 0.f), 16.f * is) * 0.0625f);
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        finish_px(__fdiv_rn(R[j], is * 16.f), __fdiv_rn(G[j], is * 16.f), __fdiv_rn(B[j], is * 16.f), o + 3 * j);
+    }
+    store_px8<T, true>(out + ((size_t)row * W + 8 * tcol) * 3, o, 8);
+  }
+};
+
+// ---------------------------------------------------------------- per-pixel kernel
+// Literal bayer.py:137-155 (see pixel_ops.cuh): whole image (mixed dtypes, widths that are not a
+// multiple of 8, unaligned views) or only the 2-pixel frame after a streaming launch.
+template <typename T> struct PlaneSrc {
+  const T* base; int W;
+  __device__ __forceinline__ float at(int, int r, int c) const { return to_f32(base[(size_t)r * W + c]); }
+};
+
+template <typename InT, typename OutT>
+__global__ void __launch_bounds__(256) demosaic_pixel_kernel(const InT* __restrict__ bayer, OutT* __restrict__ out,
+                                                             int H, int W, int pattern, int ccm, const float9 m,
+                                                             int border_only, long long count) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= count) return;
+  int row, col;
+  if (border_only) border_coord(idx, H, W, row, col);
+  else { row = (int)(idx / W); col = (int)(idx % W); }
+  const PlaneSrc<InT> src{bayer, W};
+  float c[3], t[3];
+  malvar_pixel(src, 0, pattern, row, col, H, W, c, t);
+  constexpr float is = DT<InT>::scale, os = DT<OutT>::scale;
+  float cr = __fdiv_rn(c[0], __fmul_rn(is, t[0])), cg = __fdiv_rn(c[1], __fmul_rn(is, t[1])), cb = __fdiv_rn(c[2], __fmul_rn(is, t[2]));
+  if (ccm) ccm_apply(m.v, cr, cg, cb);
+  OutT* o = out + ((size_t)row * W + col) * 3;
+  o[0] = cast_from_f32<OutT>(__fmul_rn(clamp01(cr), os));
+  o[1] = cast_from_f32<OutT>(__fmul_rn(clamp01(cg), os));
+  o[2] = cast_from_f32<OutT>(__fmul_rn(clamp01(cb), os));
+}
+
+template <typename InT, typename OutT>
+static int run_demosaic_pixel(const void* bayer, void* rgb, int H, int W, int pattern, const float* ccm,
+                              bool border_only, cudaStream_t s) {
+  float9 m;
+  for (int i = 0; i < 9; ++i) m.v[i] = ccm ? ccm[i] : 0.f;
+  const long long count = border_only ? border_count(H, W) : (long long)H * W;
+  demosaic_pixel_kernel<InT, OutT><<<(unsigned)((count + 255) / 256), 256, 0, s>>>(
+      (const InT*)bayer, (OutT*)rgb, H, W, pattern, ccm != nullptr, m, border_only ? 1 : 0, count);
+  return cuda_status(cudaPeekAtLastError(), "demosaic_pixel_kernel");
+}
+
+template <typename T>
+static int run_demosaic_stream(const void* bayer, void* rgb, int H, int W, int pattern, const float* ccm, cudaStream_t s) {
+  PlaneLoader<T, true> ld;
+  ld.base = (const T*)bayer;
+  EpiDemosaic<T> epi;
+  epi.out = (T*)rgb; epi.W = W; epi.ccm = ccm != nullptr;
+  for (int i = 0; i < 9; ++i) epi.m[i] = ccm ? ccm[i] : 0.f;
+  const StreamGeom g = make_geom(H, W, 1, 0);
+  ISP_DISPATCH_PATTERN(pattern, P, {
+    const int st = launch_stream<P>(ld, epi, g, s, "bayer_to_rgb");
+    if (st) return st;
+  });
+  return run_demosaic_pixel<T, T>(bayer, rgb, H, W, pattern, ccm, true, s);
+}
+
+// ---------------------------------------------------------------- rgb_to_bayer (bayer.py:101-112)
+// pixel_orders (bayer.py:85-90): channel at ((r0,c0),(r0,c1),(r1,c0),(r1,c1)), 2 bits each
+template <typename T>
+__global__ void __launch_bounds__(256) rgb_to_bayer_kernel(const T* __restrict__ rgb, T* __restrict__ bayer,
+                                                           int H, int W, unsigned order) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  const int r = blockIdx.y;
+  if (c >= (W & ~1) || r >= (H & ~1)) return;
+  const int ch = (order >> (2 * ((r & 1) * 2 + (c & 1)))) & 3;
+  bayer[(size_t)r * W + c] = rgb[((size_t)r * W + c) * 3 + ch];
+}
+
+}  // namespace isp
+
+using namespace isp;
+
+extern "C" int b200isp_rgb_to_bayer(const void* rgb, void* bayer, int dtype, int height, int width,
+                                    int pattern, b200isp_stream stream) {
+  ISP_REQUIRE(height >= 0 && width >= 0, B200ISP_E_SHAPE, "rgb_to_bayer: negative size");
+  ISP_REQUIRE(pattern >= 0 && pattern <= 3, B200ISP_E_ARG, "rgb_to_bayer: unknown pattern %d", pattern);
+  if (height < 2 || width < 2) return B200ISP_OK;
+  ISP_REQUIRE(rgb && bayer, B200ISP_E_ARG, "rgb_to_bayer: null pointer");
+  // RGGB (0,1,1,2) GRBG (1,0,2,1) GBRG (1,2,0,1) BGGR (2,1,1,0)
+  const unsigned orders[4] = {0u | (1u << 2) | (1u << 4) | (2u << 6), 1u | (0u << 2) | (2u << 4) | (1u << 6),
+                              1u | (2u << 2) | (0u << 4) | (1u << 6), 2u | (1u << 2) | (1u << 4) | (0u << 6)};
+  const dim3 grid((width + 255) / 256, height);
+  cudaStream_t s = (cudaStream_t)stream;
+  ISP_DISPATCH_DTYPE(dtype, T, (rgb_to_bayer_kernel<T><<<grid, 256, 0, s>>>((const T*)rgb, (T*)bayer, height, width, orders[pattern])));
+  ISP_LAUNCH_CHECK("rgb_to_bayer_kernel");
+  return B200ISP_OK;
+}
+
+extern "C" int b200isp_bayer_to_rgb(const void* bayer, int in_dtype, void* rgb, int out_dtype,
+                                    int height, int width, int pattern, const float* ccm9_host,
+                                    b200isp_stream stream) {
+  ISP_REQUIRE(height >= 0 && width >= 0 && height % 2 == 0 && width % 2 == 0, B200ISP_E_SHAPE,
+              "bayer_to_rgb: image must be even size, got %dx%d", height, width);
+  ISP_REQUIRE(pattern >= 0 && pattern <= 3, B200ISP_E_ARG, "bayer_to_rgb: unknown pattern %d", pattern);
+  ISP_REQUIRE(valid_dtype(in_dtype) && valid_dtype(out_dtype), B200ISP_E_DTYPE, "bayer_to_rgb: bad dtype");
+  if (height == 0 || width == 0) return B200ISP_OK;
+  ISP_REQUIRE(bayer && rgb, B200ISP_E_ARG, "bayer_to_rgb: null pointer");
+  cudaStream_t s = (cudaStream_t)stream;
+  const bool aligned = (width % 8 == 0) && ((reinterpret_cast<uintptr_t>(bayer) | reinterpret_cast<uintptr_t>(rgb)) & 15u) == 0;
+  if (aligned && in_dtype == out_dtype && height >= 4 && width >= 8) {
+    ISP_DISPATCH_DTYPE(in_dtype, T, return (run_demosaic_stream<T>(bayer, rgb, height, width, pattern, ccm9_host, s)));
+  }
+  ISP_DISPATCH_DTYPE(in_dtype, InT, {
+    ISP_DISPATCH_DTYPE(out_dtype, OutT, return (run_demosaic_pixel<InT, OutT>(bayer, rgb, height, width, pattern, ccm9_host, false, s)));
+  });
+  return B200ISP_OK;
+}

@@ -1,0 +1,168 @@
+// Joint two-phase metering of the ISP (reference: camera_isp.py:102-175) as two deterministic
+// reductions: per-thread sequential accumulate -> warp shuffle tree -> block tree -> per-block
+// partial in the workspace -> the last block to finish (ticket counter) folds the partials in fixed
+// order and applies the moving-average blend on the device.  No host synchronisation, and the
+// result is bit-reproducible run to run (the reference's float atomics are not).
+//
+//   phase 1: (mn, mx) over all sampled values; b = lerp(alpha, (mn,mx), prev.bounds)      :149-157
+//   phase 2: per sample  scaled = (rgb - b.min) / (b.max - b.min + 1e-6)                  :119
+//            gray = rgb_gray(scaled); lg = log(max(gray, 1e-4)); min/max lg, sums         :120-128
+//            normalise by n; metrics = lerp(alpha, [b, lmin, lmax, lmean, mean, rgb], prev) :131-134, :164-166
+// `alpha` is the weight of the PREVIOUS value: lerp(t,a,b) = a + t*(b-a) (util.py:82-84).
+#pragma once
+#include "common.cuh"
+
+namespace isp {
+
+// Sampler concept:  __device__ void sample(long long idx, float (&rgb)[3]) const;   idx in [0, n)
+//                   rgb as stored by the ISP (already rounded through the ISP dtype).
+
+template <int NV>
+__device__ __forceinline__ void block_fold(float (&v)[NV], const int (&op)[NV], float* smem /* [8][NV] */) {
+  // op: 0 = min, 1 = max, 2 = sum
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int k = 0; k < NV; ++k) v[k] = op[k] == 0 ? warp_min(v[k]) : (op[k] == 1 ? warp_max(v[k]) : warp_sum(v[k]));
+  if (lane == 0) {
+#pragma unroll
+    for (int k = 0; k < NV; ++k) smem[warp * NV + k] = v[k];
+  }
+  __syncthreads();
+  if (warp == 0) {
+    const int nw = blockDim.x >> 5;
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      float x = lane < nw ? smem[lane * NV + k] : (op[k] == 0 ? INFINITY : (op[k] == 1 ? -INFINITY : 0.f));
+      v[k] = op[k] == 0 ? warp_min(x) : (op[k] == 1 ? warp_max(x) : warp_sum(x));
+    }
+  }
+  __syncthreads();
+}
+
+// Returns true in ALL threads of the last block to arrive; partials of every block are then visible.
+__device__ __forceinline__ bool last_block_ticket(unsigned int* counter) {
+  __shared__ bool s_last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned int t = atomicAdd(counter, 1u);
+    s_last = (t == gridDim.x - 1);
+    if (s_last) *counter = 0u;   // leave the workspace zeroed for the next launch
+  }
+  __syncthreads();
+  if (s_last) __threadfence();
+  return s_last;
+}
+
+template <class Sampler>
+__global__ void __launch_bounds__(256) meter_phase1_kernel(const Sampler smp, long long n, float alpha,
+                                                           const float* __restrict__ prev, Workspace* ws) {
+  __shared__ float smem[8 * 2];
+  float v[2] = {INFINITY, -INFINITY};
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    float rgb[3];
+    smp.sample(i, rgb);
+    v[0] = fminf(v[0], fminf(rgb[0], fminf(rgb[1], rgb[2])));
+    v[1] = fmaxf(v[1], fmaxf(rgb[0], fmaxf(rgb[1], rgb[2])));
+  }
+  const int op[2] = {0, 1};
+  block_fold<2>(v, op, smem);
+  if (threadIdx.x == 0) {
+    ws->partials[blockIdx.x * kPartialStride + 0] = v[0];
+    ws->partials[blockIdx.x * kPartialStride + 1] = v[1];
+  }
+  if (last_block_ticket(&ws->counter[0])) {
+    float f[2] = {INFINITY, -INFINITY};
+    for (int b = threadIdx.x; b < (int)gridDim.x; b += blockDim.x) {
+      f[0] = fminf(f[0], __ldcg(&ws->partials[b * kPartialStride + 0]));
+      f[1] = fmaxf(f[1], __ldcg(&ws->partials[b * kPartialStride + 1]));
+    }
+    block_fold<2>(f, op, smem);
+    if (threadIdx.x == 0) {
+      // b = lerp(alpha, new, prev) = new + alpha * (prev - new)          camera_isp.py:156
+      ws->bounds[0] = __fadd_rn(f[0], __fmul_rn(alpha, __fsub_rn(prev[0], f[0])));
+      ws->bounds[1] = __fadd_rn(f[1], __fmul_rn(alpha, __fsub_rn(prev[1], f[1])));
+    }
+  }
+}
+
+template <class Sampler>
+__global__ void __launch_bounds__(256) meter_phase2_kernel(const Sampler smp, long long n, float alpha,
+                                                           float* __restrict__ metrics, Workspace* ws) {
+  __shared__ float smem[8 * 7];
+  const float bmin = __ldcg(&ws->bounds[0]), bmax = __ldcg(&ws->bounds[1]);
+  const float den = __fadd_rn(__fsub_rn(bmax, bmin), 1e-6f);
+  float v[7] = {INFINITY, -INFINITY, 0.f, 0.f, 0.f, 0.f, 0.f};
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    float rgb[3];
+    smp.sample(i, rgb);
+    const float r = __fdiv_rn(__fsub_rn(rgb[0], bmin), den);
+    const float g = __fdiv_rn(__fsub_rn(rgb[1], bmin), den);
+    const float b = __fdiv_rn(__fsub_rn(rgb[2], bmin), den);
+    const float gray = rgb_gray(r, g, b);
+    const float lg = logf(fmaxf(gray, 1e-4f));
+    v[0] = fminf(v[0], lg);
+    v[1] = fmaxf(v[1], lg);
+    v[2] += lg; v[3] += gray; v[4] += r; v[5] += g; v[6] += b;
+  }
+  const int op[7] = {0, 1, 2, 2, 2, 2, 2};
+  block_fold<7>(v, op, smem);
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int k = 0; k < 7; ++k) ws->partials[blockIdx.x * kPartialStride + k] = v[k];
+  }
+  if (last_block_ticket(&ws->counter[0])) {
+    float f[7] = {INFINITY, -INFINITY, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int b = threadIdx.x; b < (int)gridDim.x; b += blockDim.x) {
+      f[0] = fminf(f[0], __ldcg(&ws->partials[b * kPartialStride + 0]));
+      f[1] = fmaxf(f[1], __ldcg(&ws->partials[b * kPartialStride + 1]));
+#pragma unroll
+      for (int k = 2; k < 7; ++k) f[k] += __ldcg(&ws->partials[b * kPartialStride + k]);
+    }
+    block_fold<7>(f, op, smem);
+    if (threadIdx.x == 0) {
+      const float fn = (float)n;                                          // camera_isp.py:131-134
+      const float stats[9] = {bmin, bmax, f[0], f[1], __fdiv_rn(f[2], fn), __fdiv_rn(f[3], fn),
+                              __fdiv_rn(f[4], fn), __fdiv_rn(f[5], fn), __fdiv_rn(f[6], fn)};
+#pragma unroll
+      for (int k = 0; k < 9; ++k) {                                       // camera_isp.py:165-166
+        const float p = metrics[k];
+        metrics[k] = __fadd_rn(stats[k], __fmul_rn(alpha, __fsub_rn(p, stats[k])));
+      }
+    }
+  }
+}
+
+inline int meter_grid(long long n) {
+  long long b = (n + 256 * 4 - 1) / (256 * 4);
+  if (b < 1) b = 1;
+  if (b > 4 * kNumSMs) b = 4 * kNumSMs;
+  return (int)b;
+}
+
+template <class Sampler>
+inline int launch_metering(const Sampler& smp, long long n, float alpha, float* metrics, Workspace* ws, cudaStream_t s) {
+  const int grid = meter_grid(n);
+  meter_phase1_kernel<Sampler><<<grid, 256, 0, s>>>(smp, n, alpha, metrics, ws);
+  int st = cuda_status(cudaPeekAtLastError(), "meter_phase1_kernel");
+  if (st) return st;
+  meter_phase2_kernel<Sampler><<<grid, 256, 0, s>>>(smp, n, alpha, metrics, ws);
+  return cuda_status(cudaPeekAtLastError(), "meter_phase2_kernel");
+}
+
+// Sampler over materialised (H, W, 3) images of the ISP dtype (camera_isp.py:168-170)
+template <typename T>
+struct ImageSampler {
+  const T* img[B200ISP_MAX_FRAMES];
+  int W, stride, hs, ws_;     // hs = ceil(H/stride), ws_ = ceil(W/stride)
+  __device__ __forceinline__ void sample(long long idx, float (&rgb)[3]) const {
+    const int j = (int)(idx % ws_);
+    const long long q = idx / ws_;
+    const int i = (int)(q % hs);
+    const int f = (int)(q / hs);
+    const T* p = img[f] + ((size_t)i * stride * W + (size_t)j * stride) * 3;
+    rgb[0] = to_f32(p[0]); rgb[1] = to_f32(p[1]); rgb[2] = to_f32(p[2]);
+  }
+};
+
+}  // namespace isp

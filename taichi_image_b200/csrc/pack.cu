@@ -1,0 +1,256 @@
+// 12-bit pack / unpack and raw-16 decode (reference: packed.py:12-210).
+//
+// Layouts (3 bytes <-> 2 pixels), little-endian 24-bit group x = b0 | b1<<8 | b2<<16:
+//   standard (packed.py:12-31): p0 = x & 0xFFF,              p1 = x >> 12
+//   IDS      (packed.py:36-55): p0 = b0<<4 | (b2 & 0xF),     p1 = b1<<4 | b2>>4   (decode)
+//                               b0 = p0>>4, b1 = p1>>4, b2 = (p0&0xF)<<4 | (p1&0xF) (encode; as
+//                               written the reference's IDS encode is NOT the inverse of its decode)
+// Vector path: one thread converts 32 pixels = 48 packed bytes = 3 x 16-byte loads.
+#include "common.cuh"
+
+namespace isp {
+
+template <bool IDS> __device__ __forceinline__ void decode_pair(uint32_t x, uint32_t& p0, uint32_t& p1) {
+  if constexpr (!IDS) {
+    p0 = x & 0xFFFu;
+    p1 = (x >> 12) & 0xFFFu;
+  } else {
+    const uint32_t b0 = x & 0xFFu, b1 = (x >> 8) & 0xFFu, b2 = (x >> 16) & 0xFFu;
+    p0 = (b0 << 4) | (b2 & 0xFu);
+    p1 = (b1 << 4) | (b2 >> 4);
+  }
+}
+
+template <bool IDS> __device__ __forceinline__ uint32_t encode_pair(uint32_t p0, uint32_t p1) {
+  uint32_t b0, b1, b2;
+  if constexpr (!IDS) {
+    b0 = p0 & 0xFFu;
+    b1 = (((p1 & 0xFu) << 4) | (p0 >> 8)) & 0xFFu;
+    b2 = (p1 >> 4) & 0xFFu;
+  } else {
+    b0 = (p0 >> 4) & 0xFFu;
+    b1 = (p1 >> 4) & 0xFFu;
+    b2 = (((p0 & 0xFu) << 4) | (p1 & 0xFu)) & 0xFFu;
+  }
+  return b0 | (b1 << 8) | (b2 << 16);
+}
+
+// packed.py:98-104 write_value_{scaled,direct}
+template <typename T, bool SCALED> __device__ __forceinline__ T decoded_value(uint32_t v, float k) {
+  if constexpr (SCALED) return cast_from_f32<T>(__fmul_rn((float)v, k));
+  else if constexpr (DT<T>::is_int) return (T)v;
+  else return cast_from_f32<T>((float)v);
+}
+
+// packed.py:66-73 read_value_{scaled,direct}
+template <typename T, bool SCALED> __device__ __forceinline__ uint32_t value_to_u12(T v, float k) {
+  if constexpr (SCALED) {
+    const float r = roundf(__fmul_rn(to_f32(v), k));      // ti.round: half away from zero
+    return (uint32_t)(uint16_t)(int)r;
+  } else if constexpr (DT<T>::is_int) {
+    return (uint32_t)(uint16_t)v;
+  } else {
+    return (uint32_t)(uint16_t)(int)to_f32(v);
+  }
+}
+
+template <typename T, int N> __device__ __forceinline__ void store_items(T* dst, const T (&v)[N]) {
+  constexpr int kBytes = N * (int)sizeof(T);
+  static_assert(kBytes % 16 == 0, "vector store needs 16-byte multiples");
+  const uint4* s = reinterpret_cast<const uint4*>(v);
+  uint4* d = reinterpret_cast<uint4*>(dst);
+#pragma unroll
+  for (int i = 0; i < kBytes / 16; ++i) d[i] = s[i];
+}
+
+template <typename T, int N> __device__ __forceinline__ void load_items(const T* src, T (&v)[N]) {
+  constexpr int kBytes = N * (int)sizeof(T);
+  static_assert(kBytes % 16 == 0, "vector load needs 16-byte multiples");
+  uint4* d = reinterpret_cast<uint4*>(v);
+  const uint4* s = reinterpret_cast<const uint4*>(src);
+#pragma unroll
+  for (int i = 0; i < kBytes / 16; ++i) d[i] = __ldg(s + i);
+}
+
+// ---------------------------------------------------------------- decode12
+template <typename T, bool SCALED, bool IDS>
+__global__ void __launch_bounds__(256) decode12_vec_kernel(const uint8_t* __restrict__ enc, T* __restrict__ out,
+                                                           int64_t n_groups, float k) {
+  const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= n_groups) return;
+  alignas(16) uint32_t w[12];
+  load_items<uint32_t, 12>(reinterpret_cast<const uint32_t*>(enc + g * 48), w);
+  alignas(16) T v[32];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const int k0 = (3 * i) / 4, off = (24 * i) % 32;
+    const uint32_t x = (off == 0 ? w[k0] : (off == 8 ? (w[k0] >> 8) : __funnelshift_r(w[k0], w[k0 + 1], off))) & 0xFFFFFFu;
+    uint32_t p0, p1;
+    decode_pair<IDS>(x, p0, p1);
+    v[2 * i] = decoded_value<T, SCALED>(p0, k);
+    v[2 * i + 1] = decoded_value<T, SCALED>(p1, k);
+  }
+  store_items<T, 32>(out + g * 32, v);
+}
+
+template <typename T, bool SCALED, bool IDS>
+__global__ void __launch_bounds__(256) decode12_pair_kernel(const uint8_t* __restrict__ enc, T* __restrict__ out,
+                                                            int64_t pair_begin, int64_t n_pairs, float k) {
+  const int64_t i = pair_begin + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_pairs) return;
+  const uint8_t* b = enc + 3 * i;
+  const uint32_t x = (uint32_t)b[0] | ((uint32_t)b[1] << 8) | ((uint32_t)b[2] << 16);
+  uint32_t p0, p1;
+  decode_pair<IDS>(x, p0, p1);
+  out[2 * i] = decoded_value<T, SCALED>(p0, k);
+  out[2 * i + 1] = decoded_value<T, SCALED>(p1, k);
+}
+
+// ---------------------------------------------------------------- encode12
+template <typename T, bool SCALED, bool IDS>
+__global__ void __launch_bounds__(256) encode12_vec_kernel(const T* __restrict__ values, uint8_t* __restrict__ enc,
+                                                           int64_t n_groups, float k) {
+  const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= n_groups) return;
+  alignas(16) T v[32];
+  load_items<T, 32>(values + g * 32, v);
+  alignas(16) uint32_t w[12];
+#pragma unroll
+  for (int i = 0; i < 12; ++i) w[i] = 0u;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const uint32_t x = encode_pair<IDS>(value_to_u12<T, SCALED>(v[2 * i], k), value_to_u12<T, SCALED>(v[2 * i + 1], k));
+    const int k0 = (3 * i) / 4, off = (24 * i) % 32;
+    w[k0] |= x << off;
+    if (off > 8) w[k0 + 1] |= x >> (32 - off);
+  }
+  store_items<uint32_t, 12>(reinterpret_cast<uint32_t*>(enc + g * 48), w);
+}
+
+template <typename T, bool SCALED, bool IDS>
+__global__ void __launch_bounds__(256) encode12_pair_kernel(const T* __restrict__ values, uint8_t* __restrict__ enc,
+                                                            int64_t pair_begin, int64_t n_pairs, float k) {
+  const int64_t i = pair_begin + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_pairs) return;
+  const uint32_t x = encode_pair<IDS>(value_to_u12<T, SCALED>(values[2 * i], k), value_to_u12<T, SCALED>(values[2 * i + 1], k));
+  enc[3 * i] = (uint8_t)x;
+  enc[3 * i + 1] = (uint8_t)(x >> 8);
+  enc[3 * i + 2] = (uint8_t)(x >> 16);
+}
+
+// ---------------------------------------------------------------- decode16 (packed.py:149-157)
+template <typename T, bool SCALED>
+__global__ void __launch_bounds__(256) decode16_kernel(const uint8_t* __restrict__ enc, T* __restrict__ out,
+                                                       int64_t n, float k, bool vec) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (vec) {     // 8 values per thread, 16-byte load
+    const int64_t i = t * 8;
+    if (i + 8 <= n) {
+      const uint4 q = __ldg(reinterpret_cast<const uint4*>(enc) + t);
+      const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const uint32_t v = (w[j >> 1] >> (16 * (j & 1))) & 0xFFFFu;   // little-endian byte pair
+        out[i + j] = decoded_value<T, SCALED>(v, k);
+      }
+      return;
+    }
+    for (int64_t j = i; j < n; ++j) {
+      const uint32_t v = (uint32_t)enc[2 * j] | ((uint32_t)enc[2 * j + 1] << 8);
+      out[j] = decoded_value<T, SCALED>(v, k);
+    }
+  } else if (t < n) {
+    const uint32_t v = (uint32_t)enc[2 * t] | ((uint32_t)enc[2 * t + 1] << 8);
+    out[t] = decoded_value<T, SCALED>(v, k);
+  }
+}
+
+static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+template <typename T, bool SCALED, bool IDS>
+static int launch_decode12(const uint8_t* enc, T* out, int64_t n_values, float k, cudaStream_t s) {
+  const int64_t n_pairs = n_values / 2;
+  int64_t n_groups = (aligned16(enc) && aligned16(out)) ? n_values / 32 : 0;
+  if (n_groups > 0) {
+    decode12_vec_kernel<T, SCALED, IDS><<<(unsigned)((n_groups + 255) / 256), 256, 0, s>>>(enc, out, n_groups, k);
+    ISP_LAUNCH_CHECK("decode12_vec_kernel");
+  }
+  const int64_t rest = n_pairs - n_groups * 16;
+  if (rest > 0) {
+    decode12_pair_kernel<T, SCALED, IDS><<<(unsigned)((rest + 255) / 256), 256, 0, s>>>(enc, out, n_groups * 16, n_pairs, k);
+    ISP_LAUNCH_CHECK("decode12_pair_kernel");
+  }
+  return B200ISP_OK;
+}
+
+template <typename T, bool SCALED, bool IDS>
+static int launch_encode12(const T* values, uint8_t* enc, int64_t n_values, float k, cudaStream_t s) {
+  const int64_t n_pairs = n_values / 2;
+  int64_t n_groups = (aligned16(enc) && aligned16(values)) ? n_values / 32 : 0;
+  if (n_groups > 0) {
+    encode12_vec_kernel<T, SCALED, IDS><<<(unsigned)((n_groups + 255) / 256), 256, 0, s>>>(values, enc, n_groups, k);
+    ISP_LAUNCH_CHECK("encode12_vec_kernel");
+  }
+  const int64_t rest = n_pairs - n_groups * 16;
+  if (rest > 0) {
+    encode12_pair_kernel<T, SCALED, IDS><<<(unsigned)((rest + 255) / 256), 256, 0, s>>>(values, enc, n_groups * 16, n_pairs, k);
+    ISP_LAUNCH_CHECK("encode12_pair_kernel");
+  }
+  return B200ISP_OK;
+}
+
+}  // namespace isp
+
+using namespace isp;
+
+extern "C" int b200isp_decode12(const uint8_t* encoded, int64_t n_values, void* out, int out_dtype,
+                                int scaled, int ids_format, b200isp_stream stream) {
+  ISP_REQUIRE(n_values >= 0 && n_values % 2 == 0, B200ISP_E_SHAPE, "decode12: n_values must be even, got %lld", (long long)n_values);
+  if (n_values == 0) return B200ISP_OK;
+  ISP_REQUIRE(encoded && out, B200ISP_E_ARG, "decode12: null pointer");
+  cudaStream_t s = (cudaStream_t)stream;
+  ISP_DISPATCH_DTYPE(out_dtype, T, {
+    const float k = (float)((double)DT<T>::scale / 4095.0);   // packed.py:99 (python double -> f32 constant)
+    T* o = (T*)out;
+    if (scaled) return ids_format ? launch_decode12<T, true, true>(encoded, o, n_values, k, s)
+                                  : launch_decode12<T, true, false>(encoded, o, n_values, k, s);
+    return ids_format ? launch_decode12<T, false, true>(encoded, o, n_values, k, s)
+                      : launch_decode12<T, false, false>(encoded, o, n_values, k, s);
+  });
+  return B200ISP_OK;
+}
+
+extern "C" int b200isp_encode12(const void* values, int in_dtype, int64_t n_values, uint8_t* encoded,
+                                int scaled, int ids_format, b200isp_stream stream) {
+  ISP_REQUIRE(n_values >= 0 && n_values % 2 == 0, B200ISP_E_SHAPE, "encode12: n_values must be even, got %lld", (long long)n_values);
+  if (n_values == 0) return B200ISP_OK;
+  ISP_REQUIRE(encoded && values, B200ISP_E_ARG, "encode12: null pointer");
+  cudaStream_t s = (cudaStream_t)stream;
+  ISP_DISPATCH_DTYPE(in_dtype, T, {
+    const float k = (float)(4095.0 / (double)DT<T>::scale);   // packed.py:67
+    const T* v = (const T*)values;
+    if (scaled) return ids_format ? launch_encode12<T, true, true>(v, encoded, n_values, k, s)
+                                  : launch_encode12<T, true, false>(v, encoded, n_values, k, s);
+    return ids_format ? launch_encode12<T, false, true>(v, encoded, n_values, k, s)
+                      : launch_encode12<T, false, false>(v, encoded, n_values, k, s);
+  });
+  return B200ISP_OK;
+}
+
+extern "C" int b200isp_decode16(const uint8_t* encoded, int64_t n_values, void* out, int out_dtype,
+                                int scaled, b200isp_stream stream) {
+  ISP_REQUIRE(n_values >= 0, B200ISP_E_SHAPE, "decode16: negative size");
+  if (n_values == 0) return B200ISP_OK;
+  ISP_REQUIRE(encoded && out, B200ISP_E_ARG, "decode16: null pointer");
+  cudaStream_t s = (cudaStream_t)stream;
+  const bool vec = aligned16(encoded);
+  const int64_t threads = vec ? (n_values + 7) / 8 : n_values;
+  const unsigned blocks = (unsigned)((threads + 255) / 256);
+  ISP_DISPATCH_DTYPE(out_dtype, T, {
+    const float k = (float)((double)DT<T>::scale / 65535.0);  // packed.py:140
+    if (scaled) decode16_kernel<T, true><<<blocks, 256, 0, s>>>(encoded, (T*)out, n_values, k, vec);
+    else        decode16_kernel<T, false><<<blocks, 256, 0, s>>>(encoded, (T*)out, n_values, k, vec);
+  });
+  ISP_LAUNCH_CHECK("decode16_kernel");
+  return B200ISP_OK;
+}

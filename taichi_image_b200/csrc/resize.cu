@@ -1,0 +1,188 @@
+// Gather kernels: bilinear resize, area resize (extension) and the 8 rotate/flip transforms
+// (reference: interpolate.py:19-66 bilinear, :36-56 / :93-108 transform).
+#include "common.cuh"
+
+namespace isp {
+
+__device__ __forceinline__ float mixf(float a, float b, float t) {   // GLSL mix: a*(1-t) + b*t, rounded per op
+  return __fadd_rn(__fmul_rn(a, __fsub_rn(1.0f, t)), __fmul_rn(b, t));
+}
+
+// interpolate.py:59-66: p = I / scale (no half-pixel offset), p1 = trunc(p), clamp-to-edge taps,
+// mix along dim 0 first (frac.x), then dim 1; cast(out * intensity_scale) truncating.
+template <typename InT, typename OutT>
+__global__ void __launch_bounds__(256) bilinear_kernel(const InT* __restrict__ src, int hs, int ws,
+                                                       OutT* __restrict__ dst, int hd, int wd,
+                                                       float scale_r, float scale_c, float intensity) {
+  const int col = blockIdx.x * blockDim.x + threadIdx.x;
+  const int row = blockIdx.y;
+  if (col >= wd) return;
+  const float pr = __fdiv_rn((float)row, scale_r), pc = __fdiv_rn((float)col, scale_c);
+  const int r1 = (int)pr, c1 = (int)pc;
+  const float fr = __fsub_rn(pr, (float)r1), fc = __fsub_rn(pc, (float)c1);
+  const int ra = min(max(r1, 0), hs - 1), rb = min(max(r1 + 1, 0), hs - 1);
+  const int ca = min(max(c1, 0), ws - 1), cb = min(max(c1 + 1, 0), ws - 1);
+  const InT* s00 = src + ((size_t)ra * ws + ca) * 3;
+  const InT* s10 = src + ((size_t)rb * ws + ca) * 3;
+  const InT* s01 = src + ((size_t)ra * ws + cb) * 3;
+  const InT* s11 = src + ((size_t)rb * ws + cb) * 3;
+  OutT* o = dst + ((size_t)row * wd + col) * 3;
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    const float y1 = mixf(to_f32(s00[k]), to_f32(s10[k]), fr);
+    const float y2 = mixf(to_f32(s01[k]), to_f32(s11[k]), fr);
+    o[k] = cast_from_f32<OutT>(__fmul_rn(mixf(y1, y2, fc), intensity));
+  }
+}
+
+// EXTENSION (no reference kernel): exact box filter.  Output pixel (i, j) averages the source over
+// [i*hs/hd, (i+1)*hs/hd) x [j*ws/wd, (j+1)*ws/wd) with fractional coverage weights.
+template <typename InT, typename OutT>
+__global__ void __launch_bounds__(256) area_kernel(const InT* __restrict__ src, int hs, int ws,
+                                                   OutT* __restrict__ dst, int hd, int wd, float intensity) {
+  const int col = blockIdx.x * blockDim.x + threadIdx.x;
+  const int row = blockIdx.y;
+  if (col >= wd) return;
+  const float fr = (float)hs / (float)hd, fc = (float)ws / (float)wd;
+  const float r0 = row * fr, r1 = fminf((row + 1) * fr, (float)hs);
+  const float c0 = col * fc, c1 = fminf((col + 1) * fc, (float)ws);
+  float acc[3] = {0.f, 0.f, 0.f}, wsum = 0.f;
+  for (int r = (int)r0; r < hs && (float)r < r1; ++r) {
+    const float wr = fminf(r1, (float)(r + 1)) - fmaxf(r0, (float)r);
+    if (wr <= 0.f) continue;
+    for (int c = (int)c0; c < ws && (float)c < c1; ++c) {
+      const float wc = fminf(c1, (float)(c + 1)) - fmaxf(c0, (float)c);
+      if (wc <= 0.f) continue;
+      const float w = wr * wc;
+      const InT* p = src + ((size_t)r * ws + c) * 3;
+      acc[0] = fmaf(w, to_f32(p[0]), acc[0]);
+      acc[1] = fmaf(w, to_f32(p[1]), acc[1]);
+      acc[2] = fmaf(w, to_f32(p[2]), acc[2]);
+      wsum += w;
+    }
+  }
+  OutT* o = dst + ((size_t)row * wd + col) * 3;
+  const float inv = wsum > 0.f ? intensity / wsum : 0.f;
+#pragma unroll
+  for (int k = 0; k < 3; ++k) o[k] = cast_from_f32<OutT>(acc[k] * inv);
+}
+
+// interpolate.py:36-56: source index for destination (r, c); (H, W) = SOURCE shape.
+// rotate_90 is clockwise; transverse is the corrected anti-transpose.
+__device__ __forceinline__ void transformed(int t, int r, int c, int H, int W, int& sr, int& sc) {
+  switch (t) {
+    case B200ISP_T_ROT90:      sr = H - 1 - c; sc = r;         break;
+    case B200ISP_T_ROT180:     sr = H - 1 - r; sc = W - 1 - c; break;
+    case B200ISP_T_ROT270:     sr = c;         sc = W - 1 - r; break;
+    case B200ISP_T_TRANSPOSE:  sr = c;         sc = r;         break;
+    case B200ISP_T_FLIP_VERT:  sr = H - 1 - r; sc = c;         break;
+    case B200ISP_T_FLIP_HORIZ: sr = r;         sc = W - 1 - c; break;
+    case B200ISP_T_TRANSVERSE: sr = H - 1 - c; sc = W - 1 - r; break;
+    default:                   sr = r;         sc = c;         break;
+  }
+}
+
+// 32x32-pixel tiles staged through shared memory so that both the read and the write side stay
+// row-contiguous for the transposing transforms.
+template <typename T>
+__global__ void __launch_bounds__(256) transform_kernel(const T* __restrict__ src, T* __restrict__ dst,
+                                                        int H, int W, int hd, int wd, int t) {
+  __shared__ T tile[32][32 * 3 + 1];
+  const bool swaps = (t == B200ISP_T_ROT90 || t == B200ISP_T_ROT270 || t == B200ISP_T_TRANSPOSE || t == B200ISP_T_TRANSVERSE);
+  const int dr0 = blockIdx.y * 32, dc0 = blockIdx.x * 32;      // destination tile origin
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;      // 32 x 8 threads
+  if (!swaps) {
+    // row-preserving: each destination row maps to one source row, columns possibly reversed
+    for (int y = ty; y < 32; y += 8) {
+      const int r = dr0 + y;
+      if (r >= hd) continue;
+      for (int e = tx; e < 96; e += 32) {
+        const int c = dc0 + e / 3, k = e % 3;
+        if (c >= wd) continue;
+        int sr, sc;
+        transformed(t, r, c, H, W, sr, sc);
+        dst[((size_t)r * wd + c) * 3 + k] = src[((size_t)sr * W + sc) * 3 + k];
+      }
+    }
+    return;
+  }
+  // transposing: load the source tile row-wise (source rows <-> destination columns)
+  for (int y = ty; y < 32; y += 8) {
+    // source pixel for destination (dr0 + x, dc0 + y): walk x fastest on the destination ROW index so
+    // that consecutive threads read consecutive source columns.
+    for (int e = tx; e < 96; e += 32) {
+      const int x = e / 3, k = e % 3;
+      const int r = dr0 + x, c = dc0 + y;
+      if (r < hd && c < wd) {
+        int sr, sc;
+        transformed(t, r, c, H, W, sr, sc);
+        tile[x][y * 3 + k] = src[((size_t)sr * W + sc) * 3 + k];
+      }
+    }
+  }
+  __syncthreads();
+  for (int y = ty; y < 32; y += 8) {
+    const int r = dr0 + y;
+    if (r >= hd) continue;
+    for (int e = tx; e < 96; e += 32) {
+      const int c = dc0 + e / 3;
+      if (c < wd) dst[((size_t)r * wd + c) * 3 + e % 3] = tile[y][e];
+    }
+  }
+}
+
+}  // namespace isp
+
+using namespace isp;
+
+extern "C" int b200isp_resize_bilinear(const void* src, int in_dtype, int src_h, int src_w, void* dst, int out_dtype,
+                                       int dst_h, int dst_w, float scale_row, float scale_col, b200isp_stream stream) {
+  ISP_REQUIRE(src_h > 0 && src_w > 0 && dst_h >= 0 && dst_w >= 0, B200ISP_E_SHAPE, "resize_bilinear: bad shape");
+  ISP_REQUIRE(scale_row > 0.f && scale_col > 0.f, B200ISP_E_ARG, "resize_bilinear: scale must be positive");
+  if (dst_h == 0 || dst_w == 0) return B200ISP_OK;
+  ISP_REQUIRE(src && dst, B200ISP_E_ARG, "resize_bilinear: null pointer");
+  const dim3 grid((dst_w + 255) / 256, dst_h);
+  cudaStream_t s = (cudaStream_t)stream;
+  ISP_DISPATCH_DTYPE(in_dtype, InT, {
+    ISP_DISPATCH_DTYPE(out_dtype, OutT, {
+      const float intensity = (float)((double)DT<OutT>::scale / (double)DT<InT>::scale);   // interpolate.py:78
+      bilinear_kernel<InT, OutT><<<grid, 256, 0, s>>>((const InT*)src, src_h, src_w, (OutT*)dst, dst_h, dst_w,
+                                                      scale_row, scale_col, intensity);
+    });
+  });
+  ISP_LAUNCH_CHECK("bilinear_kernel");
+  return B200ISP_OK;
+}
+
+extern "C" int b200isp_resize_area(const void* src, int in_dtype, int src_h, int src_w, void* dst, int out_dtype,
+                                   int dst_h, int dst_w, b200isp_stream stream) {
+  ISP_REQUIRE(src_h > 0 && src_w > 0 && dst_h >= 0 && dst_w >= 0, B200ISP_E_SHAPE, "resize_area: bad shape");
+  if (dst_h == 0 || dst_w == 0) return B200ISP_OK;
+  ISP_REQUIRE(src && dst, B200ISP_E_ARG, "resize_area: null pointer");
+  const dim3 grid((dst_w + 255) / 256, dst_h);
+  cudaStream_t s = (cudaStream_t)stream;
+  ISP_DISPATCH_DTYPE(in_dtype, InT, {
+    ISP_DISPATCH_DTYPE(out_dtype, OutT, {
+      const float intensity = (float)((double)DT<OutT>::scale / (double)DT<InT>::scale);
+      area_kernel<InT, OutT><<<grid, 256, 0, s>>>((const InT*)src, src_h, src_w, (OutT*)dst, dst_h, dst_w, intensity);
+    });
+  });
+  ISP_LAUNCH_CHECK("area_kernel");
+  return B200ISP_OK;
+}
+
+extern "C" int b200isp_transform(const void* src, void* dst, int dtype, int src_h, int src_w, int transform,
+                                 b200isp_stream stream) {
+  ISP_REQUIRE(src_h >= 0 && src_w >= 0, B200ISP_E_SHAPE, "transform: bad shape");
+  ISP_REQUIRE(transform >= B200ISP_T_NONE && transform <= B200ISP_T_TRANSVERSE, B200ISP_E_ARG, "transform: unknown transform %d", transform);
+  if (src_h == 0 || src_w == 0) return B200ISP_OK;
+  ISP_REQUIRE(src && dst, B200ISP_E_ARG, "transform: null pointer");
+  const bool swaps = (transform == B200ISP_T_ROT90 || transform == B200ISP_T_ROT270 ||
+                      transform == B200ISP_T_TRANSPOSE || transform == B200ISP_T_TRANSVERSE);
+  const int hd = swaps ? src_w : src_h, wd = swaps ? src_h : src_w;
+  const dim3 grid((wd + 31) / 32, (hd + 31) / 32);
+  cudaStream_t s = (cudaStream_t)stream;
+  ISP_DISPATCH_DTYPE(dtype, T, (transform_kernel<T><<<grid, 256, 0, s>>>((const T*)src, (T*)dst, src_h, src_w, hd, wd, transform)));
+  ISP_LAUNCH_CHECK("transform_kernel");
+  return B200ISP_OK;
+}

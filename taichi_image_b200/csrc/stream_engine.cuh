@@ -1,0 +1,176 @@
+// Register-window streaming engine for the Malvar-He-Cutler demosaic (reference: bayer.py:114-177).
+//
+// B200 mapping: one thread owns 8 consecutive pixel columns and walks DOWN the image keeping a
+// 6-row x 12-column window of the CFA in registers (8 own columns + 2 halo columns per side), so
+// every CFA sample is fetched from memory once per row-chunk and decoded once; no shared memory, no
+// block barriers.  A warp covers a 256-pixel strip (coalesced 384-byte packed12 rows / 256..1024
+// byte typed rows), a "task" is (frame, row-chunk, strip) and tasks are laid out so that the warps
+// of a block sit on adjacent strips of the same rows (halo words hit L1).  The grid has one warp
+// per task; rows_per_task sizes it to several waves over the 148 SMs.
+//
+// The 13-tap filters are evaluated through shared partial sums:
+//   NS(c) = v[r-1][c]+v[r+1][c]   EW = v[r][c-1]+v[r][c+1]   NNSS = v[r-2][c]+v[r+2][c]
+//   EEWW = v[r][c-2]+v[r][c+2]    D = NS(c-1)+NS(c+1)
+//   R/B site:  own = 16C   G = 8C+4(NS+EW)-2(NNSS+EEWW)   opposite = 12C+4D-3(NNSS+EEWW)
+//   G site:    G = 16C     colour with horizontal neighbours = 10C+8EW-2D-2EEWW+NNSS
+//                          colour with vertical neighbours   = 10C+8NS-2D-2NNSS+EEWW
+// which are the tables of bayer.py:30-55 (x16).  The sums are exact for integer-valued inputs
+// (|sum| < 2^24), so the evaluation order does not matter there.  Out-of-image taps read as 0 and
+// the streaming kernel normalises every pixel by 16; the 2-pixel image frame, where the reference
+// renormalises by the in-bounds weight sum (bayer.py:145-151), is then rewritten by a per-pixel
+// border kernel (border.cuh) launched right after on the same stream.
+#pragma once
+#include "common.cuh"
+
+namespace isp {
+
+struct StreamGeom {
+  int H, W;
+  int ntcols;          // ceil(W / 8): thread columns per row
+  int warps_per_row;   // ceil(ntcols / 32)
+  int rows_per_task;   // even
+  int nchunks;         // ceil(H / rows_per_task)
+  int nframes;
+  long long total_tasks;   // nframes * nchunks * warps_per_row (warp tasks)
+};
+
+inline StreamGeom make_geom(int H, int W, int nframes, int rows_per_task) {
+  StreamGeom g;
+  g.H = H; g.W = W;
+  g.ntcols = (W + 7) / 8;
+  g.warps_per_row = (g.ntcols + 31) / 32;
+  if (rows_per_task <= 0) {
+    // aim at >= ~6 waves of 16 warps on 148 SMs, keep the 4 halo rows <= ~12 % of the loads
+    rows_per_task = 48;
+    while (rows_per_task > 12 &&
+           (long long)nframes * ((H + rows_per_task - 1) / rows_per_task) * g.warps_per_row < 6LL * 16 * kNumSMs)
+      rows_per_task -= 12;
+  }
+  rows_per_task += rows_per_task & 1;
+  g.rows_per_task = rows_per_task;
+  g.nchunks = (H + rows_per_task - 1) / rows_per_task;
+  g.nframes = nframes;
+  g.total_tasks = (long long)nframes * g.nchunks * g.warps_per_row;
+  return g;
+}
+
+template <bool BROW, bool GFIRST>
+__device__ __forceinline__ void malvar_row(const float (&m2)[12], const float (&m1)[12], const float (&z)[12],
+                                           const float (&p1)[12], const float (&p2)[12],
+                                           float (&R)[8], float (&G)[8], float (&B)[8]) {
+  float ns[10];
+#pragma unroll
+  for (int k = 0; k < 10; ++k) ns[k] = m1[k + 1] + p1[k + 1];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float C = z[j + 2];
+    const float EW = z[j + 1] + z[j + 3];
+    const float EEWW = z[j] + z[j + 4];
+    const float NS = ns[j + 1];
+    const float D = ns[j] + ns[j + 2];
+    const float NNSS = m2[j + 2] + p2[j + 2];
+    const bool gsite = (((j & 1) == 0) == GFIRST);
+    if (!gsite) {
+      const float A = NS + EW, Bq = NNSS + EEWW;
+      const float Gc = fmaf(4.f, A, fmaf(-2.f, Bq, 8.f * C));
+      const float Y = fmaf(4.f, D, fmaf(-3.f, Bq, 12.f * C));
+      const float X = 16.f * C;
+      G[j] = Gc;
+      R[j] = BROW ? Y : X;
+      B[j] = BROW ? X : Y;
+    } else {
+      const float T = fmaf(-2.f, D, 10.f * C);
+      const float Hc = fmaf(8.f, EW, fmaf(-2.f, EEWW, T)) + NNSS;
+      const float Vc = fmaf(8.f, NS, fmaf(-2.f, NNSS, T)) + EEWW;
+      G[j] = 16.f * C;
+      R[j] = BROW ? Vc : Hc;
+      B[j] = BROW ? Hc : Vc;
+    }
+  }
+}
+
+// Loader concept:
+//   struct Raw;                                                         raw registers of one row
+//   void fetch(int frame, int row, int tcol, const StreamGeom&, Raw&)   issue the global loads
+//   void decode(const Raw&, float (&v)[12])                             v[j] = CFA at column 8*tcol-2+j (0 outside)
+// Epilogue concept:
+//   struct State;  void init(State&, int frame) ;  void finish(State&, int frame, int lane)
+//   void emit(State&, int frame, int row, int tcol, R, G, B)   raw filter sums (x16), t = 16 assumed
+template <int PATTERN, class Loader, class Epi>
+__global__ void __launch_bounds__(256, 2) stream_kernel(const Loader ld, const Epi epi, const StreamGeom g) {
+  constexpr bool BROW0 = (PATTERN == B200ISP_GBRG || PATTERN == B200ISP_BGGR);
+  constexpr bool GFIRST0 = (PATTERN == B200ISP_GRBG || PATTERN == B200ISP_GBRG);
+  const int lane = threadIdx.x & 31;
+  long long task = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const bool task_ok = task < g.total_tasks;
+  if (!task_ok) task = 0;
+  const int strip = (int)(task % g.warps_per_row);
+  const long long t2 = task / g.warps_per_row;
+  const int chunk = (int)(t2 % g.nchunks);
+  const int frame = (int)(t2 / g.nchunks);
+  const int tcol = strip * 32 + lane;
+  const bool active = task_ok && tcol < g.ntcols;
+
+  typename Epi::State st;
+  epi.init(st, frame);
+
+  if (active) {
+    const int r0 = chunk * g.rows_per_task;
+    const int rend = min(r0 + g.rows_per_task, g.H);
+
+    float win[6][12];
+    typename Loader::Raw raw0, raw1;
+    // prologue: rows r0-2 .. r0+1 -> slots 0..3
+    ld.fetch(frame, r0 - 2, tcol, g, raw0);
+    ld.fetch(frame, r0 - 1, tcol, g, raw1);
+    ld.decode(raw0, win[0]);
+    ld.decode(raw1, win[1]);
+    ld.fetch(frame, r0, tcol, g, raw0);
+    ld.fetch(frame, r0 + 1, tcol, g, raw1);
+    ld.decode(raw0, win[2]);
+    ld.decode(raw1, win[3]);
+    ld.fetch(frame, r0 + 2, tcol, g, raw0);
+    ld.fetch(frame, r0 + 3, tcol, g, raw1);
+
+    for (int rb = r0; rb < rend; rb += 6) {
+#pragma unroll
+      for (int u = 0; u < 3; ++u) {
+        const int row = rb + 2 * u;
+        if (row < rend) {
+          // rows row+2, row+3 were fetched one step ago
+          ld.decode(raw0, win[(2 * u + 4) % 6]);
+          ld.decode(raw1, win[(2 * u + 5) % 6]);
+          if (row + 4 < rend + 2) ld.fetch(frame, row + 4, tcol, g, raw0);   // next step's rows (warp-uniform)
+          if (row + 5 < rend + 2) ld.fetch(frame, row + 5, tcol, g, raw1);
+          float R[8], G[8], B[8];
+          malvar_row<BROW0, GFIRST0>(win[(2 * u) % 6], win[(2 * u + 1) % 6], win[(2 * u + 2) % 6],
+                                     win[(2 * u + 3) % 6], win[(2 * u + 4) % 6], R, G, B);
+          epi.emit(st, frame, row, tcol, R, G, B);
+          malvar_row<!BROW0, !GFIRST0>(win[(2 * u + 1) % 6], win[(2 * u + 2) % 6], win[(2 * u + 3) % 6],
+                                       win[(2 * u + 4) % 6], win[(2 * u + 5) % 6], R, G, B);
+          epi.emit(st, frame, row + 1, tcol, R, G, B);
+        }
+      }
+    }
+  }
+  epi.finish(st, frame, lane, task_ok);
+}
+
+template <int PATTERN, class Loader, class Epi>
+inline int launch_stream(const Loader& ld, const Epi& epi, const StreamGeom& g, cudaStream_t s, const char* what) {
+  if (g.total_tasks == 0) return B200ISP_OK;
+  const long long blocks = (g.total_tasks + 7) / 8;
+  stream_kernel<PATTERN, Loader, Epi><<<(unsigned)blocks, 256, 0, s>>>(ld, epi, g);
+  return cuda_status(cudaPeekAtLastError(), what);
+}
+
+#define ISP_DISPATCH_PATTERN(p, P, ...)                                        \
+  switch (p) {                                                                 \
+    case B200ISP_RGGB: { constexpr int P = B200ISP_RGGB; __VA_ARGS__; break; } \
+    case B200ISP_GRBG: { constexpr int P = B200ISP_GRBG; __VA_ARGS__; break; } \
+    case B200ISP_GBRG: { constexpr int P = B200ISP_GBRG; __VA_ARGS__; break; } \
+    case B200ISP_BGGR: { constexpr int P = B200ISP_BGGR; __VA_ARGS__; break; } \
+    default: isp::set_error("unknown bayer pattern %d", (int)(p)); return B200ISP_E_ARG; \
+  }
+
+}  // namespace isp

@@ -1,0 +1,359 @@
+// Eager (per-stage) tone-mapping kernels on materialised float RGB images.
+//   b200isp_bounds              util.py:49-60 bounds_func
+//   b200isp_linear              tonemap.py:11-17 linear_func (tonemap.linear_kernel and ISP linear_kernel)
+//   b200isp_reinhard_standalone tonemap.py:134-168 (five dependent passes, 4 launches, no host sync)
+//   b200isp_metering_update     camera_isp.py:142-175
+//   b200isp_isp_reinhard        camera_isp.py:177-218
+//   b200isp_load_convert        camera_isp.py:82-99
+#include "metering.cuh"
+#include "reinhard.cuh"
+
+namespace isp {
+
+static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+// ---------------------------------------------------------------- 4-element vector access
+template <typename T> __device__ __forceinline__ void load4(const T* p, float (&v)[4]) {
+  if constexpr (sizeof(T) == 4) {
+    const float4 q = *reinterpret_cast<const float4*>(p);
+    v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
+  } else if constexpr (sizeof(T) == 2) {
+    const uint2 q = *reinterpret_cast<const uint2*>(p);
+    const T* t = reinterpret_cast<const T*>(&q);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) v[i] = to_f32(t[i]);
+  } else {
+    const uint32_t q = *reinterpret_cast<const uint32_t*>(p);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) v[i] = (float)((q >> (8 * i)) & 0xFFu);
+  }
+}
+template <typename T> __device__ __forceinline__ void store4(T* p, const T (&v)[4]) {
+  if constexpr (sizeof(T) == 4) *reinterpret_cast<uint4*>(p) = *reinterpret_cast<const uint4*>(v);
+  else if constexpr (sizeof(T) == 2) *reinterpret_cast<uint2*>(p) = *reinterpret_cast<const uint2*>(v);
+  else *reinterpret_cast<uint32_t*>(p) = *reinterpret_cast<const uint32_t*>(v);
+}
+
+// ---------------------------------------------------------------- bounds (util.py:49-60)
+template <typename T>
+__global__ void __launch_bounds__(256) bounds_kernel(const T* __restrict__ x, long long n, bool vec, float* out, Workspace* ws) {
+  __shared__ float smem[8 * 2];
+  float v[2] = {INFINITY, -INFINITY};
+  const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x, nth = (long long)gridDim.x * blockDim.x;
+  if (vec) {
+    const long long n4 = n / 4;
+    for (long long i = tid; i < n4; i += nth) {
+      float a[4];
+      load4<T>(x + 4 * i, a);
+      v[0] = fminf(v[0], fminf(fminf(a[0], a[1]), fminf(a[2], a[3])));
+      v[1] = fmaxf(v[1], fmaxf(fmaxf(a[0], a[1]), fmaxf(a[2], a[3])));
+    }
+    for (long long i = n4 * 4 + tid; i < n; i += nth) { const float a = to_f32(x[i]); v[0] = fminf(v[0], a); v[1] = fmaxf(v[1], a); }
+  } else {
+    for (long long i = tid; i < n; i += nth) { const float a = to_f32(x[i]); v[0] = fminf(v[0], a); v[1] = fmaxf(v[1], a); }
+  }
+  const int op[2] = {0, 1};
+  block_fold<2>(v, op, smem);
+  if (threadIdx.x == 0) {
+    ws->partials[blockIdx.x * kPartialStride + 0] = v[0];
+    ws->partials[blockIdx.x * kPartialStride + 1] = v[1];
+  }
+  if (last_block_ticket(&ws->counter[0])) {
+    float f[2] = {INFINITY, -INFINITY};
+    for (int b = threadIdx.x; b < (int)gridDim.x; b += blockDim.x) {
+      f[0] = fminf(f[0], __ldcg(&ws->partials[b * kPartialStride + 0]));
+      f[1] = fmaxf(f[1], __ldcg(&ws->partials[b * kPartialStride + 1]));
+    }
+    block_fold<2>(f, op, smem);
+    if (threadIdx.x == 0) { out[0] = f[0]; out[1] = f[1]; }
+  }
+}
+
+static inline int reduce_grid(long long n_items_per_thread_units) {
+  long long b = (n_items_per_thread_units + 256 * 8 - 1) / (256 * 8);
+  if (b < 1) b = 1;
+  if (b > 8 * kNumSMs) b = 8 * kNumSMs;
+  return (int)b;
+}
+
+template <typename T>
+static int launch_bounds_kernel(const T* x, long long n, float* out, Workspace* ws, cudaStream_t s) {
+  const bool vec = aligned16(x);
+  bounds_kernel<T><<<reduce_grid(vec ? n / 4 : n), 256, 0, s>>>(x, n, vec, out, ws);
+  return cuda_status(cudaPeekAtLastError(), "bounds_kernel");
+}
+
+// ---------------------------------------------------------------- linear_func (tonemap.py:11-17)
+template <typename InT, typename OutT>
+__device__ __forceinline__ OutT linear_value(float x, float bmin, float inv_range, float inv_gamma, bool has_gamma) {
+  float y = __fmul_rn(__fsub_rn(x, bmin), inv_range);
+  if (has_gamma) y = powf(y, inv_gamma);
+  return cast_from_f32<OutT>(__fmul_rn(clamp01(y), DT<OutT>::scale));   // NaN -> 0 through the saturating clamp
+}
+
+template <typename InT, typename OutT>
+__global__ void __launch_bounds__(256) linear_kernel(const InT* __restrict__ src, OutT* __restrict__ dst, long long n,
+                                                     const float* __restrict__ bounds, float gamma, bool vec) {
+  const float bmin = bounds[0], bmax = bounds[1];
+  const float inv_range = __fdiv_rn(1.0f, __fsub_rn(bmax, bmin));
+  const float inv_gamma = __fdiv_rn(1.0f, gamma);
+  const bool has_gamma = gamma != 1.0f;
+  const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (vec) {
+    const long long i = tid * 4;
+    if (i + 4 <= n) {
+      float a[4];
+      load4<InT>(src + i, a);
+      alignas(16) OutT o[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) o[k] = linear_value<InT, OutT>(a[k], bmin, inv_range, inv_gamma, has_gamma);
+      store4<OutT>(dst + i, o);
+    } else {
+      for (long long j = i; j < n; ++j) dst[j] = linear_value<InT, OutT>(to_f32(src[j]), bmin, inv_range, inv_gamma, has_gamma);
+    }
+  } else if (tid < n) {
+    dst[tid] = linear_value<InT, OutT>(to_f32(src[tid]), bmin, inv_range, inv_gamma, has_gamma);
+  }
+}
+
+template <typename InT, typename OutT>
+static int launch_linear(const InT* src, OutT* dst, long long n, const float* bounds, float gamma, cudaStream_t s) {
+  const bool vec = aligned16(src) && aligned16(dst);
+  const long long threads = vec ? (n + 3) / 4 : n;
+  linear_kernel<InT, OutT><<<(unsigned)((threads + 255) / 256), 256, 0, s>>>(src, dst, n, bounds, gamma, vec);
+  return cuda_status(cudaPeekAtLastError(), "linear_kernel");
+}
+
+// ---------------------------------------------------------------- stand-alone Reinhard (tonemap.py:134-168)
+// pass A: temp = clamp((src - min) / range, 0, 1) as f32 (linear_func gamma 1, scale 1) fused with
+//         metering_func(temp, Bounds(0,1)) (tonemap.py:77-103): log-gray min/max, sums.
+template <typename InT>
+__global__ void __launch_bounds__(256) sa_normalise_meter_kernel(const InT* __restrict__ src, float* __restrict__ temp,
+                                                                 long long n_px, const float* __restrict__ b, Workspace* ws) {
+  __shared__ float smem[8 * 7];
+  const float bmin = b[0];
+  const float inv_range = __fdiv_rn(1.0f, __fsub_rn(b[1], bmin));
+  float v[7] = {INFINITY, -INFINITY, 0.f, 0.f, 0.f, 0.f, 0.f};
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_px; i += (long long)gridDim.x * blockDim.x) {
+    float s[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      s[k] = clamp01(__fmul_rn(__fsub_rn(to_f32(src[3 * i + k]), bmin), inv_range));
+      temp[3 * i + k] = s[k];
+    }
+    const float gray = rgb_gray(s[0], s[1], s[2]);     // (temp - 0) / (1 - 0) == temp
+    const float lg = logf(fmaxf(gray, 1e-4f));
+    v[0] = fminf(v[0], lg); v[1] = fmaxf(v[1], lg);
+    v[2] += lg; v[3] += gray; v[4] += s[0]; v[5] += s[1]; v[6] += s[2];
+  }
+  const int op[7] = {0, 1, 2, 2, 2, 2, 2};
+  block_fold<7>(v, op, smem);
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int k = 0; k < 7; ++k) ws->partials[blockIdx.x * kPartialStride + k] = v[k];
+  }
+  if (last_block_ticket(&ws->counter[0])) {
+    float f[7] = {INFINITY, -INFINITY, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int bk = threadIdx.x; bk < (int)gridDim.x; bk += blockDim.x) {
+      f[0] = fminf(f[0], __ldcg(&ws->partials[bk * kPartialStride + 0]));
+      f[1] = fmaxf(f[1], __ldcg(&ws->partials[bk * kPartialStride + 1]));
+#pragma unroll
+      for (int k = 2; k < 7; ++k) f[k] += __ldcg(&ws->partials[bk * kPartialStride + k]);
+    }
+    block_fold<7>(f, op, smem);
+    if (threadIdx.x == 0) {
+      const float fn = (float)n_px;
+      // 9-float record in the ISP layout so reinhard_params() can be shared:
+      // [bounds.min=0, bounds.max=1, log_b.min, log_b.max, log_mean, mean, rgb_mean]
+      // with log_bounds = Bounds(log_min, -log_max) exactly as written at tonemap.py:102.
+      float* m = ws->scratch + 8;
+      m[0] = 0.f; m[1] = 1.f; m[2] = f[0]; m[3] = -f[1];
+      m[4] = __fdiv_rn(f[2], fn); m[5] = __fdiv_rn(f[3], fn);
+      m[6] = __fdiv_rn(f[4], fn); m[7] = __fdiv_rn(f[5], fn); m[8] = __fdiv_rn(f[6], fn);
+    }
+  }
+}
+
+// pass B: Reinhard in place on temp (tonemap.py:107-131) fused with bounds_func(temp) (:146)
+__global__ void __launch_bounds__(256) sa_reinhard_kernel(float* __restrict__ temp, long long n_px, float intensity,
+                                                          float la, float ca, Workspace* ws) {
+  __shared__ float smem[8 * 2];
+  const ReinhardParams p = reinhard_params(ws->scratch + 8, intensity, la, ca);
+  float v[2] = {INFINITY, -INFINITY};
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_px; i += (long long)gridDim.x * blockDim.x) {
+    const float x[3] = {temp[3 * i], temp[3 * i + 1], temp[3 * i + 2]};
+    float o[3];
+    reinhard_map_exact(p, x, o);      // bmin = 0, range = 1: (x - 0) / 1 == x
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      temp[3 * i + k] = o[k];
+      v[0] = fminf(v[0], o[k]); v[1] = fmaxf(v[1], o[k]);
+    }
+  }
+  const int op[2] = {0, 1};
+  block_fold<2>(v, op, smem);
+  if (threadIdx.x == 0) {
+    ws->partials[blockIdx.x * kPartialStride + 0] = v[0];
+    ws->partials[blockIdx.x * kPartialStride + 1] = v[1];
+  }
+  if (last_block_ticket(&ws->counter[0])) {
+    float f[2] = {INFINITY, -INFINITY};
+    for (int b = threadIdx.x; b < (int)gridDim.x; b += blockDim.x) {
+      f[0] = fminf(f[0], __ldcg(&ws->partials[b * kPartialStride + 0]));
+      f[1] = fmaxf(f[1], __ldcg(&ws->partials[b * kPartialStride + 1]));
+    }
+    block_fold<2>(f, op, smem);
+    if (threadIdx.x == 0) { ws->scratch[2] = f[0]; ws->scratch[3] = f[1]; }
+  }
+}
+
+// ---------------------------------------------------------------- ISP Reinhard (camera_isp.py:177-218)
+// pass 1: p -> image (ISP dtype), max over f32 p.  pass 2: (image / max_out)^(1/gamma) * scale -> out.
+template <typename T>
+__global__ void __launch_bounds__(256) isp_reinhard_pass1_kernel(T* __restrict__ image, long long n_px,
+                                                                 const float* __restrict__ metrics, float intensity,
+                                                                 float la, float ca, Workspace* ws) {
+  __shared__ float smem[8];
+  const ReinhardParams p = reinhard_params(metrics, intensity, la, ca);
+  float mx = 0.f;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_px; i += (long long)gridDim.x * blockDim.x) {
+    const float x[3] = {to_f32(image[3 * i]), to_f32(image[3 * i + 1]), to_f32(image[3 * i + 2])};
+    float o[3];
+    reinhard_map_exact(p, x, o);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      image[3 * i + k] = cast_from_f32<T>(o[k]);
+      mx = fmaxf(mx, o[k]);
+    }
+  }
+  mx = warp_max(mx);
+  if ((threadIdx.x & 31) == 0) smem[threadIdx.x >> 5] = mx;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    mx = threadIdx.x < (blockDim.x >> 5) ? smem[threadIdx.x] : 0.f;
+    mx = warp_max(mx);
+    if (threadIdx.x == 0 && mx > 0.f) atomicMax(reinterpret_cast<unsigned int*>(&ws->frame_max[0]), __float_as_uint(mx));
+  }
+}
+
+template <typename T, typename OutT>
+__global__ void __launch_bounds__(256) isp_reinhard_pass2_kernel(const T* __restrict__ image, OutT* __restrict__ out,
+                                                                 long long n_elems, float gamma, Workspace* ws) {
+  const float max_out = fmaxf(1e-6f, __ldcg(&ws->frame_max[0]));
+  const float inv_gamma = (float)(1.0 / (double)gamma);     // python double 1.0 / gamma -> f32 constant (:217)
+  const bool has_gamma = gamma != 1.0f;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_elems; i += (long long)gridDim.x * blockDim.x) {
+    float q = __fdiv_rn(to_f32(image[i]), max_out);
+    if (has_gamma) q = powf(q, inv_gamma);
+    out[i] = cast_from_f32<OutT>(__fmul_rn(DT<OutT>::scale, q));
+  }
+  if (last_block_ticket(&ws->counter[1]) && threadIdx.x == 0) ws->frame_max[0] = 0.f;
+}
+
+// ---------------------------------------------------------------- loaders (camera_isp.py:82-99)
+template <typename InT, typename OutT, int MODE>
+__global__ void __launch_bounds__(256) load_convert_kernel(const InT* __restrict__ src, OutT* __restrict__ dst, long long n) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float x = to_f32(src[i]);
+  if (MODE == 0) x = __fdiv_rn(x, 65535.0f);
+  dst[i] = cast_from_f32<OutT>(x);
+}
+
+}  // namespace isp
+
+using namespace isp;
+
+extern "C" int b200isp_bounds(const void* src, int dtype, int64_t n_elems, float* bounds_out, void* workspace,
+                              b200isp_stream stream) {
+  ISP_REQUIRE(src && bounds_out && workspace && n_elems > 0, B200ISP_E_ARG, "bounds: bad argument");
+  ISP_DISPATCH_DTYPE(dtype, T, return (launch_bounds_kernel<T>((const T*)src, n_elems, bounds_out, (Workspace*)workspace, (cudaStream_t)stream)));
+  return B200ISP_OK;
+}
+
+extern "C" int b200isp_linear(const void* src, int in_dtype, void* dst, int out_dtype, int64_t n_elems,
+                              const float* bounds, float gamma, b200isp_stream stream) {
+  ISP_REQUIRE(n_elems >= 0, B200ISP_E_SHAPE, "linear: negative size");
+  if (n_elems == 0) return B200ISP_OK;
+  ISP_REQUIRE(src && dst && bounds, B200ISP_E_ARG, "linear: null pointer");
+  ISP_REQUIRE(gamma > 0.f, B200ISP_E_ARG, "linear: gamma must be positive");
+  ISP_DISPATCH_DTYPE(in_dtype, InT, {
+    ISP_DISPATCH_DTYPE(out_dtype, OutT, return (launch_linear<InT, OutT>((const InT*)src, (OutT*)dst, n_elems, bounds, gamma, (cudaStream_t)stream)));
+  });
+  return B200ISP_OK;
+}
+
+extern "C" int b200isp_reinhard_standalone(const void* src, int in_dtype, float* temp, void* dst, int out_dtype,
+                                           int64_t n_pixels, float gamma, float intensity, float light_adapt,
+                                           float color_adapt, void* workspace, b200isp_stream stream) {
+  ISP_REQUIRE(n_pixels > 0 && src && temp && dst && workspace, B200ISP_E_ARG, "reinhard_standalone: bad argument");
+  ISP_REQUIRE(gamma > 0.f, B200ISP_E_ARG, "reinhard_standalone: gamma must be positive");
+  Workspace* ws = (Workspace*)workspace;
+  cudaStream_t s = (cudaStream_t)stream;
+  float* ws_bounds = reinterpret_cast<float*>(reinterpret_cast<char*>(ws) + offsetof(Workspace, scratch));
+  const int grid = meter_grid(n_pixels);
+  ISP_DISPATCH_DTYPE(in_dtype, InT, {
+    int st = launch_bounds_kernel<InT>((const InT*)src, n_pixels * 3, ws_bounds, ws, s);       // tonemap.py:146
+    if (st) return st;
+    sa_normalise_meter_kernel<InT><<<grid, 256, 0, s>>>((const InT*)src, temp, n_pixels, ws_bounds, ws);   // :147-149
+  });
+  ISP_LAUNCH_CHECK("sa_normalise_meter_kernel");
+  sa_reinhard_kernel<<<grid, 256, 0, s>>>(temp, n_pixels, intensity, light_adapt, color_adapt, ws);   // :150-153
+  ISP_LAUNCH_CHECK("sa_reinhard_kernel");
+  ISP_DISPATCH_DTYPE(out_dtype, OutT, return (launch_linear<float, OutT>(temp, (OutT*)dst, n_pixels * 3, ws_bounds + 2, gamma, s)));  // :154
+  return B200ISP_OK;
+}
+
+extern "C" int b200isp_metering_update(const void* const* images_host, int n_images, int dtype, int height, int width,
+                                       int stride, float alpha, float* metrics, void* workspace, b200isp_stream stream) {
+  ISP_REQUIRE(images_host && metrics && workspace, B200ISP_E_ARG, "metering_update: null pointer");
+  ISP_REQUIRE(n_images >= 1 && n_images <= B200ISP_MAX_FRAMES, B200ISP_E_FRAMES,
+              "metering_update: %d images (1..%d supported per call)", n_images, B200ISP_MAX_FRAMES);
+  ISP_REQUIRE(height > 0 && width > 0 && stride > 0, B200ISP_E_SHAPE, "metering_update: bad shape");
+  ISP_REQUIRE(dtype == B200ISP_F16 || dtype == B200ISP_F32, B200ISP_E_DTYPE, "metering_update: ISP dtype must be f16 or f32");
+  const int hs = (height + stride - 1) / stride, wsamp = (width + stride - 1) / stride;
+  const long long n = (long long)n_images * hs * wsamp;
+  ISP_DISPATCH_DTYPE(dtype, T, {
+    ImageSampler<T> smp;
+    for (int i = 0; i < n_images; ++i) smp.img[i] = (const T*)images_host[i];
+    smp.W = width; smp.stride = stride; smp.hs = hs; smp.ws_ = wsamp;
+    return launch_metering(smp, n, alpha, metrics, (Workspace*)workspace, (cudaStream_t)stream);
+  });
+  return B200ISP_OK;
+}
+
+extern "C" int b200isp_isp_reinhard(void* image, int dtype, void* output, int out_dtype, int64_t n_pixels,
+                                    const float* metrics, float gamma, float intensity, float light_adapt,
+                                    float color_adapt, void* workspace, b200isp_stream stream) {
+  ISP_REQUIRE(image && output && metrics && workspace && n_pixels > 0, B200ISP_E_ARG, "isp_reinhard: bad argument");
+  ISP_REQUIRE(dtype == B200ISP_F16 || dtype == B200ISP_F32, B200ISP_E_DTYPE, "isp_reinhard: ISP dtype must be f16 or f32");
+  ISP_REQUIRE(gamma > 0.f, B200ISP_E_ARG, "isp_reinhard: gamma must be positive");
+  Workspace* ws = (Workspace*)workspace;
+  cudaStream_t s = (cudaStream_t)stream;
+  const int grid = meter_grid(n_pixels);
+  ISP_DISPATCH_DTYPE(dtype, T, {
+    isp_reinhard_pass1_kernel<T><<<grid, 256, 0, s>>>((T*)image, n_pixels, metrics, intensity, light_adapt, color_adapt, ws);
+    ISP_LAUNCH_CHECK("isp_reinhard_pass1_kernel");
+    ISP_DISPATCH_DTYPE(out_dtype, OutT,
+      (isp_reinhard_pass2_kernel<T, OutT><<<grid, 256, 0, s>>>((const T*)image, (OutT*)output, n_pixels * 3, gamma, ws)));
+  });
+  ISP_LAUNCH_CHECK("isp_reinhard_pass2_kernel");
+  return B200ISP_OK;
+}
+
+extern "C" int b200isp_load_convert(const void* src, void* dst, int out_dtype, int64_t n_elems, int mode,
+                                    b200isp_stream stream) {
+  ISP_REQUIRE(n_elems >= 0 && mode >= 0 && mode <= 2, B200ISP_E_ARG, "load_convert: bad argument");
+  if (n_elems == 0) return B200ISP_OK;
+  ISP_REQUIRE(src && dst, B200ISP_E_ARG, "load_convert: null pointer");
+  ISP_REQUIRE(out_dtype == B200ISP_F16 || out_dtype == B200ISP_F32, B200ISP_E_DTYPE, "load_convert: ISP dtype must be f16 or f32");
+  cudaStream_t s = (cudaStream_t)stream;
+  const unsigned blocks = (unsigned)((n_elems + 255) / 256);
+  ISP_DISPATCH_DTYPE(out_dtype, OutT, {
+    if (mode == 0) load_convert_kernel<uint16_t, OutT, 0><<<blocks, 256, 0, s>>>((const uint16_t*)src, (OutT*)dst, n_elems);
+    else if (mode == 1) load_convert_kernel<float, OutT, 1><<<blocks, 256, 0, s>>>((const float*)src, (OutT*)dst, n_elems);
+    else load_convert_kernel<uint16_t, OutT, 2><<<blocks, 256, 0, s>>>((const uint16_t*)src, (OutT*)dst, n_elems);
+  });
+  ISP_LAUNCH_CHECK("load_convert_kernel");
+  return B200ISP_OK;
+}

@@ -1,0 +1,180 @@
+"""GPU parity: camera_isp.py -- eager stage-by-stage API and the fused packed12 sweep against the
+oracle ISP (Camera16 / Camera32, metering moving average, Reinhard / linear, u8 / u16 / f16 outputs)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import isp_oracle as O
+from tests.util import rng, packed_frame, to_cuda, to_np, assert_close_int, assert_close_float
+
+pytestmark = pytest.mark.gpu
+CAMS = {"f16": "Camera16", "f32": "Camera32"}
+
+
+def make_isp(dt, **kw):
+    from taichi_image_b200 import camera_isp, bayer
+    kw = dict(kw)
+    pattern = kw.pop("bayer_pattern", "RGGB")
+    return getattr(camera_isp, CAMS[dt])(bayer.BayerPattern[pattern], **kw)
+
+
+def frames(r, n, h, w, pattern="RGGB"):
+    return [packed_frame(r, h, w, pattern) for _ in range(n)]
+
+
+@pytest.mark.parametrize("dt", ["f16", "f32"])
+@pytest.mark.parametrize("pattern", O.PATTERNS)
+@pytest.mark.parametrize("shape", [(32, 48), (30, 36)])     # fused loader / generic (width % 8 != 0)
+@pytest.mark.parametrize("ccm", [False, True])
+def test_load_packed12(cuda, dt, pattern, shape, ccm):
+    pk = packed_frame(rng(30), *shape, pattern)
+    isp = make_isp(dt, bayer_pattern=pattern, correct_colors=ccm)
+    got = to_np(isp.load_packed12(to_cuda(pk)))
+    ref = O.ISP(dt, pattern, correct_colors=ccm).load_packed12(pk)
+    assert got.dtype == ref.dtype and got.shape == ref.shape
+    assert_close_float(got, ref, rtol=1e-3, atol=1e-3 if dt == "f16" else 2e-6, what=f"{dt} {pattern}")
+
+
+@pytest.mark.parametrize("dt", ["f16", "f32"])
+def test_load_other_formats(cuda, dt):
+    r = rng(31)
+    raw16 = r.integers(0, 65536, size=(16, 24)).astype(np.uint16)
+    isp, ref = make_isp(dt), O.ISP(dt)
+    assert_close_float(to_np(isp.load_16u(to_cuda(raw16))), ref.load_16u(raw16), atol=1e-3 if dt == "f16" else 2e-6)
+    f = r.random((16, 24), dtype=np.float32)
+    assert_close_float(to_np(isp.load_32f(to_cuda(f))), ref.load_32f(f), atol=1e-3 if dt == "f16" else 2e-6)
+    b = raw16.view(np.uint8).reshape(16, 48)
+    assert_close_float(to_np(isp.load_packed16(to_cuda(b))), ref.load_packed16(b), atol=1e-3 if dt == "f16" else 2e-6)
+    pk = O.encode12(r.integers(0, 4096, size=(16, 24)).astype(np.uint16), ids_format=True)
+    assert_close_float(to_np(isp.load_packed12(to_cuda(pk), ids_format=True)), ref.load_packed12(pk, ids_format=True),
+                       atol=1e-3 if dt == "f16" else 2e-6)
+
+
+@pytest.mark.parametrize("dt", ["f16", "f32"])
+@pytest.mark.parametrize("stride", [8, 3])
+def test_metering_moving_average(cuda, dt, stride):
+    r = rng(32)
+    isp, ref = make_isp(dt, metering_stride=stride, moving_alpha=0.1), O.ISP(dt, metering_stride=stride, moving_alpha=0.1)
+    for step in range(3):
+        fr = frames(r, 3, 40, 56)
+        ims_ref = [ref.load_packed12(f) for f in fr]
+        ims = [to_cuda(i) for i in ims_ref]           # identical inputs: isolates the metering kernels
+        isp.update_metering(ims)
+        ref.update_metering(ims_ref)
+        assert_close_float(to_np(isp.metrics), ref.metrics, rtol=2e-5, atol=2e-6, what=f"step {step}")
+
+
+TM = [dict(), dict(gamma=0.6), dict(gamma=0.9, intensity=3.0, light_adapt=0.9, color_adapt=0.0),
+      dict(gamma=0.8, intensity=2.0, light_adapt=0.7, color_adapt=0.3)]
+
+
+@pytest.mark.parametrize("dt", ["f16", "f32"])
+@pytest.mark.parametrize("tm", TM)
+def test_eager_tonemap_reinhard(cuda, dt, tm):
+    r = rng(33)
+    isp, ref = make_isp(dt), O.ISP(dt)
+    for step in range(2):
+        fr = frames(r, 2, 32, 48)
+        got = isp.tonemap_reinhard([isp.load_packed12(to_cuda(f)) for f in fr], **tm)
+        exp = ref.tonemap_reinhard([ref.load_packed12(f) for f in fr], **tm)
+        for g, e in zip(got, exp):
+            assert g.dtype == torch.uint8
+            assert_close_int(to_np(g), e, 1, f"{dt} {tm} step {step}")
+    assert_close_float(to_np(isp.metrics), ref.metrics, rtol=1e-4, atol=1e-5)
+
+
+@pytest.mark.parametrize("dt", ["f16", "f32"])
+@pytest.mark.parametrize("gamma", [1.0, 0.7])
+def test_eager_tonemap_linear(cuda, dt, gamma):
+    r = rng(34)
+    isp, ref = make_isp(dt), O.ISP(dt)
+    fr = frames(r, 2, 32, 48)
+    got = isp.tonemap_linear([isp.load_packed12(to_cuda(f)) for f in fr], gamma=gamma)
+    exp = ref.tonemap_linear([ref.load_packed12(f) for f in fr], gamma=gamma)
+    for g, e in zip(got, exp):
+        assert_close_int(to_np(g), e, 1, f"{dt} gamma {gamma}")
+
+
+@pytest.mark.parametrize("dt", ["f16", "f32"])
+@pytest.mark.parametrize("pattern", O.PATTERNS)
+@pytest.mark.parametrize("tm", TM[:3])
+def test_fused_reinhard_u8(cuda, dt, pattern, tm):
+    r = rng(35)
+    isp, ref = make_isp(dt, bayer_pattern=pattern), O.ISP(dt, pattern)
+    for step in range(3):
+        fr = frames(r, 3, 40, 64, pattern)
+        got = isp.process_packed12([to_cuda(f) for f in fr], tonemap="reinhard", **tm)
+        exp = ref.tonemap_reinhard([ref.load_packed12(f) for f in fr], **tm)
+        for g, e in zip(got, exp):
+            assert_close_int(to_np(g), e, 1, f"{dt} {pattern} {tm} step {step}")
+        assert_close_float(to_np(isp.metrics), ref.metrics, rtol=1e-4, atol=1e-5, what="metrics")
+
+
+@pytest.mark.parametrize("dt,out,lsb", [("f32", "u8", 1), ("f32", "u16", 1), ("f16", "u8", 1), ("f16", "u16", 33)])
+@pytest.mark.parametrize("gamma", [1.0, 0.7])
+@pytest.mark.parametrize("ccm", [False, True])
+def test_fused_linear(cuda, dt, out, lsb, gamma, ccm):
+    """u16 from Camera16 is allowed one f16 ulp of the intermediate (<= 32 LSB of u16), see DESIGN.md"""
+    r = rng(36)
+    isp, ref = make_isp(dt, correct_colors=ccm), O.ISP(dt, correct_colors=ccm)
+    for step in range(2):
+        fr = frames(r, 2, 36, 72)
+        got = isp.process_packed12([to_cuda(f) for f in fr], tonemap="linear", gamma=gamma, dtype=out)
+        exp = ref.tonemap_linear([ref.load_packed12(f) for f in fr], gamma=gamma, out_dtype=out)
+        for g, e in zip(got, exp):
+            frac = assert_close_int(to_np(g), e, lsb if gamma == 1.0 else max(lsb, 8 if out == "u16" else 1), f"{dt}->{out}")
+            if dt == "f16" and out == "u16":
+                assert frac < 0.02 or gamma != 1.0
+
+
+@pytest.mark.parametrize("dt", ["f16", "f32"])
+def test_fused_f16_output_and_transform(cuda, dt):
+    from taichi_image_b200.interpolate import ImageTransform
+    r = rng(37)
+    isp, ref = make_isp(dt, transform=ImageTransform.rotate_90), O.ISP(dt, transform="rotate_90")
+    fr = frames(r, 2, 32, 40)
+    got = isp.process_packed12([to_cuda(f) for f in fr], tonemap="reinhard", gamma=0.8, dtype="f16")
+    exp = ref.tonemap_reinhard([ref.load_packed12(f) for f in fr], gamma=0.8, out_dtype="f16")
+    for g, e in zip(got, exp):
+        assert g.dtype == torch.float16 and tuple(g.shape) == (40, 32, 3)
+        assert_close_float(to_np(g), e, rtol=2e-3, atol=1e-3)
+
+
+@pytest.mark.parametrize("dt", ["f16", "f32"])
+def test_fused_with_resize_falls_back_to_staged_kernels(cuda, dt):
+    r = rng(38)
+    isp, ref = make_isp(dt, resize_width=40), O.ISP(dt, resize_width=40)
+    fr = frames(r, 2, 48, 80)
+    got = isp.process_packed12([to_cuda(f) for f in fr], tonemap="reinhard", gamma=0.6)
+    exp = ref.tonemap_reinhard([ref.load_packed12(f) for f in fr], gamma=0.6)
+    for g, e in zip(got, exp):
+        assert tuple(g.shape) == e.shape == (24, 40, 3)
+        assert_close_int(to_np(g), e, 1, "resize")
+
+
+def test_fused_random_frames_worst_case(cuda):
+    """pure-random 12-bit frames: heavy clamping, full dynamic range"""
+    r = rng(39)
+    isp, ref = make_isp("f32"), O.ISP("f32")
+    fr = [packed_frame(r, 64, 96, smooth=False) for _ in range(2)]
+    got = isp.process_packed12([to_cuda(f) for f in fr], tonemap="reinhard", gamma=0.9, intensity=3.0, light_adapt=0.9)
+    exp = ref.tonemap_reinhard([ref.load_packed12(f) for f in fr], gamma=0.9, intensity=3.0, light_adapt=0.9)
+    for g, e in zip(got, exp):
+        assert_close_int(to_np(g), e, 1, "random frames")
+
+
+def test_isp_api_surface(cuda):
+    from taichi_image_b200 import camera_isp, bayer
+    isp = camera_isp.Camera32(bayer.BayerPattern.RGGB, moving_alpha=0.2)
+    assert camera_isp.Camera16.__qualname__ == "Camera16" and isp.metrics is None
+    isp.set(resize_width=100)
+    assert isp.resize_width == 100 and isp.scale is None
+    isp.set(scale=0.5)
+    assert isp.scale == 0.5 and isp.resize_width == 0
+    assert isp.color_correct_matrix is None
+    isp.set(correct_colors=True)
+    assert np.allclose(isp.color_correct_matrix, O.DEFAULT_CC * O.DEFAULT_WB)
+    with pytest.raises(Exception):
+        camera_isp.Camera32("RGGB")          # beartype: pattern must be a BayerPattern
+    with pytest.raises(AssertionError):
+        camera_isp.Camera32(bayer.BayerPattern.RGGB, scale=0.5, resize_width=10)
