@@ -148,6 +148,8 @@ typedef struct {
                                    1 - moving_alpha afterwards (camera_isp.py:376-385) */
   int update_metering;          /* 1: run the two metering phases on these frames first */
   int rows_per_task;            /* 0 = default */
+  void* profile_start;          /* optional cudaEvent_t pair recorded on `stream` immediately before / after */
+  void* profile_stop;           /*   the dominant streaming kernel (bench.py's live roofline timing); NULL = off */
 } b200isp_fused_params;
 
 /* camera_isp.py:333-340 load_packed12 + :376-385 update_metering + :394-413 tonemap_* over a

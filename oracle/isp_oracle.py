@@ -380,6 +380,11 @@ def isp_reinhard(image: np.ndarray, metrics: np.ndarray, gamma, intensity, light
         max_out = max(f32(1e-6), f32(np.nanmax(p)))
         stored = p.astype(image.dtype)                                   # :211
         q = _pow(stored.astype(f32) / max_out, 1.0 / gamma)              # :217
+        # pixels darker than the (sub-sampled, moving-average) lower bound give negative / NaN q; the
+        # reference then casts a negative or NaN float to u8 (undefined).  Defined here as 0.
+        q = np.where(q > 0, q, f32(0)).astype(f32)
+        if out_dtype in ("u8", "u16", "i16"):
+            q = np.minimum(q, f32(1))
         out = cast_to(f32(SCALE[out_dtype]) * q, out_dtype)               # :218 (255*p for u8)
     return (out, stored, max_out) if return_intermediate else out
 

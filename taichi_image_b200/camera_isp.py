@@ -19,7 +19,7 @@ with the un-normalised map (Q6); ``process_packed12`` never touches its inputs.
 """
 from __future__ import annotations
 
-from typing import List, Optional, Sequence
+from typing import Optional, Sequence
 
 import numpy as np
 import torch
@@ -234,7 +234,7 @@ def camera_isp(name: str, dtype=f32):
             return interpolate.transform(output, self.transform)
 
         @beartype
-        def tonemap_reinhard(self, images: List[torch.Tensor], gamma: float = 1.0, intensity: float = 1.0,
+        def tonemap_reinhard(self, images: list[torch.Tensor], gamma: float = 1.0, intensity: float = 1.0,
                              light_adapt: float = 1.0, color_adapt: float = 0.0, dtype=u8):
             """camera_isp.py:394-403 (``dtype``: u8 like the reference, or u16 / f16)"""
             out_dtype = as_dtype(dtype)
@@ -245,7 +245,7 @@ def camera_isp(name: str, dtype=f32):
             return [interpolate.transform(output, self.transform) for output in outputs]
 
         @beartype
-        def tonemap_linear(self, images: List[torch.Tensor], gamma: float = 1.0, dtype=u8):
+        def tonemap_linear(self, images: list[torch.Tensor], gamma: float = 1.0, dtype=u8):
             """camera_isp.py:405-413"""
             out_dtype = as_dtype(dtype)
             self.update_metering(images)
@@ -255,7 +255,8 @@ def camera_isp(name: str, dtype=f32):
             return [interpolate.transform(output, self.transform) for output in outputs]
 
         # ------------------------------------------------------------ fused path
-        def _run_fused(self, frames, tonemap, out_dtype, out, tm, update_metering=False, alpha=0.0, rows_per_task=0):
+        def _run_fused(self, frames, tonemap, out_dtype, out, tm, update_metering=False, alpha=0.0, rows_per_task=0,
+                       profile_events=None):
             h, w3 = frames[0].shape
             w = w3 * 2 // 3
             p = _lib.FusedParams()
@@ -271,6 +272,8 @@ def camera_isp(name: str, dtype=f32):
             p.color_adapt = float(tm.get("color_adapt", 0.0))
             p.metering_stride, p.alpha = int(self.metering_stride), float(alpha)
             p.update_metering, p.rows_per_task = int(update_metering), int(rows_per_task)
+            if profile_events is not None:      # (start, stop) torch.cuda.Event pair, see bench.py
+                p.profile_start, p.profile_stop = profile_events[0].cuda_event, profile_events[1].cuda_event
             if out is None:
                 out = [torch.empty((h, w, 3), dtype=out_dtype.torch, device=self.device) for _ in frames]
             else:
@@ -286,8 +289,8 @@ def camera_isp(name: str, dtype=f32):
 
         def process_packed12(self, frames: Sequence[torch.Tensor], tonemap: str = "reinhard", gamma: float = 1.0,
                              intensity: float = 1.0, light_adapt: float = 1.0, color_adapt: float = 0.0,
-                             dtype=u8, ids_format: bool = False, out: Optional[List[torch.Tensor]] = None,
-                             rows_per_task: int = 0):
+                             dtype=u8, ids_format: bool = False, out: Optional[list] = None,
+                             rows_per_task: int = 0, profile_events=None):
             """Fused equivalent of ``[load_packed12(f) for f in frames]`` followed by
             ``tonemap_reinhard`` / ``tonemap_linear`` (camera_isp.py:333-340, :376-413): joint metering of
             all frames with the moving-average update of ``self.metrics``, then one sweep per frame.
@@ -310,7 +313,7 @@ def camera_isp(name: str, dtype=f32):
             alpha = self._metrics_and_alpha()
             tm = dict(gamma=gamma, intensity=intensity, light_adapt=light_adapt, color_adapt=color_adapt)
             outputs = self._run_fused(frames, tonemap, out_dtype, out, tm, update_metering=True, alpha=alpha,
-                                      rows_per_task=rows_per_task)
+                                      rows_per_task=rows_per_task, profile_events=profile_events)
             return [interpolate.transform(o, self.transform) for o in outputs]
 
     ISP.reinhard_kernel = staticmethod(_reinhard_kernel)     # camera_isp.py:415-416

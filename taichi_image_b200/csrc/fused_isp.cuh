@@ -222,23 +222,25 @@ template <typename OutT> __device__ __forceinline__ void store_px(void* frame_ou
 }
 
 // ---------------------------------------------------------------- tone-map stages (per pixel, shared by hot + border)
-struct LinearConsts { float a, b, inv_gamma; int has_gamma; };
+struct LinearConsts { float a, bmin, inv_gamma; int has_gamma; };
 
 __device__ __forceinline__ LinearConsts linear_consts(const float* __restrict__ metrics, float gamma) {
   LinearConsts c;
   const float bmin = metrics[0], bmax = metrics[1];
   c.a = __fdiv_rn(1.0f, __fsub_rn(bmax, bmin));        // tonemap.py:12
-  c.b = -bmin * c.a;
+  c.bmin = bmin;
   c.inv_gamma = __fdiv_rn(1.0f, gamma);
   c.has_gamma = gamma != 1.0f;
   return c;
 }
 
-// tonemap.py:15-16: clamp(((x - min) * inv_range)^(1/gamma), 0, 1)
+// tonemap.py:15-16: clamp(((x - min) * inv_range)^(1/gamma), 0, 1).  The subtraction and the product
+// are rounded separately, exactly like the reference expression: saturated pixels (x == max) then hit
+// the same side of the truncating quantiser as the reference (an FMA would not).
 __device__ __forceinline__ void linear_px(const LinearConsts& c, const float (&rgb)[3], float (&y)[3]) {
 #pragma unroll
   for (int k = 0; k < 3; ++k) {
-    float v = __saturatef(fmaf(rgb[k], c.a, c.b));
+    float v = __saturatef(__fmul_rn(__fsub_rn(rgb[k], c.bmin), c.a));
     if (c.has_gamma) v = __saturatef(fast_pow(v, c.inv_gamma));
     y[k] = v;
   }
@@ -438,18 +440,21 @@ struct Packed12Sampler {
 
 // ---------------------------------------------------------------- host orchestration
 template <bool CAM16, int MODE, typename OutT>
-static int run_pass(const FramePtrs& fp, IspConsts k, int frame0, int nframes, int rows_per_task, cudaStream_t s) {
+static int run_pass(const FramePtrs& fp, IspConsts k, int frame0, int nframes, int rows_per_task, cudaStream_t s,
+                    void* ev_start = nullptr, void* ev_stop = nullptr) {
   k.frame0 = frame0;
   const StreamGeom g = make_geom(k.H, k.W, nframes, rows_per_task);
   Packed12Loader<CAM16> ld;
   ld.fp = fp; ld.pitch_words = k.W * 3 / 8; ld.frame0 = frame0;
   int st = B200ISP_OK;
+  if (ev_start) cudaEventRecord((cudaEvent_t)ev_start, s);
   ISP_DISPATCH_PATTERN(k.pattern, P, {
     if constexpr (MODE == MODE_RGB) { EpiRgb<CAM16, OutT> e{fp, k}; st = launch_stream<P>(ld, e, g, s, "isp_stream<rgb>"); }
     else if constexpr (MODE == MODE_LINEAR) { EpiLinear<CAM16, OutT> e{fp, k}; st = launch_stream<P>(ld, e, g, s, "isp_stream<linear>"); }
     else if constexpr (MODE == MODE_RMAX) { EpiReinhardMax<CAM16> e{k}; st = launch_stream<P>(ld, e, g, s, "isp_stream<reinhard_max>"); }
     else { EpiReinhard<CAM16, OutT> e{fp, k}; st = launch_stream<P>(ld, e, g, s, "isp_stream<reinhard>"); }
   });
+  if (ev_stop) cudaEventRecord((cudaEvent_t)ev_stop, s);
   if (st) return st;
   Packed12Src<CAM16> src{fp, k.W * 3 / 2};
   const long long per_frame = border_count(k.H, k.W);
@@ -470,14 +475,14 @@ int run_fused(const FramePtrs& fp, int n_frames, const b200isp_fused_params& p, 
   const int rpt = p.rows_per_task;
   constexpr bool kIspOut = (CAM16 && std::is_same<OutT, __half>::value) || (!CAM16 && std::is_same<OutT, float>::value);
   if (p.tonemap == B200ISP_TM_NONE) {
-    if constexpr (kIspOut) return run_pass<CAM16, MODE_RGB, OutT>(fp, k, 0, n_frames, rpt, s);
+    if constexpr (kIspOut) return run_pass<CAM16, MODE_RGB, OutT>(fp, k, 0, n_frames, rpt, s, p.profile_start, p.profile_stop);
     else { set_error("process_packed12: TM_NONE writes the ISP dtype"); return B200ISP_E_DTYPE; }
   }
   if constexpr (std::is_same<OutT, float>::value) {
     set_error("process_packed12: tone-mapped output must be u8, u16 or f16");
     return B200ISP_E_DTYPE;
   } else {
-    if (p.tonemap == B200ISP_TM_LINEAR) return run_pass<CAM16, MODE_LINEAR, OutT>(fp, k, 0, n_frames, rpt, s);
+    if (p.tonemap == B200ISP_TM_LINEAR) return run_pass<CAM16, MODE_LINEAR, OutT>(fp, k, 0, n_frames, rpt, s, p.profile_start, p.profile_stop);
     // Reinhard: the second sweep should find the packed frames in L2 -> interleave max / write passes
     // per group of frames whose packed bytes stay well inside the 126 MB L2.
     int st = cuda_status(cudaMemsetAsync(k.ws->frame_max, 0, sizeof(float) * B200ISP_MAX_FRAMES, s), "memset frame_max");
@@ -489,7 +494,7 @@ int run_fused(const FramePtrs& fp, int n_frames, const b200isp_fused_params& p, 
       const int n = (n_frames - f < group) ? n_frames - f : group;
       st = run_rmax<CAM16>(fp, k, f, n, rpt, s);
       if (st) return st;
-      st = run_pass<CAM16, MODE_REINHARD, OutT>(fp, k, f, n, rpt, s);
+      st = run_pass<CAM16, MODE_REINHARD, OutT>(fp, k, f, n, rpt, s, f == 0 ? p.profile_start : nullptr, f == 0 ? p.profile_stop : nullptr);
       if (st) return st;
     }
     return B200ISP_OK;

@@ -247,7 +247,6 @@ __global__ void __launch_bounds__(256) isp_reinhard_pass2_kernel(const T* __rest
     if (has_gamma) q = powf(q, inv_gamma);
     out[i] = cast_from_f32<OutT>(__fmul_rn(DT<OutT>::scale, q));
   }
-  if (last_block_ticket(&ws->counter[1]) && threadIdx.x == 0) ws->frame_max[0] = 0.f;
 }
 
 // ---------------------------------------------------------------- loaders (camera_isp.py:82-99)
@@ -331,6 +330,10 @@ extern "C" int b200isp_isp_reinhard(void* image, int dtype, void* output, int ou
   Workspace* ws = (Workspace*)workspace;
   cudaStream_t s = (cudaStream_t)stream;
   const int grid = meter_grid(n_pixels);
+  {
+    const int st = cuda_status(cudaMemsetAsync(&ws->frame_max[0], 0, sizeof(float), s), "memset frame_max");
+    if (st) return st;
+  }
   ISP_DISPATCH_DTYPE(dtype, T, {
     isp_reinhard_pass1_kernel<T><<<grid, 256, 0, s>>>((T*)image, n_pixels, metrics, intensity, light_adapt, color_adapt, ws);
     ISP_LAUNCH_CHECK("isp_reinhard_pass1_kernel");

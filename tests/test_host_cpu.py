@@ -1,0 +1,144 @@
+"""CPU-only: host logic, the C ABI surface and oracle properties (no GPU compute calls)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from oracle import isp_oracle as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_loads_and_exports_every_declared_symbol():
+    from taichi_image_b200 import _lib
+    header = open(os.path.join(ROOT, "include", "b200isp.h")).read()
+    declared = set(re.findall(r"\b(b200isp_[a-z0-9_]+)\s*\(", header))
+    declared -= {"b200isp_fused_params"}
+    assert declared, "no declarations found"
+    lib = ctypes.CDLL(str(_lib.LIB_PATH))
+    for name in sorted(declared):
+        assert hasattr(lib, name), f"{name} declared in include/b200isp.h but not exported"
+    assert declared == set(_lib.EXPORTS), declared ^ set(_lib.EXPORTS)
+    assert _lib.lib.b200isp_version() == 100
+    assert _lib.WORKSPACE_BYTES >= 4096
+
+
+def test_fused_params_struct_matches_header():
+    from taichi_image_b200 import _lib
+    # 7 ints, 9 floats, 4 floats, int, float, 2 ints (24 x 4 bytes, no padding) + 2 pointers
+    assert ctypes.sizeof(_lib.FusedParams) == 4 * (7 + 9 + 4 + 1 + 1 + 2) + 2 * ctypes.sizeof(ctypes.c_void_p)
+    header = open(os.path.join(ROOT, "include", "b200isp.h")).read()
+    body = header[header.index("typedef struct {"):header.index("} b200isp_fused_params;")]
+    names = re.findall(r"\b(?:int|float|void\*)\s+([a-z_0-9, \[\]]+);", body)
+    flat = [n.strip().split("[")[0] for group in names for n in group.split(",")]
+    assert flat == [f[0] for f in _lib.FusedParams._fields_], flat
+
+
+def test_error_paths_do_not_need_a_gpu():
+    from taichi_image_b200 import _lib
+    lib = _lib.lib
+    assert lib.b200isp_decode12(None, 3, None, 1, 0, 0, None) == -3       # odd size
+    assert b"even" in lib.b200isp_last_error()
+    assert lib.b200isp_bayer_to_rgb(None, 0, None, 0, 3, 4, 0, None, None) == -3
+    assert lib.b200isp_bayer_to_rgb(None, 0, None, 0, 4, 4, 9, None, None) == -1
+    assert lib.b200isp_transform(None, None, 0, 4, 4, 99, None) == -1
+    assert lib.b200isp_decode12(None, 0, None, 1, 0, 0, None) == 0        # empty input is a no-op
+    p = _lib.FusedParams()
+    p.height, p.width = 10, 12                                            # width % 8 != 0
+    arr = (ctypes.c_void_p * 1)()
+    assert lib.b200isp_process_packed12(arr, arr, 1, p, None, ctypes.c_void_p(8), None) == -3
+    assert lib.b200isp_process_packed12(arr, arr, 65, p, None, ctypes.c_void_p(8), None) == -6
+
+
+def test_no_cpu_fallback():
+    import torch
+    from taichi_image_b200 import packed, bayer, types
+    if torch.cuda.is_available():
+        pytest.skip("CUDA present")
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        packed.encode12(np.zeros(4, np.uint16))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        bayer.bayer_to_rgb(np.zeros((4, 4), np.uint8))
+    with pytest.raises(Exception):
+        packed.decode12_kernel(types.u16)(torch.zeros(3, dtype=torch.uint8), torch.zeros(2, dtype=torch.uint16))
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "taichi_image_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert "import oracle" not in text and "from oracle" not in text, f
+
+
+def test_dtypes_and_types_tables():
+    import torch
+    from taichi_image_b200 import dtypes, types, u8, u16, f16, f32, uint8
+    assert u8 is uint8 and dtypes.as_dtype(torch.float16) is f16 and dtypes.as_dtype(np.uint16) is u16
+    assert dtypes.as_dtype("f32") is f32 and dtypes.as_dtype("float32") is f32 and dtypes.as_dtype(np.dtype("uint8")) is u8
+    assert types.scale_factor[u8] == 255 and types.scale_factor[u16] == 65535 and types.scale_factor[dtypes.i16] == 32767
+    assert types.ti_type(np.zeros(1, np.float16)) is f16 and types.ti_type(torch.zeros(1, dtype=torch.uint16)) is u16
+    e = types.empty_like(np.zeros((2, 3), np.uint8), (4, 5), f32)
+    assert e.shape == (4, 5) and e.dtype == np.float32
+    with pytest.raises(KeyError):
+        dtypes.as_dtype(torch.float64)
+    with pytest.raises(ValueError):
+        types.ti_type([1, 2, 3])
+
+
+def test_shard_cameras_partition():
+    from taichi_image_b200.distributed import shard_cameras
+    for n, w in [(12, 8), (12, 2), (12, 4), (6, 1), (3, 8), (64, 8)]:
+        parts = [list(shard_cameras(n, w, r)) for r in range(w)]
+        assert sorted(sum(parts, [])) == list(range(n))
+        assert max(map(len, parts)) - min(map(len, parts)) <= 1
+    assert max(len(shard_cameras(12, 8, r)) for r in range(8)) == 2      # 12 cameras on 8 GPUs cap at 6x
+
+
+def test_integer_demosaic_equals_floor_division():
+    """The float quantisation chain of bayer.py:150-155 equals clamp(floor(S / t), 0, scale) for every
+    reachable integer tap sum S and every border normaliser t -- the identity the CUDA integer path uses."""
+    for s in (255, 65535, 32767):
+        for t in (10, 11, 12, 13, 14, 15, 16, 17, 18, 20):
+            S = np.arange(-64, t * s + 65, dtype=np.int64)
+            f = np.clip(S.astype(np.float32) / np.float32(np.float32(s) * np.float32(t)), np.float32(0), np.float32(1))
+            out = np.trunc(f * np.float32(s)).astype(np.int64)
+            assert np.array_equal(out, np.clip(S // t, 0, s)), (s, t)
+
+
+def test_border_normaliser_never_zero_and_constant_images():
+    for p in O.PATTERNS:
+        for shape in [(2, 2), (2, 4), (4, 2), (4, 6), (6, 6), (8, 10)]:
+            b = np.full(shape, 200, np.uint8)
+            assert np.all(O.bayer_to_rgb(b, p) == 200), (p, shape)
+
+
+def test_malvar_matches_published_coefficients():
+    from scipy.ndimage import correlate
+    r = np.random.default_rng(0)
+    cfa = (r.integers(0, 4096, size=(16, 20)) / 4095).astype(np.float32)
+    rgb = O.demosaic_unit(cfa, "RGGB")
+    g_at_rb = np.array([[0, 0, -1, 0, 0], [0, 0, 2, 0, 0], [-1, 2, 4, 2, -1], [0, 0, 2, 0, 0], [0, 0, -1, 0, 0]]) / 8
+    r_at_g_rrow = np.array([[0, 0, .5, 0, 0], [0, -1, 0, -1, 0], [-1, 4, 5, 4, -1], [0, -1, 0, -1, 0], [0, 0, .5, 0, 0]]) / 8
+    r_at_b = np.array([[0, 0, -1.5, 0, 0], [0, 2, 0, 2, 0], [-1.5, 0, 6, 0, -1.5], [0, 2, 0, 2, 0], [0, 0, -1.5, 0, 0]]) / 8
+    f = lambda k: np.clip(correlate(cfa.astype(np.float64), k, mode="constant"), 0, 1)
+    assert np.abs(f(g_at_rb)[2:-2:2, 2:-2:2] - rgb[2:-2:2, 2:-2:2, 1]).max() < 1e-6
+    assert np.abs(f(r_at_g_rrow)[2:-2:2, 3:-2:2] - rgb[2:-2:2, 3:-2:2, 0]).max() < 1e-6
+    assert np.abs(f(r_at_g_rrow.T)[3:-2:2, 2:-2:2] - rgb[3:-2:2, 2:-2:2, 0]).max() < 1e-6
+    assert np.abs(f(r_at_b)[3:-2:2, 3:-2:2] - rgb[3:-2:2, 3:-2:2, 0]).max() < 1e-6
+
+
+def test_packed_roundtrip_and_ids_quirk():
+    r = np.random.default_rng(1)
+    for _ in range(20):                                   # reference test/packed.py:6-15
+        x = r.integers(0, 4096, size=int(r.integers(1000)) * 2).astype(np.uint16)
+        assert np.array_equal(O.decode12(O.encode12(x)), x)
+    x = r.integers(0, 4096, size=64).astype(np.uint16)
+    y = O.decode12(O.encode12(x, ids_format=True), ids_format=True)
+    exp = x.copy()                                        # the reference's IDS encode swaps the low nibbles
+    exp[0::2] = (x[0::2] & 0xFF0) | (x[1::2] & 0xF)
+    exp[1::2] = (x[1::2] & 0xFF0) | (x[0::2] & 0xF)
+    assert np.array_equal(y, exp)
