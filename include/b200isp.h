@@ -150,6 +150,8 @@ typedef struct {
   int rows_per_task;            /* 0 = default */
   void* profile_start;          /* optional cudaEvent_t pair recorded on `stream` immediately before / after */
   void* profile_stop;           /*   the dominant streaming kernel (bench.py's live roofline timing); NULL = off */
+  void* meter_cache;            /* optional device scratch: >= n_frames*ceil(H/stride)*ceil(W/stride)*12 bytes; the second */
+  size_t meter_cache_bytes;     /*   metering phase then re-reads the phase-1 samples instead of recomputing them */
 } b200isp_fused_params;
 
 /* camera_isp.py:333-340 load_packed12 + :376-385 update_metering + :394-413 tonemap_* over a

@@ -30,7 +30,8 @@ class FusedParams(C.Structure):
                 ("gamma", C.c_float), ("intensity", C.c_float), ("light_adapt", C.c_float),
                 ("color_adapt", C.c_float), ("metering_stride", C.c_int), ("alpha", C.c_float),
                 ("update_metering", C.c_int), ("rows_per_task", C.c_int),
-                ("profile_start", C.c_void_p), ("profile_stop", C.c_void_p)]
+                ("profile_start", C.c_void_p), ("profile_stop", C.c_void_p),
+                ("meter_cache", C.c_void_p), ("meter_cache_bytes", C.c_size_t)]
 
 
 _vp, _i, _i64, _f = C.c_void_p, C.c_int, C.c_int64, C.c_float

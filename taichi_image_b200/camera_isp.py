@@ -272,6 +272,13 @@ def camera_isp(name: str, dtype=f32):
             p.color_adapt = float(tm.get("color_adapt", 0.0))
             p.metering_stride, p.alpha = int(self.metering_stride), float(alpha)
             p.update_metering, p.rows_per_task = int(update_metering), int(rows_per_task)
+            if update_metering:                  # scratch for the phase-1 samples (re-read by phase 2)
+                stride = max(int(self.metering_stride), 1)
+                need = len(frames) * (-(-h // stride)) * (-(-w // stride)) * 12
+                cache = getattr(self, "_meter_cache", None)
+                if cache is None or cache.numel() < need or cache.device != torch.device(self.device):
+                    cache = self._meter_cache = torch.empty(need, dtype=torch.uint8, device=self.device)
+                p.meter_cache, p.meter_cache_bytes = cache.data_ptr(), cache.numel()
             if profile_events is not None:      # (start, stop) torch.cuda.Event pair, see bench.py
                 p.profile_start, p.profile_stop = profile_events[0].cuda_event, profile_events[1].cuda_event
             if out is None:

@@ -56,13 +56,22 @@ extern "C" int b200isp_process_packed12(const uint8_t* const* packed_host, void*
     const int stride = p.metering_stride > 0 ? p.metering_stride : 8;
     const int hs = (p.height + stride - 1) / stride, wsamp = (p.width + stride - 1) / stride;
     const long long n = (long long)n_frames * hs * wsamp;
+    float* cache = (p.meter_cache && p.meter_cache_bytes >= (size_t)n * 3 * sizeof(float)) ? (float*)p.meter_cache : nullptr;
     int st;
-    if (cam16) {
+    if (stride % 8 == 0) {
+      if (cam16) {
+        Packed12FastSampler<true> smp{Packed12Src<true>{fp, p.width * 3 / 2}, k, stride, hs, wsamp, p.width * 3 / 8};
+        st = launch_metering(smp, n, p.alpha, metrics, k.ws, s, cache);
+      } else {
+        Packed12FastSampler<false> smp{Packed12Src<false>{fp, p.width * 3 / 2}, k, stride, hs, wsamp, p.width * 3 / 8};
+        st = launch_metering(smp, n, p.alpha, metrics, k.ws, s, cache);
+      }
+    } else if (cam16) {
       Packed12Sampler<true> smp{Packed12Src<true>{fp, p.width * 3 / 2}, k, stride, hs, wsamp};
-      st = launch_metering(smp, n, p.alpha, metrics, k.ws, s);
+      st = launch_metering(smp, n, p.alpha, metrics, k.ws, s, cache);
     } else {
       Packed12Sampler<false> smp{Packed12Src<false>{fp, p.width * 3 / 2}, k, stride, hs, wsamp};
-      st = launch_metering(smp, n, p.alpha, metrics, k.ws, s);
+      st = launch_metering(smp, n, p.alpha, metrics, k.ws, s, cache);
     }
     if (st) return st;
   }

@@ -126,7 +126,7 @@ __device__ __forceinline__ void isp_rgb_pixel(const Packed12Src<CAM16>& src, con
 }
 
 // hot-path front end: raw filter sums (x16; biased by 16 for Camera32) -> ISP RGB in [0,1]
-template <bool CAM16>
+template <bool CAM16, bool CCM>
 __device__ __forceinline__ void isp_rgb_fast(const IspConsts& k, float sr, float sg, float sb, float (&rgb)[3]) {
   float r, g, b;
   if constexpr (CAM16) {
@@ -135,7 +135,7 @@ __device__ __forceinline__ void isp_rgb_fast(const IspConsts& k, float sr, float
     constexpr float kn = 256.f * kInv4095;           // 4096 * f32(1/4095) / 16
     r = fmaf(sr, kn, -16.f * kn); g = fmaf(sg, kn, -16.f * kn); b = fmaf(sb, kn, -16.f * kn);
   }
-  if (k.ccm) {
+  if constexpr (CCM) {
     const float x = fmaf(b, k.m[2], fmaf(g, k.m[1], r * k.m[0]));
     const float y = fmaf(b, k.m[5], fmaf(g, k.m[4], r * k.m[3]));
     const float z = fmaf(b, k.m[8], fmaf(g, k.m[7], r * k.m[6]));
@@ -237,38 +237,47 @@ __device__ __forceinline__ LinearConsts linear_consts(const float* __restrict__ 
 // tonemap.py:15-16: clamp(((x - min) * inv_range)^(1/gamma), 0, 1).  The subtraction and the product
 // are rounded separately, exactly like the reference expression: saturated pixels (x == max) then hit
 // the same side of the truncating quantiser as the reference (an FMA would not).
+template <bool GAMMA>
 __device__ __forceinline__ void linear_px(const LinearConsts& c, const float (&rgb)[3], float (&y)[3]) {
 #pragma unroll
   for (int k = 0; k < 3; ++k) {
     float v = __saturatef(__fmul_rn(__fsub_rn(rgb[k], c.bmin), c.a));
-    if (c.has_gamma) v = __saturatef(fast_pow(v, c.inv_gamma));
+    if constexpr (GAMMA) v = __saturatef(fast_pow(v, c.inv_gamma));
     y[k] = v;
   }
 }
 
 struct ReinhardConsts { ReinhardParams p; float b; float out_scale_inv_max; float inv_gamma; int has_gamma; int ca0; };
 
-template <bool CAM16>
+template <bool CAM16, bool CA0>
 __device__ __forceinline__ void reinhard_p(const ReinhardConsts& c, const float (&rgb)[3], float (&p)[3]) {
   float s[3];
 #pragma unroll
   for (int k = 0; k < 3; ++k) s[k] = fmaf(rgb[k], c.p.inv_range, c.b);
-  if (c.ca0) reinhard_map_fast<true>(c.p, s, p);
-  else reinhard_map_fast<false>(c.p, s, p);
+  reinhard_map_fast<CA0>(c.p, s, p);
 }
 
 // camera_isp.py:211-218: stored = cast_T(p); out = trunc(scale * (stored / max_out)^(1/gamma))
-template <bool CAM16>
+template <bool CAM16, bool GAMMA>
 __device__ __forceinline__ void reinhard_out(const ReinhardConsts& c, const float (&p)[3], float (&y)[3]) {
 #pragma unroll
   for (int k = 0; k < 3; ++k) {
     float q = fmaxf(round_isp<CAM16>(p[k]) * c.out_scale_inv_max, 0.f);     // NaN / negative -> 0
-    if (c.has_gamma) q = fast_pow(q, c.inv_gamma);
+    if constexpr (GAMMA) q = fast_pow(q, c.inv_gamma);
     y[k] = fminf(q, 1.0f);     // the reference does not clamp (q <= 1 + one f16 ulp); saturate for the RZ-FMA quantiser
   }
 }
 
 // ---------------------------------------------------------------- hot-path epilogues
+// The per-pixel code is branch-free: the runtime options (CCM on/off, gamma != 1, color_adapt == 0) are
+// template flags of emit_t and are selected once per 8-pixel row by a warp-uniform switch, so the
+// compiler can interleave the eight independent pixel chains of a row.
+#define ISP_FLAG_DISPATCH2(F0, F1, CALL)                               \
+  do {                                                                 \
+    if (F0) { if (F1) { CALL(true, true); } else { CALL(true, false); } } \
+    else    { if (F1) { CALL(false, true); } else { CALL(false, false); } } \
+  } while (0)
+
 template <bool CAM16, typename OutT>
 struct EpiRgb {       // load_packed12: ISP-dtype float RGB out
   FramePtrs fp;
@@ -276,16 +285,22 @@ struct EpiRgb {       // load_packed12: ISP-dtype float RGB out
   struct State {};
   __device__ __forceinline__ void init(State&, int) const {}
   __device__ __forceinline__ void finish(State&, int, int, bool) const {}
-  __device__ __forceinline__ void emit(State&, int frame, int row, int tcol,
-                                       const float (&R)[8], const float (&G)[8], const float (&B)[8]) const {
+  template <bool CCM>
+  __device__ __forceinline__ void emit_t(int frame, int row, int tcol,
+                                         const float (&R)[8], const float (&G)[8], const float (&B)[8]) const {
     uint32_t v[24];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       float rgb[3];
-      isp_rgb_fast<CAM16>(k, R[j], G[j], B[j], rgb);
+      isp_rgb_fast<CAM16, CCM>(k, R[j], G[j], B[j], rgb);
       v[3 * j] = __float_as_uint(rgb[0]); v[3 * j + 1] = __float_as_uint(rgb[1]); v[3 * j + 2] = __float_as_uint(rgb[2]);
     }
     store_row8<OutT>(fp.out[k.frame0 + frame], k.W, row, tcol, v);
+  }
+  __device__ __forceinline__ void emit(State&, int frame, int row, int tcol,
+                                       const float (&R)[8], const float (&G)[8], const float (&B)[8]) const {
+    if (k.ccm) emit_t<true>(frame, row, tcol, R, G, B);
+    else emit_t<false>(frame, row, tcol, R, G, B);
   }
 };
 
@@ -296,17 +311,24 @@ struct EpiLinear {
   struct State { LinearConsts c; };
   __device__ __forceinline__ void init(State& st, int) const { st.c = linear_consts(k.metrics, k.gamma); }
   __device__ __forceinline__ void finish(State&, int, int, bool) const {}
-  __device__ __forceinline__ void emit(State& st, int frame, int row, int tcol,
-                                       const float (&R)[8], const float (&G)[8], const float (&B)[8]) const {
+  template <bool CCM, bool GAMMA>
+  __device__ __forceinline__ void emit_t(const State& st, int frame, int row, int tcol,
+                                         const float (&R)[8], const float (&G)[8], const float (&B)[8]) const {
     uint32_t v[24];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       float rgb[3], y[3];
-      isp_rgb_fast<CAM16>(k, R[j], G[j], B[j], rgb);
-      linear_px(st.c, rgb, y);
+      isp_rgb_fast<CAM16, CCM>(k, R[j], G[j], B[j], rgb);
+      linear_px<GAMMA>(st.c, rgb, y);
       v[3 * j] = Quant<OutT>::q(y[0]); v[3 * j + 1] = Quant<OutT>::q(y[1]); v[3 * j + 2] = Quant<OutT>::q(y[2]);
     }
     store_row8<OutT>(fp.out[k.frame0 + frame], k.W, row, tcol, v);
+  }
+  __device__ __forceinline__ void emit(State& st, int frame, int row, int tcol,
+                                       const float (&R)[8], const float (&G)[8], const float (&B)[8]) const {
+#define ISP_CALL(A, B_) emit_t<A, B_>(st, frame, row, tcol, R, G, B)
+    ISP_FLAG_DISPATCH2(k.ccm, st.c.has_gamma, ISP_CALL);
+#undef ISP_CALL
   }
 };
 
@@ -327,20 +349,29 @@ struct EpiReinhardMax {      // pass 1 without the write-back: frame-global max 
   IspConsts k;
   struct State { ReinhardConsts c; float mx; };
   __device__ __forceinline__ void init(State& st, int frame) const { st.c = reinhard_consts(k, frame, false); st.mx = 0.f; }
+  template <bool CCM, bool CA0>
+  __device__ __forceinline__ void emit_t(State& st, int tcol,
+                                         const float (&R)[8], const float (&G)[8], const float (&B)[8]) const {
+    const bool first = tcol == 0, last = tcol == (k.W >> 3) - 1;
+    float mx = st.mx;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float rgb[3], p[3];
+      isp_rgb_fast<CAM16, CCM>(k, R[j], G[j], B[j], rgb);
+      reinhard_p<CAM16, CA0>(st.c, rgb, p);
+      float m = fmaxf(p[0], fmaxf(p[1], p[2]));
+      if ((j < 2 && first) || (j >= 6 && last)) m = 0.f;     // image frame: border kernel
+      mx = fmaxf(mx, m);
+    }
+    st.mx = mx;
+  }
   __device__ __forceinline__ void emit(State& st, int, int row, int tcol,
                                        const float (&R)[8], const float (&G)[8], const float (&B)[8]) const {
     // the 2-pixel image frame is handled (with the exact border normalisation) by the border kernel
     if (row < 2 || row >= k.H - 2) return;
-    const bool first = tcol == 0, last = tcol == (k.W >> 3) - 1;
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      float rgb[3], p[3];
-      isp_rgb_fast<CAM16>(k, R[j], G[j], B[j], rgb);
-      reinhard_p<CAM16>(st.c, rgb, p);
-      float m = fmaxf(p[0], fmaxf(p[1], p[2]));
-      if ((j < 2 && first) || (j >= 6 && last)) m = 0.f;
-      st.mx = fmaxf(st.mx, m);
-    }
+#define ISP_CALL(A, B_) emit_t<A, B_>(st, tcol, R, G, B)
+    ISP_FLAG_DISPATCH2(k.ccm, st.c.ca0, ISP_CALL);
+#undef ISP_CALL
   }
   __device__ __forceinline__ void finish(State& st, int frame, int lane, bool task_ok) const {
     const float m = warp_max(st.mx);
@@ -356,18 +387,31 @@ struct EpiReinhard {         // pass 2 recomputed from the packed frame: map, no
   struct State { ReinhardConsts c; };
   __device__ __forceinline__ void init(State& st, int frame) const { st.c = reinhard_consts(k, frame, true); }
   __device__ __forceinline__ void finish(State&, int, int, bool) const {}
-  __device__ __forceinline__ void emit(State& st, int frame, int row, int tcol,
-                                       const float (&R)[8], const float (&G)[8], const float (&B)[8]) const {
+  template <bool CCM, bool CA0, bool GAMMA>
+  __device__ __forceinline__ void emit_t(const State& st, int frame, int row, int tcol,
+                                         const float (&R)[8], const float (&G)[8], const float (&B)[8]) const {
     uint32_t v[24];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       float rgb[3], p[3], y[3];
-      isp_rgb_fast<CAM16>(k, R[j], G[j], B[j], rgb);
-      reinhard_p<CAM16>(st.c, rgb, p);
-      reinhard_out<CAM16>(st.c, p, y);
+      isp_rgb_fast<CAM16, CCM>(k, R[j], G[j], B[j], rgb);
+      reinhard_p<CAM16, CA0>(st.c, rgb, p);
+      reinhard_out<CAM16, GAMMA>(st.c, p, y);
       v[3 * j] = Quant<OutT>::q(y[0]); v[3 * j + 1] = Quant<OutT>::q(y[1]); v[3 * j + 2] = Quant<OutT>::q(y[2]);
     }
     store_row8<OutT>(fp.out[k.frame0 + frame], k.W, row, tcol, v);
+  }
+  __device__ __forceinline__ void emit(State& st, int frame, int row, int tcol,
+                                       const float (&R)[8], const float (&G)[8], const float (&B)[8]) const {
+    if (st.c.has_gamma) {
+#define ISP_CALL(A, B_) emit_t<A, B_, true>(st, frame, row, tcol, R, G, B)
+      ISP_FLAG_DISPATCH2(k.ccm, st.c.ca0, ISP_CALL);
+#undef ISP_CALL
+    } else {
+#define ISP_CALL(A, B_) emit_t<A, B_, false>(st, frame, row, tcol, R, G, B)
+      ISP_FLAG_DISPATCH2(k.ccm, st.c.ca0, ISP_CALL);
+#undef ISP_CALL
+    }
   }
 };
 
@@ -393,17 +437,17 @@ __global__ void __launch_bounds__(256) isp_border_kernel(const Packed12Src<CAM16
     } else if constexpr (MODE == MODE_LINEAR) {
       const LinearConsts c = linear_consts(k.metrics, k.gamma);
       float y[3];
-      linear_px(c, rgb, y);
+      if (c.has_gamma) linear_px<true>(c, rgb, y); else linear_px<false>(c, rgb, y);
       store_px<OutT>(out, k.W, row, col, y);
     } else {
       const ReinhardConsts c = reinhard_consts(k, frame, MODE == MODE_REINHARD);
       float p[3];
-      reinhard_p<CAM16>(c, rgb, p);
+      if (c.ca0) reinhard_p<CAM16, true>(c, rgb, p); else reinhard_p<CAM16, false>(c, rgb, p);
       if constexpr (MODE == MODE_RMAX) {
         mx = fmaxf(p[0], fmaxf(p[1], p[2]));
       } else {
         float y[3];
-        reinhard_out<CAM16>(c, p, y);
+        if (c.has_gamma) reinhard_out<CAM16, true>(c, p, y); else reinhard_out<CAM16, false>(c, p, y);
         store_px<OutT>(out, k.W, row, col, y);
       }
     }
@@ -423,7 +467,8 @@ __global__ void __launch_bounds__(256) isp_border_kernel(const Packed12Src<CAM16
   }
 }
 
-// ---------------------------------------------------------------- metering sampler straight from packed12
+// ---------------------------------------------------------------- metering samplers straight from packed12
+// generic: any stride, literal per-pixel demosaic
 template <bool CAM16>
 struct Packed12Sampler {
   Packed12Src<CAM16> src;
@@ -435,6 +480,74 @@ struct Packed12Sampler {
     const int i = (int)(q % hs);
     const int f = (int)(q / hs);
     isp_rgb_pixel<CAM16>(src, k, f, i * stride, j * stride, rgb);
+  }
+};
+
+// stride % 8 == 0 (the default 8): a sample is pixel 0 of thread column col/8 of the streaming kernel.
+// It reads nine 32-bit words (1/2/3/2/1 over the five rows; consecutive samples of a row are 12 bytes
+// apart, so a warp's loads are contiguous) and evaluates exactly the partial-sum formulas of
+// malvar_row + isp_rgb_fast, i.e. the very value the sweep will produce for that pixel.  Samples on the
+// 2-pixel image frame (row 0, column 0) take the literal border path.
+template <bool CAM16>
+struct Packed12FastSampler {
+  Packed12Src<CAM16> src;
+  IspConsts k;
+  int stride, hs, ws_;
+  int pitch_words;
+
+  static __device__ __forceinline__ float dec(uint32_t shifted) {
+    const float b = __uint_as_float((shifted & 0x007FF800u) | 0x3F800000u);      // 1 + v/4096
+    if constexpr (CAM16) {
+      constexpr float kk = 4096.f * kInv4095;
+      return __half2float(__float2half_rn(fmaf(b, kk, -kk)));
+    } else {
+      return b;
+    }
+  }
+
+  __device__ __forceinline__ void sample(long long idx, float (&rgb)[3]) const {
+    const int j = (int)(idx % ws_);
+    const long long q = idx / ws_;
+    const int i = (int)(q % hs);
+    const int f = (int)(q / hs);
+    const int row = i * stride, col = j * stride;
+    if (row < 2 || row >= k.H - 2 || col < 2 || col >= k.W - 2) {
+      isp_rgb_pixel<CAM16>(src, k, f, row, col, rgb);
+      return;
+    }
+    const uint32_t* p = reinterpret_cast<const uint32_t*>(src.fp.in[f]) + (size_t)row * pitch_words + 3 * (col >> 3);
+    const uint32_t a0 = __ldg(p - 2 * pitch_words);                                   // row-2: col
+    const uint32_t bm = __ldg(p - pitch_words - 1), b0 = __ldg(p - pitch_words);      // row-1: col-1..col+1
+    const uint32_t cm = __ldg(p - 1), c0 = __ldg(p), c1 = __ldg(p + 1);               // row  : col-2..col+2
+    const uint32_t dm = __ldg(p + pitch_words - 1), d0 = __ldg(p + pitch_words);      // row+1
+    const uint32_t e0 = __ldg(p + 2 * pitch_words);                                   // row+2
+    // pixel col-2 = bits 8..19 of word -1, col-1 = bits 20..31; col = bits 0..11 of word 0, col+1 = bits 12..23,
+    // col+2 = bits 24..35 of (word 1 : word 0)
+    const float C = dec(c0 << 11);
+    const float EW = dec(cm >> 9) + dec(c0 >> 1);
+    const float EEWW = dec(cm << 3) + dec(__funnelshift_r(c0, c1, 13));
+    const float NS = dec(b0 << 11) + dec(d0 << 11);
+    const float D = (dec(bm >> 9) + dec(dm >> 9)) + (dec(b0 >> 1) + dec(d0 >> 1));
+    const float NNSS = dec(a0 << 11) + dec(e0 << 11);
+    const bool brow0 = (k.pattern == B200ISP_GBRG || k.pattern == B200ISP_BGGR);
+    const bool gfirst0 = (k.pattern == B200ISP_GRBG || k.pattern == B200ISP_GBRG);
+    const bool brow = brow0 != ((row & 1) != 0), gsite = gfirst0 != ((row & 1) != 0);
+    float R, G, B;
+    if (!gsite) {
+      const float A = NS + EW, Bq = NNSS + EEWW;
+      G = fmaf(4.f, A, fmaf(-2.f, Bq, 8.f * C));
+      const float Y = fmaf(4.f, D, fmaf(-3.f, Bq, 12.f * C));
+      const float X = 16.f * C;
+      R = brow ? Y : X; B = brow ? X : Y;
+    } else {
+      const float T = fmaf(-2.f, D, 10.f * C);
+      const float Hc = fmaf(8.f, EW, fmaf(-2.f, EEWW, T)) + NNSS;
+      const float Vc = fmaf(8.f, NS, fmaf(-2.f, NNSS, T)) + EEWW;
+      G = 16.f * C;
+      R = brow ? Vc : Hc; B = brow ? Hc : Vc;
+    }
+    if (k.ccm) isp_rgb_fast<CAM16, true>(k, R, G, B, rgb);
+    else isp_rgb_fast<CAM16, false>(k, R, G, B, rgb);
   }
 };
 

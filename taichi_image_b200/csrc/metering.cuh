@@ -56,12 +56,14 @@ __device__ __forceinline__ bool last_block_ticket(unsigned int* counter) {
 
 template <class Sampler>
 __global__ void __launch_bounds__(256) meter_phase1_kernel(const Sampler smp, long long n, float alpha,
-                                                           const float* __restrict__ prev, Workspace* ws) {
+                                                           const float* __restrict__ prev, Workspace* ws,
+                                                           float* __restrict__ cache /* n*3 floats or null */) {
   __shared__ float smem[8 * 2];
   float v[2] = {INFINITY, -INFINITY};
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     float rgb[3];
     smp.sample(i, rgb);
+    if (cache) { cache[3 * i] = rgb[0]; cache[3 * i + 1] = rgb[1]; cache[3 * i + 2] = rgb[2]; }
     v[0] = fminf(v[0], fminf(rgb[0], fminf(rgb[1], rgb[2])));
     v[1] = fmaxf(v[1], fmaxf(rgb[0], fmaxf(rgb[1], rgb[2])));
   }
@@ -140,13 +142,25 @@ inline int meter_grid(long long n) {
   return (int)b;
 }
 
+// samples cached by phase 1 (3 floats each), read back coalesced by phase 2
+struct CachedSampler {
+  const float* cache;
+  __device__ __forceinline__ void sample(long long idx, float (&rgb)[3]) const {
+    rgb[0] = __ldcg(cache + 3 * idx); rgb[1] = __ldcg(cache + 3 * idx + 1); rgb[2] = __ldcg(cache + 3 * idx + 2);
+  }
+};
+
+// cache: optional device scratch of n*3 floats -- phase 2 then re-reads the phase-1 samples instead of
+// recomputing them (the samples are identical either way).
 template <class Sampler>
-inline int launch_metering(const Sampler& smp, long long n, float alpha, float* metrics, Workspace* ws, cudaStream_t s) {
+inline int launch_metering(const Sampler& smp, long long n, float alpha, float* metrics, Workspace* ws, cudaStream_t s,
+                           float* cache = nullptr) {
   const int grid = meter_grid(n);
-  meter_phase1_kernel<Sampler><<<grid, 256, 0, s>>>(smp, n, alpha, metrics, ws);
+  meter_phase1_kernel<Sampler><<<grid, 256, 0, s>>>(smp, n, alpha, metrics, ws, cache);
   int st = cuda_status(cudaPeekAtLastError(), "meter_phase1_kernel");
   if (st) return st;
-  meter_phase2_kernel<Sampler><<<grid, 256, 0, s>>>(smp, n, alpha, metrics, ws);
+  if (cache) meter_phase2_kernel<CachedSampler><<<grid, 256, 0, s>>>(CachedSampler{cache}, n, alpha, metrics, ws);
+  else meter_phase2_kernel<Sampler><<<grid, 256, 0, s>>>(smp, n, alpha, metrics, ws);
   return cuda_status(cudaPeekAtLastError(), "meter_phase2_kernel");
 }
 
