@@ -9,16 +9,22 @@ namespace isp {
 // ALIGNED: W % 8 == 0 and 16-byte aligned base -> word/vector loads; else per-element predicated loads.
 template <typename T, bool ALIGNED> struct PlaneLoader;
 
+template <typename T> struct PlaneCursor { const T* p; bool left, right; };
+
 template <> struct PlaneLoader<uint8_t, true> {
   const uint8_t* base;
   struct Raw { uint32_t w[4]; };
-  __device__ __forceinline__ void fetch(int, int row, int tcol, const StreamGeom& g, Raw& raw) const {
-    if (row < 0 || row >= g.H) { raw.w[0] = raw.w[1] = raw.w[2] = raw.w[3] = 0u; return; }
-    const uint32_t* p = reinterpret_cast<const uint32_t*>(base + (size_t)row * g.W) + 2 * tcol;
-    raw.w[0] = tcol > 0 ? __ldg(p - 1) : 0u;
-    raw.w[1] = __ldg(p);
-    raw.w[2] = __ldg(p + 1);
-    raw.w[3] = tcol < g.ntcols - 1 ? __ldg(p + 2) : 0u;
+  using Cursor = PlaneCursor<uint8_t>;
+  __device__ __forceinline__ void open(Cursor& c, int, int tcol, const StreamGeom& g) const {
+    c.p = base + 8 * tcol; c.left = tcol > 0; c.right = tcol < g.ntcols - 1;
+  }
+  __device__ __forceinline__ void fetch(const Cursor& c, int row, const StreamGeom& g, Raw& raw) const {
+    const bool rv = (unsigned)row < (unsigned)g.H;
+    const uint32_t* p = reinterpret_cast<const uint32_t*>(c.p + (rv ? (unsigned)row * (unsigned)g.W : 0u));
+    raw.w[0] = (rv && c.left) ? __ldg(p - 1) : 0u;
+    raw.w[1] = rv ? __ldg(p) : 0u;
+    raw.w[2] = rv ? __ldg(p + 1) : 0u;
+    raw.w[3] = (rv && c.right) ? __ldg(p + 2) : 0u;
   }
   __device__ __forceinline__ void decode(const Raw& raw, float (&v)[12]) const {
 #pragma unroll
@@ -29,17 +35,18 @@ template <> struct PlaneLoader<uint8_t, true> {
 template <typename T> struct PlaneLoader16 {   // u16 / i16 / f16
   const T* base;
   struct Raw { uint32_t w[6]; };
-  __device__ __forceinline__ void fetch(int, int row, int tcol, const StreamGeom& g, Raw& raw) const {
-    if (row < 0 || row >= g.H) {
-#pragma unroll
-      for (int i = 0; i < 6; ++i) raw.w[i] = 0u;
-      return;
-    }
-    const uint32_t* p = reinterpret_cast<const uint32_t*>(base + (size_t)row * g.W) + 4 * tcol;
-    raw.w[0] = tcol > 0 ? __ldg(p - 1) : 0u;
-    const uint4 q = __ldg(reinterpret_cast<const uint4*>(p));
+  using Cursor = PlaneCursor<T>;
+  __device__ __forceinline__ void open(Cursor& c, int, int tcol, const StreamGeom& g) const {
+    c.p = base + 8 * tcol; c.left = tcol > 0; c.right = tcol < g.ntcols - 1;
+  }
+  __device__ __forceinline__ void fetch(const Cursor& c, int row, const StreamGeom& g, Raw& raw) const {
+    const bool rv = (unsigned)row < (unsigned)g.H;
+    const uint32_t* p = reinterpret_cast<const uint32_t*>(c.p + (rv ? (unsigned)row * (unsigned)g.W : 0u));
+    raw.w[0] = (rv && c.left) ? __ldg(p - 1) : 0u;
+    uint4 q = make_uint4(0u, 0u, 0u, 0u);
+    if (rv) q = __ldg(reinterpret_cast<const uint4*>(p));
     raw.w[1] = q.x; raw.w[2] = q.y; raw.w[3] = q.z; raw.w[4] = q.w;
-    raw.w[5] = tcol < g.ntcols - 1 ? __ldg(p + 4) : 0u;
+    raw.w[5] = (rv && c.right) ? __ldg(p + 4) : 0u;
   }
   __device__ __forceinline__ void decode(const Raw& raw, float (&v)[12]) const {
 #pragma unroll
@@ -58,18 +65,18 @@ template <> struct PlaneLoader<__half, true> : PlaneLoader16<__half> {};
 template <> struct PlaneLoader<float, true> {
   const float* base;
   struct Raw { float v[12]; };
-  __device__ __forceinline__ void fetch(int, int row, int tcol, const StreamGeom& g, Raw& raw) const {
-    if (row < 0 || row >= g.H) {
-#pragma unroll
-      for (int i = 0; i < 12; ++i) raw.v[i] = 0.f;
-      return;
-    }
-    const float* p = base + (size_t)row * g.W + 8 * tcol;
+  using Cursor = PlaneCursor<float>;
+  __device__ __forceinline__ void open(Cursor& c, int, int tcol, const StreamGeom& g) const {
+    c.p = base + 8 * tcol; c.left = tcol > 0; c.right = tcol < g.ntcols - 1;
+  }
+  __device__ __forceinline__ void fetch(const Cursor& c, int row, const StreamGeom& g, Raw& raw) const {
+    const bool rv = (unsigned)row < (unsigned)g.H;
+    const float* p = c.p + (rv ? (unsigned)row * (unsigned)g.W : 0u);
     float2 l = make_float2(0.f, 0.f), r = make_float2(0.f, 0.f);
-    if (tcol > 0) l = __ldg(reinterpret_cast<const float2*>(p - 2));
-    const float4 a = __ldg(reinterpret_cast<const float4*>(p));
-    const float4 b = __ldg(reinterpret_cast<const float4*>(p + 4));
-    if (tcol < g.ntcols - 1) r = __ldg(reinterpret_cast<const float2*>(p + 8));
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+    if (rv && c.left) l = __ldg(reinterpret_cast<const float2*>(p - 2));
+    if (rv) { a = __ldg(reinterpret_cast<const float4*>(p)); b = __ldg(reinterpret_cast<const float4*>(p + 4)); }
+    if (rv && c.right) r = __ldg(reinterpret_cast<const float2*>(p + 8));
     raw.v[0] = l.x; raw.v[1] = l.y;
     raw.v[2] = a.x; raw.v[3] = a.y; raw.v[4] = a.z; raw.v[5] = a.w;
     raw.v[6] = b.x; raw.v[7] = b.y; raw.v[8] = b.z; raw.v[9] = b.w;
@@ -116,8 +123,8 @@ struct EpiDemosaic {
   int W;
   int ccm;          // runtime (warp-uniform) flag
   float m[9];
-  struct State {};
-  __device__ __forceinline__ void init(State&, int) const {}
+  struct State { T* out; };
+  __device__ __forceinline__ void init(State& st, int, int tcol) const { st.out = out + 24 * tcol; }
   __device__ __forceinline__ void finish(State&, int, int, bool) const {}
 
   __device__ __forceinline__ void finish_px(float cr, float cg, float cb, T* o) const {
@@ -128,23 +135,25 @@ struct EpiDemosaic {
     o[2] = cast_from_f32<T>(__fmul_rn(clamp01(cb), os));
   }
 
-  __device__ __forceinline__ void emit(State&, int, int row, int tcol,
-                                       const float (&R)[8], const float (&G)[8], const float (&B)[8]) const {
+  template <bool BROW, bool GFIRST>
+  __device__ __forceinline__ void emit(State& st, int row, const float (&R)[8], const float (&G)[8], const float (&B)[8]) const {
+    using SS = SiteScale<BROW, GFIRST>;
     constexpr float is = DT<T>::scale;
     alignas(16) T o[24];
     if (DT<T>::is_int && !ccm) {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        o[3 * j]     = (T)(int)(fminf(fmaxf(R[j], 0.f), 16.f * is) * 0.0625f);
-        o[3 * j + 1] = (T)(int)(fminf(fmaxf(G[j], 0.f), 16.f * is) * 0.0625f);
-        o[3 * j + 2] = (T)(int)(fminf(fmaxf(B[j], 0.f), 16.f * is) * 0.0625f);
+      for (int j = 0; j < 8; ++j) {      // value * scale / 16 is an exact power-of-two scaling of the integer sum
+        o[3 * j]     = (T)(int)fminf(fmaxf(R[j] * (SS::r(j) * 0.0625f), 0.f), is);
+        o[3 * j + 1] = (T)(int)fminf(fmaxf(G[j] * (SS::g(j) * 0.0625f), 0.f), is);
+        o[3 * j + 2] = (T)(int)fminf(fmaxf(B[j] * (SS::b(j) * 0.0625f), 0.f), is);
       }
     } else {
 #pragma unroll
       for (int j = 0; j < 8; ++j)
-        finish_px(__fdiv_rn(R[j], is * 16.f), __fdiv_rn(G[j], is * 16.f), __fdiv_rn(B[j], is * 16.f), o + 3 * j);
+        finish_px(__fdiv_rn(R[j] * SS::r(j), is * 16.f), __fdiv_rn(G[j] * SS::g(j), is * 16.f),
+                  __fdiv_rn(B[j] * SS::b(j), is * 16.f), o + 3 * j);
     }
-    store_px8<T, true>(out + ((size_t)row * W + 8 * tcol) * 3, o, 8);
+    store_px8<T, true>(st.out + (size_t)((unsigned)row * (unsigned)W) * 3, o, 8);
   }
 };
 

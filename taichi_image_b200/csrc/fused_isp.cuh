@@ -36,45 +36,54 @@ struct FramePtrs {
 // come out as 16 + S/4096 exactly and the bias folds into the epilogue's FMA.
 // Camera16: the reference stores cfa = f16(v * f32(1/4095)); the same value is produced with one FMA
 // (exact product, single rounding) and a packed f32->f16->f32 round trip.
+// (x & 0x007FF800) | 0x3F800000 in ONE LOP3 (the compiler splits the two immediates into two)
+__device__ __forceinline__ float biased_from_shifted(uint32_t shifted, uint32_t mask, uint32_t one) {
+  uint32_t r;
+  asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"(r) : "r"(shifted), "r"(mask), "r"(one));
+  return __uint_as_float(r);
+}
+
 template <bool CAM16>
 struct Packed12Loader {
   FramePtrs fp;
   int pitch_words;       // W * 3 / 8
   int frame0;
   struct Raw { uint32_t w[5]; };
+  struct Cursor { const uint32_t* p; bool left, right; };
 
-  __device__ __forceinline__ void fetch(int frame, int row, int tcol, const StreamGeom& g, Raw& raw) const {
-    if (row < 0 || row >= g.H) {
-#pragma unroll
-      for (int i = 0; i < 5; ++i) raw.w[i] = 0u;
-      return;
-    }
-    const uint32_t* p = reinterpret_cast<const uint32_t*>(fp.in[frame0 + frame]) + (size_t)row * pitch_words + 3 * tcol;
-    raw.w[0] = tcol > 0 ? __ldg(p - 1) : 0u;
-    raw.w[1] = __ldg(p);
-    raw.w[2] = __ldg(p + 1);
-    raw.w[3] = __ldg(p + 2);
-    raw.w[4] = tcol < g.ntcols - 1 ? __ldg(p + 3) : 0u;
+  __device__ __forceinline__ void open(Cursor& c, int frame, int tcol, const StreamGeom& g) const {
+    c.p = reinterpret_cast<const uint32_t*>(fp.in[frame0 + frame]) + 3 * tcol;
+    c.left = tcol > 0;
+    c.right = tcol < g.ntcols - 1;
   }
 
-  static __device__ __forceinline__ float biased(uint32_t shifted) {
-    return __uint_as_float((shifted & 0x007FF800u) | 0x3F800000u);
+  __device__ __forceinline__ void fetch(const Cursor& c, int row, const StreamGeom& g, Raw& raw) const {
+    const bool rv = (unsigned)row < (unsigned)g.H;
+    const uint32_t* p = c.p + (rv ? (unsigned)row * (unsigned)pitch_words : 0u);
+    raw.w[0] = (rv && c.left) ? __ldg(p - 1) : 0u;
+    raw.w[1] = rv ? __ldg(p) : 0u;
+    raw.w[2] = rv ? __ldg(p + 1) : 0u;
+    raw.w[3] = rv ? __ldg(p + 2) : 0u;
+    raw.w[4] = (rv && c.right) ? __ldg(p + 3) : 0u;
   }
 
   __device__ __forceinline__ void decode(const Raw& raw, float (&v)[12]) const {
     const uint32_t w0 = raw.w[0], w1 = raw.w[1], w2 = raw.w[2], w3 = raw.w[3], w4 = raw.w[4];
-    v[0] = biased(w0 << 3);                          // pixel -2: bits 8..19 of w0
-    v[1] = biased(w0 >> 9);                          // pixel -1: bits 20..31 of w0
-    v[2] = biased(w1 << 11);                         // pixel 0 : bits 0..11 of w1
-    v[3] = biased(w1 >> 1);                          // pixel 1 : bits 12..23
-    v[4] = biased(__funnelshift_r(w1, w2, 13));      // pixel 2 : bits 24..35 of (w2:w1)
-    v[5] = biased(w2 << 7);                          // pixel 3 : bits 4..15 of w2
-    v[6] = biased(w2 >> 5);                          // pixel 4 : bits 16..27 of w2
-    v[7] = biased(__funnelshift_r(w2, w3, 17));      // pixel 5 : bits 28..39 of (w3:w2)
-    v[8] = biased(w3 << 3);                          // pixel 6 : bits 8..19 of w3
-    v[9] = biased(w3 >> 9);                          // pixel 7 : bits 20..31 of w3
-    v[10] = biased(w4 << 11);                        // pixel 8
-    v[11] = biased(w4 >> 1);                         // pixel 9
+    const uint32_t mask = 0x007FF800u, one = 0x3F800000u;
+#define ISP_B(x) biased_from_shifted((x), mask, one)
+    v[0] = ISP_B(w0 << 3);                          // pixel -2: bits 8..19 of w0
+    v[1] = ISP_B(w0 >> 9);                          // pixel -1: bits 20..31 of w0
+    v[2] = ISP_B(w1 << 11);                         // pixel 0 : bits 0..11 of w1
+    v[3] = ISP_B(w1 >> 1);                          // pixel 1 : bits 12..23
+    v[4] = ISP_B(__funnelshift_r(w1, w2, 13));      // pixel 2 : bits 24..35 of (w2:w1)
+    v[5] = ISP_B(w2 << 7);                          // pixel 3 : bits 4..15 of w2
+    v[6] = ISP_B(w2 >> 5);                          // pixel 4 : bits 16..27 of w2
+    v[7] = ISP_B(__funnelshift_r(w2, w3, 17));      // pixel 5 : bits 28..39 of (w3:w2)
+    v[8] = ISP_B(w3 << 3);                          // pixel 6 : bits 8..19 of w3
+    v[9] = ISP_B(w3 >> 9);                          // pixel 7 : bits 20..31 of w3
+    v[10] = ISP_B(w4 << 11);                        // pixel 8
+    v[11] = ISP_B(w4 >> 1);                         // pixel 9
+#undef ISP_B
     if constexpr (CAM16) {
       constexpr float k = 4096.f * kInv4095;         // (b - 1) * 4096 * f32(1/4095), one rounding
 #pragma unroll
@@ -125,15 +134,17 @@ __device__ __forceinline__ void isp_rgb_pixel(const Packed12Src<CAM16>& src, con
   rgb[2] = round_isp<CAM16>(clamp01(b));
 }
 
-// hot-path front end: raw filter sums (x16; biased by 16 for Camera32) -> ISP RGB in [0,1]
+// hot-path front end: scaled filter sums (value * scale = x16 sum; biased by 16 for Camera32) -> ISP RGB in [0,1]
+// cr/cg/cb are the compile-time SiteScale factors of this pixel; they fold into the constants.
 template <bool CAM16, bool CCM>
-__device__ __forceinline__ void isp_rgb_fast(const IspConsts& k, float sr, float sg, float sb, float (&rgb)[3]) {
+__device__ __forceinline__ void isp_rgb_fast(const IspConsts& k, float sr, float sg, float sb, float cr, float cg, float cb,
+                                             float (&rgb)[3]) {
   float r, g, b;
   if constexpr (CAM16) {
-    r = sr * 0.0625f; g = sg * 0.0625f; b = sb * 0.0625f;
+    r = sr * (cr * 0.0625f); g = sg * (cg * 0.0625f); b = sb * (cb * 0.0625f);
   } else {
     constexpr float kn = 256.f * kInv4095;           // 4096 * f32(1/4095) / 16
-    r = fmaf(sr, kn, -16.f * kn); g = fmaf(sg, kn, -16.f * kn); b = fmaf(sb, kn, -16.f * kn);
+    r = fmaf(sr, cr * kn, -16.f * kn); g = fmaf(sg, cg * kn, -16.f * kn); b = fmaf(sb, cb * kn, -16.f * kn);
   }
   if constexpr (CCM) {
     const float x = fmaf(b, k.m[2], fmaf(g, k.m[1], r * k.m[0]));
@@ -196,11 +207,11 @@ template <> struct Quant<float> {
 };
 
 template <typename OutT>
-__device__ __forceinline__ void store_row8(void* frame_out, int W, int row, int tcol, const uint32_t (&v)[24]) {
+__device__ __forceinline__ void store_row8(OutT* thread_out /* frame + 24 * tcol */, int W, int row, const uint32_t (&v)[24]) {
   constexpr int NW = Quant<OutT>::kWords;
   alignas(16) uint32_t w[NW];
   Quant<OutT>::pack(v, w);
-  OutT* dst = reinterpret_cast<OutT*>(frame_out) + ((size_t)row * W + 8 * tcol) * 3;
+  OutT* dst = thread_out + (size_t)((unsigned)row * (unsigned)W) * 3;
   if constexpr (NW % 4 == 0) {
     uint4* d = reinterpret_cast<uint4*>(dst);
 #pragma unroll
@@ -282,25 +293,27 @@ template <bool CAM16, typename OutT>
 struct EpiRgb {       // load_packed12: ISP-dtype float RGB out
   FramePtrs fp;
   IspConsts k;
-  struct State {};
-  __device__ __forceinline__ void init(State&, int) const {}
+  struct State { OutT* out; };
+  __device__ __forceinline__ void init(State& st, int frame, int tcol) const {
+    st.out = reinterpret_cast<OutT*>(fp.out[k.frame0 + frame]) + 24 * tcol;
+  }
   __device__ __forceinline__ void finish(State&, int, int, bool) const {}
-  template <bool CCM>
-  __device__ __forceinline__ void emit_t(int frame, int row, int tcol,
-                                         const float (&R)[8], const float (&G)[8], const float (&B)[8]) const {
+  template <bool BROW, bool GFIRST, bool CCM>
+  __device__ __forceinline__ void emit_t(const State& st, int row, const float (&R)[8], const float (&G)[8], const float (&B)[8]) const {
+    using SS = SiteScale<BROW, GFIRST>;
     uint32_t v[24];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       float rgb[3];
-      isp_rgb_fast<CAM16, CCM>(k, R[j], G[j], B[j], rgb);
+      isp_rgb_fast<CAM16, CCM>(k, R[j], G[j], B[j], SS::r(j), SS::g(j), SS::b(j), rgb);
       v[3 * j] = __float_as_uint(rgb[0]); v[3 * j + 1] = __float_as_uint(rgb[1]); v[3 * j + 2] = __float_as_uint(rgb[2]);
     }
-    store_row8<OutT>(fp.out[k.frame0 + frame], k.W, row, tcol, v);
+    store_row8<OutT>(st.out, k.W, row, v);
   }
-  __device__ __forceinline__ void emit(State&, int frame, int row, int tcol,
-                                       const float (&R)[8], const float (&G)[8], const float (&B)[8]) const {
-    if (k.ccm) emit_t<true>(frame, row, tcol, R, G, B);
-    else emit_t<false>(frame, row, tcol, R, G, B);
+  template <bool BROW, bool GFIRST>
+  __device__ __forceinline__ void emit(State& st, int row, const float (&R)[8], const float (&G)[8], const float (&B)[8]) const {
+    if (k.ccm) emit_t<BROW, GFIRST, true>(st, row, R, G, B);
+    else emit_t<BROW, GFIRST, false>(st, row, R, G, B);
   }
 };
 
@@ -308,25 +321,28 @@ template <bool CAM16, typename OutT>
 struct EpiLinear {
   FramePtrs fp;
   IspConsts k;
-  struct State { LinearConsts c; };
-  __device__ __forceinline__ void init(State& st, int) const { st.c = linear_consts(k.metrics, k.gamma); }
+  struct State { LinearConsts c; OutT* out; };
+  __device__ __forceinline__ void init(State& st, int frame, int tcol) const {
+    st.c = linear_consts(k.metrics, k.gamma);
+    st.out = reinterpret_cast<OutT*>(fp.out[k.frame0 + frame]) + 24 * tcol;
+  }
   __device__ __forceinline__ void finish(State&, int, int, bool) const {}
-  template <bool CCM, bool GAMMA>
-  __device__ __forceinline__ void emit_t(const State& st, int frame, int row, int tcol,
-                                         const float (&R)[8], const float (&G)[8], const float (&B)[8]) const {
+  template <bool BROW, bool GFIRST, bool CCM, bool GAMMA>
+  __device__ __forceinline__ void emit_t(const State& st, int row, const float (&R)[8], const float (&G)[8], const float (&B)[8]) const {
+    using SS = SiteScale<BROW, GFIRST>;
     uint32_t v[24];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       float rgb[3], y[3];
-      isp_rgb_fast<CAM16, CCM>(k, R[j], G[j], B[j], rgb);
+      isp_rgb_fast<CAM16, CCM>(k, R[j], G[j], B[j], SS::r(j), SS::g(j), SS::b(j), rgb);
       linear_px<GAMMA>(st.c, rgb, y);
       v[3 * j] = Quant<OutT>::q(y[0]); v[3 * j + 1] = Quant<OutT>::q(y[1]); v[3 * j + 2] = Quant<OutT>::q(y[2]);
     }
-    store_row8<OutT>(fp.out[k.frame0 + frame], k.W, row, tcol, v);
+    store_row8<OutT>(st.out, k.W, row, v);
   }
-  __device__ __forceinline__ void emit(State& st, int frame, int row, int tcol,
-                                       const float (&R)[8], const float (&G)[8], const float (&B)[8]) const {
-#define ISP_CALL(A, B_) emit_t<A, B_>(st, frame, row, tcol, R, G, B)
+  template <bool BROW, bool GFIRST>
+  __device__ __forceinline__ void emit(State& st, int row, const float (&R)[8], const float (&G)[8], const float (&B)[8]) const {
+#define ISP_CALL(A, B_) emit_t<BROW, GFIRST, A, B_>(st, row, R, G, B)
     ISP_FLAG_DISPATCH2(k.ccm, st.c.has_gamma, ISP_CALL);
 #undef ISP_CALL
   }
@@ -347,29 +363,33 @@ __device__ __forceinline__ ReinhardConsts reinhard_consts(const IspConsts& k, in
 template <bool CAM16>
 struct EpiReinhardMax {      // pass 1 without the write-back: frame-global max of the mapped values
   IspConsts k;
-  struct State { ReinhardConsts c; float mx; };
-  __device__ __forceinline__ void init(State& st, int frame) const { st.c = reinhard_consts(k, frame, false); st.mx = 0.f; }
-  template <bool CCM, bool CA0>
-  __device__ __forceinline__ void emit_t(State& st, int tcol,
-                                         const float (&R)[8], const float (&G)[8], const float (&B)[8]) const {
-    const bool first = tcol == 0, last = tcol == (k.W >> 3) - 1;
+  struct State { ReinhardConsts c; float mx; bool first, last; };
+  __device__ __forceinline__ void init(State& st, int frame, int tcol) const {
+    st.c = reinhard_consts(k, frame, false);
+    st.mx = 0.f;
+    st.first = tcol == 0;
+    st.last = tcol == (k.W >> 3) - 1;
+  }
+  template <bool BROW, bool GFIRST, bool CCM, bool CA0>
+  __device__ __forceinline__ void emit_t(State& st, const float (&R)[8], const float (&G)[8], const float (&B)[8]) const {
+    using SS = SiteScale<BROW, GFIRST>;
     float mx = st.mx;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       float rgb[3], p[3];
-      isp_rgb_fast<CAM16, CCM>(k, R[j], G[j], B[j], rgb);
+      isp_rgb_fast<CAM16, CCM>(k, R[j], G[j], B[j], SS::r(j), SS::g(j), SS::b(j), rgb);
       reinhard_p<CAM16, CA0>(st.c, rgb, p);
       float m = fmaxf(p[0], fmaxf(p[1], p[2]));
-      if ((j < 2 && first) || (j >= 6 && last)) m = 0.f;     // image frame: border kernel
+      if ((j < 2 && st.first) || (j >= 6 && st.last)) m = 0.f;     // image frame: border kernel
       mx = fmaxf(mx, m);
     }
     st.mx = mx;
   }
-  __device__ __forceinline__ void emit(State& st, int, int row, int tcol,
-                                       const float (&R)[8], const float (&G)[8], const float (&B)[8]) const {
+  template <bool BROW, bool GFIRST>
+  __device__ __forceinline__ void emit(State& st, int row, const float (&R)[8], const float (&G)[8], const float (&B)[8]) const {
     // the 2-pixel image frame is handled (with the exact border normalisation) by the border kernel
     if (row < 2 || row >= k.H - 2) return;
-#define ISP_CALL(A, B_) emit_t<A, B_>(st, tcol, R, G, B)
+#define ISP_CALL(A, B_) emit_t<BROW, GFIRST, A, B_>(st, R, G, B)
     ISP_FLAG_DISPATCH2(k.ccm, st.c.ca0, ISP_CALL);
 #undef ISP_CALL
   }
@@ -384,31 +404,34 @@ template <bool CAM16, typename OutT>
 struct EpiReinhard {         // pass 2 recomputed from the packed frame: map, normalise by the max, gamma, quantise
   FramePtrs fp;
   IspConsts k;
-  struct State { ReinhardConsts c; };
-  __device__ __forceinline__ void init(State& st, int frame) const { st.c = reinhard_consts(k, frame, true); }
+  struct State { ReinhardConsts c; OutT* out; };
+  __device__ __forceinline__ void init(State& st, int frame, int tcol) const {
+    st.c = reinhard_consts(k, frame, true);
+    st.out = reinterpret_cast<OutT*>(fp.out[k.frame0 + frame]) + 24 * tcol;
+  }
   __device__ __forceinline__ void finish(State&, int, int, bool) const {}
-  template <bool CCM, bool CA0, bool GAMMA>
-  __device__ __forceinline__ void emit_t(const State& st, int frame, int row, int tcol,
-                                         const float (&R)[8], const float (&G)[8], const float (&B)[8]) const {
+  template <bool BROW, bool GFIRST, bool CCM, bool CA0, bool GAMMA>
+  __device__ __forceinline__ void emit_t(const State& st, int row, const float (&R)[8], const float (&G)[8], const float (&B)[8]) const {
+    using SS = SiteScale<BROW, GFIRST>;
     uint32_t v[24];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       float rgb[3], p[3], y[3];
-      isp_rgb_fast<CAM16, CCM>(k, R[j], G[j], B[j], rgb);
+      isp_rgb_fast<CAM16, CCM>(k, R[j], G[j], B[j], SS::r(j), SS::g(j), SS::b(j), rgb);
       reinhard_p<CAM16, CA0>(st.c, rgb, p);
       reinhard_out<CAM16, GAMMA>(st.c, p, y);
       v[3 * j] = Quant<OutT>::q(y[0]); v[3 * j + 1] = Quant<OutT>::q(y[1]); v[3 * j + 2] = Quant<OutT>::q(y[2]);
     }
-    store_row8<OutT>(fp.out[k.frame0 + frame], k.W, row, tcol, v);
+    store_row8<OutT>(st.out, k.W, row, v);
   }
-  __device__ __forceinline__ void emit(State& st, int frame, int row, int tcol,
-                                       const float (&R)[8], const float (&G)[8], const float (&B)[8]) const {
+  template <bool BROW, bool GFIRST>
+  __device__ __forceinline__ void emit(State& st, int row, const float (&R)[8], const float (&G)[8], const float (&B)[8]) const {
     if (st.c.has_gamma) {
-#define ISP_CALL(A, B_) emit_t<A, B_, true>(st, frame, row, tcol, R, G, B)
+#define ISP_CALL(A, B_) emit_t<BROW, GFIRST, A, B_, true>(st, row, R, G, B)
       ISP_FLAG_DISPATCH2(k.ccm, st.c.ca0, ISP_CALL);
 #undef ISP_CALL
     } else {
-#define ISP_CALL(A, B_) emit_t<A, B_, false>(st, frame, row, tcol, R, G, B)
+#define ISP_CALL(A, B_) emit_t<BROW, GFIRST, A, B_, false>(st, row, R, G, B)
       ISP_FLAG_DISPATCH2(k.ccm, st.c.ca0, ISP_CALL);
 #undef ISP_CALL
     }
@@ -532,22 +555,22 @@ struct Packed12FastSampler {
     const bool brow0 = (k.pattern == B200ISP_GBRG || k.pattern == B200ISP_BGGR);
     const bool gfirst0 = (k.pattern == B200ISP_GRBG || k.pattern == B200ISP_GBRG);
     const bool brow = brow0 != ((row & 1) != 0), gsite = gfirst0 != ((row & 1) != 0);
-    float R, G, B;
+    float R, G, B, cr, cg, cb;
     if (!gsite) {
-      const float A = NS + EW, Bq = NNSS + EEWW;
-      G = fmaf(4.f, A, fmaf(-2.f, Bq, 8.f * C));
-      const float Y = fmaf(4.f, D, fmaf(-3.f, Bq, 12.f * C));
-      const float X = 16.f * C;
-      R = brow ? Y : X; B = brow ? X : Y;
+      float g2, opp4;
+      malvar_csite(C, NS, EW, NNSS, EEWW, D, g2, opp4);
+      G = g2; cg = 2.f;
+      R = brow ? opp4 : C; cr = brow ? 4.f : 16.f;
+      B = brow ? C : opp4; cb = brow ? 16.f : 4.f;
     } else {
-      const float T = fmaf(-2.f, D, 10.f * C);
-      const float Hc = fmaf(8.f, EW, fmaf(-2.f, EEWW, T)) + NNSS;
-      const float Vc = fmaf(8.f, NS, fmaf(-2.f, NNSS, T)) + EEWW;
-      G = 16.f * C;
-      R = brow ? Vc : Hc; B = brow ? Hc : Vc;
+      float h2, v2;
+      malvar_gsite(C, NS, EW, NNSS, EEWW, D, h2, v2);
+      G = C; cg = 16.f;
+      R = brow ? v2 : h2; cr = 2.f;
+      B = brow ? h2 : v2; cb = 2.f;
     }
-    if (k.ccm) isp_rgb_fast<CAM16, true>(k, R, G, B, rgb);
-    else isp_rgb_fast<CAM16, false>(k, R, G, B, rgb);
+    if (k.ccm) isp_rgb_fast<CAM16, true>(k, R, G, B, cr, cg, cb, rgb);
+    else isp_rgb_fast<CAM16, false>(k, R, G, B, cr, cg, cb, rgb);
   }
 };
 

@@ -6,7 +6,8 @@
 // block barriers.  A warp covers a 256-pixel strip (coalesced 384-byte packed12 rows / 256..1024
 // byte typed rows), a "task" is (frame, row-chunk, strip) and tasks are laid out so that the warps
 // of a block sit on adjacent strips of the same rows (halo words hit L1).  The grid has one warp
-// per task; rows_per_task sizes it to several waves over the 148 SMs.
+// per task; rows_per_task sizes it to several waves over the 148 SMs.  Rows are fetched one step
+// (two rows) ahead of their use, so the global-load latency is covered by a whole step of math.
 //
 // The 13-tap filters are evaluated through shared partial sums:
 //   NS(c) = v[r-1][c]+v[r+1][c]   EW = v[r][c-1]+v[r][c+1]   NNSS = v[r-2][c]+v[r+2][c]
@@ -14,13 +15,19 @@
 //   R/B site:  own = 16C   G = 8C+4(NS+EW)-2(NNSS+EEWW)   opposite = 12C+4D-3(NNSS+EEWW)
 //   G site:    G = 16C     colour with horizontal neighbours = 10C+8EW-2D-2EEWW+NNSS
 //                          colour with vertical neighbours   = 10C+8NS-2D-2NNSS+EEWW
-// which are the tables of bayer.py:30-55 (x16).  The sums are exact for integer-valued inputs
-// (|sum| < 2^24), so the evaluation order does not matter there.  Out-of-image taps read as 0 and
-// the streaming kernel normalises every pixel by 16; the 2-pixel image frame, where the reference
-// renormalises by the in-bounds weight sum (bayer.py:145-151), is then rewritten by a per-pixel
-// border kernel (border.cuh) launched right after on the same stream.
+// which are the tables of bayer.py:30-55 (x16).  To save multiplies the engine hands the epilogue
+// SCALED sums (own/16, G/2, opposite/4, G-site colours/2; see SiteScale) -- the epilogue folds the
+// power-of-two factor into the normalisation constant it multiplies with anyway.  The sums are exact
+// for integer-valued inputs (|sum| < 2^24), so the evaluation order does not matter there.
+// Out-of-image taps read as 0 and the streaming kernel normalises every pixel by 16; the 2-pixel
+// image frame, where the reference renormalises by the in-bounds weight sum (bayer.py:145-151), is
+// then rewritten by a per-pixel border kernel (pixel_ops.cuh) launched right after on the same stream.
 #pragma once
 #include "common.cuh"
+
+#ifndef ISP_ENGINE_UNROLL3
+#define ISP_ENGINE_UNROLL3 0
+#endif
 
 namespace isp {
 
@@ -54,6 +61,31 @@ inline StreamGeom make_geom(int H, int W, int nframes, int rows_per_task) {
   return g;
 }
 
+// ---------------------------------------------------------------- per-site filter formulas (scaled)
+// R/B site: own colour = C (x16), G = 4C + 2(NS+EW) - (NNSS+EEWW) (x2), opposite = 3C + D - 0.75(NNSS+EEWW) (x4)
+__device__ __forceinline__ void malvar_csite(float C, float NS, float EW, float NNSS, float EEWW, float D,
+                                             float& g2, float& opp4) {
+  const float A = NS + EW, Bq = NNSS + EEWW;
+  g2 = fmaf(4.f, C, fmaf(2.f, A, -Bq));
+  opp4 = fmaf(-0.75f, Bq, fmaf(3.f, C, D));
+}
+// G site: G = C (x16), horizontal-neighbour colour = 5C - D + 4EW - EEWW + 0.5NNSS (x2), vertical likewise
+__device__ __forceinline__ void malvar_gsite(float C, float NS, float EW, float NNSS, float EEWW, float D,
+                                             float& h2, float& v2) {
+  const float T = fmaf(5.f, C, -D);
+  h2 = fmaf(0.5f, NNSS, fmaf(4.f, EW, T) - EEWW);
+  v2 = fmaf(0.5f, EEWW, fmaf(4.f, NS, T) - NNSS);
+}
+
+// scale that turns the engine's value for (row type, pixel j, channel) back into the x16 filter sum
+template <bool BROW, bool GFIRST>
+struct SiteScale {
+  static __host__ __device__ constexpr bool gsite(int j) { return ((j & 1) == 0) == GFIRST; }
+  static __host__ __device__ constexpr float r(int j) { return gsite(j) ? 2.f : (BROW ? 4.f : 16.f); }
+  static __host__ __device__ constexpr float g(int j) { return gsite(j) ? 16.f : 2.f; }
+  static __host__ __device__ constexpr float b(int j) { return gsite(j) ? 2.f : (BROW ? 16.f : 4.f); }
+};
+
 template <bool BROW, bool GFIRST>
 __device__ __forceinline__ void malvar_row(const float (&m2)[12], const float (&m1)[12], const float (&z)[12],
                                            const float (&p1)[12], const float (&p2)[12],
@@ -69,33 +101,30 @@ __device__ __forceinline__ void malvar_row(const float (&m2)[12], const float (&
     const float NS = ns[j + 1];
     const float D = ns[j] + ns[j + 2];
     const float NNSS = m2[j + 2] + p2[j + 2];
-    const bool gsite = (((j & 1) == 0) == GFIRST);
-    if (!gsite) {
-      const float A = NS + EW, Bq = NNSS + EEWW;
-      const float Gc = fmaf(4.f, A, fmaf(-2.f, Bq, 8.f * C));
-      const float Y = fmaf(4.f, D, fmaf(-3.f, Bq, 12.f * C));
-      const float X = 16.f * C;
-      G[j] = Gc;
-      R[j] = BROW ? Y : X;
-      B[j] = BROW ? X : Y;
+    if (!SiteScale<BROW, GFIRST>::gsite(j)) {
+      float g2, opp4;
+      malvar_csite(C, NS, EW, NNSS, EEWW, D, g2, opp4);
+      G[j] = g2;
+      R[j] = BROW ? opp4 : C;
+      B[j] = BROW ? C : opp4;
     } else {
-      const float T = fmaf(-2.f, D, 10.f * C);
-      const float Hc = fmaf(8.f, EW, fmaf(-2.f, EEWW, T)) + NNSS;
-      const float Vc = fmaf(8.f, NS, fmaf(-2.f, NNSS, T)) + EEWW;
-      G[j] = 16.f * C;
-      R[j] = BROW ? Vc : Hc;
-      B[j] = BROW ? Hc : Vc;
+      float h2, v2;
+      malvar_gsite(C, NS, EW, NNSS, EEWW, D, h2, v2);
+      G[j] = C;
+      R[j] = BROW ? v2 : h2;
+      B[j] = BROW ? h2 : v2;
     }
   }
 }
 
 // Loader concept:
-//   struct Raw;                                                         raw registers of one row
-//   void fetch(int frame, int row, int tcol, const StreamGeom&, Raw&)   issue the global loads
-//   void decode(const Raw&, float (&v)[12])                             v[j] = CFA at column 8*tcol-2+j (0 outside)
+//   struct Raw;  struct Cursor;
+//   void open(Cursor&, int frame, int tcol, const StreamGeom&)           per-task base pointer / edge flags
+//   void fetch(const Cursor&, int row, const StreamGeom&, Raw&)          issue the global loads of one row (0 outside)
+//   void decode(const Raw&, float (&v)[12])                              v[j] = CFA at column 8*tcol-2+j
 // Epilogue concept:
-//   struct State;  void init(State&, int frame) ;  void finish(State&, int frame, int lane)
-//   void emit(State&, int frame, int row, int tcol, R, G, B)   raw filter sums (x16), t = 16 assumed
+//   struct State;  void init(State&, int frame, int tcol);  void finish(State&, int frame, int lane, bool task_ok)
+//   template <bool BROW, bool GFIRST> void emit(State&, int row, R, G, B)   scaled filter sums, see SiteScale
 template <int PATTERN, class Loader, class Epi>
 __global__ void __launch_bounds__(256, 2) stream_kernel(const Loader ld, const Epi epi, const StreamGeom g) {
   constexpr bool BROW0 = (PATTERN == B200ISP_GBRG || PATTERN == B200ISP_BGGR);
@@ -108,50 +137,76 @@ __global__ void __launch_bounds__(256, 2) stream_kernel(const Loader ld, const E
   const long long t2 = task / g.warps_per_row;
   const int chunk = (int)(t2 % g.nchunks);
   const int frame = (int)(t2 / g.nchunks);
-  const int tcol = strip * 32 + lane;
-  const bool active = task_ok && tcol < g.ntcols;
+  const int tcol = min(strip * 32 + lane, g.ntcols - 1);
+  const bool active = task_ok && (strip * 32 + lane) < g.ntcols;
 
   typename Epi::State st;
-  epi.init(st, frame);
+  epi.init(st, frame, tcol);
 
   if (active) {
     const int r0 = chunk * g.rows_per_task;
     const int rend = min(r0 + g.rows_per_task, g.H);
+    typename Loader::Cursor cur;
+    ld.open(cur, frame, tcol, g);
 
     float win[6][12];
     typename Loader::Raw raw0, raw1;
     // prologue: rows r0-2 .. r0+1 -> slots 0..3
-    ld.fetch(frame, r0 - 2, tcol, g, raw0);
-    ld.fetch(frame, r0 - 1, tcol, g, raw1);
+    ld.fetch(cur, r0 - 2, g, raw0);
+    ld.fetch(cur, r0 - 1, g, raw1);
     ld.decode(raw0, win[0]);
     ld.decode(raw1, win[1]);
-    ld.fetch(frame, r0, tcol, g, raw0);
-    ld.fetch(frame, r0 + 1, tcol, g, raw1);
+    ld.fetch(cur, r0, g, raw0);
+    ld.fetch(cur, r0 + 1, g, raw1);
     ld.decode(raw0, win[2]);
     ld.decode(raw1, win[3]);
-    ld.fetch(frame, r0 + 2, tcol, g, raw0);
-    ld.fetch(frame, r0 + 3, tcol, g, raw1);
+    ld.fetch(cur, r0 + 2, g, raw0);
+    ld.fetch(cur, r0 + 3, g, raw1);
 
+#if ISP_ENGINE_UNROLL3
+    // variant A: 6-slot window addressed modulo 6, three steps unrolled (no register moves, 3x the code)
     for (int rb = r0; rb < rend; rb += 6) {
 #pragma unroll
       for (int u = 0; u < 3; ++u) {
         const int row = rb + 2 * u;
         if (row < rend) {
-          // rows row+2, row+3 were fetched one step ago
           ld.decode(raw0, win[(2 * u + 4) % 6]);
           ld.decode(raw1, win[(2 * u + 5) % 6]);
-          if (row + 4 < rend + 2) ld.fetch(frame, row + 4, tcol, g, raw0);   // next step's rows (warp-uniform)
-          if (row + 5 < rend + 2) ld.fetch(frame, row + 5, tcol, g, raw1);
+          ld.fetch(cur, row + 4 < rend + 2 ? row + 4 : -1, g, raw0);
+          ld.fetch(cur, row + 5 < rend + 2 ? row + 5 : -1, g, raw1);
           float R[8], G[8], B[8];
           malvar_row<BROW0, GFIRST0>(win[(2 * u) % 6], win[(2 * u + 1) % 6], win[(2 * u + 2) % 6],
                                      win[(2 * u + 3) % 6], win[(2 * u + 4) % 6], R, G, B);
-          epi.emit(st, frame, row, tcol, R, G, B);
+          epi.template emit<BROW0, GFIRST0>(st, row, R, G, B);
           malvar_row<!BROW0, !GFIRST0>(win[(2 * u + 1) % 6], win[(2 * u + 2) % 6], win[(2 * u + 3) % 6],
                                        win[(2 * u + 4) % 6], win[(2 * u + 5) % 6], R, G, B);
-          epi.emit(st, frame, row + 1, tcol, R, G, B);
+          epi.template emit<!BROW0, !GFIRST0>(st, row + 1, R, G, B);
         }
       }
     }
+#else
+    // variant B (default): one step (two rows) per loop trip, the window slides by register moves.  The
+    // loop body stays ~11 KB of SASS, well inside the 32 KB instruction cache shared by the SM's warps;
+    // the 3x-unrolled variant A measured ~31 KB and lost ~25 % of its issue slots to instruction fetch.
+#pragma unroll 1
+    for (int row = r0; row < rend; row += 2) {
+      // rows row+2, row+3 were fetched one step ago
+      ld.decode(raw0, win[4]);
+      ld.decode(raw1, win[5]);
+      // next step's rows (rows past the chunk halo or the image come back as zeros and are never used)
+      ld.fetch(cur, row + 4 < rend + 2 ? row + 4 : -1, g, raw0);
+      ld.fetch(cur, row + 5 < rend + 2 ? row + 5 : -1, g, raw1);
+      float R[8], G[8], B[8];
+      malvar_row<BROW0, GFIRST0>(win[0], win[1], win[2], win[3], win[4], R, G, B);
+      epi.template emit<BROW0, GFIRST0>(st, row, R, G, B);
+      malvar_row<!BROW0, !GFIRST0>(win[1], win[2], win[3], win[4], win[5], R, G, B);
+      epi.template emit<!BROW0, !GFIRST0>(st, row + 1, R, G, B);
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+#pragma unroll
+        for (int j = 0; j < 12; ++j) win[k][j] = win[k + 2][j];
+    }
+#endif
   }
   epi.finish(st, frame, lane, task_ok);
 }
