@@ -28,7 +28,7 @@ ORACLE_SRC = ROOT / "oracle" / "c" / "isp_oracle.c"
 ORACLE_LIB = ROOT / "oracle" / "_build" / "libisp_oracle.so"
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-              "-Xcompiler", "-fPIC", "--threads", "1"]
+              "-Xcompiler", "-fPIC", "--threads", "1"] + os.environ.get("B200ISP_NVCC_EXTRA", "").split()
 
 FUSED_OUT = {"u8": "uint8_t", "u16": "uint16_t", "f16": "__half", "f32": "float"}
 

@@ -26,6 +26,7 @@ template <> struct PlaneLoader<uint8_t, true> {
     raw.w[2] = rv ? __ldg(p + 1) : 0u;
     raw.w[3] = (rv && c.right) ? __ldg(p + 2) : 0u;
   }
+  __device__ __forceinline__ void prefetch(const Cursor&, int, const StreamGeom&) const {}
   __device__ __forceinline__ void decode(const Raw& raw, float (&v)[12]) const {
 #pragma unroll
     for (int j = 0; j < 12; ++j) v[j] = (float)((raw.w[(j + 2) >> 2] >> (8 * ((j + 2) & 3))) & 0xFFu);
@@ -48,6 +49,7 @@ template <typename T> struct PlaneLoader16 {   // u16 / i16 / f16
     raw.w[1] = q.x; raw.w[2] = q.y; raw.w[3] = q.z; raw.w[4] = q.w;
     raw.w[5] = (rv && c.right) ? __ldg(p + 4) : 0u;
   }
+  __device__ __forceinline__ void prefetch(const Cursor&, int, const StreamGeom&) const {}
   __device__ __forceinline__ void decode(const Raw& raw, float (&v)[12]) const {
 #pragma unroll
     for (int j = 0; j < 12; ++j) {
@@ -82,6 +84,7 @@ template <> struct PlaneLoader<float, true> {
     raw.v[6] = b.x; raw.v[7] = b.y; raw.v[8] = b.z; raw.v[9] = b.w;
     raw.v[10] = r.x; raw.v[11] = r.y;
   }
+  __device__ __forceinline__ void prefetch(const Cursor&, int, const StreamGeom&) const {}
   __device__ __forceinline__ void decode(const Raw& raw, float (&v)[12]) const {
 #pragma unroll
     for (int j = 0; j < 12; ++j) v[j] = raw.v[j];

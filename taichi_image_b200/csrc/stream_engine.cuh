@@ -1,7 +1,7 @@
 // Register-window streaming engine for the Malvar-He-Cutler demosaic (reference: bayer.py:114-177).
 //
 // B200 mapping: one thread owns 8 consecutive pixel columns and walks DOWN the image keeping a
-// 6-row x 12-column window of the CFA in registers (8 own columns + 2 halo columns per side), so
+// 6-row window of the CFA in registers (8 own columns + 2 halo columns per side), so
 // every CFA sample is fetched from memory once per row-chunk and decoded once; no shared memory, no
 // block barriers.  A warp covers a 256-pixel strip (coalesced 384-byte packed12 rows / 256..1024
 // byte typed rows), a "task" is (frame, row-chunk, strip) and tasks are laid out so that the warps
@@ -25,9 +25,6 @@
 #pragma once
 #include "common.cuh"
 
-#ifndef ISP_ENGINE_UNROLL3
-#define ISP_ENGINE_UNROLL3 0
-#endif
 
 namespace isp {
 
@@ -86,13 +83,17 @@ struct SiteScale {
   static __host__ __device__ constexpr float b(int j) { return gsite(j) ? 2.f : (BROW ? 16.f : 4.f); }
 };
 
-template <bool BROW, bool GFIRST>
-__device__ __forceinline__ void malvar_row(const float (&m2)[12], const float (&m1)[12], const float (&z)[12],
-                                           const float (&p1)[12], const float (&p2)[12],
+// One output row of 8 pixels.  z / p1 / p2 are full 12-wide rows (column c0-2+i at index i); the two rows
+// above are passed as pointers with a compile-time column offset because the engine only carries the
+// columns that are still needed of them: m2[(j+2) + M2OFF] is column j+2 (NN tap), m1[(k+1) + M1OFF]
+// column k+1 (N / NW / NE taps).
+template <bool BROW, bool GFIRST, int M2OFF, int M1OFF>
+__device__ __forceinline__ void malvar_row(const float* __restrict__ m2, const float* __restrict__ m1,
+                                           const float (&z)[12], const float (&p1)[12], const float (&p2)[12],
                                            float (&R)[8], float (&G)[8], float (&B)[8]) {
   float ns[10];
 #pragma unroll
-  for (int k = 0; k < 10; ++k) ns[k] = m1[k + 1] + p1[k + 1];
+  for (int k = 0; k < 10; ++k) ns[k] = m1[k + 1 + M1OFF] + p1[k + 1];
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     const float C = z[j + 2];
@@ -100,7 +101,7 @@ __device__ __forceinline__ void malvar_row(const float (&m2)[12], const float (&
     const float EEWW = z[j] + z[j + 4];
     const float NS = ns[j + 1];
     const float D = ns[j] + ns[j + 2];
-    const float NNSS = m2[j + 2] + p2[j + 2];
+    const float NNSS = m2[j + 2 + M2OFF] + p2[j + 2];
     if (!SiteScale<BROW, GFIRST>::gsite(j)) {
       float g2, opp4;
       malvar_csite(C, NS, EW, NNSS, EEWW, D, g2, opp4);
@@ -117,10 +118,38 @@ __device__ __forceinline__ void malvar_row(const float (&m2)[12], const float (&
   }
 }
 
+// One step = two output rows (row, row+1).  cA/cB are rows row / row+1, nA/nB receive rows row+2 / row+3
+// (fetched one step earlier), oA / oB hold what is still needed of rows row-2 (columns 2..9) and row-1
+// (columns 1..10).  The rows for the NEXT step are requested before the math so their latency is covered.
+template <bool BROW0, bool GFIRST0, class Loader, class Epi>
+__device__ __forceinline__ void stream_step(const Loader& ld, const Epi& epi, typename Epi::State& st,
+                                            const typename Loader::Cursor& cur, const StreamGeom& g, int row, int rend,
+                                            typename Loader::Raw& raw0, typename Loader::Raw& raw1,
+                                            float (&oA)[8], float (&oB)[10], const float (&cA)[12], const float (&cB)[12],
+                                            float (&nA)[12], float (&nB)[12]) {
+  ld.decode(raw0, nA);
+  ld.decode(raw1, nB);
+  // rows past the chunk halo or the image come back as zeros and are never used
+  ld.fetch(cur, row + 4 < rend + 2 ? row + 4 : -1, g, raw0);
+  ld.fetch(cur, row + 5 < rend + 2 ? row + 5 : -1, g, raw1);
+  ld.prefetch(cur, row + 8, g);
+  ld.prefetch(cur, row + 9, g);
+  float R[8], G[8], B[8];
+  malvar_row<BROW0, GFIRST0, -2, -1>(oA, oB, cA, cB, nA, R, G, B);
+  epi.template emit<BROW0, GFIRST0>(st, row, R, G, B);
+  malvar_row<!BROW0, !GFIRST0, -1, 0>(oB, cA, cB, nA, nB, R, G, B);
+  epi.template emit<!BROW0, !GFIRST0>(st, row + 1, R, G, B);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) oA[j] = cA[j + 2];
+#pragma unroll
+  for (int j = 0; j < 10; ++j) oB[j] = cB[j + 1];
+}
+
 // Loader concept:
 //   struct Raw;  struct Cursor;
 //   void open(Cursor&, int frame, int tcol, const StreamGeom&)           per-task base pointer / edge flags
 //   void fetch(const Cursor&, int row, const StreamGeom&, Raw&)          issue the global loads of one row (0 outside)
+//   void prefetch(const Cursor&, int row, const StreamGeom&)             optional L2 prefetch of a later row
 //   void decode(const Raw&, float (&v)[12])                              v[j] = CFA at column 8*tcol-2+j
 // Epilogue concept:
 //   struct State;  void init(State&, int frame, int tcol);  void finish(State&, int frame, int lane, bool task_ok)
@@ -149,64 +178,38 @@ __global__ void __launch_bounds__(256, 2) stream_kernel(const Loader ld, const E
     typename Loader::Cursor cur;
     ld.open(cur, frame, tcol, g);
 
-    float win[6][12];
+    // The window: two 2-row buffers that alternate between "centre rows" and "incoming rows" (the loop is
+    // unrolled twice so no row is ever copied) plus the 18 values still needed of the two rows above.
+    float b0A[12], b0B[12], b1A[12], b1B[12], oA[8], oB[10];
     typename Loader::Raw raw0, raw1;
-    // prologue: rows r0-2 .. r0+1 -> slots 0..3
-    ld.fetch(cur, r0 - 2, g, raw0);
-    ld.fetch(cur, r0 - 1, g, raw1);
-    ld.decode(raw0, win[0]);
-    ld.decode(raw1, win[1]);
+    {
+      float t[12];
+      ld.fetch(cur, r0 - 2, g, raw0);
+      ld.fetch(cur, r0 - 1, g, raw1);
+      ld.decode(raw0, t);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) oA[j] = t[j + 2];
+      ld.decode(raw1, t);
+#pragma unroll
+      for (int j = 0; j < 10; ++j) oB[j] = t[j + 1];
+    }
     ld.fetch(cur, r0, g, raw0);
     ld.fetch(cur, r0 + 1, g, raw1);
-    ld.decode(raw0, win[2]);
-    ld.decode(raw1, win[3]);
+    ld.decode(raw0, b0A);
+    ld.decode(raw1, b0B);
     ld.fetch(cur, r0 + 2, g, raw0);
     ld.fetch(cur, r0 + 3, g, raw1);
+    ld.prefetch(cur, r0 + 4, g); ld.prefetch(cur, r0 + 5, g);
+    ld.prefetch(cur, r0 + 6, g); ld.prefetch(cur, r0 + 7, g);
 
-#if ISP_ENGINE_UNROLL3
-    // variant A: 6-slot window addressed modulo 6, three steps unrolled (no register moves, 3x the code)
-    for (int rb = r0; rb < rend; rb += 6) {
-#pragma unroll
-      for (int u = 0; u < 3; ++u) {
-        const int row = rb + 2 * u;
-        if (row < rend) {
-          ld.decode(raw0, win[(2 * u + 4) % 6]);
-          ld.decode(raw1, win[(2 * u + 5) % 6]);
-          ld.fetch(cur, row + 4 < rend + 2 ? row + 4 : -1, g, raw0);
-          ld.fetch(cur, row + 5 < rend + 2 ? row + 5 : -1, g, raw1);
-          float R[8], G[8], B[8];
-          malvar_row<BROW0, GFIRST0>(win[(2 * u) % 6], win[(2 * u + 1) % 6], win[(2 * u + 2) % 6],
-                                     win[(2 * u + 3) % 6], win[(2 * u + 4) % 6], R, G, B);
-          epi.template emit<BROW0, GFIRST0>(st, row, R, G, B);
-          malvar_row<!BROW0, !GFIRST0>(win[(2 * u + 1) % 6], win[(2 * u + 2) % 6], win[(2 * u + 3) % 6],
-                                       win[(2 * u + 4) % 6], win[(2 * u + 5) % 6], R, G, B);
-          epi.template emit<!BROW0, !GFIRST0>(st, row + 1, R, G, B);
-        }
-      }
-    }
-#else
-    // variant B (default): one step (two rows) per loop trip, the window slides by register moves.  The
-    // loop body stays ~11 KB of SASS, well inside the 32 KB instruction cache shared by the SM's warps;
-    // the 3x-unrolled variant A measured ~31 KB and lost ~25 % of its issue slots to instruction fetch.
 #pragma unroll 1
-    for (int row = r0; row < rend; row += 2) {
-      // rows row+2, row+3 were fetched one step ago
-      ld.decode(raw0, win[4]);
-      ld.decode(raw1, win[5]);
-      // next step's rows (rows past the chunk halo or the image come back as zeros and are never used)
-      ld.fetch(cur, row + 4 < rend + 2 ? row + 4 : -1, g, raw0);
-      ld.fetch(cur, row + 5 < rend + 2 ? row + 5 : -1, g, raw1);
-      float R[8], G[8], B[8];
-      malvar_row<BROW0, GFIRST0>(win[0], win[1], win[2], win[3], win[4], R, G, B);
-      epi.template emit<BROW0, GFIRST0>(st, row, R, G, B);
-      malvar_row<!BROW0, !GFIRST0>(win[1], win[2], win[3], win[4], win[5], R, G, B);
-      epi.template emit<!BROW0, !GFIRST0>(st, row + 1, R, G, B);
-#pragma unroll
-      for (int k = 0; k < 4; ++k)
-#pragma unroll
-        for (int j = 0; j < 12; ++j) win[k][j] = win[k + 2][j];
+    for (int row = r0; row < rend; row += 4) {
+      stream_step<BROW0, GFIRST0>(ld, epi, st, cur, g, row, rend, raw0, raw1, oA, oB, b0A, b0B, b1A, b1B);
+      if (row + 2 < rend)
+        stream_step<BROW0, GFIRST0>(ld, epi, st, cur, g, row + 2, rend, raw0, raw1, oA, oB, b1A, b1B, b0A, b0B);
+      else
+        break;
     }
-#endif
   }
   epi.finish(st, frame, lane, task_ok);
 }
