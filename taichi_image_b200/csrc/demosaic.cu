@@ -126,8 +126,10 @@ struct EpiDemosaic {
   int W;
   int ccm;          // runtime (warp-uniform) flag
   float m[9];
-  struct State { T* out; };
-  __device__ __forceinline__ void init(State& st, int, int tcol) const { st.out = out + 24 * tcol; }
+  static constexpr int kRowWords = 24 * (int)sizeof(T) / 4;       // 32-bit words of one thread's 8 output pixels
+  static constexpr int kStageWords = 32 * kRowWords;
+  struct State { T* out; WarpCtx wc; };
+  __device__ __forceinline__ void init(State& st, int, int, const WarpCtx& wc) const { st.out = out + 24 * wc.tcol0; st.wc = wc; }
   __device__ __forceinline__ void finish(State&, int, int, bool) const {}
 
   __device__ __forceinline__ void finish_px(float cr, float cg, float cb, T* o) const {
@@ -156,7 +158,10 @@ struct EpiDemosaic {
         finish_px(__fdiv_rn(R[j] * SS::r(j), is * 16.f), __fdiv_rn(G[j] * SS::g(j), is * 16.f),
                   __fdiv_rn(B[j] * SS::b(j), is * 16.f), o + 3 * j);
     }
-    store_px8<T, true>(st.out + (size_t)((unsigned)row * (unsigned)W) * 3, o, 8);
+    uint32_t w[kRowWords];
+#pragma unroll
+    for (int i = 0; i < kRowWords; ++i) w[i] = reinterpret_cast<const uint32_t*>(o)[i];
+    warp_store_row<kRowWords>(st.wc, st.out + (size_t)((unsigned)row * (unsigned)W) * 3, w);
   }
 };
 

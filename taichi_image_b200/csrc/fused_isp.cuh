@@ -213,21 +213,14 @@ template <> struct Quant<float> {
   }
 };
 
+// quantised row of 8 pixels -> packed words -> warp-cooperative contiguous store (stream_engine.cuh)
 template <typename OutT>
-__device__ __forceinline__ void store_row8(OutT* thread_out /* frame + 24 * tcol */, int W, int row, const uint32_t (&v)[24]) {
+__device__ __forceinline__ void store_row8(const WarpCtx& wc, OutT* warp_out /* frame + 24 * tcol0 */, int W, int row,
+                                           const uint32_t (&v)[24]) {
   constexpr int NW = Quant<OutT>::kWords;
-  alignas(16) uint32_t w[NW];
+  uint32_t w[NW];
   Quant<OutT>::pack(v, w);
-  OutT* dst = thread_out + (size_t)((unsigned)row * (unsigned)W) * 3;
-  if constexpr (NW % 4 == 0) {
-    uint4* d = reinterpret_cast<uint4*>(dst);
-#pragma unroll
-    for (int i = 0; i < NW / 4; ++i) d[i] = make_uint4(w[4 * i], w[4 * i + 1], w[4 * i + 2], w[4 * i + 3]);
-  } else {
-    uint2* d = reinterpret_cast<uint2*>(dst);
-#pragma unroll
-    for (int i = 0; i < NW / 2; ++i) d[i] = make_uint2(w[2 * i], w[2 * i + 1]);
-  }
+  warp_store_row<NW>(wc, warp_out + (size_t)((unsigned)row * (unsigned)W) * 3, w);
 }
 
 template <typename OutT> __device__ __forceinline__ void store_px(void* frame_out, int W, int row, int col, const float (&y)[3]) {
@@ -300,9 +293,11 @@ template <bool CAM16, typename OutT>
 struct EpiRgb {       // load_packed12: ISP-dtype float RGB out
   FramePtrs fp;
   IspConsts k;
-  struct State { OutT* out; };
-  __device__ __forceinline__ void init(State& st, int frame, int tcol) const {
-    st.out = reinterpret_cast<OutT*>(fp.out[k.frame0 + frame]) + 24 * tcol;
+  static constexpr int kStageWords = 32 * Quant<OutT>::kWords;
+  struct State { OutT* out; WarpCtx wc; };
+  __device__ __forceinline__ void init(State& st, int frame, int, const WarpCtx& wc) const {
+    st.out = reinterpret_cast<OutT*>(fp.out[k.frame0 + frame]) + 24 * wc.tcol0;
+    st.wc = wc;
   }
   __device__ __forceinline__ void finish(State&, int, int, bool) const {}
   template <bool BROW, bool GFIRST, bool CCM>
@@ -315,7 +310,7 @@ struct EpiRgb {       // load_packed12: ISP-dtype float RGB out
       isp_rgb_fast<CAM16, CCM>(k, R[j], G[j], B[j], SS::r(j), SS::g(j), SS::b(j), rgb);
       v[3 * j] = __float_as_uint(rgb[0]); v[3 * j + 1] = __float_as_uint(rgb[1]); v[3 * j + 2] = __float_as_uint(rgb[2]);
     }
-    store_row8<OutT>(st.out, k.W, row, v);
+    store_row8<OutT>(st.wc, st.out, k.W, row, v);
   }
   template <bool BROW, bool GFIRST>
   __device__ __forceinline__ void emit(State& st, int row, const float (&R)[8], const float (&G)[8], const float (&B)[8]) const {
@@ -328,10 +323,12 @@ template <bool CAM16, typename OutT>
 struct EpiLinear {
   FramePtrs fp;
   IspConsts k;
-  struct State { LinearConsts c; OutT* out; };
-  __device__ __forceinline__ void init(State& st, int frame, int tcol) const {
+  static constexpr int kStageWords = 32 * Quant<OutT>::kWords;
+  struct State { LinearConsts c; OutT* out; WarpCtx wc; };
+  __device__ __forceinline__ void init(State& st, int frame, int, const WarpCtx& wc) const {
     st.c = linear_consts(k.metrics, k.gamma);
-    st.out = reinterpret_cast<OutT*>(fp.out[k.frame0 + frame]) + 24 * tcol;
+    st.out = reinterpret_cast<OutT*>(fp.out[k.frame0 + frame]) + 24 * wc.tcol0;
+    st.wc = wc;
   }
   __device__ __forceinline__ void finish(State&, int, int, bool) const {}
   template <bool BROW, bool GFIRST, bool CCM, bool GAMMA>
@@ -345,7 +342,7 @@ struct EpiLinear {
       linear_px<GAMMA>(st.c, rgb, y);
       v[3 * j] = Quant<OutT>::q(y[0]); v[3 * j + 1] = Quant<OutT>::q(y[1]); v[3 * j + 2] = Quant<OutT>::q(y[2]);
     }
-    store_row8<OutT>(st.out, k.W, row, v);
+    store_row8<OutT>(st.wc, st.out, k.W, row, v);
   }
   template <bool BROW, bool GFIRST>
   __device__ __forceinline__ void emit(State& st, int row, const float (&R)[8], const float (&G)[8], const float (&B)[8]) const {
@@ -370,8 +367,9 @@ __device__ __forceinline__ ReinhardConsts reinhard_consts(const IspConsts& k, in
 template <bool CAM16>
 struct EpiReinhardMax {      // pass 1 without the write-back: frame-global max of the mapped values
   IspConsts k;
+  static constexpr int kStageWords = 0;
   struct State { ReinhardConsts c; float mx; bool first, last; };
-  __device__ __forceinline__ void init(State& st, int frame, int tcol) const {
+  __device__ __forceinline__ void init(State& st, int frame, int tcol, const WarpCtx&) const {
     st.c = reinhard_consts(k, frame, false);
     st.mx = 0.f;
     st.first = tcol == 0;
@@ -411,10 +409,12 @@ template <bool CAM16, typename OutT>
 struct EpiReinhard {         // pass 2 recomputed from the packed frame: map, normalise by the max, gamma, quantise
   FramePtrs fp;
   IspConsts k;
-  struct State { ReinhardConsts c; OutT* out; };
-  __device__ __forceinline__ void init(State& st, int frame, int tcol) const {
+  static constexpr int kStageWords = 32 * Quant<OutT>::kWords;
+  struct State { ReinhardConsts c; OutT* out; WarpCtx wc; };
+  __device__ __forceinline__ void init(State& st, int frame, int, const WarpCtx& wc) const {
     st.c = reinhard_consts(k, frame, true);
-    st.out = reinterpret_cast<OutT*>(fp.out[k.frame0 + frame]) + 24 * tcol;
+    st.out = reinterpret_cast<OutT*>(fp.out[k.frame0 + frame]) + 24 * wc.tcol0;
+    st.wc = wc;
   }
   __device__ __forceinline__ void finish(State&, int, int, bool) const {}
   template <bool BROW, bool GFIRST, bool CCM, bool CA0, bool GAMMA>
@@ -429,7 +429,7 @@ struct EpiReinhard {         // pass 2 recomputed from the packed frame: map, no
       reinhard_out<CAM16, GAMMA>(st.c, p, y);
       v[3 * j] = Quant<OutT>::q(y[0]); v[3 * j + 1] = Quant<OutT>::q(y[1]); v[3 * j + 2] = Quant<OutT>::q(y[2]);
     }
-    store_row8<OutT>(st.out, k.W, row, v);
+    store_row8<OutT>(st.wc, st.out, k.W, row, v);
   }
   template <bool BROW, bool GFIRST>
   __device__ __forceinline__ void emit(State& st, int row, const float (&R)[8], const float (&G)[8], const float (&B)[8]) const {

@@ -145,6 +145,53 @@ __device__ __forceinline__ void stream_step(const Loader& ld, const Epi& epi, ty
   for (int j = 0; j < 10; ++j) oB[j] = cB[j + 1];
 }
 
+// ---------------------------------------------------------------- warp-cooperative row store
+// A lane owns 8 pixels x 3 channels = NW 32-bit words of an output row, i.e. a 4*NW-byte segment with a
+// 4*NW-byte lane stride: stored straight from registers, every STG.128 would touch 32 scattered 16-byte
+// pieces (half sectors) of twelve 128-byte lines.  Measured on B200 with the sweep's 1.5 B : 6 B traffic
+// mix (profiles/r01_membench.txt) that shape tops out at ~3.9 TB/s, the same bytes written as whole
+// contiguous 512-byte runs reach ~5.8 TB/s.  So each warp transposes the row through a private
+// shared-memory stage (conflict-free for NW = 6 and 12) and writes it as consecutive 16-byte (8-byte when
+// the row pitch is only 8-byte aligned: RGB8) chunks; only __syncwarp, no block barrier.
+struct WarpCtx {
+  int lane;
+  int tcol0;            // first thread column of the warp's strip
+  int nvalid;           // lanes of the strip that map to real thread columns (the others compute a clamped copy)
+  uint32_t* stage;      // this warp's staging buffer, Epi::kStageWords words
+};
+
+template <int NW>
+__device__ __forceinline__ void warp_store_row(const WarpCtx& wc, void* row_dst /* warp's first byte of the row */,
+                                               const uint32_t (&w)[NW]) {
+  constexpr int CW = (NW % 4 == 0) ? 4 : 2;     // words per chunk
+  constexpr int PER_LANE = NW / CW;
+  const int nchunks = wc.nvalid * PER_LANE;
+  __syncwarp();
+  if constexpr (CW == 4) {
+    uint4* s = reinterpret_cast<uint4*>(wc.stage);
+#pragma unroll
+    for (int i = 0; i < PER_LANE; ++i) s[PER_LANE * wc.lane + i] = make_uint4(w[4 * i], w[4 * i + 1], w[4 * i + 2], w[4 * i + 3]);
+    __syncwarp();
+    uint4* d = reinterpret_cast<uint4*>(row_dst);
+#pragma unroll
+    for (int i = 0; i < PER_LANE; ++i) {
+      const int idx = i * 32 + wc.lane;
+      if (idx < nchunks) d[idx] = s[idx];
+    }
+  } else {
+    uint2* s = reinterpret_cast<uint2*>(wc.stage);
+#pragma unroll
+    for (int i = 0; i < PER_LANE; ++i) s[PER_LANE * wc.lane + i] = make_uint2(w[2 * i], w[2 * i + 1]);
+    __syncwarp();
+    uint2* d = reinterpret_cast<uint2*>(row_dst);
+#pragma unroll
+    for (int i = 0; i < PER_LANE; ++i) {
+      const int idx = i * 32 + wc.lane;
+      if (idx < nchunks) d[idx] = s[idx];
+    }
+  }
+}
+
 // Loader concept:
 //   struct Raw;  struct Cursor;
 //   void open(Cursor&, int frame, int tcol, const StreamGeom&)           per-task base pointer / edge flags
@@ -152,7 +199,8 @@ __device__ __forceinline__ void stream_step(const Loader& ld, const Epi& epi, ty
 //   void prefetch(const Cursor&, int row, const StreamGeom&)             optional L2 prefetch of a later row
 //   void decode(const Raw&, float (&v)[12])                              v[j] = CFA at column 8*tcol-2+j
 // Epilogue concept:
-//   struct State;  void init(State&, int frame, int tcol);  void finish(State&, int frame, int lane, bool task_ok)
+//   static constexpr int kStageWords                                      per-warp staging words (0: stores nothing)
+//   struct State;  void init(State&, int frame, int tcol, const WarpCtx&);  void finish(State&, int frame, int lane, bool task_ok)
 //   template <bool BROW, bool GFIRST> void emit(State&, int row, R, G, B)   scaled filter sums, see SiteScale
 template <int PATTERN, class Loader, class Epi>
 __global__ void __launch_bounds__(256, 2) stream_kernel(const Loader ld, const Epi epi, const StreamGeom g) {
@@ -166,13 +214,19 @@ __global__ void __launch_bounds__(256, 2) stream_kernel(const Loader ld, const E
   const long long t2 = task / g.warps_per_row;
   const int chunk = (int)(t2 % g.nchunks);
   const int frame = (int)(t2 / g.nchunks);
-  const int tcol = min(strip * 32 + lane, g.ntcols - 1);
-  const bool active = task_ok && (strip * 32 + lane) < g.ntcols;
+  const int tcol = min(strip * 32 + lane, g.ntcols - 1);   // lanes past the last column recompute it (never stored)
+
+  __shared__ __align__(16) uint32_t stage[8][Epi::kStageWords > 0 ? Epi::kStageWords : 1];
+  WarpCtx wc;
+  wc.lane = lane;
+  wc.tcol0 = strip * 32;
+  wc.nvalid = min(32, g.ntcols - strip * 32);
+  wc.stage = stage[threadIdx.x >> 5];
 
   typename Epi::State st;
-  epi.init(st, frame, tcol);
+  epi.init(st, frame, tcol, wc);
 
-  if (active) {
+  if (task_ok) {
     const int r0 = chunk * g.rows_per_task;
     const int rend = min(r0 + g.rows_per_task, g.H);
     typename Loader::Cursor cur;
