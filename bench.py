@@ -251,21 +251,20 @@ def main():
     achieved = kern_bytes / (kern_avg_ms * 1e-3) / 1e9
     value = world * px_per_step * args.steps / (elapsed_ms * 1e-3) / 1e9
 
-    # launches of our kernels per step: metering 2 (+2 pack/unpack for shared exposure) + sweeps + border kernels
+    # launches of our kernels per step: metering 2 (shared exposure: + bounds fold + finalize) + sweeps + border kernels
     if tonemap == "reinhard":
         ngroups = (n + group - 1) // group
         launches = 2 + 4 * ngroups
     else:
         launches = 2 + 2
     if shared and world > 1:
-        launches += 1
+        launches += 2
 
     # ---------------- end to end through the public API with host buffers
     e2e = None
     if not args.no_e2e:
         ksteps = args.e2e_steps or min(args.steps, 12)
-        base = isp.isp if hasattr(isp, "isp") else isp
-        pipe = RigPipeline(base, n, h, w, tonemap=tonemap, dtype=out_dt, depth=2, **tm)
+        pipe = RigPipeline(isp, n, h, w, tonemap=tonemap, dtype=out_dt, depth=2, **tm)
         pinned = RigPipeline.pin(host)
         for _ in range(3):
             pipe.process(pinned)

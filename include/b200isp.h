@@ -162,6 +162,36 @@ int b200isp_process_packed12(const uint8_t* const* packed_host, void* const* out
                              const b200isp_fused_params* params, float* metrics,
                              void* workspace, b200isp_stream stream);
 
+/* ---- multi-GPU shared exposure (no reference counterpart: the reference is single-GPU) ----
+ * The reference meters all cameras of a time step jointly (camera_isp.py:168-175).  With one camera
+ * shard per GPU the two dependent reductions of metering_kernel (camera_isp.py:149-166) are split at
+ * their exchange points; between the calls the host all-gathers the per-rank records
+ * (torch.distributed / NCCL, <= 32 bytes per rank) and every rank folds them in rank order, so all
+ * ranks end with bit-identical metrics:
+ *   record 1 (2 floats): {min, max} over this rank's samples
+ *   record 2 (8 floats): {log_min, log_max, sum_log, sum_gray, sum_r, sum_g, sum_b, n_samples}
+ *   phase1  -> rec1;  all_gather -> gathered1 [world][2]
+ *   phase2(gathered1, alpha, metrics_prev) -> rec2 w.r.t. the blended joint bounds;  all_gather -> gathered2 [world][8]
+ *   finalize(gathered1, gathered2, alpha) -> metrics = lerp(alpha, joint stats, metrics)
+ * With world == 1 the three calls equal b200isp_metering_update. */
+#define B200ISP_REC1 2
+#define B200ISP_REC2 8
+int b200isp_metering_phase1(const void* const* images_host, int n_images, int dtype, int height, int width,
+                            int stride, float* rec1, void* workspace, b200isp_stream stream);
+int b200isp_metering_phase2(const void* const* images_host, int n_images, int dtype, int height, int width,
+                            int stride, const float* gathered1, int world, float alpha,
+                            const float* metrics_prev, float* rec2, void* workspace, b200isp_stream stream);
+int b200isp_metering_finalize(const float* gathered1, const float* gathered2, int world, float alpha,
+                              float* metrics, b200isp_stream stream);
+/* the same two phases straight from packed12 frames (the sampler of b200isp_process_packed12);
+ * params->alpha, metering_stride, meter_cache as in the fused call. */
+int b200isp_meter_packed12_phase1(const uint8_t* const* packed_host, int n_frames,
+                                  const b200isp_fused_params* params, float* rec1,
+                                  void* workspace, b200isp_stream stream);
+int b200isp_meter_packed12_phase2(const uint8_t* const* packed_host, int n_frames,
+                                  const b200isp_fused_params* params, const float* gathered1, int world,
+                                  const float* metrics_prev, float* rec2, void* workspace, b200isp_stream stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -369,6 +369,50 @@ def metering_update(images, prev: np.ndarray, alpha: float, stride: int = 8) -> 
     return (stats + a * (prev - stats)).astype(f32)
 
 
+# -- the same update split at its two exchange points (multi-GPU shared exposure): every rank
+#    computes a record over its own images, the records are gathered and folded in rank order.
+def _meter_stack(images, stride):
+    return np.stack([im[::stride, ::stride, :] for im in images], 0).astype(f32)
+
+
+def metering_phase1(images, stride: int = 8) -> np.ndarray:
+    """camera_isp.py:149-154 over this rank's images: {min, max}"""
+    stack = _meter_stack(images, stride)
+    return np.array([stack.min(), stack.max()], f32)
+
+
+def metering_fold_bounds(gathered1, alpha, prev):
+    """camera_isp.py:156 with the joint min / max of all ranks"""
+    g1 = np.asarray(gathered1, f32).reshape(-1, 2)
+    a, prev = f32(alpha), np.asarray(prev, f32)
+    mn, mx = f32(g1[:, 0].min()), f32(g1[:, 1].max())
+    return mn + a * (prev[0] - mn), mx + a * (prev[1] - mx)
+
+
+def metering_phase2(images, gathered1, alpha, prev, stride: int = 8) -> np.ndarray:
+    """camera_isp.py:158-161 over this rank's images w.r.t. the joint blended bounds:
+    {log_min, log_max, sum_log, sum_gray, sum_r, sum_g, sum_b, n}"""
+    stack = _meter_stack(images, stride)
+    bmin, bmax = metering_fold_bounds(gathered1, alpha, prev)
+    scaled = (stack - bmin) / (bmax - bmin + f32(1e-6))
+    gray = rgb_gray(scaled)
+    log_gray = np.log(np.maximum(gray, f32(1e-4))).astype(f32)
+    n = stack.shape[0] * stack.shape[1] * stack.shape[2]
+    return np.array([log_gray.min(), log_gray.max(), log_gray.astype(np.float64).sum(), gray.astype(np.float64).sum(),
+                     *scaled.astype(np.float64).sum(axis=(0, 1, 2)), n], f32)
+
+
+def metering_finalize(gathered1, gathered2, alpha, prev) -> np.ndarray:
+    """camera_isp.py:131-134, :164-166 with the folded records"""
+    g2 = np.asarray(gathered2, f32).reshape(-1, 8)
+    a, prev = f32(alpha), np.asarray(prev, f32)
+    bmin, bmax = metering_fold_bounds(gathered1, alpha, prev)
+    sums = g2[:, 2:].astype(np.float64).sum(0).astype(f32)
+    n = sums[5]
+    stats = np.array([bmin, bmax, g2[:, 0].min(), g2[:, 1].max(), *(sums[:5] / n)], f32)
+    return (stats + a * (prev - stats)).astype(f32)
+
+
 def isp_reinhard(image: np.ndarray, metrics: np.ndarray, gamma, intensity, light_adapt,
                  color_adapt, out_dtype: str = "u8", return_intermediate=False):
     """camera_isp.py:177-218.  `image` is the ISP-dtype RGB; the f16/f32 rounding of the

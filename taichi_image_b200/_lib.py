@@ -53,6 +53,11 @@ SIGNATURES = {
     "b200isp_metering_update": [C.POINTER(_vp), _i, _i, _i, _i, _i, _f, _vp, _vp, _vp],
     "b200isp_isp_reinhard": [_vp, _i, _vp, _i, _i64, _vp, _f, _f, _f, _f, _vp, _vp],
     "b200isp_process_packed12": [C.POINTER(_vp), C.POINTER(_vp), _i, C.POINTER(FusedParams), _vp, _vp, _vp],
+    "b200isp_metering_phase1": [C.POINTER(_vp), _i, _i, _i, _i, _i, _vp, _vp, _vp],
+    "b200isp_metering_phase2": [C.POINTER(_vp), _i, _i, _i, _i, _i, _vp, _i, _f, _vp, _vp, _vp, _vp],
+    "b200isp_metering_finalize": [_vp, _vp, _i, _f, _vp, _vp],
+    "b200isp_meter_packed12_phase1": [C.POINTER(_vp), _i, C.POINTER(FusedParams), _vp, _vp, _vp],
+    "b200isp_meter_packed12_phase2": [C.POINTER(_vp), _i, C.POINTER(FusedParams), _vp, _i, _vp, _vp, _vp, _vp],
 }
 _SPECIAL = {"b200isp_version": ([], C.c_int), "b200isp_last_error": ([], C.c_char_p),
             "b200isp_workspace_bytes": ([], C.c_size_t)}

@@ -226,6 +226,67 @@ def camera_isp(name: str, dtype=f32):
                     alpha, self.metrics.data_ptr(), _lib.workspace(self.device).data_ptr(),
                     _lib.stream_ptr(self.device)), "metering_update")
 
+        # ------------------------------------------------------------ metering split for multi-GPU shared exposure
+        # (distributed.SharedExposure; include/b200isp.h "multi-GPU shared exposure").  ``source`` is either a list
+        # of packed12 frames (uint8, 2-D: the fused sampler) or a list of ISP-dtype RGB images.
+        def _meter_source(self, source):
+            source = list(source)
+            packed12 = source[0].dtype == torch.uint8 and source[0].ndim == 2
+            shape = source[0].shape
+            for t in source:
+                _lib.require_cuda(t, "metering")
+                assert t.shape == shape and t.is_contiguous(), "metering needs same-shape contiguous tensors"
+                assert packed12 or t.dtype == torch_dtype, "metering images must have the ISP dtype"
+            assert 1 <= len(source) <= _lib.MAX_FRAMES
+            return source, packed12
+
+        def meter_phase1(self, source) -> torch.Tensor:
+            """{min, max} over this rank's metering samples -> 2 floats on the device"""
+            source, packed12 = self._meter_source(source)
+            rec = torch.empty(2, dtype=torch.float32, device=self.device)
+            ws, st = _lib.workspace(self.device).data_ptr(), _lib.stream_ptr(self.device)
+            with torch.cuda.device(self.device):
+                if packed12:
+                    p = self._fused_params(source, "linear", u8, {}, update_metering=True)
+                    _lib.check(_lib.lib.b200isp_meter_packed12_phase1(_lib.ptr_array(source), len(source), p,
+                                                                       rec.data_ptr(), ws, st), "meter_packed12_phase1")
+                else:
+                    h, w = source[0].shape[:2]
+                    _lib.check(_lib.lib.b200isp_metering_phase1(_lib.ptr_array(source), len(source), isp_dtype.code, h, w,
+                                                                 int(self.metering_stride), rec.data_ptr(), ws, st),
+                               "metering_phase1")
+            return rec
+
+        def meter_phase2(self, source, gathered1: torch.Tensor, alpha: float) -> torch.Tensor:
+            """statistics of this rank's samples w.r.t. the joint blended bounds -> 8 floats on the device"""
+            source, packed12 = self._meter_source(source)
+            assert gathered1.dtype == torch.float32 and gathered1.is_contiguous() and gathered1.numel() % 2 == 0
+            world = gathered1.numel() // 2
+            rec = torch.empty(8, dtype=torch.float32, device=self.device)
+            ws, st = _lib.workspace(self.device).data_ptr(), _lib.stream_ptr(self.device)
+            with torch.cuda.device(self.device):
+                if packed12:
+                    p = self._fused_params(source, "linear", u8, {}, update_metering=True, alpha=alpha)
+                    _lib.check(_lib.lib.b200isp_meter_packed12_phase2(
+                        _lib.ptr_array(source), len(source), p, gathered1.data_ptr(), world, self.metrics.data_ptr(),
+                        rec.data_ptr(), ws, st), "meter_packed12_phase2")
+                else:
+                    h, w = source[0].shape[:2]
+                    _lib.check(_lib.lib.b200isp_metering_phase2(
+                        _lib.ptr_array(source), len(source), isp_dtype.code, h, w, int(self.metering_stride),
+                        gathered1.data_ptr(), world, float(alpha), self.metrics.data_ptr(), rec.data_ptr(), ws, st),
+                        "metering_phase2")
+            return rec
+
+        def meter_finalize(self, gathered1: torch.Tensor, gathered2: torch.Tensor, alpha: float):
+            """metrics = lerp(alpha, joint statistics of all ranks, metrics)   (camera_isp.py:164-166)"""
+            world = gathered1.numel() // 2
+            assert gathered2.numel() == 8 * world and gathered2.is_contiguous() and gathered1.is_contiguous()
+            with torch.cuda.device(self.device):
+                _lib.check(_lib.lib.b200isp_metering_finalize(gathered1.data_ptr(), gathered2.data_ptr(), world, float(alpha),
+                                                               self.metrics.data_ptr(), _lib.stream_ptr(self.device)),
+                           "metering_finalize")
+
         # ------------------------------------------------------------ tone mapping (eager API)
         def tonemap_only(self, image, metrics, gamma, intensity, light_adapt, color_adapt):
             """camera_isp.py:387-390"""
@@ -235,28 +296,32 @@ def camera_isp(name: str, dtype=f32):
 
         @beartype
         def tonemap_reinhard(self, images: list[torch.Tensor], gamma: float = 1.0, intensity: float = 1.0,
-                             light_adapt: float = 1.0, color_adapt: float = 0.0, dtype=u8):
-            """camera_isp.py:394-403 (``dtype``: u8 like the reference, or u16 / f16)"""
+                             light_adapt: float = 1.0, color_adapt: float = 0.0, dtype=u8, update_metering: bool = True):
+            """camera_isp.py:394-403 (``dtype``: u8 like the reference, or u16 / f16; ``update_metering=False``:
+            the caller -- distributed.SharedExposure -- has already updated ``self.metrics``)"""
             out_dtype = as_dtype(dtype)
-            self.update_metering(images)
+            if update_metering:
+                self.update_metering(images)
             outputs = [torch.empty(image.shape, dtype=out_dtype.torch, device=self.device) for image in images]
             for output, image in zip(outputs, images):
                 _reinhard_kernel(image, output, self.metrics, gamma, intensity, light_adapt, color_adapt)
             return [interpolate.transform(output, self.transform) for output in outputs]
 
         @beartype
-        def tonemap_linear(self, images: list[torch.Tensor], gamma: float = 1.0, dtype=u8):
+        def tonemap_linear(self, images: list[torch.Tensor], gamma: float = 1.0, dtype=u8, update_metering: bool = True):
             """camera_isp.py:405-413"""
             out_dtype = as_dtype(dtype)
-            self.update_metering(images)
+            if update_metering:
+                self.update_metering(images)
             outputs = [torch.empty(image.shape, dtype=out_dtype.torch, device=self.device) for image in images]
             for output, image in zip(outputs, images):
                 _linear_kernel(image, output, self.metrics, gamma)
             return [interpolate.transform(output, self.transform) for output in outputs]
 
         # ------------------------------------------------------------ fused path
-        def _run_fused(self, frames, tonemap, out_dtype, out, tm, update_metering=False, alpha=0.0, rows_per_task=0,
-                       profile_events=None):
+        def _fused_params(self, frames, tonemap, out_dtype, tm, update_metering=False, alpha=0.0, rows_per_task=0,
+                          profile_events=None):
+            """b200isp_fused_params for a list of same-shape packed12 frames (include/b200isp.h)"""
             h, w3 = frames[0].shape
             w = w3 * 2 // 3
             p = _lib.FusedParams()
@@ -281,6 +346,13 @@ def camera_isp(name: str, dtype=f32):
                 p.meter_cache, p.meter_cache_bytes = cache.data_ptr(), cache.numel()
             if profile_events is not None:      # (start, stop) torch.cuda.Event pair, see bench.py
                 p.profile_start, p.profile_stop = profile_events[0].cuda_event, profile_events[1].cuda_event
+            return p
+
+        def _run_fused(self, frames, tonemap, out_dtype, out, tm, update_metering=False, alpha=0.0, rows_per_task=0,
+                       profile_events=None):
+            h, w3 = frames[0].shape
+            w = w3 * 2 // 3
+            p = self._fused_params(frames, tonemap, out_dtype, tm, update_metering, alpha, rows_per_task, profile_events)
             if out is None:
                 out = [torch.empty((h, w, 3), dtype=out_dtype.torch, device=self.device) for _ in frames]
             else:
@@ -297,7 +369,7 @@ def camera_isp(name: str, dtype=f32):
         def process_packed12(self, frames: Sequence[torch.Tensor], tonemap: str = "reinhard", gamma: float = 1.0,
                              intensity: float = 1.0, light_adapt: float = 1.0, color_adapt: float = 0.0,
                              dtype=u8, ids_format: bool = False, out: Optional[list] = None,
-                             rows_per_task: int = 0, profile_events=None):
+                             rows_per_task: int = 0, profile_events=None, update_metering: bool = True):
             """Fused equivalent of ``[load_packed12(f) for f in frames]`` followed by
             ``tonemap_reinhard`` / ``tonemap_linear`` (camera_isp.py:333-340, :376-413): joint metering of
             all frames with the moving-average update of ``self.metrics``, then one sweep per frame.
@@ -314,12 +386,14 @@ def camera_isp(name: str, dtype=f32):
             if not fused:
                 images = [self.load_packed12(f, ids_format) for f in frames]
                 if tonemap == "linear":
-                    return self.tonemap_linear(images, gamma=float(gamma), dtype=out_dtype)
+                    return self.tonemap_linear(images, gamma=float(gamma), dtype=out_dtype, update_metering=update_metering)
                 return self.tonemap_reinhard(images, gamma=float(gamma), intensity=float(intensity),
-                                             light_adapt=float(light_adapt), color_adapt=float(color_adapt), dtype=out_dtype)
-            alpha = self._metrics_and_alpha()
+                                             light_adapt=float(light_adapt), color_adapt=float(color_adapt), dtype=out_dtype,
+                                             update_metering=update_metering)
+            alpha = self._metrics_and_alpha() if update_metering else 0.0
+            assert self.metrics is not None, "update_metering=False needs metrics from an earlier call"
             tm = dict(gamma=gamma, intensity=intensity, light_adapt=light_adapt, color_adapt=color_adapt)
-            outputs = self._run_fused(frames, tonemap, out_dtype, out, tm, update_metering=True, alpha=alpha,
+            outputs = self._run_fused(frames, tonemap, out_dtype, out, tm, update_metering=update_metering, alpha=alpha,
                                       rows_per_task=rows_per_task, profile_events=profile_events)
             return [interpolate.transform(o, self.transform) for o in outputs]
 

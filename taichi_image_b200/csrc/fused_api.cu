@@ -13,20 +13,94 @@ extern template int run_fused<false, float>(const FramePtrs&, int, const b200isp
 
 using namespace isp;
 
+// Common argument checks + frame table + constants of the fused entry points.
+static int fused_setup(const char* what, const uint8_t* const* packed_host, void* const* out_host, int n_frames,
+                       const b200isp_fused_params* params, float* metrics, void* workspace, FramePtrs& fp, IspConsts& k) {
+  ISP_REQUIRE(packed_host && params && workspace, B200ISP_E_ARG, "%s: null pointer", what);
+  const b200isp_fused_params& p = *params;
+  ISP_REQUIRE(n_frames >= 1 && n_frames <= B200ISP_MAX_FRAMES, B200ISP_E_FRAMES,
+              "%s: %d frames (1..%d supported per call)", what, n_frames, B200ISP_MAX_FRAMES);
+  ISP_REQUIRE(p.height >= 4 && p.width >= 8 && p.height % 2 == 0 && p.width % 8 == 0, B200ISP_E_SHAPE,
+              "%s: fused path needs even height >= 4 and width %% 8 == 0, got %dx%d", what, p.height, p.width);
+  ISP_REQUIRE(p.pattern >= 0 && p.pattern <= 3, B200ISP_E_ARG, "%s: unknown pattern %d", what, p.pattern);
+  ISP_REQUIRE(p.isp_dtype == B200ISP_F16 || p.isp_dtype == B200ISP_F32, B200ISP_E_DTYPE, "%s: isp_dtype must be f16/f32", what);
+  for (int i = 0; i < n_frames; ++i) {
+    fp.in[i] = packed_host[i];
+    fp.out[i] = out_host ? out_host[i] : nullptr;
+    ISP_REQUIRE(fp.in[i] && (fp.out[i] || !out_host), B200ISP_E_ARG, "%s: null frame pointer %d", what, i);
+    ISP_REQUIRE(((reinterpret_cast<uintptr_t>(fp.in[i]) & 3u) == 0) && ((reinterpret_cast<uintptr_t>(fp.out[i]) & 15u) == 0),
+                B200ISP_E_ALIGN, "%s: frame %d needs 4-byte aligned input and 16-byte aligned output", what, i);
+  }
+  k.H = p.height; k.W = p.width; k.pattern = p.pattern;
+  k.ccm = p.has_ccm ? 1 : 0;
+  for (int i = 0; i < 9; ++i) k.m[i] = p.ccm[i];
+  k.gamma = p.gamma; k.intensity = p.intensity; k.la = p.light_adapt; k.ca = p.color_adapt;
+  k.metrics = metrics; k.ws = (Workspace*)workspace; k.frame0 = 0;
+  return B200ISP_OK;
+}
+
+// Builds the metering sampler for the packed frames (stride % 8 == 0: word-aligned fast sampler) and
+// hands it to f(sampler, n_samples, cache).
+template <class F>
+static int with_packed12_sampler(const FramePtrs& fp, const b200isp_fused_params& p, const IspConsts& k, int n_frames, F f) {
+  const int stride = p.metering_stride > 0 ? p.metering_stride : 8;
+  const int hs = (p.height + stride - 1) / stride, wsamp = (p.width + stride - 1) / stride;
+  const long long n = (long long)n_frames * hs * wsamp;
+  float* cache = (p.meter_cache && p.meter_cache_bytes >= (size_t)n * 3 * sizeof(float)) ? (float*)p.meter_cache : nullptr;
+  const bool cam16 = p.isp_dtype == B200ISP_F16;
+  if (stride % 8 == 0) {
+    if (cam16) return f(Packed12FastSampler<true>{Packed12Src<true>{fp, p.width * 3 / 2}, k, stride, hs, wsamp, p.width * 3 / 8}, n, cache);
+    return f(Packed12FastSampler<false>{Packed12Src<false>{fp, p.width * 3 / 2}, k, stride, hs, wsamp, p.width * 3 / 8}, n, cache);
+  }
+  if (cam16) return f(Packed12Sampler<true>{Packed12Src<true>{fp, p.width * 3 / 2}, k, stride, hs, wsamp}, n, cache);
+  return f(Packed12Sampler<false>{Packed12Src<false>{fp, p.width * 3 / 2}, k, stride, hs, wsamp}, n, cache);
+}
+
+extern "C" int b200isp_meter_packed12_phase1(const uint8_t* const* packed_host, int n_frames, const b200isp_fused_params* params,
+                                             float* rec1, void* workspace, b200isp_stream stream) {
+  FramePtrs fp; IspConsts k;
+  const int st = fused_setup("meter_packed12_phase1", packed_host, nullptr, n_frames, params, nullptr, workspace, fp, k);
+  if (st) return st;
+  ISP_REQUIRE(rec1, B200ISP_E_ARG, "meter_packed12_phase1: null record");
+  cudaStream_t s = (cudaStream_t)stream;
+  return with_packed12_sampler(fp, *params, k, n_frames, [&](const auto& smp, long long n, float* cache) {
+    return launch_metering_phase1(smp, n, k.ws, s, cache, rec1);
+  });
+}
+
+extern "C" int b200isp_meter_packed12_phase2(const uint8_t* const* packed_host, int n_frames, const b200isp_fused_params* params,
+                                             const float* gathered1, int world, const float* metrics_prev, float* rec2,
+                                             void* workspace, b200isp_stream stream) {
+  FramePtrs fp; IspConsts k;
+  const int st = fused_setup("meter_packed12_phase2", packed_host, nullptr, n_frames, params, nullptr, workspace, fp, k);
+  if (st) return st;
+  ISP_REQUIRE(gathered1 && metrics_prev && rec2 && world >= 1, B200ISP_E_ARG, "meter_packed12_phase2: bad argument");
+  cudaStream_t s = (cudaStream_t)stream;
+  const float alpha = params->alpha;
+  return with_packed12_sampler(fp, *params, k, n_frames, [&](const auto& smp, long long n, float* cache) {
+    return launch_metering_phase2(smp, n, gathered1, world, alpha, metrics_prev, k.ws, s, cache, rec2);
+  });
+}
+
+extern "C" int b200isp_metering_finalize(const float* gathered1, const float* gathered2, int world, float alpha, float* metrics,
+                                         b200isp_stream stream) {
+  ISP_REQUIRE(gathered1 && gathered2 && metrics && world >= 1, B200ISP_E_ARG, "metering_finalize: bad argument");
+  meter_finalize_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(gathered1, gathered2, world, alpha, metrics);
+  ISP_LAUNCH_CHECK("meter_finalize_kernel");
+  return B200ISP_OK;
+}
+
 extern "C" int b200isp_process_packed12(const uint8_t* const* packed_host, void* const* out_host, int n_frames,
                                         const b200isp_fused_params* params, float* metrics, void* workspace,
                                         b200isp_stream stream) {
-  ISP_REQUIRE(packed_host && params && workspace, B200ISP_E_ARG, "process_packed12: null pointer");
+  FramePtrs fp; IspConsts k;
+  ISP_REQUIRE(out_host, B200ISP_E_ARG, "process_packed12: null output list");
+  {
+    const int st = fused_setup("process_packed12", packed_host, out_host, n_frames, params, metrics, workspace, fp, k);
+    if (st) return st;
+  }
   const b200isp_fused_params& p = *params;
-  ISP_REQUIRE(n_frames >= 1 && n_frames <= B200ISP_MAX_FRAMES, B200ISP_E_FRAMES,
-              "process_packed12: %d frames (1..%d supported per call)", n_frames, B200ISP_MAX_FRAMES);
-  ISP_REQUIRE(p.height >= 4 && p.width >= 8 && p.height % 2 == 0 && p.width % 8 == 0, B200ISP_E_SHAPE,
-              "process_packed12: fused path needs even height >= 4 and width %% 8 == 0, got %dx%d", p.height, p.width);
-  ISP_REQUIRE(p.pattern >= 0 && p.pattern <= 3, B200ISP_E_ARG, "process_packed12: unknown pattern %d", p.pattern);
-  ISP_REQUIRE(p.isp_dtype == B200ISP_F16 || p.isp_dtype == B200ISP_F32, B200ISP_E_DTYPE, "process_packed12: isp_dtype must be f16/f32");
   ISP_REQUIRE(p.tonemap >= B200ISP_TM_LINEAR && p.tonemap <= B200ISP_TM_NONE, B200ISP_E_ARG, "process_packed12: unknown tonemap %d", p.tonemap);
-  const bool needs_out = true;
-  ISP_REQUIRE(!needs_out || out_host, B200ISP_E_ARG, "process_packed12: null output list");
   ISP_REQUIRE(p.tonemap == B200ISP_TM_NONE || metrics, B200ISP_E_ARG, "process_packed12: metrics required for tone mapping");
   ISP_REQUIRE(p.tonemap == B200ISP_TM_NONE || p.gamma > 0.f, B200ISP_E_ARG, "process_packed12: gamma must be positive");
   if (p.tonemap == B200ISP_TM_NONE)
@@ -34,45 +108,13 @@ extern "C" int b200isp_process_packed12(const uint8_t* const* packed_host, void*
   else
     ISP_REQUIRE(p.out_dtype == B200ISP_U8 || p.out_dtype == B200ISP_U16 || p.out_dtype == B200ISP_F16, B200ISP_E_DTYPE,
                 "process_packed12: tone-mapped output must be u8, u16 or f16");
-
-  FramePtrs fp;
-  for (int i = 0; i < n_frames; ++i) {
-    fp.in[i] = packed_host[i];
-    fp.out[i] = out_host[i];
-    ISP_REQUIRE(fp.in[i] && fp.out[i], B200ISP_E_ARG, "process_packed12: null frame pointer %d", i);
-    ISP_REQUIRE(((reinterpret_cast<uintptr_t>(fp.in[i]) & 3u) == 0) && ((reinterpret_cast<uintptr_t>(fp.out[i]) & 15u) == 0),
-                B200ISP_E_ALIGN, "process_packed12: frame %d needs 4-byte aligned input and 16-byte aligned output", i);
-  }
-  IspConsts k;
-  k.H = p.height; k.W = p.width; k.pattern = p.pattern;
-  k.ccm = p.has_ccm ? 1 : 0;
-  for (int i = 0; i < 9; ++i) k.m[i] = p.ccm[i];
-  k.gamma = p.gamma; k.intensity = p.intensity; k.la = p.light_adapt; k.ca = p.color_adapt;
-  k.metrics = metrics; k.ws = (Workspace*)workspace; k.frame0 = 0;
   cudaStream_t s = (cudaStream_t)stream;
   const bool cam16 = p.isp_dtype == B200ISP_F16;
 
   if (p.update_metering && p.tonemap != B200ISP_TM_NONE) {
-    const int stride = p.metering_stride > 0 ? p.metering_stride : 8;
-    const int hs = (p.height + stride - 1) / stride, wsamp = (p.width + stride - 1) / stride;
-    const long long n = (long long)n_frames * hs * wsamp;
-    float* cache = (p.meter_cache && p.meter_cache_bytes >= (size_t)n * 3 * sizeof(float)) ? (float*)p.meter_cache : nullptr;
-    int st;
-    if (stride % 8 == 0) {
-      if (cam16) {
-        Packed12FastSampler<true> smp{Packed12Src<true>{fp, p.width * 3 / 2}, k, stride, hs, wsamp, p.width * 3 / 8};
-        st = launch_metering(smp, n, p.alpha, metrics, k.ws, s, cache);
-      } else {
-        Packed12FastSampler<false> smp{Packed12Src<false>{fp, p.width * 3 / 2}, k, stride, hs, wsamp, p.width * 3 / 8};
-        st = launch_metering(smp, n, p.alpha, metrics, k.ws, s, cache);
-      }
-    } else if (cam16) {
-      Packed12Sampler<true> smp{Packed12Src<true>{fp, p.width * 3 / 2}, k, stride, hs, wsamp};
-      st = launch_metering(smp, n, p.alpha, metrics, k.ws, s, cache);
-    } else {
-      Packed12Sampler<false> smp{Packed12Src<false>{fp, p.width * 3 / 2}, k, stride, hs, wsamp};
-      st = launch_metering(smp, n, p.alpha, metrics, k.ws, s, cache);
-    }
+    const int st = with_packed12_sampler(fp, p, k, n_frames, [&](const auto& smp, long long n, float* cache) {
+      return launch_metering(smp, n, p.alpha, metrics, k.ws, s, cache);
+    });
     if (st) return st;
   }
 

@@ -57,7 +57,8 @@ __device__ __forceinline__ bool last_block_ticket(unsigned int* counter) {
 template <class Sampler>
 __global__ void __launch_bounds__(256) meter_phase1_kernel(const Sampler smp, long long n, float alpha,
                                                            const float* __restrict__ prev, Workspace* ws,
-                                                           float* __restrict__ cache /* n*3 floats or null */) {
+                                                           float* __restrict__ cache /* n*3 floats or null */,
+                                                           float* __restrict__ rec_out = nullptr /* shared exposure: raw {min,max} */) {
   __shared__ float smem[8 * 2];
   float v[2] = {INFINITY, -INFINITY};
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
@@ -81,16 +82,21 @@ __global__ void __launch_bounds__(256) meter_phase1_kernel(const Sampler smp, lo
     }
     block_fold<2>(f, op, smem);
     if (threadIdx.x == 0) {
-      // b = lerp(alpha, new, prev) = new + alpha * (prev - new)          camera_isp.py:156
-      ws->bounds[0] = __fadd_rn(f[0], __fmul_rn(alpha, __fsub_rn(prev[0], f[0])));
-      ws->bounds[1] = __fadd_rn(f[1], __fmul_rn(alpha, __fsub_rn(prev[1], f[1])));
+      if (rec_out) {                       // multi-GPU: the ranks' records are folded after the exchange
+        rec_out[0] = f[0]; rec_out[1] = f[1];
+      } else {
+        // b = lerp(alpha, new, prev) = new + alpha * (prev - new)          camera_isp.py:156
+        ws->bounds[0] = __fadd_rn(f[0], __fmul_rn(alpha, __fsub_rn(prev[0], f[0])));
+        ws->bounds[1] = __fadd_rn(f[1], __fmul_rn(alpha, __fsub_rn(prev[1], f[1])));
+      }
     }
   }
 }
 
 template <class Sampler>
 __global__ void __launch_bounds__(256) meter_phase2_kernel(const Sampler smp, long long n, float alpha,
-                                                           float* __restrict__ metrics, Workspace* ws) {
+                                                           float* __restrict__ metrics, Workspace* ws,
+                                                           float* __restrict__ rec_out = nullptr /* shared exposure: raw record 2 */) {
   __shared__ float smem[8 * 7];
   const float bmin = __ldcg(&ws->bounds[0]), bmax = __ldcg(&ws->bounds[1]);
   const float den = __fadd_rn(__fsub_rn(bmax, bmin), 1e-6f);
@@ -122,7 +128,11 @@ __global__ void __launch_bounds__(256) meter_phase2_kernel(const Sampler smp, lo
       for (int k = 2; k < 7; ++k) f[k] += __ldcg(&ws->partials[b * kPartialStride + k]);
     }
     block_fold<7>(f, op, smem);
-    if (threadIdx.x == 0) {
+    if (threadIdx.x == 0 && rec_out) {
+#pragma unroll
+      for (int k = 0; k < 7; ++k) rec_out[k] = f[k];
+      rec_out[7] = (float)n;
+    } else if (threadIdx.x == 0) {
       const float fn = (float)n;                                          // camera_isp.py:131-134
       const float stats[9] = {bmin, bmax, f[0], f[1], __fdiv_rn(f[2], fn), __fdiv_rn(f[3], fn),
                               __fdiv_rn(f[4], fn), __fdiv_rn(f[5], fn), __fdiv_rn(f[6], fn)};
@@ -132,6 +142,42 @@ __global__ void __launch_bounds__(256) meter_phase2_kernel(const Sampler smp, lo
         metrics[k] = __fadd_rn(stats[k], __fmul_rn(alpha, __fsub_rn(p, stats[k])));
       }
     }
+  }
+}
+
+// ---------------------------------------------------------------- multi-GPU shared exposure
+// gathered1: [world][2] = every rank's {min, max}; gathered2: [world][8] = {log_min, log_max, sum_log, sum_gray,
+// sum_r, sum_g, sum_b, n}.  Folded in rank order -> every rank computes bit-identical metrics.
+__device__ __forceinline__ void fold_bounds(const float* __restrict__ g1, int world, float alpha, const float* __restrict__ prev,
+                                            float& bmin, float& bmax) {
+  float mn = INFINITY, mx = -INFINITY;
+  for (int r = 0; r < world; ++r) { mn = fminf(mn, g1[2 * r]); mx = fmaxf(mx, g1[2 * r + 1]); }
+  bmin = __fadd_rn(mn, __fmul_rn(alpha, __fsub_rn(prev[0], mn)));          // camera_isp.py:156
+  bmax = __fadd_rn(mx, __fmul_rn(alpha, __fsub_rn(prev[1], mx)));
+}
+
+static __global__ void meter_fold_bounds_kernel(const float* __restrict__ g1, int world, float alpha, const float* __restrict__ prev,
+                                         Workspace* ws) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) fold_bounds(g1, world, alpha, prev, ws->bounds[0], ws->bounds[1]);
+}
+
+static __global__ void meter_finalize_kernel(const float* __restrict__ g1, const float* __restrict__ g2, int world, float alpha,
+                                      float* __restrict__ metrics) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  float bmin, bmax;
+  fold_bounds(g1, world, alpha, metrics, bmin, bmax);
+  float f[8] = {INFINITY, -INFINITY, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  for (int r = 0; r < world; ++r) {
+    f[0] = fminf(f[0], g2[8 * r]);
+    f[1] = fmaxf(f[1], g2[8 * r + 1]);
+    for (int k = 2; k < 8; ++k) f[k] += g2[8 * r + k];
+  }
+  const float fn = f[7];                                                  // camera_isp.py:131-134 with n = all ranks' samples
+  const float stats[9] = {bmin, bmax, f[0], f[1], __fdiv_rn(f[2], fn), __fdiv_rn(f[3], fn),
+                          __fdiv_rn(f[4], fn), __fdiv_rn(f[5], fn), __fdiv_rn(f[6], fn)};
+  for (int k = 0; k < 9; ++k) {                                           // camera_isp.py:165-166
+    const float p = metrics[k];
+    metrics[k] = __fadd_rn(stats[k], __fmul_rn(alpha, __fsub_rn(p, stats[k])));
   }
 }
 
@@ -161,6 +207,22 @@ inline int launch_metering(const Sampler& smp, long long n, float alpha, float* 
   if (st) return st;
   if (cache) meter_phase2_kernel<CachedSampler><<<grid, 256, 0, s>>>(CachedSampler{cache}, n, alpha, metrics, ws);
   else meter_phase2_kernel<Sampler><<<grid, 256, 0, s>>>(smp, n, alpha, metrics, ws);
+  return cuda_status(cudaPeekAtLastError(), "meter_phase2_kernel");
+}
+
+// the two halves of launch_metering for the shared-exposure exchange
+template <class Sampler>
+inline int launch_metering_phase1(const Sampler& smp, long long n, Workspace* ws, cudaStream_t s, float* cache, float* rec1) {
+  meter_phase1_kernel<Sampler><<<meter_grid(n), 256, 0, s>>>(smp, n, 0.f, nullptr, ws, cache, rec1);
+  return cuda_status(cudaPeekAtLastError(), "meter_phase1_kernel");
+}
+template <class Sampler>
+inline int launch_metering_phase2(const Sampler& smp, long long n, const float* g1, int world, float alpha, const float* prev,
+                                  Workspace* ws, cudaStream_t s, const float* cache, float* rec2) {
+  meter_fold_bounds_kernel<<<1, 32, 0, s>>>(g1, world, alpha, prev, ws);
+  const int grid = meter_grid(n);
+  if (cache) meter_phase2_kernel<CachedSampler><<<grid, 256, 0, s>>>(CachedSampler{cache}, n, alpha, nullptr, ws, rec2);
+  else meter_phase2_kernel<Sampler><<<grid, 256, 0, s>>>(smp, n, alpha, nullptr, ws, rec2);
   return cuda_status(cudaPeekAtLastError(), "meter_phase2_kernel");
 }
 

@@ -321,6 +321,44 @@ extern "C" int b200isp_metering_update(const void* const* images_host, int n_ima
   return B200ISP_OK;
 }
 
+// shared-exposure halves of b200isp_metering_update (see include/b200isp.h)
+template <class F>
+static int with_image_sampler(const char* what, const void* const* images_host, int n_images, int dtype, int height, int width,
+                              int stride, F f) {
+  ISP_REQUIRE(images_host, B200ISP_E_ARG, "%s: null pointer", what);
+  ISP_REQUIRE(n_images >= 1 && n_images <= B200ISP_MAX_FRAMES, B200ISP_E_FRAMES,
+              "%s: %d images (1..%d supported per call)", what, n_images, B200ISP_MAX_FRAMES);
+  ISP_REQUIRE(height > 0 && width > 0 && stride > 0, B200ISP_E_SHAPE, "%s: bad shape", what);
+  ISP_REQUIRE(dtype == B200ISP_F16 || dtype == B200ISP_F32, B200ISP_E_DTYPE, "%s: ISP dtype must be f16 or f32", what);
+  const int hs = (height + stride - 1) / stride, wsamp = (width + stride - 1) / stride;
+  const long long n = (long long)n_images * hs * wsamp;
+  ISP_DISPATCH_DTYPE(dtype, T, {
+    ImageSampler<T> smp;
+    for (int i = 0; i < n_images; ++i) smp.img[i] = (const T*)images_host[i];
+    smp.W = width; smp.stride = stride; smp.hs = hs; smp.ws_ = wsamp;
+    return f(smp, n);
+  });
+  return B200ISP_OK;
+}
+
+extern "C" int b200isp_metering_phase1(const void* const* images_host, int n_images, int dtype, int height, int width,
+                                       int stride, float* rec1, void* workspace, b200isp_stream stream) {
+  ISP_REQUIRE(rec1 && workspace, B200ISP_E_ARG, "metering_phase1: null pointer");
+  return with_image_sampler("metering_phase1", images_host, n_images, dtype, height, width, stride, [&](const auto& smp, long long n) {
+    return launch_metering_phase1(smp, n, (Workspace*)workspace, (cudaStream_t)stream, nullptr, rec1);
+  });
+}
+
+extern "C" int b200isp_metering_phase2(const void* const* images_host, int n_images, int dtype, int height, int width,
+                                       int stride, const float* gathered1, int world, float alpha, const float* metrics_prev,
+                                       float* rec2, void* workspace, b200isp_stream stream) {
+  ISP_REQUIRE(gathered1 && metrics_prev && rec2 && workspace && world >= 1, B200ISP_E_ARG, "metering_phase2: bad argument");
+  return with_image_sampler("metering_phase2", images_host, n_images, dtype, height, width, stride, [&](const auto& smp, long long n) {
+    return launch_metering_phase2(smp, n, gathered1, world, alpha, metrics_prev, (Workspace*)workspace, (cudaStream_t)stream,
+                                  nullptr, rec2);
+  });
+}
+
 extern "C" int b200isp_isp_reinhard(void* image, int dtype, void* output, int out_dtype, int64_t n_pixels,
                                     const float* metrics, float gamma, float intensity, float light_adapt,
                                     float color_adapt, void* workspace, b200isp_stream stream) {

@@ -1,7 +1,30 @@
 """Multi-GPU camera sharding: one process per GPU, one camera stream (or a contiguous
-group of streams) per rank, no bulk pixel traffic between GPUs.  The only exchange is the optional
-rig-wide shared-exposure metering, see ``SharedExposure`` (added with the multi-GPU milestone)."""
+group of streams) per rank, no pixel traffic between GPUs.
+
+The only coupling between cameras in the reference is the *joint* metering of all cameras of a time
+step (camera_isp.py:168-175, :376-385): one min/max reduction, a moving-average blend of the bounds,
+a second reduction w.r.t. the blended bounds, and the moving-average update of the 9-float metrics.
+``SharedExposure`` reproduces that across ranks by splitting the two reductions at their exchange
+points (include/b200isp.h, "multi-GPU shared exposure"):
+
+    rec1 = phase1(local frames)                      {min, max}                        2 floats
+    g1   = all_gather(rec1)                                                            NCCL, 8 B / rank
+    rec2 = phase2(local frames, g1, alpha, metrics)  {lmin, lmax, 5 sums, n}            8 floats
+    g2   = all_gather(rec2)                                                            NCCL, 32 B / rank
+    finalize(g1, g2, alpha)                          metrics = lerp(alpha, joint stats, metrics)
+
+Every rank folds the gathered records in rank order, so all ranks hold bit-identical ``metrics``
+without a broadcast, and a rank with fewer cameras (12 cameras on 8 GPUs) simply contributes a smaller
+``n``.  The messages are latency-only; the collectives are enqueued by torch.distributed behind the
+compute stream and nothing synchronises with the host.  Without shared exposure the ranks are
+independent replicas and no collective runs at all.
+"""
 from __future__ import annotations
+
+from typing import Optional, Sequence
+
+import torch
+import torch.distributed as dist
 
 
 def shard_cameras(n_cameras: int, world_size: int, rank: int) -> range:
@@ -9,3 +32,90 @@ def shard_cameras(n_cameras: int, world_size: int, rank: int) -> range:
     base, extra = divmod(n_cameras, world_size)
     start = rank * base + min(rank, extra)
     return range(start, start + base + (1 if rank < extra else 0))
+
+
+def max_cameras_per_rank(n_cameras: int, world_size: int) -> int:
+    """Cameras on the most loaded rank = what bounds the step time (12 cameras on 8 GPUs -> 2)."""
+    return -(-n_cameras // world_size)
+
+
+class CudaMeteringBackend:
+    """The three local steps of the exchange on the CUDA kernels of an ``ISP`` (camera_isp.py)."""
+
+    def __init__(self, isp):
+        self.isp = isp
+
+    def begin(self) -> float:
+        """allocates ``metrics`` on the first call; returns the weight of the previous metrics
+        (0 on the first call, 1 - moving_alpha afterwards; camera_isp.py:376-385)"""
+        return self.isp._metrics_and_alpha()
+
+    def phase1(self, source) -> torch.Tensor:
+        return self.isp.meter_phase1(source)
+
+    def phase2(self, source, gathered1: torch.Tensor, alpha: float) -> torch.Tensor:
+        return self.isp.meter_phase2(source, gathered1, alpha)
+
+    def finalize(self, gathered1: torch.Tensor, gathered2: torch.Tensor, alpha: float) -> None:
+        self.isp.meter_finalize(gathered1, gathered2, alpha)
+
+
+def exchange(record: torch.Tensor, group=None) -> torch.Tensor:
+    """all-gather one small per-rank record -> (world, len(record)), rank order"""
+    world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+    if world == 1:
+        return record.reshape(1, -1).clone()
+    out = torch.empty(world * record.numel(), dtype=record.dtype, device=record.device)
+    dist.all_gather_into_tensor(out, record.contiguous().view(-1), group=group)
+    return out.view(world, record.numel())
+
+
+def shared_metering(backend, source, group=None) -> None:
+    """One joint metering update over the frames of ALL ranks (each rank passes its own ``source``)."""
+    alpha = backend.begin()
+    g1 = exchange(backend.phase1(source), group)
+    g2 = exchange(backend.phase2(source, g1, alpha), group)
+    backend.finalize(g1, g2, alpha)
+
+
+class SharedExposure:
+    """Wraps a ``Camera16`` / ``Camera32`` so that its tone-mapping calls meter jointly with the other
+    ranks of ``group`` (rig-wide shared exposure).  Same call signatures as the wrapped ISP; everything
+    else (``set``, ``load_*``, attributes) is forwarded."""
+
+    def __init__(self, isp, group=None, backend=None):
+        self.isp = isp
+        self.group = group
+        self.backend = backend if backend is not None else CudaMeteringBackend(isp)
+
+    def __getattr__(self, name):
+        return getattr(self.isp, name)
+
+    @property
+    def metrics(self):
+        return self.isp.metrics
+
+    def update_metering(self, images: Sequence[torch.Tensor]) -> None:
+        shared_metering(self.backend, images, self.group)
+
+    def tonemap_reinhard(self, images, gamma: float = 1.0, intensity: float = 1.0, light_adapt: float = 1.0,
+                         color_adapt: float = 0.0, **kw):
+        self.update_metering(images)
+        return self.isp.tonemap_reinhard(images, gamma, intensity, light_adapt, color_adapt, update_metering=False, **kw)
+
+    def tonemap_linear(self, images, gamma: float = 1.0, **kw):
+        self.update_metering(images)
+        return self.isp.tonemap_linear(images, gamma, update_metering=False, **kw)
+
+    def process_packed12(self, frames, tonemap: str = "reinhard", ids_format: bool = False, **kw):
+        """fused path: the joint statistics come straight from the packed frames of every rank"""
+        isp = self.isp
+        frames = [f.to(isp.device) for f in frames]
+        if all(isp._fused_ok(f, ids_format) for f in frames) and not isp._resizes:
+            shared_metering(self.backend, frames, self.group)
+            return isp.process_packed12(frames, tonemap=tonemap, ids_format=ids_format, update_metering=False, **kw)
+        images = [isp.load_packed12(f, ids_format) for f in frames]
+        kw.pop("out", None); kw.pop("rows_per_task", None); kw.pop("profile_events", None)
+        if tonemap == "linear":
+            return self.tonemap_linear(images, kw.pop("gamma", 1.0), **kw)
+        return self.tonemap_reinhard(images, **kw)
