@@ -117,6 +117,14 @@ def measured_peak():
         return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def host_threads() -> int:
+    """all host cores this process may use (torchrun exports OMP_NUM_THREADS=1, which must not cap the CPU arm)"""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
 def cpu_baseline(workload, budget_s=20.0, threads=0):
     """C/OpenMP restatement of the reference path on the host cores, on a bounded sample: a horizontal
     band of one frame of the workload (same width, same tone map, same dtype)."""
@@ -124,6 +132,7 @@ def cpu_baseline(workload, budget_s=20.0, threads=0):
     n, h, w, isp_dt, tonemap, out_dt, tm, _ = WORKLOADS[workload]
     band_h = h                                    # one whole frame of the workload per repetition
     frame = synth_frames(1, band_h, w)[0]
+    threads = threads or host_threads()
     kw = dict(pattern="RGGB", cam16=isp_dt == "f16", out_dtype="u16" if out_dt == "u16" else "u8", tonemap=tonemap,
               stride=8, nthreads=threads, **tm)
     c_oracle.process([frame], **kw)                 # warm-up (page faults, thread pool)
@@ -135,7 +144,7 @@ def cpu_baseline(workload, budget_s=20.0, threads=0):
         if time.perf_counter() - t0 > budget_s or reps >= 50:
             break
     dt = (time.perf_counter() - t0) / reps
-    return {"value": band_h * w / dt / 1e9, "unit": "Gpixel/s", "cores": threads or c_oracle.max_threads(), "kind": "port",
+    return {"value": band_h * w / dt / 1e9, "unit": "Gpixel/s", "cores": threads, "kind": "port",
             "sample": f"{reps} x one {w}x{band_h} frame of the workload through oracle/c/isp_oracle.c "
                       f"(literal 13-tap demosaic, metering, {tonemap}, {out_dt}); Taichi CPU backend not installable"}, dt
 
@@ -148,7 +157,9 @@ def run_reference(args):
     from oracle import c_oracle
     band_h = h                                    # each step = one whole frame of the workload
     frame = synth_frames(1, band_h, w)[0]
-    kw = dict(pattern="RGGB", cam16=isp_dt == "f16", out_dtype="u16" if out_dt == "u16" else "u8", tonemap=tonemap, stride=8, **tm)
+    cores = host_threads()
+    kw = dict(pattern="RGGB", cam16=isp_dt == "f16", out_dtype="u16" if out_dt == "u16" else "u8", tonemap=tonemap, stride=8,
+              nthreads=cores, **tm)
     for _ in range(args.warmup):
         c_oracle.process([frame], **kw)
     t0 = time.perf_counter()
@@ -156,7 +167,6 @@ def run_reference(args):
         c_oracle.process([frame], **kw)
     dt = time.perf_counter() - t0
     value = args.steps * band_h * w / dt / 1e9
-    cores = c_oracle.max_threads()
     sample = (f"each step = one {w}x{band_h} frame of the workload through oracle/c/isp_oracle.c "
               f"(OpenMP, {cores} threads); the reference's Taichi CPU backend is not installable here")
     print(json.dumps({

@@ -28,7 +28,7 @@ ORACLE_SRC = ROOT / "oracle" / "c" / "isp_oracle.c"
 ORACLE_LIB = ROOT / "oracle" / "_build" / "libisp_oracle.so"
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-              "-Xcompiler", "-fPIC", "--threads", "1"] + os.environ.get("B200ISP_NVCC_EXTRA", "").split()
+              "-Xcompiler", "-fPIC", "--threads", "1", "-Xfatbin", "-compress-all"] + os.environ.get("B200ISP_NVCC_EXTRA", "").split()
 
 FUSED_OUT = {"u8": "uint8_t", "u16": "uint16_t", "f16": "__half", "f32": "float"}
 
@@ -62,7 +62,13 @@ def nvcc_path() -> str:
     raise RuntimeError("nvcc not found: the CUDA extension cannot be built")
 
 
-def build_cuda(force=False, jobs=None, verbose=False) -> Path:
+def build_cuda(force=False, jobs=None, verbose=False, out: Path | None = None) -> Path:
+    """out: alternative output path for an experimental variant (objects go to build/obj_<stem>); the variant's
+    flags come from B200ISP_NVCC_EXTRA and it is selected at run time with B200ISP_LIB=<path>."""
+    global OBJ, LIB
+    if out is not None:
+        LIB = Path(out).resolve()
+        OBJ = ROOT / "build" / f"obj_{LIB.stem}"
     sources = list(CSRC.glob("*.cu")) + list(CSRC.glob("*.cuh")) + [ROOT / "include" / "b200isp.h"]
     stamp = _digest(sources, " ".join(NVCC_FLAGS))
     stamp_file = OBJ / "stamp"
@@ -116,8 +122,9 @@ def main(argv=None):
     ap.add_argument("--jobs", type=int, default=None)
     ap.add_argument("--verbose", action="store_true", help="keep ptxas -v logs under build/obj")
     ap.add_argument("--no-oracle", action="store_true")
+    ap.add_argument("--out", default=None, help="build an experimental variant into this .so (see build_cuda)")
     a = ap.parse_args(argv)
-    print("built", build_cuda(a.force, a.jobs, a.verbose))
+    print("built", build_cuda(a.force, a.jobs, a.verbose, a.out))
     if not a.no_oracle:
         print("built", build_oracle(a.force))
 

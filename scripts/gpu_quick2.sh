@@ -11,5 +11,5 @@ tail -2 gpurun_out/bench_$wl.err
 done
 CMD="python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-e2e"
 $CMD > gpurun_out/plain.log 2>&1 && ncu --metrics gpu__time_duration.sum --clock-control none -c 40 --csv --log-file gpurun_out/launches_cfg2.csv $CMD > gpurun_out/ncu1.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:stream_kernel -s 3 -c 1 -f -o gpurun_out/prof_stream $CMD > gpurun_out/ncu_full.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:stream2_kernel -s 3 -c 1 -f -o gpurun_out/prof_stream $CMD > gpurun_out/ncu_full.log 2>&1
 echo "ncu rc=$?"

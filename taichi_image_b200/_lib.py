@@ -10,8 +10,11 @@ from pathlib import Path
 
 import torch
 
+import os
+
 _HERE = Path(__file__).resolve().parent
-LIB_PATH = _HERE / "libb200isp.so"
+# B200ISP_LIB selects an experimental build of the same library (build.py --out); default: the in-tree product
+LIB_PATH = Path(os.environ["B200ISP_LIB"]).resolve() if os.environ.get("B200ISP_LIB") else _HERE / "libb200isp.so"
 
 MAX_FRAMES = 64
 

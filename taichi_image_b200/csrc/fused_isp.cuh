@@ -14,7 +14,8 @@
 //               stream<EpiReinhard>    + border   (second sweep re-reads the packed frame from L2)
 //   none        stream<EpiRgb> + border           (load_packed12 only: float RGB out)
 #pragma once
-#include "stream_engine.cuh"
+#include "stream2.cuh"
+#include "border_fix.cuh"
 #include "pixel_ops.cuh"
 #include "metering.cuh"
 #include "reinhard.cuh"
@@ -43,56 +44,67 @@ __device__ __forceinline__ float biased_from_shifted(uint32_t shifted, uint32_t 
   return __uint_as_float(r);
 }
 
+// ---------------------------------------------------------------- packed12 row loader of the pair engine (stream2.cuh)
+// Same words and the same one-LOP3 decode as Packed12Loader, but: the decode mask is a register (0 for rows
+// outside the image and for the halo columns of the first / last thread column -> "zero sample"), the halo
+// loads are predicated on per-thread constants instead of being zero-filled, and the row is delivered as the
+// eight pairs (v[k], v[k+4]).
 template <bool CAM16>
-struct Packed12Loader {
+struct Packed12Loader2 {
   FramePtrs fp;
   int pitch_words;       // W * 3 / 8
   int frame0;
+  static constexpr uint32_t kRowMask = 0x007FF800u;
   struct Raw { uint32_t w[5]; };
-  struct Cursor { const uint32_t* p; bool left, right; };
+  struct Cursor { const uint32_t* p; uint32_t mL, mR; bool left, right, pf; };
 
+  __device__ __forceinline__ ptrdiff_t pitch() const { return pitch_words; }
+
+  template <int KIND>
   __device__ __forceinline__ void open(Cursor& c, int frame, int tcol, const StreamGeom& g) const {
     c.p = reinterpret_cast<const uint32_t*>(fp.in[frame0 + frame]) + 3 * tcol;
-    c.left = tcol > 0;
-    c.right = tcol < g.ntcols - 1;
+    c.left = KIND == K_CORE || tcol > 0;
+    c.right = KIND == K_CORE || tcol < g.ntcols - 1;
+    c.mL = c.left ? 0xFFFFFFFFu : 0u;
+    c.mR = c.right ? 0xFFFFFFFFu : 0u;
+    const int lane = threadIdx.x & 31;
+    c.pf = (lane & 7) == 0 || lane == 31;      // 12-byte segments 96 bytes apart touch every 128-byte line of the strip
   }
 
-  __device__ __forceinline__ void fetch(const Cursor& c, int row, const StreamGeom& g, Raw& raw) const {
-    const bool rv = (unsigned)row < (unsigned)g.H;
-    const uint32_t* p = c.p + (rv ? (unsigned)row * (unsigned)pitch_words : 0u);
-    raw.w[0] = (rv && c.left) ? __ldg(p - 1) : 0u;
-    raw.w[1] = rv ? __ldg(p) : 0u;
-    raw.w[2] = rv ? __ldg(p + 1) : 0u;
-    raw.w[3] = rv ? __ldg(p + 2) : 0u;
-    raw.w[4] = (rv && c.right) ? __ldg(p + 3) : 0u;
+  template <int KIND>
+  __device__ __forceinline__ void fetch(const Cursor& c, const uint32_t* p, Raw& raw) const {
+    if (KIND == K_CORE || c.left) raw.w[0] = __ldg(p - 1);       // not loaded -> stale register, masked by mL in decode
+    raw.w[1] = __ldg(p);
+    raw.w[2] = __ldg(p + 1);
+    raw.w[3] = __ldg(p + 2);
+    if (KIND == K_CORE || c.right) raw.w[4] = __ldg(p + 3);
   }
 
-  // L2 prefetch of a row several steps ahead: the 32 lanes' 12-byte segments form one contiguous 384-byte
-  // run, so every 10th lane touching its own address covers all of its 128-byte lines.
-  __device__ __forceinline__ void prefetch(const Cursor& c, int row, const StreamGeom& g) const {
-    if ((unsigned)row < (unsigned)g.H && (threadIdx.x & 31) % 10 == 0)
-      asm volatile("prefetch.global.L2 [%0];" ::"l"(c.p + (unsigned)row * (unsigned)pitch_words));
+  __device__ __forceinline__ void prefetch(const Cursor& c, const uint32_t* p) const {
+    if (c.pf) asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
   }
 
-  __device__ __forceinline__ void decode(const Raw& raw, float (&v)[12]) const {
+  template <int KIND>
+  __device__ __forceinline__ void decode(const Cursor& c, const Raw& raw, uint32_t m, f2 (&P)[8]) const {
     const uint32_t w0 = raw.w[0], w1 = raw.w[1], w2 = raw.w[2], w3 = raw.w[3], w4 = raw.w[4];
-    const uint32_t mask = 0x007FF800u, one = 0x3F800000u;
-#define ISP_B(x) biased_from_shifted((x), mask, one)
-    v[0] = ISP_B(w0 << 3);                          // pixel -2: bits 8..19 of w0
-    v[1] = ISP_B(w0 >> 9);                          // pixel -1: bits 20..31 of w0
-    v[2] = ISP_B(w1 << 11);                         // pixel 0 : bits 0..11 of w1
-    v[3] = ISP_B(w1 >> 1);                          // pixel 1 : bits 12..23
-    v[4] = ISP_B(__funnelshift_r(w1, w2, 13));      // pixel 2 : bits 24..35 of (w2:w1)
-    v[5] = ISP_B(w2 << 7);                          // pixel 3 : bits 4..15 of w2
-    v[6] = ISP_B(w2 >> 5);                          // pixel 4 : bits 16..27 of w2
-    v[7] = ISP_B(__funnelshift_r(w2, w3, 17));      // pixel 5 : bits 28..39 of (w3:w2)
-    v[8] = ISP_B(w3 << 3);                          // pixel 6 : bits 8..19 of w3
-    v[9] = ISP_B(w3 >> 9);                          // pixel 7 : bits 20..31 of w3
-    v[10] = ISP_B(w4 << 11);                        // pixel 8
-    v[11] = ISP_B(w4 >> 1);                         // pixel 9
-#undef ISP_B
+    const uint32_t one = 0x3F800000u;
+    if (KIND != K_GENERAL) m = kRowMask;                     // immediates: one LOP3 per pixel
+    const uint32_t mL = KIND == K_CORE ? kRowMask : (m & c.mL), mR = KIND == K_CORE ? kRowMask : (m & c.mR);
+    float v[12];
+    v[0] = biased_from_shifted(w0 << 3, mL, one);                      // pixel -2: bits 8..19 of w0
+    v[1] = biased_from_shifted(w0 >> 9, mL, one);                      // pixel -1: bits 20..31 of w0
+    v[2] = biased_from_shifted(w1 << 11, m, one);                      // pixel 0 : bits 0..11 of w1
+    v[3] = biased_from_shifted(w1 >> 1, m, one);                       // pixel 1 : bits 12..23
+    v[4] = biased_from_shifted(__funnelshift_r(w1, w2, 13), m, one);   // pixel 2 : bits 24..35 of (w2:w1)
+    v[5] = biased_from_shifted(w2 << 7, m, one);                       // pixel 3 : bits 4..15 of w2
+    v[6] = biased_from_shifted(w2 >> 5, m, one);                       // pixel 4 : bits 16..27 of w2
+    v[7] = biased_from_shifted(__funnelshift_r(w2, w3, 17), m, one);   // pixel 5 : bits 28..39 of (w3:w2)
+    v[8] = biased_from_shifted(w3 << 3, m, one);                       // pixel 6 : bits 8..19 of w3
+    v[9] = biased_from_shifted(w3 >> 9, m, one);                       // pixel 7 : bits 20..31 of w3
+    v[10] = biased_from_shifted(w4 << 11, mR, one);                    // pixel 8
+    v[11] = biased_from_shifted(w4 >> 1, mR, one);                     // pixel 9
     if constexpr (CAM16) {
-      constexpr float k = 4096.f * kInv4095;         // (b - 1) * 4096 * f32(1/4095), one rounding
+      constexpr float k = 4096.f * kInv4095;         // (b - 1) * 4096 * f32(1/4095), one rounding, then through f16
 #pragma unroll
       for (int j = 0; j < 12; j += 2) {
         const __half2 h = __floats2half2_rn(fmaf(v[j], k, -k), fmaf(v[j + 1], k, -k));
@@ -100,6 +112,8 @@ struct Packed12Loader {
         v[j + 1] = __high2float(h);
       }
     }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) P[i] = pk(v[i], v[i + 4]);
   }
 };
 
@@ -214,13 +228,13 @@ template <> struct Quant<float> {
 };
 
 // quantised row of 8 pixels -> packed words -> warp-cooperative contiguous store (stream_engine.cuh)
-template <typename OutT>
+template <typename OutT, bool FULL = false>
 __device__ __forceinline__ void store_row8(const WarpCtx& wc, OutT* warp_out /* frame + 24 * tcol0 */, int W, int row,
                                            const uint32_t (&v)[24]) {
   constexpr int NW = Quant<OutT>::kWords;
   uint32_t w[NW];
   Quant<OutT>::pack(v, w);
-  warp_store_row<NW>(wc, warp_out + (size_t)((unsigned)row * (unsigned)W) * 3, w);
+  warp_store_row<NW, FULL>(wc, warp_out + (size_t)((unsigned)row * (unsigned)W) * 3, w);
 }
 
 template <typename OutT> __device__ __forceinline__ void store_px(void* frame_out, int W, int row, int col, const float (&y)[3]) {
@@ -268,6 +282,13 @@ __device__ __forceinline__ void reinhard_p(const ReinhardConsts& c, const float 
   reinhard_map_fast<CA0>(c.p, s, p);
 }
 
+// run-time colour-adapt switch (kernel-uniform) for the pair-engine epilogues
+template <bool CAM16>
+__device__ __forceinline__ void reinhard_p_rt(const ReinhardConsts& c, const float (&rgb)[3], float (&p)[3]) {
+  if (c.ca0) reinhard_p<CAM16, true>(c, rgb, p);
+  else reinhard_p<CAM16, false>(c, rgb, p);
+}
+
 // camera_isp.py:211-218: stored = cast_T(p); out = trunc(scale * (stored / max_out)^(1/gamma))
 template <bool CAM16, bool GAMMA>
 __device__ __forceinline__ void reinhard_out(const ReinhardConsts& c, const float (&p)[3], float (&y)[3]) {
@@ -278,79 +299,6 @@ __device__ __forceinline__ void reinhard_out(const ReinhardConsts& c, const floa
     y[k] = fminf(q, 1.0f);     // the reference does not clamp (q <= 1 + one f16 ulp); saturate for the RZ-FMA quantiser
   }
 }
-
-// ---------------------------------------------------------------- hot-path epilogues
-// The per-pixel code is branch-free: the runtime options (CCM on/off, gamma != 1, color_adapt == 0) are
-// template flags of emit_t and are selected once per 8-pixel row by a warp-uniform switch, so the
-// compiler can interleave the eight independent pixel chains of a row.
-#define ISP_FLAG_DISPATCH2(F0, F1, CALL)                               \
-  do {                                                                 \
-    if (F0) { if (F1) { CALL(true, true); } else { CALL(true, false); } } \
-    else    { if (F1) { CALL(false, true); } else { CALL(false, false); } } \
-  } while (0)
-
-template <bool CAM16, typename OutT>
-struct EpiRgb {       // load_packed12: ISP-dtype float RGB out
-  FramePtrs fp;
-  IspConsts k;
-  static constexpr int kStageWords = 32 * Quant<OutT>::kWords;
-  struct State { OutT* out; WarpCtx wc; };
-  __device__ __forceinline__ void init(State& st, int frame, int, const WarpCtx& wc) const {
-    st.out = reinterpret_cast<OutT*>(fp.out[k.frame0 + frame]) + 24 * wc.tcol0;
-    st.wc = wc;
-  }
-  __device__ __forceinline__ void finish(State&, int, int, bool) const {}
-  template <bool BROW, bool GFIRST, bool CCM>
-  __device__ __forceinline__ void emit_t(const State& st, int row, const float (&R)[8], const float (&G)[8], const float (&B)[8]) const {
-    using SS = SiteScale<BROW, GFIRST>;
-    uint32_t v[24];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      float rgb[3];
-      isp_rgb_fast<CAM16, CCM>(k, R[j], G[j], B[j], SS::r(j), SS::g(j), SS::b(j), rgb);
-      v[3 * j] = __float_as_uint(rgb[0]); v[3 * j + 1] = __float_as_uint(rgb[1]); v[3 * j + 2] = __float_as_uint(rgb[2]);
-    }
-    store_row8<OutT>(st.wc, st.out, k.W, row, v);
-  }
-  template <bool BROW, bool GFIRST>
-  __device__ __forceinline__ void emit(State& st, int row, const float (&R)[8], const float (&G)[8], const float (&B)[8]) const {
-    if (k.ccm) emit_t<BROW, GFIRST, true>(st, row, R, G, B);
-    else emit_t<BROW, GFIRST, false>(st, row, R, G, B);
-  }
-};
-
-template <bool CAM16, typename OutT>
-struct EpiLinear {
-  FramePtrs fp;
-  IspConsts k;
-  static constexpr int kStageWords = 32 * Quant<OutT>::kWords;
-  struct State { LinearConsts c; OutT* out; WarpCtx wc; };
-  __device__ __forceinline__ void init(State& st, int frame, int, const WarpCtx& wc) const {
-    st.c = linear_consts(k.metrics, k.gamma);
-    st.out = reinterpret_cast<OutT*>(fp.out[k.frame0 + frame]) + 24 * wc.tcol0;
-    st.wc = wc;
-  }
-  __device__ __forceinline__ void finish(State&, int, int, bool) const {}
-  template <bool BROW, bool GFIRST, bool CCM, bool GAMMA>
-  __device__ __forceinline__ void emit_t(const State& st, int row, const float (&R)[8], const float (&G)[8], const float (&B)[8]) const {
-    using SS = SiteScale<BROW, GFIRST>;
-    uint32_t v[24];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      float rgb[3], y[3];
-      isp_rgb_fast<CAM16, CCM>(k, R[j], G[j], B[j], SS::r(j), SS::g(j), SS::b(j), rgb);
-      linear_px<GAMMA>(st.c, rgb, y);
-      v[3 * j] = Quant<OutT>::q(y[0]); v[3 * j + 1] = Quant<OutT>::q(y[1]); v[3 * j + 2] = Quant<OutT>::q(y[2]);
-    }
-    store_row8<OutT>(st.wc, st.out, k.W, row, v);
-  }
-  template <bool BROW, bool GFIRST>
-  __device__ __forceinline__ void emit(State& st, int row, const float (&R)[8], const float (&G)[8], const float (&B)[8]) const {
-#define ISP_CALL(A, B_) emit_t<BROW, GFIRST, A, B_>(st, row, R, G, B)
-    ISP_FLAG_DISPATCH2(k.ccm, st.c.has_gamma, ISP_CALL);
-#undef ISP_CALL
-  }
-};
 
 __device__ __forceinline__ ReinhardConsts reinhard_consts(const IspConsts& k, int frame, bool with_max) {
   ReinhardConsts c;
@@ -364,39 +312,269 @@ __device__ __forceinline__ ReinhardConsts reinhard_consts(const IspConsts& k, in
   return c;
 }
 
+// ================================================================ pair-engine epilogues (stream2.cuh)
+// Conventions: pixel q (0..7) of a thread = pair q & 3, lane q >> 2.  "raw" = demosaiced value normalised by 16,
+// unclamped, before CCM.  The 2-pixel image frame is renormalised on the raw values (border_fix.cuh):
+// whole border rows through the out-of-line frame_patch_nl, the frame COLUMNS of interior rows (pixels 0,1 of
+// the first thread column, 6,7 of the last) in line.
+__device__ __forceinline__ int edge_bits(int tcol, int W) { return (tcol == 0 ? 1 : 0) | (tcol == (W >> 3) - 1 ? 2 : 0); }
+
+template <bool CAM16, bool BROW, bool GFIRST>
+__device__ __forceinline__ void pairs_to_raw(const f2 (&R)[4], const f2 (&G)[4], const f2 (&B)[4], Vals24& x) {
+  using SS = SiteScale2<BROW, GFIRST>;
+  constexpr float kn = 256.f * kInv4095;           // 4096 * f32(1/4095) / 16
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    float s[3][2];
+    upk(R[j], s[0][0], s[0][1]); upk(G[j], s[1][0], s[1][1]); upk(B[j], s[2][0], s[2][1]);
+    const float sc[3] = {SS::r(j), SS::g(j), SS::b(j)};
+#pragma unroll
+    for (int ch = 0; ch < 3; ++ch)
+#pragma unroll
+      for (int l = 0; l < 2; ++l)
+        x.v[3 * (j + 4 * l) + ch] = CAM16 ? s[ch][l] * (sc[ch] * 0.0625f) : fmaf(s[ch][l], sc[ch] * kn, -16.f * kn);
+  }
+}
+
+// Renormalisation of the frame columns of an interior row on the raw values, exact (division) form: pixels
+// 0,1 of the first thread column / 6,7 of the last (edge != 0 only there).
+template <bool BROW, bool GFIRST>
+__device__ __forceinline__ void patch_cols(Vals24& x, int edge) {
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    if (q >= 2 && q < 6) continue;
+    if ((q < 2 && (edge & 1)) || (q >= 6 && (edge & 2))) {
+      const int K = site_kernel_of(BROW, SiteScale2<BROW, GFIRST>::gsite(q & 3));
+      const float* t = c_border.t[K][2][q < 2 ? q : q - 3];
+      x.v[3 * q] = frame_exact(x.v[3 * q], t[0]);
+      x.v[3 * q + 1] = frame_exact(x.v[3 * q + 1], t[1]);
+      x.v[3 * q + 2] = frame_exact(x.v[3 * q + 2], t[2]);
+    }
+  }
+}
+
+// K_GENERAL front end, out of line and rolled (cold code: border tasks): pair sums -> raw values, every pixel
+// renormalised by the in-bounds weight sum of its own (row class, column class) -- t = 16, an exact no-op, for
+// pixels that are not on the image frame.  brow / gfirst = row type at run time.
+struct Pairs12 { f2 R[4], G[4], B[4]; };
 template <bool CAM16>
-struct EpiReinhardMax {      // pass 1 without the write-back: frame-global max of the mapped values
+static __device__ __noinline__ Vals24 general_raw(Pairs12 s, int rc, int edge, int brow, int gfirst) {
+  Vals24 x;
+  constexpr float kn = 256.f * kInv4095;
+#pragma unroll 1
+  for (int j = 0; j < 4; ++j) {
+    const bool gsite = ((j & 1) == 0) == (gfirst != 0);
+    const float sc[3] = {gsite ? -2.f : (brow ? 4.f : 16.f), gsite ? 16.f : -2.f, gsite ? -2.f : (brow ? 16.f : 4.f)};
+    float v[3][2];
+    upk(s.R[j], v[0][0], v[0][1]); upk(s.G[j], v[1][0], v[1][1]); upk(s.B[j], v[2][0], v[2][1]);
+    const int K = site_kernel_of(brow != 0, gsite);
+#pragma unroll 1
+    for (int l = 0; l < 2; ++l) {
+      const int q = j + 4 * l;
+      const float* t = c_border.t[K][rc][col_class(q, edge)];
+#pragma unroll
+      for (int ch = 0; ch < 3; ++ch) {
+        const float raw = CAM16 ? v[ch][l] * (sc[ch] * 0.0625f) : fmaf(v[ch][l], sc[ch] * kn, -16.f * kn);
+        x.v[3 * q + ch] = frame_exact(raw, t[ch]);
+      }
+    }
+  }
+  return x;
+}
+
+template <bool CAM16, bool BROW, bool GFIRST, int KIND>
+__device__ __forceinline__ void raw_with_frame(const f2 (&R)[4], const f2 (&G)[4], const f2 (&B)[4], int row, int H, int edge,
+                                               Vals24& x) {
+  if constexpr (KIND == K_GENERAL) {
+    Pairs12 s;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { s.R[j] = R[j]; s.G[j] = G[j]; s.B[j] = B[j]; }
+    x = general_raw<CAM16>(s, edge_class(row, H), edge, BROW, GFIRST);
+  } else {
+    pairs_to_raw<CAM16, BROW, GFIRST>(R, G, B, x);
+    if (KIND == K_EDGE && edge) patch_cols<BROW, GFIRST>(x, edge);
+  }
+}
+
+// raw -> ISP RGB in [0,1]: CCM, clamp (bayer.py:152-155), rounding through the ISP dtype
+template <bool CAM16>
+__device__ __forceinline__ void raw_to_rgb(const IspConsts& k, const float* x, float (&rgb)[3]) {
+  // The matrix is applied unconditionally: without colour correction the host passes the identity, for which
+  // fma(b, 0, fma(g, 0, r * 1)) == r exactly -- one code copy, no branch.
+  const float u = fmaf(x[2], k.m[2], fmaf(x[1], k.m[1], x[0] * k.m[0]));
+  const float v = fmaf(x[2], k.m[5], fmaf(x[1], k.m[4], x[0] * k.m[3]));
+  const float w = fmaf(x[2], k.m[8], fmaf(x[1], k.m[7], x[0] * k.m[6]));
+  float r = u, g = v, b = w;
+  r = clamp01(r); g = clamp01(g); b = clamp01(b);
+  if constexpr (CAM16) {
+    const __half2 h = __floats2half2_rn(r, g);
+    rgb[0] = __low2float(h); rgb[1] = __high2float(h); rgb[2] = __half2float(__float2half_rn(b));
+  } else {
+    rgb[0] = r; rgb[1] = g; rgb[2] = b;
+  }
+}
+
+template <bool CAM16, typename OutT>
+struct EpiRgb2 {      // load_packed12: ISP-dtype float RGB out
+  FramePtrs fp;
+  IspConsts k;
+  static constexpr int kStageWords = 32 * Quant<OutT>::kWords;
+  struct State { OutT* out; WarpCtx wc; int edge; };
+  __device__ __forceinline__ void init(State& st, int frame, int tcol, const WarpCtx& wc) const {
+    st.out = reinterpret_cast<OutT*>(fp.out[k.frame0 + frame]) + 24 * wc.tcol0;
+    st.wc = wc;
+    st.edge = edge_bits(tcol, k.W);
+  }
+  __device__ __forceinline__ void finish(State&, int, int, bool) const {}
+  static constexpr bool kSplitEdge = false;
+  __device__ __forceinline__ bool fast_kinds_ok(const State&) const { return true; }
+  template <bool BROW, bool GFIRST, int KIND>
+  __device__ __forceinline__ void emit(State& st, int row, const f2 (&R)[4], const f2 (&G)[4], const f2 (&B)[4]) const {
+    Vals24 x;
+    raw_with_frame<CAM16, BROW, GFIRST, KIND>(R, G, B, row, k.H, st.edge, x);
+    uint32_t v[24];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      float rgb[3];
+      raw_to_rgb<CAM16>(k, &x.v[3 * q], rgb);
+      v[3 * q] = __float_as_uint(rgb[0]); v[3 * q + 1] = __float_as_uint(rgb[1]); v[3 * q + 2] = __float_as_uint(rgb[2]);
+    }
+    store_row8<OutT>(st.wc, st.out, k.W, row, v);
+  }
+};
+
+// FAST: Camera32, no CCM, gamma 1 -- the configuration the roofline is quoted on; everything stays in pairs.
+template <bool CAM16, typename OutT, bool FAST>
+struct EpiLinear2 {
+  static_assert(!(FAST && CAM16), "the packed fast path is Camera32 only");
+  FramePtrs fp;
+  IspConsts k;
+  static constexpr int kStageWords = 32 * Quant<OutT>::kWords;
+  struct State { LinearConsts c; OutT* out; WarpCtx wc; int edge; bool inside; };
+  __device__ __forceinline__ void init(State& st, int frame, int tcol, const WarpCtx& wc) const {
+    st.c = linear_consts(k.metrics, k.gamma);
+    st.out = reinterpret_cast<OutT*>(fp.out[k.frame0 + frame]) + 24 * wc.tcol0;
+    st.wc = wc;
+    st.edge = edge_bits(tcol, k.W);
+    // With bounds inside [0,1] (always true for metered bounds: the metered images are clamped to [0,1],
+    // bayer.py:155)  clamp((clamp(c,0,1) - min) * inv, 0, 1) == clamp((c - min) * inv, 0, 1), so the demosaic
+    // clamp needs no instruction of its own.  Other bounds take the generic row routine.
+    st.inside = st.c.bmin >= 0.f && k.metrics[1] <= 1.0f;
+  }
+  __device__ __forceinline__ void finish(State&, int, int, bool) const {}
+
+  static constexpr bool kSplitEdge = FAST;
+  template <bool GAMMA>
+  __device__ __forceinline__ void emit_t(const State& st, int row, const Vals24& x) const {
+    uint32_t v[24];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      float rgb[3], y[3];
+      raw_to_rgb<CAM16>(k, &x.v[3 * q], rgb);
+      linear_px<GAMMA>(st.c, rgb, y);
+      v[3 * q] = Quant<OutT>::q(y[0]); v[3 * q + 1] = Quant<OutT>::q(y[1]); v[3 * q + 2] = Quant<OutT>::q(y[2]);
+    }
+    store_row8<OutT>(st.wc, st.out, k.W, row, v);
+  }
+  template <bool BROW, bool GFIRST, int KIND>
+  __device__ __forceinline__ void emit_generic(const State& st, int row, const f2 (&R)[4], const f2 (&G)[4], const f2 (&B)[4]) const {
+    Vals24 x;
+    raw_with_frame<CAM16, BROW, GFIRST, KIND>(R, G, B, row, k.H, st.edge, x);
+    if (st.c.has_gamma) emit_t<true>(st, row, x);
+    else emit_t<false>(st, row, x);
+  }
+
+  // the packed kinds need bounds inside [0,1]; otherwise every task takes K_GENERAL (generic arithmetic)
+  __device__ __forceinline__ bool fast_kinds_ok(const State& st) const { return !FAST || st.inside; }
+
+  template <bool BROW, bool GFIRST, int KIND>
+  __device__ __forceinline__ void emit(State& st, int row, const f2 (&R)[4], const f2 (&G)[4], const f2 (&B)[4]) const {
+    if constexpr (!FAST || KIND == K_GENERAL) {
+      emit_generic<BROW, GFIRST, KIND>(st, row, R, G, B);
+    } else {
+      using SS = SiteScale2<BROW, GFIRST>;
+      constexpr float kn = 256.f * kInv4095;             // 4096 * f32(1/4095) / 16
+      f2 X[4][3];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        X[j][0] = fma2k(SS::r(j) * kn, R[j], bc(-16.f * kn));      // demosaiced value (unclamped)
+        X[j][1] = fma2k(SS::g(j) * kn, G[j], bc(-16.f * kn));
+        X[j][2] = fma2k(SS::b(j) * kn, B[j], bc(-16.f * kn));
+      }
+      if (KIND == K_EDGE && st.edge) {       // frame columns: only the lanes of the first / last thread column
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          if (q >= 2 && q < 6) continue;
+          if ((q < 2 && (st.edge & 1)) || (q >= 6 && (st.edge & 2))) {
+            const int K = site_kernel_of(BROW, SS::gsite(q & 3));
+            const float* f = c_border.f[K][2][q < 2 ? q : q - 3];
+#pragma unroll
+            for (int ch = 0; ch < 3; ++ch) {
+              float lo, hi;
+              upk(X[q & 3][ch], lo, hi);
+              if (q < 4) lo *= f[ch]; else hi *= f[ch];
+              X[q & 3][ch] = pk(lo, hi);
+            }
+          }
+        }
+      }
+      const f2 nbmin = bc(-st.c.bmin);
+      const float a = st.c.a;
+      uint32_t v[24];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+#pragma unroll
+        for (int ch = 0; ch < 3; ++ch) {
+          float lo, hi;
+          upk(add2(X[j][ch], nbmin), lo, hi);                       // tonemap.py:15  (x - min) ...
+          lo = __saturatef(__fmul_rn(lo, a));                       //                ... * inv, clamp
+          hi = __saturatef(__fmul_rn(hi, a));
+          if constexpr (DT<OutT>::is_int) {
+            float qlo, qhi;
+            upk(fma2_rz(pk(lo, hi), bc(DT<OutT>::scale), bc(8388608.f)), qlo, qhi);
+            v[3 * j + ch] = __float_as_uint(qlo);
+            v[3 * (j + 4) + ch] = __float_as_uint(qhi);
+          } else {
+            v[3 * j + ch] = __float_as_uint(lo);
+            v[3 * (j + 4) + ch] = __float_as_uint(hi);
+          }
+        }
+      }
+      store_row8<OutT, KIND == K_CORE>(st.wc, st.out, k.W, row, v);
+    }
+  }
+};
+
+template <bool CAM16>
+struct EpiReinhardMax2 {      // pass 1 without the write-back: frame-global max of the mapped values
   IspConsts k;
   static constexpr int kStageWords = 0;
-  struct State { ReinhardConsts c; float mx; bool first, last; };
+  struct State { ReinhardConsts c; float mx; int edge; };
   __device__ __forceinline__ void init(State& st, int frame, int tcol, const WarpCtx&) const {
     st.c = reinhard_consts(k, frame, false);
     st.mx = 0.f;
-    st.first = tcol == 0;
-    st.last = tcol == (k.W >> 3) - 1;
+    st.edge = edge_bits(tcol, k.W);
   }
-  template <bool BROW, bool GFIRST, bool CCM, bool CA0>
-  __device__ __forceinline__ void emit_t(State& st, const float (&R)[8], const float (&G)[8], const float (&B)[8]) const {
-    using SS = SiteScale<BROW, GFIRST>;
+  static constexpr bool kSplitEdge = false;
+  __device__ __forceinline__ bool fast_kinds_ok(const State&) const { return true; }
+  template <bool CA0>
+  __device__ __forceinline__ void emit_t(State& st, const Vals24& x) const {
     float mx = st.mx;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
+    for (int q = 0; q < 8; ++q) {
       float rgb[3], p[3];
-      isp_rgb_fast<CAM16, CCM>(k, R[j], G[j], B[j], SS::r(j), SS::g(j), SS::b(j), rgb);
+      raw_to_rgb<CAM16>(k, &x.v[3 * q], rgb);
       reinhard_p<CAM16, CA0>(st.c, rgb, p);
-      float m = fmaxf(p[0], fmaxf(p[1], p[2]));
-      if ((j < 2 && st.first) || (j >= 6 && st.last)) m = 0.f;     // image frame: border kernel
-      mx = fmaxf(mx, m);
+      mx = fmaxf(mx, fmaxf(p[0], fmaxf(p[1], p[2])));
     }
     st.mx = mx;
   }
-  template <bool BROW, bool GFIRST>
-  __device__ __forceinline__ void emit(State& st, int row, const float (&R)[8], const float (&G)[8], const float (&B)[8]) const {
-    // the 2-pixel image frame is handled (with the exact border normalisation) by the border kernel
-    if (row < 2 || row >= k.H - 2) return;
-#define ISP_CALL(A, B_) emit_t<BROW, GFIRST, A, B_>(st, R, G, B)
-    ISP_FLAG_DISPATCH2(k.ccm, st.c.ca0, ISP_CALL);
-#undef ISP_CALL
+  template <bool BROW, bool GFIRST, int KIND>
+  __device__ __forceinline__ void emit(State& st, int row, const f2 (&R)[4], const f2 (&G)[4], const f2 (&B)[4]) const {
+    Vals24 x;
+    raw_with_frame<CAM16, BROW, GFIRST, KIND>(R, G, B, row, k.H, st.edge, x);
+    if (st.c.ca0) emit_t<true>(st, x);          // kernel-uniform, one branch per row
+    else emit_t<false>(st, x);
   }
   __device__ __forceinline__ void finish(State& st, int frame, int lane, bool task_ok) const {
     const float m = warp_max(st.mx);
@@ -406,96 +584,46 @@ struct EpiReinhardMax {      // pass 1 without the write-back: frame-global max 
 };
 
 template <bool CAM16, typename OutT>
-struct EpiReinhard {         // pass 2 recomputed from the packed frame: map, normalise by the max, gamma, quantise
+struct EpiReinhard2 {         // pass 2 recomputed from the packed frame: map, normalise by the max, gamma, quantise
   FramePtrs fp;
   IspConsts k;
   static constexpr int kStageWords = 32 * Quant<OutT>::kWords;
-  struct State { ReinhardConsts c; OutT* out; WarpCtx wc; };
-  __device__ __forceinline__ void init(State& st, int frame, int, const WarpCtx& wc) const {
+  struct State { ReinhardConsts c; OutT* out; WarpCtx wc; int edge; };
+  __device__ __forceinline__ void init(State& st, int frame, int tcol, const WarpCtx& wc) const {
     st.c = reinhard_consts(k, frame, true);
     st.out = reinterpret_cast<OutT*>(fp.out[k.frame0 + frame]) + 24 * wc.tcol0;
     st.wc = wc;
+    st.edge = edge_bits(tcol, k.W);
   }
   __device__ __forceinline__ void finish(State&, int, int, bool) const {}
-  template <bool BROW, bool GFIRST, bool CCM, bool CA0, bool GAMMA>
-  __device__ __forceinline__ void emit_t(const State& st, int row, const float (&R)[8], const float (&G)[8], const float (&B)[8]) const {
-    using SS = SiteScale<BROW, GFIRST>;
+  static constexpr bool kSplitEdge = false;
+  template <bool CA0, bool GAMMA>
+  __device__ __forceinline__ void emit_t(const State& st, int row, const Vals24& x) const {
     uint32_t v[24];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
+    for (int q = 0; q < 8; ++q) {
       float rgb[3], p[3], y[3];
-      isp_rgb_fast<CAM16, CCM>(k, R[j], G[j], B[j], SS::r(j), SS::g(j), SS::b(j), rgb);
+      raw_to_rgb<CAM16>(k, &x.v[3 * q], rgb);
       reinhard_p<CAM16, CA0>(st.c, rgb, p);
       reinhard_out<CAM16, GAMMA>(st.c, p, y);
-      v[3 * j] = Quant<OutT>::q(y[0]); v[3 * j + 1] = Quant<OutT>::q(y[1]); v[3 * j + 2] = Quant<OutT>::q(y[2]);
+      v[3 * q] = Quant<OutT>::q(y[0]); v[3 * q + 1] = Quant<OutT>::q(y[1]); v[3 * q + 2] = Quant<OutT>::q(y[2]);
     }
     store_row8<OutT>(st.wc, st.out, k.W, row, v);
   }
-  template <bool BROW, bool GFIRST>
-  __device__ __forceinline__ void emit(State& st, int row, const float (&R)[8], const float (&G)[8], const float (&B)[8]) const {
-    if (st.c.has_gamma) {
-#define ISP_CALL(A, B_) emit_t<BROW, GFIRST, A, B_, true>(st, row, R, G, B)
-      ISP_FLAG_DISPATCH2(k.ccm, st.c.ca0, ISP_CALL);
-#undef ISP_CALL
+  __device__ __forceinline__ bool fast_kinds_ok(const State&) const { return true; }
+  template <bool BROW, bool GFIRST, int KIND>
+  __device__ __forceinline__ void emit(State& st, int row, const f2 (&R)[4], const f2 (&G)[4], const f2 (&B)[4]) const {
+    Vals24 x;
+    raw_with_frame<CAM16, BROW, GFIRST, KIND>(R, G, B, row, k.H, st.edge, x);
+    if (st.c.ca0) {                     // kernel-uniform flags, dispatched once per row
+      if (st.c.has_gamma) emit_t<true, true>(st, row, x); else emit_t<true, false>(st, row, x);
     } else {
-#define ISP_CALL(A, B_) emit_t<BROW, GFIRST, A, B_, false>(st, row, R, G, B)
-      ISP_FLAG_DISPATCH2(k.ccm, st.c.ca0, ISP_CALL);
-#undef ISP_CALL
+      if (st.c.has_gamma) emit_t<false, true>(st, row, x); else emit_t<false, false>(st, row, x);
     }
   }
 };
 
-// ---------------------------------------------------------------- border kernel (2-pixel frame, exact normalisation)
 enum { MODE_RGB = 0, MODE_LINEAR = 1, MODE_RMAX = 2, MODE_REINHARD = 3 };
-
-template <bool CAM16, int MODE, typename OutT>
-__global__ void __launch_bounds__(256) isp_border_kernel(const Packed12Src<CAM16> src, const FramePtrs fp, const IspConsts k,
-                                                         int nframes, long long per_frame) {
-  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const bool ok = idx < per_frame * nframes;
-  float mx = 0.f;
-  int frame = 0;
-  if (ok) {
-    frame = (int)(idx / per_frame);
-    int row, col;
-    border_coord(idx % per_frame, k.H, k.W, row, col);
-    float rgb[3];
-    isp_rgb_pixel<CAM16>(src, k, k.frame0 + frame, row, col, rgb);
-    void* out = fp.out[k.frame0 + frame];
-    if constexpr (MODE == MODE_RGB) {
-      store_px<OutT>(out, k.W, row, col, rgb);
-    } else if constexpr (MODE == MODE_LINEAR) {
-      const LinearConsts c = linear_consts(k.metrics, k.gamma);
-      float y[3];
-      if (c.has_gamma) linear_px<true>(c, rgb, y); else linear_px<false>(c, rgb, y);
-      store_px<OutT>(out, k.W, row, col, y);
-    } else {
-      const ReinhardConsts c = reinhard_consts(k, frame, MODE == MODE_REINHARD);
-      float p[3];
-      if (c.ca0) reinhard_p<CAM16, true>(c, rgb, p); else reinhard_p<CAM16, false>(c, rgb, p);
-      if constexpr (MODE == MODE_RMAX) {
-        mx = fmaxf(p[0], fmaxf(p[1], p[2]));
-      } else {
-        float y[3];
-        if (c.has_gamma) reinhard_out<CAM16, true>(c, p, y); else reinhard_out<CAM16, false>(c, p, y);
-        store_px<OutT>(out, k.W, row, col, y);
-      }
-    }
-  }
-  if constexpr (MODE == MODE_RMAX) {
-    // a warp may straddle two frames only at a frame boundary; keep it simple: one atomic per thread with m > 0
-    // is avoided by a warp reduction when the whole warp sits in one frame.
-    const int f0 = __shfl_sync(0xffffffffu, frame, 0);
-    const bool uniform = __all_sync(0xffffffffu, frame == f0);
-    if (uniform) {
-      const float m = warp_max(mx);
-      if ((threadIdx.x & 31) == 0 && m > 0.f)
-        atomicMax(reinterpret_cast<unsigned int*>(&k.ws->frame_max[k.frame0 + f0]), __float_as_uint(m));
-    } else if (ok && mx > 0.f) {
-      atomicMax(reinterpret_cast<unsigned int*>(&k.ws->frame_max[k.frame0 + frame]), __float_as_uint(mx));
-    }
-  }
-}
 
 // ---------------------------------------------------------------- metering samplers straight from packed12
 // generic: any stride, literal per-pixel demosaic
@@ -586,24 +714,24 @@ template <bool CAM16, int MODE, typename OutT>
 static int run_pass(const FramePtrs& fp, IspConsts k, int frame0, int nframes, int rows_per_task, cudaStream_t s,
                     void* ev_start = nullptr, void* ev_stop = nullptr) {
   k.frame0 = frame0;
-  const StreamGeom g = make_geom(k.H, k.W, nframes, rows_per_task);
-  Packed12Loader<CAM16> ld;
+  const Stream2Geom g = make_geom2(k.H, k.W, nframes, rows_per_task);
+  Packed12Loader2<CAM16> ld;
   ld.fp = fp; ld.pitch_words = k.W * 3 / 8; ld.frame0 = frame0;
   int st = B200ISP_OK;
   if (ev_start) cudaEventRecord((cudaEvent_t)ev_start, s);
   ISP_DISPATCH_PATTERN(k.pattern, P, {
-    if constexpr (MODE == MODE_RGB) { EpiRgb<CAM16, OutT> e{fp, k}; st = launch_stream<P>(ld, e, g, s, "isp_stream<rgb>"); }
-    else if constexpr (MODE == MODE_LINEAR) { EpiLinear<CAM16, OutT> e{fp, k}; st = launch_stream<P>(ld, e, g, s, "isp_stream<linear>"); }
-    else if constexpr (MODE == MODE_RMAX) { EpiReinhardMax<CAM16> e{k}; st = launch_stream<P>(ld, e, g, s, "isp_stream<reinhard_max>"); }
-    else { EpiReinhard<CAM16, OutT> e{fp, k}; st = launch_stream<P>(ld, e, g, s, "isp_stream<reinhard>"); }
+    if constexpr (MODE == MODE_RGB) { EpiRgb2<CAM16, OutT> e{fp, k}; st = launch_stream2<P>(ld, e, g, s, "isp_stream<rgb>"); }
+    else if constexpr (MODE == MODE_LINEAR) {
+      bool fast = false;
+      if constexpr (!CAM16) fast = !k.ccm && k.gamma == 1.0f;
+      if constexpr (!CAM16) { if (fast) { EpiLinear2<false, OutT, true> e{fp, k}; st = launch_stream2<P>(ld, e, g, s, "isp_stream<linear,fast>"); } }
+      if (!fast) { EpiLinear2<CAM16, OutT, false> e{fp, k}; st = launch_stream2<P>(ld, e, g, s, "isp_stream<linear>"); }
+    }
+    else if constexpr (MODE == MODE_RMAX) { EpiReinhardMax2<CAM16> e{k}; st = launch_stream2<P>(ld, e, g, s, "isp_stream<reinhard_max>"); }
+    else { EpiReinhard2<CAM16, OutT> e{fp, k}; st = launch_stream2<P>(ld, e, g, s, "isp_stream<reinhard>"); }
   });
   if (ev_stop) cudaEventRecord((cudaEvent_t)ev_stop, s);
-  if (st) return st;
-  Packed12Src<CAM16> src{fp, k.W * 3 / 2};
-  const long long per_frame = border_count(k.H, k.W);
-  const long long total = per_frame * nframes;
-  isp_border_kernel<CAM16, MODE, OutT><<<(unsigned)((total + 255) / 256), 256, 0, s>>>(src, fp, k, nframes, per_frame);
-  return cuda_status(cudaPeekAtLastError(), "isp_border_kernel");
+  return st;     // the 2-pixel image frame is renormalised inside the sweep (border_fix.cuh): no border kernel
 }
 
 // frame-global Reinhard max for frames [frame0, frame0 + nframes): independent of the output dtype,

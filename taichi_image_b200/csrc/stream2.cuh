@@ -1,0 +1,287 @@
+// Second-generation streaming engine: the Malvar-He-Cutler sweep of stream_engine.cuh evaluated with
+// Blackwell's packed FP32 instructions (FFMA2 / FADD2 / FMUL2: two f32 lanes per issue slot).
+//
+// Why: the first engine is instruction-issue bound, not DRAM bound (profiles/r01_stream_kernel_ncu.txt:
+// 41 warp-instructions per 32 pixels, 70 % issue-active, DRAM at 51 %); 24.5 of those 41 are scalar FP32.
+// B200 keeps the FP32 lane rate for the packed forms (profiles/r01_membench.txt: 1.98 FFMA2 vs 3.86 FFMA
+// warp-instructions / clk / SM) but each one takes a single issue slot, so the same math costs half the
+// slots.  Operands that are equal in both lanes are free: ptxas encodes them as an immediate or as a
+// broadcast 32-bit register (`FFMA2 R14, R8.F32x2.HI_LO, 3, R6.F32x2.HI_LO`).
+//
+// Mapping (as before): a thread owns 8 consecutive pixel columns and walks down the image, a warp owns a
+// 256-pixel strip, a task is (frame, row chunk, strip).  New: the 12-column window row is held as eight
+// register PAIRS  P[k] = (v[k], v[k+4]),  k = 0..7  (column c0-2+k in the low lane, c0+2+k in the high
+// lane).  Pixel j (0..3) and pixel j+4 are the same CFA site type, so every partial sum and every filter
+// formula of a row is evaluated once per pair:  48 packed instructions per 8 pixels instead of 94 scalar.
+// Only columns 4..7 are needed in both lanes (4 extra decode LOP3 per row).
+//
+// The filters use the partial sums of stream_engine.cuh (NS, EW, NNSS, EEWW, D).  Signs are folded so no
+// negation is ever needed; the epilogue multiplies by the (signed) SiteScale2 factor anyway:
+//   R/B site:  own = C (x16)   G' = (NNSS+EEWW) - 2(NS+EW) - 4C (x -2)   opposite = 3C + D - 0.75(NNSS+EEWW) (x4)
+//   G site:    G = C (x16)     H' = (D - 5C) - 4EW + EEWW - 0.5NNSS (x -2)   V' likewise with NS / NNSS <-> EW / EEWW
+//
+// Rows are addressed through incrementally advanced pointers; rows outside the image are never zero-filled by
+// predicated loads: the load is clamped to a valid row and the DECODE mask of that row is 0, which yields
+// the "zero sample" (biased 1.0f for Camera32, 0 for Camera16) the border arithmetic needs.  The same trick
+// masks the halo columns of the first / last thread column.  Six full-row buffers rotate with a period of
+// three steps (the loop body is unrolled three times), so no window row is ever copied; the compiler frees
+// the dead pairs of the two oldest rows by itself.
+#pragma once
+#include "stream_engine.cuh"
+
+namespace isp {
+
+// ---------------------------------------------------------------- packed f32x2 helpers (sm_100a)
+typedef unsigned long long f2;
+__device__ __forceinline__ f2 pk(float lo, float hi) { f2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ f2 bc(float x) { return pk(x, x); }
+__device__ __forceinline__ void upk(f2 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ float lo_of(f2 v) { float a, b; upk(v, a, b); return a; }
+__device__ __forceinline__ float hi_of(f2 v) { float a, b; upk(v, a, b); return b; }
+__device__ __forceinline__ f2 add2(f2 a, f2 b) { f2 r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ f2 mul2(f2 a, f2 b) { f2 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ f2 fma2(f2 a, f2 b, f2 c) { f2 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
+__device__ __forceinline__ f2 fma2_rz(f2 a, f2 b, f2 c) { f2 r; asm("fma.rz.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
+__device__ __forceinline__ f2 fma2k(float k, f2 b, f2 c) { return fma2(bc(k), b, c); }   // k equal in both lanes: immediate / broadcast
+
+// (value * scale) = x16 filter sum, per output pair j (pixels j and j+4 of the thread's 8)
+template <bool BROW, bool GFIRST>
+struct SiteScale2 {
+  static __host__ __device__ constexpr bool gsite(int j) { return ((j & 1) == 0) == GFIRST; }
+  static __host__ __device__ constexpr float r(int j) { return gsite(j) ? -2.f : (BROW ? 4.f : 16.f); }
+  static __host__ __device__ constexpr float g(int j) { return gsite(j) ? 16.f : -2.f; }
+  static __host__ __device__ constexpr float b(int j) { return gsite(j) ? -2.f : (BROW ? 16.f : 4.f); }
+};
+
+// One output row.  All rows are full pair rows (index k = pair (column k, column k+4)); of the row two above
+// only pairs 2..5 are read, of the row above and below pairs 1..6, of the row two below pairs 2..5.
+template <bool BROW, bool GFIRST>
+__device__ __forceinline__ void malvar_row2(const f2 (&m2)[8], const f2 (&m1)[8], const f2 (&z)[8], const f2 (&p1)[8],
+                                            const f2 (&p2)[8], f2 (&R)[4], f2 (&G)[4], f2 (&B)[4]) {
+  f2 ns[8];
+#pragma unroll
+  for (int i = 1; i <= 6; ++i) ns[i] = add2(m1[i], p1[i]);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const f2 C = z[j + 2];
+    const f2 EW = add2(z[j + 1], z[j + 3]);
+    const f2 EEWW = add2(z[j], z[j + 4]);
+    const f2 NS = ns[j + 2];
+    const f2 D = add2(ns[j + 1], ns[j + 3]);
+    const f2 NNSS = add2(m2[j + 2], p2[j + 2]);
+    if (!SiteScale2<BROW, GFIRST>::gsite(j)) {
+      const f2 A = add2(NS, EW), Bq = add2(NNSS, EEWW);
+      const f2 gn = fma2k(-4.f, C, fma2k(-2.f, A, Bq));
+      const f2 opp = fma2k(-0.75f, Bq, fma2k(3.f, C, D));
+      G[j] = gn;
+      R[j] = BROW ? opp : C;
+      B[j] = BROW ? C : opp;
+    } else {
+      const f2 Tn = fma2k(-5.f, C, D);
+      const f2 hn = fma2k(-0.5f, NNSS, add2(fma2k(-4.f, EW, Tn), EEWW));
+      const f2 vn = fma2k(-0.5f, EEWW, add2(fma2k(-4.f, NS, Tn), NNSS));
+      G[j] = C;
+      R[j] = BROW ? vn : hn;
+      B[j] = BROW ? hn : vn;
+    }
+  }
+}
+
+// Task kinds.  The image rows 2 .. H-3 are cut into chunks of rows_per_task rows ("interior tasks": no row of
+// their window is ever outside the image); the four border rows of every frame form two extra 2-row tasks per
+// strip.  One warp per task; interior tasks first.  Each kind is its own instantiation of the row loop, chosen
+// by a warp-uniform branch at task start, so the hot loop carries nothing it does not need:
+//   K_CORE     interior rows, strips 1 .. last-1: no frame pixel, no masks, no predicated loads or stores
+//   K_EDGE     interior rows, first / last strip: the first / last thread column owns frame columns and reads
+//              no halo beyond the image; the last strip may be partial
+//   K_GENERAL  any rows (the border tasks; every task when the epilogue declines the fast kinds): rows outside
+//              the image are masked, every pixel is renormalised by its own in-bounds weight sum
+enum { K_CORE = 0, K_EDGE = 1, K_GENERAL = 2 };
+
+// Loader2 concept:
+//   static constexpr uint32_t kRowMask                              decode mask of a row inside the image
+//   struct Raw;  struct Cursor;
+//   template <int KIND> void open(Cursor&, int frame, int tcol, const StreamGeom&)   per-task pointer of row 0 (+ edge masks)
+//   template <int KIND> void fetch(const Cursor&, const P* row_ptr, Raw&)            loads of one (valid) row
+//   void prefetch(const Cursor&, const P* row_ptr)                                   optional L2 prefetch
+//   template <int KIND> void decode(const Cursor&, const Raw&, uint32_t row_mask, f2 (&P)[8])
+//                                                                   row_mask (K_GENERAL only) = 0 -> zero samples
+//   ptrdiff_t pitch() const                                         row pitch in elements of the cursor pointer
+// Epi2 concept:
+//   static constexpr int kStageWords
+//   struct State;  void init(State&, int frame, int tcol, const WarpCtx&);  void finish(State&, int frame, int lane, bool task_ok)
+//   static constexpr bool kSplitEdge                                false: no K_CORE instantiation, interior tasks run K_EDGE
+//   bool fast_kinds_ok(const State&)                                false -> every task runs K_GENERAL
+//   template <bool BROW, bool GFIRST, int KIND> void emit(State&, int row, const f2 (&R)[4], const f2 (&G)[4], const f2 (&B)[4])
+//       scaled filter sums (SiteScale2); out-of-image taps contributed the zero sample; the epilogue renormalises
+//       the frame pixels its KIND can contain (border_fix.cuh).
+
+struct Stream2Geom {
+  StreamGeom g;             // rows_per_task / nchunks describe the INTERIOR rows 2 .. H-3
+  long long interior_tasks; // nframes * nchunks * warps_per_row
+  long long total_tasks;    // + nframes * 2 * warps_per_row
+};
+
+inline Stream2Geom make_geom2(int H, int W, int nframes, int rows_per_task) {
+  Stream2Geom s;
+  s.g = make_geom(H - 4 > 0 ? H - 4 : 0, W, nframes, rows_per_task);      // chunking of the interior rows
+  s.g.H = H;
+  s.interior_tasks = (H > 4) ? s.g.total_tasks : 0;
+  s.total_tasks = s.interior_tasks + (long long)nframes * 2 * s.g.warps_per_row;
+  return s;
+}
+
+#ifndef ISP_S2_THREADS
+#define ISP_S2_THREADS 128      // 4 warps per CTA
+#endif
+#ifndef ISP_S2_MINBLOCKS
+#define ISP_S2_MINBLOCKS 4      // 16 warps / SM at 128 registers (measured: 175 us vs 182 us with 3 blocks / 168 registers on cfg2)
+#endif
+constexpr int kS2Warps = ISP_S2_THREADS / 32;
+
+// rows [r0, rend) of one strip of one frame; r0 even, rend - r0 even
+template <bool BROW0, bool GFIRST0, int KIND, class Loader, class Epi>
+__device__ __forceinline__ void stream2_rows(const Loader& ld, const Epi& epi, typename Epi::State& st, const StreamGeom& g,
+                                             int frame, int tcol, int r0, int rend) {
+  constexpr uint32_t kMask = Loader::kRowMask;
+  constexpr bool MASKED = KIND == K_GENERAL;
+  typename Loader::Cursor cur;
+  ld.template open<KIND>(cur, frame, tcol, g);
+  const ptrdiff_t pitch = ld.pitch();
+
+  // six full pair rows, rotating: step U reads W[(2U+k) % 6], k = 0..5 = rows row-2 .. row+3
+  f2 W[6][8];
+  typename Loader::Raw raw0{}, raw1{};
+
+  // Row pairs (rr, rr+1), rr even, are inside the image together or outside together (H is even); an outside
+  // pair is fetched from the nearest valid pair and (K_GENERAL; the other kinds never use one) decoded with mask 0.
+  auto clamped = [&](int rr) { return min(max(rr, 0), g.H - 2); };
+  auto row_mask = [&](int rr) -> uint32_t { return (!MASKED || (unsigned)rr < (unsigned)g.H) ? kMask : 0u; };
+  {
+    const auto* p = cur.p + (ptrdiff_t)clamped(r0 - 2) * pitch;
+    const uint32_t m = row_mask(r0 - 2);
+    ld.template fetch<KIND>(cur, p, raw0);
+    ld.template fetch<KIND>(cur, p + pitch, raw1);
+    ld.template decode<KIND>(cur, raw0, m, W[0]);
+    ld.template decode<KIND>(cur, raw1, m, W[1]);
+  }
+  {
+    const auto* p = cur.p + (ptrdiff_t)r0 * pitch;
+    ld.template fetch<KIND>(cur, p, raw0);
+    ld.template fetch<KIND>(cur, p + pitch, raw1);
+    ld.template decode<KIND>(cur, raw0, kMask, W[2]);
+    ld.template decode<KIND>(cur, raw1, kMask, W[3]);
+  }
+  // pn / mask describe the pair waiting in raw0 / raw1 (rows row+2, row+3 of the step about to run)
+  const auto* pn = cur.p + (ptrdiff_t)clamped(r0 + 2) * pitch;
+  uint32_t mask = row_mask(r0 + 2);
+  ld.template fetch<KIND>(cur, pn, raw0);
+  ld.template fetch<KIND>(cur, pn + pitch, raw1);
+  ld.prefetch(cur, cur.p + (ptrdiff_t)clamped(r0 + 4) * pitch);
+  ld.prefetch(cur, cur.p + (ptrdiff_t)clamped(r0 + 4) * pitch + pitch);
+
+#define ISP_STEP(U, ROW)                                                                                        \
+  {                                                                                                             \
+    const int row_ = (ROW);                                                                                     \
+    const uint32_t m_ = mask;                                                                                   \
+    ld.template decode<KIND>(cur, raw0, m_, W[(2 * (U) + 4) % 6]);                                              \
+    /* next pair: rows row+4, row+5 (clamped to the last pair when past the image) */                         \
+    const bool in_ = row_ + 4 < g.H;                                                                            \
+    pn += in_ ? 2 * pitch : 0;                                                                                  \
+    if (MASKED) mask = in_ ? kMask : 0u;                                                                        \
+    ld.template fetch<KIND>(cur, pn, raw0);                                                                     \
+    if (row_ + 6 < g.H) ld.prefetch(cur, pn + 2 * pitch);                                                       \
+    f2 R_[4], G_[4], B_[4];                                                                                     \
+    malvar_row2<BROW0, GFIRST0>(W[(2 * (U)) % 6], W[(2 * (U) + 1) % 6], W[(2 * (U) + 2) % 6],                   \
+                                W[(2 * (U) + 3) % 6], W[(2 * (U) + 4) % 6], R_, G_, B_);                        \
+    epi.template emit<BROW0, GFIRST0, KIND>(st, row_, R_, G_, B_);                                              \
+    ld.template decode<KIND>(cur, raw1, m_, W[(2 * (U) + 5) % 6]);                                              \
+    ld.template fetch<KIND>(cur, pn + pitch, raw1);                                                             \
+    if (row_ + 6 < g.H) ld.prefetch(cur, pn + 3 * pitch);                                                       \
+    malvar_row2<!BROW0, !GFIRST0>(W[(2 * (U) + 1) % 6], W[(2 * (U) + 2) % 6], W[(2 * (U) + 3) % 6],             \
+                                  W[(2 * (U) + 4) % 6], W[(2 * (U) + 5) % 6], R_, G_, B_);                      \
+    epi.template emit<!BROW0, !GFIRST0, KIND>(st, row_ + 1, R_, G_, B_);                                        \
+  }
+
+  if constexpr (KIND == K_GENERAL) {
+    // cold kind: one copy of the step, the window slides by register moves
+#pragma unroll 1
+    for (int row = r0; row < rend; row += 2) {
+      ISP_STEP(0, row);
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) W[k][i] = W[k + 2][i];
+    }
+  } else {
+#pragma unroll 1
+    for (int row = r0; row < rend; row += 6) {
+      ISP_STEP(0, row);
+      if (row + 2 >= rend) break;
+      ISP_STEP(1, row + 2);
+      if (row + 4 >= rend) break;
+      ISP_STEP(2, row + 4);
+    }
+  }
+#undef ISP_STEP
+}
+
+template <int PATTERN, class Loader, class Epi>
+__global__ void __launch_bounds__(ISP_S2_THREADS, ISP_S2_MINBLOCKS) stream2_kernel(const Loader ld, const Epi epi, const Stream2Geom sg) {
+  constexpr bool BROW0 = (PATTERN == B200ISP_GBRG || PATTERN == B200ISP_BGGR);
+  constexpr bool GFIRST0 = (PATTERN == B200ISP_GRBG || PATTERN == B200ISP_GBRG);
+  const StreamGeom& g = sg.g;
+  const int lane = threadIdx.x & 31;
+  long long task = (long long)blockIdx.x * kS2Warps + (threadIdx.x >> 5);
+  const bool task_ok = task < sg.total_tasks;
+  if (!task_ok) task = 0;
+  const bool border = task >= sg.interior_tasks;
+  int strip, frame, r0, rend;
+  if (!border) {
+    strip = (int)(task % g.warps_per_row);
+    const long long t2 = task / g.warps_per_row;
+    const int chunk = (int)(t2 % g.nchunks);
+    frame = (int)(t2 / g.nchunks);
+    r0 = 2 + chunk * g.rows_per_task;
+    rend = min(r0 + g.rows_per_task, g.H - 2);
+  } else {
+    const long long t = task - sg.interior_tasks;
+    strip = (int)(t % g.warps_per_row);
+    const long long t2 = t / g.warps_per_row;
+    frame = (int)(t2 >> 1);
+    r0 = (t2 & 1) ? g.H - 2 : 0;
+    rend = r0 + 2;
+  }
+  const int tcol = min(strip * 32 + lane, g.ntcols - 1);   // lanes past the last column recompute it (never stored)
+
+  __shared__ __align__(16) uint32_t stage[kS2Warps][Epi::kStageWords > 0 ? Epi::kStageWords : 1];
+  WarpCtx wc;
+  wc.lane = lane;
+  wc.tcol0 = strip * 32;
+  wc.nvalid = min(32, g.ntcols - strip * 32);
+  wc.stage = stage[threadIdx.x >> 5];
+
+  typename Epi::State st;
+  epi.init(st, frame, tcol, wc);
+  if (task_ok) {
+    // Epi::kSplitEdge = false: the epilogue does not want a separate K_CORE copy of the loop (K_EDGE covers it)
+    const int kind = (border || !epi.fast_kinds_ok(st)) ? K_GENERAL
+                     : ((!Epi::kSplitEdge || strip == 0 || strip == g.warps_per_row - 1) ? K_EDGE : K_CORE);
+    if constexpr (Epi::kSplitEdge) {
+      if (kind == K_CORE) stream2_rows<BROW0, GFIRST0, K_CORE>(ld, epi, st, g, frame, tcol, r0, rend);
+    }
+    if (kind == K_EDGE) stream2_rows<BROW0, GFIRST0, K_EDGE>(ld, epi, st, g, frame, tcol, r0, rend);
+    else if (kind == K_GENERAL) stream2_rows<BROW0, GFIRST0, K_GENERAL>(ld, epi, st, g, frame, tcol, r0, rend);
+  }
+  epi.finish(st, frame, lane, task_ok);
+}
+
+template <int PATTERN, class Loader, class Epi>
+inline int launch_stream2(const Loader& ld, const Epi& epi, const Stream2Geom& sg, cudaStream_t s, const char* what) {
+  if (sg.total_tasks == 0) return B200ISP_OK;
+  const long long blocks = (sg.total_tasks + kS2Warps - 1) / kS2Warps;
+  stream2_kernel<PATTERN, Loader, Epi><<<(unsigned)blocks, ISP_S2_THREADS, 0, s>>>(ld, epi, sg);
+  return cuda_status(cudaPeekAtLastError(), what);
+}
+
+}  // namespace isp

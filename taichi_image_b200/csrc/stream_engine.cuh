@@ -160,7 +160,7 @@ struct WarpCtx {
   uint32_t* stage;      // this warp's staging buffer, Epi::kStageWords words
 };
 
-template <int NW>
+template <int NW, bool FULL = false>       // FULL: all 32 lanes map to real thread columns (no store predicates)
 __device__ __forceinline__ void warp_store_row(const WarpCtx& wc, void* row_dst /* warp's first byte of the row */,
                                                const uint32_t (&w)[NW]) {
   constexpr int CW = (NW % 4 == 0) ? 4 : 2;     // words per chunk
@@ -176,7 +176,7 @@ __device__ __forceinline__ void warp_store_row(const WarpCtx& wc, void* row_dst 
 #pragma unroll
     for (int i = 0; i < PER_LANE; ++i) {
       const int idx = i * 32 + wc.lane;
-      if (idx < nchunks) d[idx] = s[idx];
+      if (FULL || idx < nchunks) d[idx] = s[idx];
     }
   } else {
     uint2* s = reinterpret_cast<uint2*>(wc.stage);
@@ -187,7 +187,7 @@ __device__ __forceinline__ void warp_store_row(const WarpCtx& wc, void* row_dst 
 #pragma unroll
     for (int i = 0; i < PER_LANE; ++i) {
       const int idx = i * 32 + wc.lane;
-      if (idx < nchunks) d[idx] = s[idx];
+      if (FULL || idx < nchunks) d[idx] = s[idx];
     }
   }
 }
