@@ -2,6 +2,7 @@
 # bench cfg2 (and optionally others) with every experimental library under variants/ plus the product build
 mkdir -p gpurun_out
 if [ "$RUN_TESTS" = "1" ]; then python -m pytest tests -m gpu -q -x > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?"; tail -3 gpurun_out/pytest_gpu.log; fi
+shopt -s nullglob
 for lib in default variants/*.so; do
   for wl in ${WORKLOADS:-cfg2}; do
     if [ "$lib" = "default" ]; then unset B200ISP_LIB; else export B200ISP_LIB=$PWD/$lib; fi

@@ -643,15 +643,17 @@ struct Packed12Sampler {
 
 // stride % 8 == 0 (the default 8): a sample is pixel 0 of thread column col/8 of the streaming kernel.
 // It reads nine 32-bit words (1/2/3/2/1 over the five rows; consecutive samples of a row are 12 bytes
-// apart, so a warp's loads are contiguous) and evaluates exactly the partial-sum formulas of
-// malvar_row + isp_rgb_fast, i.e. the very value the sweep will produce for that pixel.  Samples on the
-// 2-pixel image frame (row 0, column 0) take the literal border path.
+// apart, so a warp's loads are contiguous) and evaluates exactly the partial-sum formulas of the sweep,
+// i.e. the very value the sweep will produce for that pixel -- including the samples on the 2-pixel image
+// frame (row 0 / column 0), which use the same zero-sample + renormalisation scheme (border_fix.cuh).
 template <bool CAM16>
 struct Packed12FastSampler {
   Packed12Src<CAM16> src;
   IspConsts k;
   int stride, hs, ws_;
   int pitch_words;
+
+  static constexpr bool kRowStructured = true;
 
   static __device__ __forceinline__ float dec(uint32_t shifted) {
     const float b = __uint_as_float((shifted & 0x007FF800u) | 0x3F800000u);      // 1 + v/4096
@@ -663,22 +665,10 @@ struct Packed12FastSampler {
     }
   }
 
-  __device__ __forceinline__ void sample(long long idx, float (&rgb)[3]) const {
-    const int j = (int)(idx % ws_);
-    const long long q = idx / ws_;
-    const int i = (int)(q % hs);
-    const int f = (int)(q / hs);
-    const int row = i * stride, col = j * stride;
-    if (row < 2 || row >= k.H - 2 || col < 2 || col >= k.W - 2) {
-      isp_rgb_pixel<CAM16>(src, k, f, row, col, rgb);
-      return;
-    }
-    const uint32_t* p = reinterpret_cast<const uint32_t*>(src.fp.in[f]) + (size_t)row * pitch_words + 3 * (col >> 3);
-    const uint32_t a0 = __ldg(p - 2 * pitch_words);                                   // row-2: col
-    const uint32_t bm = __ldg(p - pitch_words - 1), b0 = __ldg(p - pitch_words);      // row-1: col-1..col+1
-    const uint32_t cm = __ldg(p - 1), c0 = __ldg(p), c1 = __ldg(p + 1);               // row  : col-2..col+2
-    const uint32_t dm = __ldg(p + pitch_words - 1), d0 = __ldg(p + pitch_words);      // row+1
-    const uint32_t e0 = __ldg(p + 2 * pitch_words);                                   // row+2
+  // the nine words of a sample -> scaled filter sums S (S * sc = x16 sum) of the three channels
+  __device__ __forceinline__ void sums_from_words(uint32_t a0, uint32_t bm, uint32_t b0, uint32_t cm, uint32_t c0, uint32_t c1,
+                                                  uint32_t dm, uint32_t d0, uint32_t e0, int row, float (&S)[3], float (&sc)[3],
+                                                  bool& brow, bool& gsite) const {
     // pixel col-2 = bits 8..19 of word -1, col-1 = bits 20..31; col = bits 0..11 of word 0, col+1 = bits 12..23,
     // col+2 = bits 24..35 of (word 1 : word 0)
     const float C = dec(c0 << 11);
@@ -689,23 +679,122 @@ struct Packed12FastSampler {
     const float NNSS = dec(a0 << 11) + dec(e0 << 11);
     const bool brow0 = (k.pattern == B200ISP_GBRG || k.pattern == B200ISP_BGGR);
     const bool gfirst0 = (k.pattern == B200ISP_GRBG || k.pattern == B200ISP_GBRG);
-    const bool brow = brow0 != ((row & 1) != 0), gsite = gfirst0 != ((row & 1) != 0);
-    float R, G, B, cr, cg, cb;
+    brow = brow0 != ((row & 1) != 0);
+    gsite = gfirst0 != ((row & 1) != 0);
     if (!gsite) {
       float g2, opp4;
       malvar_csite(C, NS, EW, NNSS, EEWW, D, g2, opp4);
-      G = g2; cg = 2.f;
-      R = brow ? opp4 : C; cr = brow ? 4.f : 16.f;
-      B = brow ? C : opp4; cb = brow ? 16.f : 4.f;
+      S[1] = g2; sc[1] = 2.f;
+      S[0] = brow ? opp4 : C; sc[0] = brow ? 4.f : 16.f;
+      S[2] = brow ? C : opp4; sc[2] = brow ? 16.f : 4.f;
     } else {
       float h2, v2;
       malvar_gsite(C, NS, EW, NNSS, EEWW, D, h2, v2);
-      G = C; cg = 16.f;
-      R = brow ? v2 : h2; cr = 2.f;
-      B = brow ? h2 : v2; cb = 2.f;
+      S[1] = C; sc[1] = 16.f;
+      S[0] = brow ? v2 : h2; sc[0] = 2.f;
+      S[2] = brow ? h2 : v2; sc[2] = 2.f;
     }
-    if (k.ccm) isp_rgb_fast<CAM16, true>(k, R, G, B, cr, cg, cb, rgb);
-    else isp_rgb_fast<CAM16, false>(k, R, G, B, cr, cg, cb, rgb);
+  }
+
+  // interior sample: p = word of pixel (row, col) (col % 8 == 0)
+  __device__ __forceinline__ void sample_fast(const uint32_t* p, int row, float (&rgb)[3]) const {
+    const uint32_t a0 = __ldg(p - 2 * pitch_words);                                   // row-2: col
+    const uint32_t bm = __ldg(p - pitch_words - 1), b0 = __ldg(p - pitch_words);      // row-1: col-1..col+1
+    const uint32_t cm = __ldg(p - 1), c0 = __ldg(p), c1 = __ldg(p + 1);               // row  : col-2..col+2
+    const uint32_t dm = __ldg(p + pitch_words - 1), d0 = __ldg(p + pitch_words);      // row+1
+    const uint32_t e0 = __ldg(p + 2 * pitch_words);                                   // row+2
+    float S[3], sc[3];
+    bool brow, gsite;
+    sums_from_words(a0, bm, b0, cm, c0, c1, dm, d0, e0, row, S, sc, brow, gsite);
+    if (k.ccm) isp_rgb_fast<CAM16, true>(k, S[0], S[1], S[2], sc[0], sc[1], sc[2], rgb);
+    else isp_rgb_fast<CAM16, false>(k, S[0], S[1], S[2], sc[0], sc[1], sc[2], rgb);
+  }
+
+  // sample on the image frame: the words outside the image are replaced by 0 (-> zero samples) and the raw
+  // values are renormalised by the in-bounds weight sum of the pixel's (row class, column class)
+  __device__ __forceinline__ void sample_frame(int f, int row, int col, float (&rgb)[3]) const {
+    const uint32_t* p = reinterpret_cast<const uint32_t*>(src.fp.in[f]) + (size_t)row * pitch_words + 3 * (col >> 3);
+    const bool m2 = row >= 2, m1 = row >= 1, p1 = row + 1 < k.H, p2 = row + 2 < k.H, cl = col >= 2;
+    const uint32_t a0 = m2 ? __ldg(p - 2 * pitch_words) : 0u;
+    const uint32_t bm = (m1 && cl) ? __ldg(p - pitch_words - 1) : 0u, b0 = m1 ? __ldg(p - pitch_words) : 0u;
+    const uint32_t cm = cl ? __ldg(p - 1) : 0u, c0 = __ldg(p), c1 = __ldg(p + 1);
+    const uint32_t dm = (p1 && cl) ? __ldg(p + pitch_words - 1) : 0u, d0 = p1 ? __ldg(p + pitch_words) : 0u;
+    const uint32_t e0 = p2 ? __ldg(p + 2 * pitch_words) : 0u;
+    float S[3], sc[3];
+    bool brow, gsite;
+    sums_from_words(a0, bm, b0, cm, c0, c1, dm, d0, e0, row, S, sc, brow, gsite);
+    const float* t = c_border.t[site_kernel_of(brow, gsite)][edge_class(row, k.H)][edge_class(col, k.W)];
+    constexpr float kn = 256.f * kInv4095;
+    float x[3];
+#pragma unroll
+    for (int ch = 0; ch < 3; ++ch) x[ch] = frame_exact(CAM16 ? S[ch] * (sc[ch] * 0.0625f) : fmaf(S[ch], sc[ch] * kn, -16.f * kn), t[ch]);
+    if (k.ccm) ccm_apply(k.m, x[0], x[1], x[2]);
+    rgb[0] = round_isp<CAM16>(clamp01(x[0])); rgb[1] = round_isp<CAM16>(clamp01(x[1])); rgb[2] = round_isp<CAM16>(clamp01(x[2]));
+  }
+
+  __device__ __forceinline__ bool on_frame(int row, int col) const { return row < 2 || row >= k.H - 2 || col < 2 || col >= k.W - 2; }
+
+  __device__ __forceinline__ void sample(long long idx, float (&rgb)[3]) const {
+    const int j = (int)(idx % ws_);
+    const long long q = idx / ws_;
+    const int i = (int)(q % hs);
+    const int f = (int)(q / hs);
+    const int row = i * stride, col = j * stride;
+    if (on_frame(row, col)) sample_frame(f, row, col, rgb);
+    else sample_fast(reinterpret_cast<const uint32_t*>(src.fp.in[f]) + (size_t)row * pitch_words + 3 * (col >> 3), row, rgb);
+  }
+
+  // Pass A -- interior samples.  A warp task = 128 consecutive samples of one interior sample row: lanes take
+  // consecutive samples (12 bytes apart, so the warp's loads are contiguous), four per lane.  The loop body is
+  // branch-free (a lane without a sample of its own -- past the row end, or the frame column j = 0 -- reloads a
+  // valid neighbour and drops the result), so all 36 loads of a lane are in flight together.
+  // Pass B -- the samples on the image frame (sample row 0 and sample column 0; a few thousand): one per thread.
+  template <class F>
+  __device__ __forceinline__ void for_each(long long n, F&& f) const {
+    const int nrows = (int)(n / ws_), nframes = nrows / hs;
+    const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+    const int wstep = stride >> 3;                       // thread columns (3 words) between samples
+    // interior sample rows: i in [i_lo, i_hi); interior sample columns: j in [j_lo, j_hi)
+    const int i_lo = (2 + stride - 1) / stride, i_hi = min(hs, (k.H - 3) / stride + 1);
+    const int j_lo = (2 + stride - 1) / stride, j_hi = min(ws_, (k.W - 3) / stride + 1);
+    const int rows_in = max(i_hi - i_lo, 0), cols_in = max(j_hi - j_lo, 0);
+    const int nseg = (cols_in + 32 * kMeterUnroll - 1) / (32 * kMeterUnroll);
+    const int ntasks = nframes * rows_in * nseg;
+    for (int task = blockIdx.x * wpb + (threadIdx.x >> 5); task < ntasks; task += gridDim.x * wpb) {
+      const int rt = task / nseg, seg = task - rt * nseg;
+      const int fr = rt / rows_in, i = i_lo + (rt - fr * rows_in);
+      const int row = i * stride;
+      const unsigned base = (unsigned)((fr * hs + i) * ws_);
+      const uint32_t* prow = reinterpret_cast<const uint32_t*>(src.fp.in[fr]) + (size_t)row * pitch_words;
+      const int j0 = j_lo + seg * 32 * kMeterUnroll + lane;
+      float rgb[kMeterUnroll][3];
+#pragma unroll
+      for (int u = 0; u < kMeterUnroll; ++u) sample_fast(prow + 3 * wstep * min(j0 + 32 * u, j_hi - 1), row, rgb[u]);
+#pragma unroll
+      for (int u = 0; u < kMeterUnroll; ++u)
+        if (j0 + 32 * u < j_hi) f((long long)(base + (unsigned)(j0 + 32 * u)), rgb[u]);
+    }
+    // frame samples: per frame, (hs - rows_in) whole sample rows + (ws_ - cols_in) columns of the interior rows
+    const int frame_rows = hs - rows_in, frame_cols = ws_ - cols_in;
+    const int per_frame = frame_rows * ws_ + rows_in * frame_cols;
+    const int total = nframes * per_frame;
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
+      const int fr = t / per_frame;
+      int r = t - fr * per_frame, i, j;
+      if (r < frame_rows * ws_) {
+        const int ri = r / ws_;
+        j = r - ri * ws_;
+        i = ri < i_lo ? ri : i_hi + (ri - i_lo);                  // sample rows before / after the interior band
+      } else {
+        r -= frame_rows * ws_;
+        const int ii = r / frame_cols, cj = r - ii * frame_cols;
+        i = i_lo + ii;
+        j = cj < j_lo ? cj : j_hi + (cj - j_lo);
+      }
+      float rgb[3];
+      sample_frame(fr, i * stride, j * stride, rgb);
+      f((long long)((fr * hs + i) * ws_ + j), rgb);
+    }
   }
 };
 

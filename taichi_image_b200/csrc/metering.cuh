@@ -17,6 +17,33 @@ namespace isp {
 // Sampler concept:  __device__ void sample(long long idx, float (&rgb)[3]) const;   idx in [0, n)
 //                   rgb as stored by the ISP (already rounded through the ISP dtype).
 
+// ---------------------------------------------------------------- sample iteration
+// for_each_sample(smp, n, f): calls f(idx, rgb) for this thread's share of the n samples.  Samplers that define
+// kRowStructured iterate themselves (Packed12FastSampler: a warp walks sample rows, no index division per
+// sample); the others take a flat grid-stride loop unrolled by 4 so that several samples' loads are in flight.
+constexpr int kMeterUnroll = 4;
+
+template <class Sampler, class = void> struct is_row_structured { static constexpr bool value = false; };
+template <class Sampler> struct is_row_structured<Sampler, std::enable_if_t<Sampler::kRowStructured>> { static constexpr bool value = true; };
+
+template <class Sampler, class F>
+__device__ __forceinline__ void for_each_sample(const Sampler& smp, long long n, F&& f) {
+  if constexpr (is_row_structured<Sampler>::value) {
+    smp.for_each(n, f);
+  } else {
+    // n < 2^31 / 3 always (<= 64 frames of <= 2^24 samples): 32-bit index arithmetic
+    const unsigned T = gridDim.x * blockDim.x, n32 = (unsigned)n;
+    for (unsigned i0 = blockIdx.x * blockDim.x + threadIdx.x; i0 < n32; i0 += T * kMeterUnroll) {
+      float rgb[kMeterUnroll][3];
+#pragma unroll
+      for (int u = 0; u < kMeterUnroll; ++u) smp.sample((long long)min(i0 + u * T, n32 - 1), rgb[u]);   // clamped: branch-free loads
+#pragma unroll
+      for (int u = 0; u < kMeterUnroll; ++u)
+        if (i0 + u * T < n32) f((long long)(i0 + u * T), rgb[u]);
+    }
+  }
+}
+
 template <int NV>
 __device__ __forceinline__ void block_fold(float (&v)[NV], const int (&op)[NV], float* smem /* [8][NV] */) {
   // op: 0 = min, 1 = max, 2 = sum
@@ -61,13 +88,11 @@ __global__ void __launch_bounds__(256) meter_phase1_kernel(const Sampler smp, lo
                                                            float* __restrict__ rec_out = nullptr /* shared exposure: raw {min,max} */) {
   __shared__ float smem[8 * 2];
   float v[2] = {INFINITY, -INFINITY};
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-    float rgb[3];
-    smp.sample(i, rgb);
-    if (cache) { cache[3 * i] = rgb[0]; cache[3 * i + 1] = rgb[1]; cache[3 * i + 2] = rgb[2]; }
+  for_each_sample(smp, n, [&](long long i, const float (&rgb)[3]) {
+    if (cache) { const unsigned o = 3u * (unsigned)i; cache[o] = rgb[0]; cache[o + 1] = rgb[1]; cache[o + 2] = rgb[2]; }
     v[0] = fminf(v[0], fminf(rgb[0], fminf(rgb[1], rgb[2])));
     v[1] = fmaxf(v[1], fmaxf(rgb[0], fmaxf(rgb[1], rgb[2])));
-  }
+  });
   const int op[2] = {0, 1};
   block_fold<2>(v, op, smem);
   if (threadIdx.x == 0) {
@@ -93,26 +118,29 @@ __global__ void __launch_bounds__(256) meter_phase1_kernel(const Sampler smp, lo
   }
 }
 
+// camera_isp.py:119-128 for one sample.  The reference divides by (max - min + 1e-6); here the reciprocal is
+// taken once (IEEE) and multiplied, and the logarithm is the hardware lg2 -- both far inside what the
+// reference's own unordered float atomics and fast-math build leave defined (~1e-6 relative).
+__device__ __forceinline__ void meter_accum(const float (&rgb)[3], float bmin, float inv_den, float (&v)[7]) {
+  const float r = __fmul_rn(__fsub_rn(rgb[0], bmin), inv_den);
+  const float g = __fmul_rn(__fsub_rn(rgb[1], bmin), inv_den);
+  const float b = __fmul_rn(__fsub_rn(rgb[2], bmin), inv_den);
+  const float gray = rgb_gray(r, g, b);
+  const float lg = __logf(fmaxf(gray, 1e-4f));
+  v[0] = fminf(v[0], lg);
+  v[1] = fmaxf(v[1], lg);
+  v[2] += lg; v[3] += gray; v[4] += r; v[5] += g; v[6] += b;
+}
+
 template <class Sampler>
 __global__ void __launch_bounds__(256) meter_phase2_kernel(const Sampler smp, long long n, float alpha,
                                                            float* __restrict__ metrics, Workspace* ws,
                                                            float* __restrict__ rec_out = nullptr /* shared exposure: raw record 2 */) {
   __shared__ float smem[8 * 7];
   const float bmin = __ldcg(&ws->bounds[0]), bmax = __ldcg(&ws->bounds[1]);
-  const float den = __fadd_rn(__fsub_rn(bmax, bmin), 1e-6f);
+  const float inv_den = __fdiv_rn(1.0f, __fadd_rn(__fsub_rn(bmax, bmin), 1e-6f));
   float v[7] = {INFINITY, -INFINITY, 0.f, 0.f, 0.f, 0.f, 0.f};
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-    float rgb[3];
-    smp.sample(i, rgb);
-    const float r = __fdiv_rn(__fsub_rn(rgb[0], bmin), den);
-    const float g = __fdiv_rn(__fsub_rn(rgb[1], bmin), den);
-    const float b = __fdiv_rn(__fsub_rn(rgb[2], bmin), den);
-    const float gray = rgb_gray(r, g, b);
-    const float lg = logf(fmaxf(gray, 1e-4f));
-    v[0] = fminf(v[0], lg);
-    v[1] = fmaxf(v[1], lg);
-    v[2] += lg; v[3] += gray; v[4] += r; v[5] += g; v[6] += b;
-  }
+  for_each_sample(smp, n, [&](long long, const float (&rgb)[3]) { meter_accum(rgb, bmin, inv_den, v); });
   const int op[7] = {0, 1, 2, 2, 2, 2, 2};
   block_fold<7>(v, op, smem);
   if (threadIdx.x == 0) {
@@ -181,6 +209,112 @@ static __global__ void meter_finalize_kernel(const float* __restrict__ g1, const
   }
 }
 
+// samples cached by phase 1 (3 floats each), read back coalesced by phase 2
+struct CachedSampler {
+  const float* cache;
+  __device__ __forceinline__ void sample(long long idx, float (&rgb)[3]) const {
+    const unsigned o = 3u * (unsigned)idx;
+    rgb[0] = __ldcg(cache + o); rgb[1] = __ldcg(cache + o + 1); rgb[2] = __ldcg(cache + o + 2);
+  }
+};
+
+// ---------------------------------------------------------------- both phases in ONE cooperative launch
+// The grid is launched with cudaLaunchCooperativeKernel (all CTAs co-resident), so the dependency between the
+// phases -- every sample's min / max before any sample's log-luminance -- is a grid barrier instead of a
+// kernel boundary: one launch, one tail, and phase 2 re-reads the samples phase 1 just wrote while they are
+// still in L2 (22 MB at cfg2).  Sample loops are unrolled by 4 so that the nine loads of several samples are
+// in flight together.  Phase-2 partials use the upper half of the partial table: a fast CTA may already be
+// writing them while a slow one still folds the phase-1 entries.
+__device__ __forceinline__ unsigned int ld_acquire_gpu(const unsigned int* p) {
+  unsigned int v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+__device__ __forceinline__ void grid_barrier(unsigned int* counter) {     // cooperative launch only
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    atomicAdd(counter, 1u);
+    while (ld_acquire_gpu(counter) < gridDim.x) __nanosleep(32);
+    __threadfence();
+  }
+  __syncthreads();
+}
+
+template <class Sampler>
+__global__ void __launch_bounds__(256) meter_fused_kernel(const Sampler smp, long long n, float alpha, float* __restrict__ metrics,
+                                                          Workspace* ws, float* __restrict__ cache /* n*3 floats or null */) {
+  __shared__ float smem[8 * 7];
+  __shared__ float s_bounds[2];
+  float* part2 = ws->partials + (kMaxPartialBlocks / 2) * kPartialStride;
+
+  // ---- phase 1: min / max of every sampled value
+  float v2[2] = {INFINITY, -INFINITY};
+  for_each_sample(smp, n, [&](long long i, const float (&rgb)[3]) {
+    if (cache) { const unsigned o = 3u * (unsigned)i; cache[o] = rgb[0]; cache[o + 1] = rgb[1]; cache[o + 2] = rgb[2]; }
+    v2[0] = fminf(v2[0], fminf(rgb[0], fminf(rgb[1], rgb[2])));
+    v2[1] = fmaxf(v2[1], fmaxf(rgb[0], fmaxf(rgb[1], rgb[2])));
+  });
+  const int op2[2] = {0, 1};
+  block_fold<2>(v2, op2, smem);
+  if (threadIdx.x == 0) {
+    ws->partials[blockIdx.x * kPartialStride + 0] = v2[0];
+    ws->partials[blockIdx.x * kPartialStride + 1] = v2[1];
+  }
+  grid_barrier(&ws->counter[1]);
+
+  // ---- every CTA folds the partials in the same order -> identical blended bounds everywhere
+  {
+    float f[2] = {INFINITY, -INFINITY};
+    for (int b = threadIdx.x; b < (int)gridDim.x; b += blockDim.x) {
+      f[0] = fminf(f[0], __ldcg(&ws->partials[b * kPartialStride + 0]));
+      f[1] = fmaxf(f[1], __ldcg(&ws->partials[b * kPartialStride + 1]));
+    }
+    block_fold<2>(f, op2, smem);
+    if (threadIdx.x == 0) {                                               // camera_isp.py:156
+      s_bounds[0] = __fadd_rn(f[0], __fmul_rn(alpha, __fsub_rn(metrics[0], f[0])));
+      s_bounds[1] = __fadd_rn(f[1], __fmul_rn(alpha, __fsub_rn(metrics[1], f[1])));
+    }
+    __syncthreads();
+  }
+  const float bmin = s_bounds[0], bmax = s_bounds[1];
+  const float inv_den = __fdiv_rn(1.0f, __fadd_rn(__fsub_rn(bmax, bmin), 1e-6f));
+
+  // ---- phase 2: statistics w.r.t. the blended bounds (samples from the L2-resident cache, else recomputed)
+  float v[7] = {INFINITY, -INFINITY, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if (cache) for_each_sample(CachedSampler{cache}, n, [&](long long, const float (&rgb)[3]) { meter_accum(rgb, bmin, inv_den, v); });
+  else for_each_sample(smp, n, [&](long long, const float (&rgb)[3]) { meter_accum(rgb, bmin, inv_den, v); });
+  const int op[7] = {0, 1, 2, 2, 2, 2, 2};
+  block_fold<7>(v, op, smem);
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int k = 0; k < 7; ++k) part2[blockIdx.x * kPartialStride + k] = v[k];
+  }
+  if (last_block_ticket(&ws->counter[0])) {
+    float f[7] = {INFINITY, -INFINITY, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int b = threadIdx.x; b < (int)gridDim.x; b += blockDim.x) {
+      f[0] = fminf(f[0], __ldcg(&part2[b * kPartialStride + 0]));
+      f[1] = fmaxf(f[1], __ldcg(&part2[b * kPartialStride + 1]));
+#pragma unroll
+      for (int k = 2; k < 7; ++k) f[k] += __ldcg(&part2[b * kPartialStride + k]);
+    }
+    block_fold<7>(f, op, smem);
+    if (threadIdx.x == 0) {
+      ws->counter[1] = 0u;                                                // barrier counter back to zero for the next launch
+      ws->bounds[0] = bmin; ws->bounds[1] = bmax;
+      const float fn = (float)n;                                          // camera_isp.py:131-134
+      const float stats[9] = {bmin, bmax, f[0], f[1], __fdiv_rn(f[2], fn), __fdiv_rn(f[3], fn),
+                              __fdiv_rn(f[4], fn), __fdiv_rn(f[5], fn), __fdiv_rn(f[6], fn)};
+#pragma unroll
+      for (int k = 0; k < 9; ++k) {                                       // camera_isp.py:165-166
+        const float p = metrics[k];
+        metrics[k] = __fadd_rn(stats[k], __fmul_rn(alpha, __fsub_rn(p, stats[k])));
+      }
+    }
+  }
+}
+
 inline int meter_grid(long long n) {
   long long b = (n + 256 * 4 - 1) / (256 * 4);
   if (b < 1) b = 1;
@@ -188,19 +322,26 @@ inline int meter_grid(long long n) {
   return (int)b;
 }
 
-// samples cached by phase 1 (3 floats each), read back coalesced by phase 2
-struct CachedSampler {
-  const float* cache;
-  __device__ __forceinline__ void sample(long long idx, float (&rgb)[3]) const {
-    rgb[0] = __ldcg(cache + 3 * idx); rgb[1] = __ldcg(cache + 3 * idx + 1); rgb[2] = __ldcg(cache + 3 * idx + 2);
-  }
-};
-
 // cache: optional device scratch of n*3 floats -- phase 2 then re-reads the phase-1 samples instead of
 // recomputing them (the samples are identical either way).
 template <class Sampler>
 inline int launch_metering(const Sampler& smp, long long n, float alpha, float* metrics, Workspace* ws, cudaStream_t s,
                            float* cache = nullptr) {
+  // one cooperative launch when the device can keep the whole grid resident (it always can: the grid is sized
+  // from the occupancy of this very kernel), two dependent launches otherwise
+  int dev = 0, sms = 0, per_sm = 0, coop = 0;
+  if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev) == cudaSuccess && coop &&
+      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess &&
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, meter_fused_kernel<Sampler>, 256, 0) == cudaSuccess && per_sm > 0) {
+    long long want = (n + 256 * kMeterUnroll - 1) / (256 * kMeterUnroll);
+    long long cap = (long long)per_sm * sms;
+    if (cap > kMaxPartialBlocks / 2) cap = kMaxPartialBlocks / 2;
+    int grid = (int)(want < 1 ? 1 : (want > cap ? cap : want));
+    void* args[] = {(void*)&smp, (void*)&n, (void*)&alpha, (void*)&metrics, (void*)&ws, (void*)&cache};
+    const cudaError_t e = cudaLaunchCooperativeKernel((const void*)meter_fused_kernel<Sampler>, dim3(grid), dim3(256), args, 0, s);
+    if (e == cudaSuccess) return B200ISP_OK;
+    (void)cudaGetLastError();         // fall through to the two-launch form
+  }
   const int grid = meter_grid(n);
   meter_phase1_kernel<Sampler><<<grid, 256, 0, s>>>(smp, n, alpha, metrics, ws, cache);
   int st = cuda_status(cudaPeekAtLastError(), "meter_phase1_kernel");
