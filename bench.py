@@ -189,6 +189,8 @@ def main():
     ap.add_argument("--shared-exposure", type=int, default=-1, help="all-reduce the metering statistics across ranks (default: on for N > 1)")
     ap.add_argument("--rows-per-task", type=int, default=0)
     ap.add_argument("--e2e-steps", type=int, default=0, help="steps of the host-buffer pipeline leg (default: min(steps, 12))")
+    ap.add_argument("--lookahead", type=int, default=1, help="announce the next batch so its metering (and exposure exchange) "
+                    "runs on a side stream under this batch's sweep (camera-stream mode; 0 = strictly serial steps)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -224,7 +226,7 @@ def main():
 
     def step(events=None):
         isp.process_packed12(frames, tonemap=tonemap, dtype=out_dt, out=outs, rows_per_task=args.rows_per_task,
-                             profile_events=events, **tm)
+                             profile_events=events, lookahead=frames if args.lookahead else None, **tm)
 
     for _ in range(max(args.warmup, 3)):
         step()
@@ -269,6 +271,8 @@ def main():
         launches = 2 + 2
     if shared and world > 1:
         launches += 2
+    if args.lookahead and not (shared and world > 1):
+        launches += 1          # look-ahead metering runs as two ordinary launches instead of one cooperative launch
 
     # ---------------- end to end through the public API with host buffers
     e2e = None
@@ -317,7 +321,7 @@ def main():
         "warmup": max(args.warmup, 3), "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": isp_dt, "data": "synthetic",
         "config": {"workload": desc, "frames_per_gpu": n, "height": h, "width": w, "tonemap": tonemap, "out_dtype": out_dt,
-                   "shared_exposure": bool(shared and world > 1),
+                   "shared_exposure": bool(shared and world > 1), "lookahead_metering": bool(args.lookahead),
                    "l2": f"inputs+outputs per step = {alg_bytes / 1e6:.0f} MB > 126 MB L2 (no flush needed)" if alg_bytes > 200e6
                          else "per-step working set fits L2: inputs are re-read from L2 between steps (stated, not flushed)"},
         "clocks": clocks,

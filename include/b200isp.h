@@ -172,7 +172,8 @@ int b200isp_process_packed12(const uint8_t* const* packed_host, void* const* out
  *   record 2 (8 floats): {log_min, log_max, sum_log, sum_gray, sum_r, sum_g, sum_b, n_samples}
  *   phase1  -> rec1;  all_gather -> gathered1 [world][2]
  *   phase2(gathered1, alpha, metrics_prev) -> rec2 w.r.t. the blended joint bounds;  all_gather -> gathered2 [world][8]
- *   finalize(gathered1, gathered2, alpha) -> metrics = lerp(alpha, joint stats, metrics)
+ *   finalize(gathered1, gathered2, alpha, prev) -> metrics_out = lerp(alpha, joint stats, metrics_prev)
+ *                                                  (metrics_out may be the same buffer as metrics_prev)
  * With world == 1 the three calls equal b200isp_metering_update. */
 #define B200ISP_REC1 2
 #define B200ISP_REC2 8
@@ -182,7 +183,7 @@ int b200isp_metering_phase2(const void* const* images_host, int n_images, int dt
                             int stride, const float* gathered1, int world, float alpha,
                             const float* metrics_prev, float* rec2, void* workspace, b200isp_stream stream);
 int b200isp_metering_finalize(const float* gathered1, const float* gathered2, int world, float alpha,
-                              float* metrics, b200isp_stream stream);
+                              const float* metrics_prev, float* metrics_out, b200isp_stream stream);
 /* the same two phases straight from packed12 frames (the sampler of b200isp_process_packed12);
  * params->alpha, metering_stride, meter_cache as in the fused call. */
 int b200isp_meter_packed12_phase1(const uint8_t* const* packed_host, int n_frames,
@@ -191,6 +192,16 @@ int b200isp_meter_packed12_phase1(const uint8_t* const* packed_host, int n_frame
 int b200isp_meter_packed12_phase2(const uint8_t* const* packed_host, int n_frames,
                                   const b200isp_fused_params* params, const float* gathered1, int world,
                                   const float* metrics_prev, float* rec2, void* workspace, b200isp_stream stream);
+
+/* camera_isp.py:376-385 update_metering on its own, straight from packed12 frames (what
+ * b200isp_process_packed12 runs first when params->update_metering is set), with separate input / output
+ * metrics so that the update for the NEXT batch can run on a side stream while the sweep of the current
+ * batch still reads the current metrics ("look-ahead metering", camera_isp.process_packed12(lookahead=...)).
+ * metrics_out may equal metrics_prev.  cooperative = 1: one cooperative launch (fastest on an idle GPU);
+ * 0: two ordinary launches whose CTAs can interleave with a concurrently running sweep. */
+int b200isp_meter_packed12(const uint8_t* const* packed_host, int n_frames,
+                           const b200isp_fused_params* params, const float* metrics_prev,
+                           float* metrics_out, int cooperative, void* workspace, b200isp_stream stream);
 
 #ifdef __cplusplus
 }

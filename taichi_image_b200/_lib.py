@@ -58,7 +58,8 @@ SIGNATURES = {
     "b200isp_process_packed12": [C.POINTER(_vp), C.POINTER(_vp), _i, C.POINTER(FusedParams), _vp, _vp, _vp],
     "b200isp_metering_phase1": [C.POINTER(_vp), _i, _i, _i, _i, _i, _vp, _vp, _vp],
     "b200isp_metering_phase2": [C.POINTER(_vp), _i, _i, _i, _i, _i, _vp, _i, _f, _vp, _vp, _vp, _vp],
-    "b200isp_metering_finalize": [_vp, _vp, _i, _f, _vp, _vp],
+    "b200isp_metering_finalize": [_vp, _vp, _i, _f, _vp, _vp, _vp],
+    "b200isp_meter_packed12": [C.POINTER(_vp), _i, C.POINTER(FusedParams), _vp, _vp, _i, _vp, _vp],
     "b200isp_meter_packed12_phase1": [C.POINTER(_vp), _i, C.POINTER(FusedParams), _vp, _vp, _vp],
     "b200isp_meter_packed12_phase2": [C.POINTER(_vp), _i, C.POINTER(FusedParams), _vp, _i, _vp, _vp, _vp, _vp],
 }

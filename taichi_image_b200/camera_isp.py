@@ -98,6 +98,12 @@ def camera_isp(name: str, dtype=f32):
             self.metrics = None
             self.device = device
             self.dtype = isp_dtype
+            # look-ahead metering state (process_packed12(lookahead=...)): second metrics buffer, side stream,
+            # the pending update for the announced next batch, completion event of the previous sweep
+            self._metrics_alt = None
+            self._side_stream = None
+            self._lookahead = None
+            self._ev_prev_sweep = None
 
         @beartype
         def set(self, moving_alpha: Optional[float] = None, resize_width: Optional[int] = None,
@@ -278,14 +284,25 @@ def camera_isp(name: str, dtype=f32):
                         "metering_phase2")
             return rec
 
-        def meter_finalize(self, gathered1: torch.Tensor, gathered2: torch.Tensor, alpha: float):
-            """metrics = lerp(alpha, joint statistics of all ranks, metrics)   (camera_isp.py:164-166)"""
+        def meter_finalize(self, gathered1: torch.Tensor, gathered2: torch.Tensor, alpha: float, out: Optional[torch.Tensor] = None):
+            """out (default: metrics, in place) = lerp(alpha, joint statistics of all ranks, metrics)   (camera_isp.py:164-166)"""
             world = gathered1.numel() // 2
             assert gathered2.numel() == 8 * world and gathered2.is_contiguous() and gathered1.is_contiguous()
+            out = self.metrics if out is None else out
             with torch.cuda.device(self.device):
                 _lib.check(_lib.lib.b200isp_metering_finalize(gathered1.data_ptr(), gathered2.data_ptr(), world, float(alpha),
-                                                               self.metrics.data_ptr(), _lib.stream_ptr(self.device)),
-                           "metering_finalize")
+                                                               self.metrics.data_ptr(), out.data_ptr(),
+                                                               _lib.stream_ptr(self.device)), "metering_finalize")
+
+        def meter_packed12(self, frames, alpha: float, out: Optional[torch.Tensor] = None, cooperative: bool = True):
+            """camera_isp.py:376-385 straight from packed12 frames on the current stream:
+            out (default: metrics, in place) = lerp(alpha, statistics(frames), metrics)"""
+            out = self.metrics if out is None else out
+            p = self._fused_params(frames, "linear", u8, {}, update_metering=True, alpha=alpha)
+            with torch.cuda.device(self.device):
+                _lib.check(_lib.lib.b200isp_meter_packed12(
+                    _lib.ptr_array(frames), len(frames), p, self.metrics.data_ptr(), out.data_ptr(), int(cooperative),
+                    _lib.workspace(self.device).data_ptr(), _lib.stream_ptr(self.device)), "meter_packed12")
 
         # ------------------------------------------------------------ tone mapping (eager API)
         def tonemap_only(self, image, metrics, gamma, intensity, light_adapt, color_adapt):
@@ -369,13 +386,20 @@ def camera_isp(name: str, dtype=f32):
         def process_packed12(self, frames: Sequence[torch.Tensor], tonemap: str = "reinhard", gamma: float = 1.0,
                              intensity: float = 1.0, light_adapt: float = 1.0, color_adapt: float = 0.0,
                              dtype=u8, ids_format: bool = False, out: Optional[list] = None,
-                             rows_per_task: int = 0, profile_events=None, update_metering: bool = True):
+                             rows_per_task: int = 0, profile_events=None, update_metering: bool = True,
+                             lookahead: Optional[Sequence[torch.Tensor]] = None, meter_fn=None):
             """Fused equivalent of ``[load_packed12(f) for f in frames]`` followed by
             ``tonemap_reinhard`` / ``tonemap_linear`` (camera_isp.py:333-340, :376-413): joint metering of
             all frames with the moving-average update of ``self.metrics``, then one sweep per frame.
             Returns the list of tone-mapped (H, W, 3) images (transformed if ``self.transform`` is set).
             Falls back to the staged CUDA kernels when the frames need resizing, use the IDS layout or
-            have a width that is not a multiple of 8 -- never to the CPU."""
+            have a width that is not a multiple of 8 -- never to the CPU.
+
+            ``lookahead``: the frames of the NEXT call (a camera stream knows them: they are being captured / copied
+            while this batch is processed).  Their metering update -- which only depends on this call's metrics --
+            is then issued on a side stream and runs under this batch's sweep; the next call finds it done.  The
+            announced tensors must not be modified before that call.  Results are identical to calling without it.
+            ``meter_fn(frames, alpha, out, cooperative)``: replaces the local metering (distributed.SharedExposure)."""
             assert tonemap in ("linear", "reinhard")
             out_dtype = as_dtype(dtype)
             frames = [f.to(self.device) for f in frames]
@@ -390,11 +414,51 @@ def camera_isp(name: str, dtype=f32):
                 return self.tonemap_reinhard(images, gamma=float(gamma), intensity=float(intensity),
                                              light_adapt=float(light_adapt), color_adapt=float(color_adapt), dtype=out_dtype,
                                              update_metering=update_metering)
-            alpha = self._metrics_and_alpha() if update_metering else 0.0
-            assert self.metrics is not None, "update_metering=False needs metrics from an earlier call"
             tm = dict(gamma=gamma, intensity=intensity, light_adapt=light_adapt, color_adapt=color_adapt)
-            outputs = self._run_fused(frames, tonemap, out_dtype, out, tm, update_metering=update_metering, alpha=alpha,
+            pipelined = update_metering and (lookahead is not None or self._lookahead is not None or meter_fn is not None)
+            if not pipelined:
+                alpha = self._metrics_and_alpha() if update_metering else 0.0
+                assert self.metrics is not None, "update_metering=False needs metrics from an earlier call"
+                outputs = self._run_fused(frames, tonemap, out_dtype, out, tm, update_metering=update_metering, alpha=alpha,
+                                          rows_per_task=rows_per_task, profile_events=profile_events)
+                return [interpolate.transform(o, self.transform) for o in outputs]
+
+            # ---- look-ahead pipeline: metering(k+1) on the side stream under sweep(k)
+            meter = meter_fn if meter_fn is not None else self.meter_packed12
+            main = torch.cuda.current_stream(self.device)
+            key = lambda fs: tuple((f.data_ptr(), tuple(f.shape)) for f in fs)
+            pending, self._lookahead = self._lookahead, None
+            if pending is not None and pending["key"] == key(frames):
+                main.wait_event(pending["event"])                      # metrics for this batch were computed ahead
+                self.metrics, self._metrics_alt = pending["out"], self.metrics
+                ready = pending["event"]
+            else:
+                alpha = self._metrics_and_alpha()
+                meter(frames, alpha, None, True)                       # in place, on the main stream
+                ready = torch.cuda.Event()
+                ready.record(main)
+            outputs = self._run_fused(frames, tonemap, out_dtype, out, tm, update_metering=False,
                                       rows_per_task=rows_per_task, profile_events=profile_events)
+            ev_sweep = torch.cuda.Event()
+            ev_sweep.record(main)
+            if lookahead is not None:
+                nxt = [f.to(self.device) for f in lookahead]
+                if all(self._fused_ok(f, ids_format) for f in nxt):
+                    with torch.cuda.device(self.device):
+                        if self._side_stream is None:
+                            self._side_stream = torch.cuda.Stream(self.device)
+                        if self._metrics_alt is None:
+                            self._metrics_alt = torch.zeros(9, dtype=torch.float32, device=self.device)
+                        side = self._side_stream
+                        side.wait_event(ready)                         # needs this batch's metrics ...
+                        if self._ev_prev_sweep is not None:
+                            side.wait_event(self._ev_prev_sweep)       # ... and overwrites the buffer the previous sweep read
+                        with torch.cuda.stream(side):
+                            meter(nxt, 1.0 - float(self.moving_alpha), self._metrics_alt, False)
+                            done = torch.cuda.Event()
+                            done.record(side)
+                    self._lookahead = dict(key=key(nxt), event=done, out=self._metrics_alt, frames=nxt)
+            self._ev_prev_sweep = ev_sweep
             return [interpolate.transform(o, self.transform) for o in outputs]
 
     ISP.reinhard_kernel = staticmethod(_reinhard_kernel)     # camera_isp.py:415-416

@@ -82,12 +82,26 @@ extern "C" int b200isp_meter_packed12_phase2(const uint8_t* const* packed_host, 
   });
 }
 
-extern "C" int b200isp_metering_finalize(const float* gathered1, const float* gathered2, int world, float alpha, float* metrics,
-                                         b200isp_stream stream) {
-  ISP_REQUIRE(gathered1 && gathered2 && metrics && world >= 1, B200ISP_E_ARG, "metering_finalize: bad argument");
-  meter_finalize_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(gathered1, gathered2, world, alpha, metrics);
+extern "C" int b200isp_metering_finalize(const float* gathered1, const float* gathered2, int world, float alpha,
+                                         const float* metrics_prev, float* metrics_out, b200isp_stream stream) {
+  ISP_REQUIRE(gathered1 && gathered2 && metrics_prev && metrics_out && world >= 1, B200ISP_E_ARG, "metering_finalize: bad argument");
+  meter_finalize_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(gathered1, gathered2, world, alpha, metrics_prev, metrics_out);
   ISP_LAUNCH_CHECK("meter_finalize_kernel");
   return B200ISP_OK;
+}
+
+extern "C" int b200isp_meter_packed12(const uint8_t* const* packed_host, int n_frames, const b200isp_fused_params* params,
+                                      const float* metrics_prev, float* metrics_out, int cooperative, void* workspace,
+                                      b200isp_stream stream) {
+  FramePtrs fp; IspConsts k;
+  const int st = fused_setup("meter_packed12", packed_host, nullptr, n_frames, params, nullptr, workspace, fp, k);
+  if (st) return st;
+  ISP_REQUIRE(metrics_prev && metrics_out, B200ISP_E_ARG, "meter_packed12: null metrics");
+  cudaStream_t s = (cudaStream_t)stream;
+  const float alpha = params->alpha;
+  return with_packed12_sampler(fp, *params, k, n_frames, [&](const auto& smp, long long n, float* cache) {
+    return launch_metering(smp, n, alpha, metrics_prev, metrics_out, k.ws, s, cache, cooperative != 0);
+  });
 }
 
 extern "C" int b200isp_process_packed12(const uint8_t* const* packed_host, void* const* out_host, int n_frames,
@@ -113,7 +127,7 @@ extern "C" int b200isp_process_packed12(const uint8_t* const* packed_host, void*
 
   if (p.update_metering && p.tonemap != B200ISP_TM_NONE) {
     const int st = with_packed12_sampler(fp, p, k, n_frames, [&](const auto& smp, long long n, float* cache) {
-      return launch_metering(smp, n, p.alpha, metrics, k.ws, s, cache);
+      return launch_metering(smp, n, p.alpha, metrics, metrics, k.ws, s, cache);
     });
     if (st) return st;
   }

@@ -646,6 +646,23 @@ struct Packed12Sampler {
 // apart, so a warp's loads are contiguous) and evaluates exactly the partial-sum formulas of the sweep,
 // i.e. the very value the sweep will produce for that pixel -- including the samples on the 2-pixel image
 // frame (row 0 / column 0), which use the same zero-sample + renormalisation scheme (border_fix.cuh).
+// The metering pass touches 5 of every 8 packed rows right before the sweep reads all of them: load them with
+// the L2 evict-last policy so the sweep finds them in the 126 MB L2 (its own output goes out evict-first).
+#ifndef ISP_METER_KEEP_L2
+#define ISP_METER_KEEP_L2 0      // measured on cfg2: no gain (533.9 vs 532.0 Gpx/s), kept as a build option
+#endif
+__device__ __forceinline__ uint32_t ldg_keep(const uint32_t* p) {
+#if ISP_METER_KEEP_L2
+  uint64_t pol;
+  uint32_t v;
+  asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+  asm volatile("ld.global.nc.L2::cache_hint.b32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(pol));
+  return v;
+#else
+  return __ldg(p);
+#endif
+}
+
 template <bool CAM16>
 struct Packed12FastSampler {
   Packed12Src<CAM16> src;
@@ -698,11 +715,11 @@ struct Packed12FastSampler {
 
   // interior sample: p = word of pixel (row, col) (col % 8 == 0)
   __device__ __forceinline__ void sample_fast(const uint32_t* p, int row, float (&rgb)[3]) const {
-    const uint32_t a0 = __ldg(p - 2 * pitch_words);                                   // row-2: col
-    const uint32_t bm = __ldg(p - pitch_words - 1), b0 = __ldg(p - pitch_words);      // row-1: col-1..col+1
-    const uint32_t cm = __ldg(p - 1), c0 = __ldg(p), c1 = __ldg(p + 1);               // row  : col-2..col+2
-    const uint32_t dm = __ldg(p + pitch_words - 1), d0 = __ldg(p + pitch_words);      // row+1
-    const uint32_t e0 = __ldg(p + 2 * pitch_words);                                   // row+2
+    const uint32_t a0 = ldg_keep(p - 2 * pitch_words);                                   // row-2: col
+    const uint32_t bm = ldg_keep(p - pitch_words - 1), b0 = ldg_keep(p - pitch_words);      // row-1: col-1..col+1
+    const uint32_t cm = ldg_keep(p - 1), c0 = ldg_keep(p), c1 = ldg_keep(p + 1);               // row  : col-2..col+2
+    const uint32_t dm = ldg_keep(p + pitch_words - 1), d0 = ldg_keep(p + pitch_words);      // row+1
+    const uint32_t e0 = ldg_keep(p + 2 * pitch_words);                                   // row+2
     float S[3], sc[3];
     bool brow, gsite;
     sums_from_words(a0, bm, b0, cm, c0, c1, dm, d0, e0, row, S, sc, brow, gsite);

@@ -134,7 +134,7 @@ __device__ __forceinline__ void meter_accum(const float (&rgb)[3], float bmin, f
 
 template <class Sampler>
 __global__ void __launch_bounds__(256) meter_phase2_kernel(const Sampler smp, long long n, float alpha,
-                                                           float* __restrict__ metrics, Workspace* ws,
+                                                           const float* prev, float* metrics /* out; may alias prev */, Workspace* ws,
                                                            float* __restrict__ rec_out = nullptr /* shared exposure: raw record 2 */) {
   __shared__ float smem[8 * 7];
   const float bmin = __ldcg(&ws->bounds[0]), bmax = __ldcg(&ws->bounds[1]);
@@ -166,7 +166,7 @@ __global__ void __launch_bounds__(256) meter_phase2_kernel(const Sampler smp, lo
                               __fdiv_rn(f[4], fn), __fdiv_rn(f[5], fn), __fdiv_rn(f[6], fn)};
 #pragma unroll
       for (int k = 0; k < 9; ++k) {                                       // camera_isp.py:165-166
-        const float p = metrics[k];
+        const float p = prev[k];
         metrics[k] = __fadd_rn(stats[k], __fmul_rn(alpha, __fsub_rn(p, stats[k])));
       }
     }
@@ -190,10 +190,10 @@ static __global__ void meter_fold_bounds_kernel(const float* __restrict__ g1, in
 }
 
 static __global__ void meter_finalize_kernel(const float* __restrict__ g1, const float* __restrict__ g2, int world, float alpha,
-                                      float* __restrict__ metrics) {
+                                      const float* prev, float* metrics /* out; may alias prev */) {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   float bmin, bmax;
-  fold_bounds(g1, world, alpha, metrics, bmin, bmax);
+  fold_bounds(g1, world, alpha, prev, bmin, bmax);
   float f[8] = {INFINITY, -INFINITY, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   for (int r = 0; r < world; ++r) {
     f[0] = fminf(f[0], g2[8 * r]);
@@ -204,7 +204,7 @@ static __global__ void meter_finalize_kernel(const float* __restrict__ g1, const
   const float stats[9] = {bmin, bmax, f[0], f[1], __fdiv_rn(f[2], fn), __fdiv_rn(f[3], fn),
                           __fdiv_rn(f[4], fn), __fdiv_rn(f[5], fn), __fdiv_rn(f[6], fn)};
   for (int k = 0; k < 9; ++k) {                                           // camera_isp.py:165-166
-    const float p = metrics[k];
+    const float p = prev[k];
     metrics[k] = __fadd_rn(stats[k], __fmul_rn(alpha, __fsub_rn(p, stats[k])));
   }
 }
@@ -243,8 +243,9 @@ __device__ __forceinline__ void grid_barrier(unsigned int* counter) {     // coo
 }
 
 template <class Sampler>
-__global__ void __launch_bounds__(256) meter_fused_kernel(const Sampler smp, long long n, float alpha, float* __restrict__ metrics,
-                                                          Workspace* ws, float* __restrict__ cache /* n*3 floats or null */) {
+__global__ void __launch_bounds__(256) meter_fused_kernel(const Sampler smp, long long n, float alpha, const float* prev,
+                                                          float* metrics /* out; may alias prev */, Workspace* ws,
+                                                          float* __restrict__ cache /* n*3 floats or null */) {
   __shared__ float smem[8 * 7];
   __shared__ float s_bounds[2];
   float* part2 = ws->partials + (kMaxPartialBlocks / 2) * kPartialStride;
@@ -273,8 +274,8 @@ __global__ void __launch_bounds__(256) meter_fused_kernel(const Sampler smp, lon
     }
     block_fold<2>(f, op2, smem);
     if (threadIdx.x == 0) {                                               // camera_isp.py:156
-      s_bounds[0] = __fadd_rn(f[0], __fmul_rn(alpha, __fsub_rn(metrics[0], f[0])));
-      s_bounds[1] = __fadd_rn(f[1], __fmul_rn(alpha, __fsub_rn(metrics[1], f[1])));
+      s_bounds[0] = __fadd_rn(f[0], __fmul_rn(alpha, __fsub_rn(prev[0], f[0])));
+      s_bounds[1] = __fadd_rn(f[1], __fmul_rn(alpha, __fsub_rn(prev[1], f[1])));
     }
     __syncthreads();
   }
@@ -308,7 +309,7 @@ __global__ void __launch_bounds__(256) meter_fused_kernel(const Sampler smp, lon
                               __fdiv_rn(f[4], fn), __fdiv_rn(f[5], fn), __fdiv_rn(f[6], fn)};
 #pragma unroll
       for (int k = 0; k < 9; ++k) {                                       // camera_isp.py:165-166
-        const float p = metrics[k];
+        const float p = prev[k];
         metrics[k] = __fadd_rn(stats[k], __fmul_rn(alpha, __fsub_rn(p, stats[k])));
       }
     }
@@ -324,30 +325,33 @@ inline int meter_grid(long long n) {
 
 // cache: optional device scratch of n*3 floats -- phase 2 then re-reads the phase-1 samples instead of
 // recomputing them (the samples are identical either way).
+// prev: metrics before this update (read), metrics: updated metrics (written; may be the same buffer).
+// cooperative = false forces the two-launch form, whose CTAs can interleave with another kernel's CTAs on a
+// busy GPU (a cooperative grid must wait until all of its CTAs fit at once): used by the look-ahead metering
+// that runs on a side stream under the previous batch's sweep.
 template <class Sampler>
-inline int launch_metering(const Sampler& smp, long long n, float alpha, float* metrics, Workspace* ws, cudaStream_t s,
-                           float* cache = nullptr) {
-  // one cooperative launch when the device can keep the whole grid resident (it always can: the grid is sized
-  // from the occupancy of this very kernel), two dependent launches otherwise
+inline int launch_metering(const Sampler& smp, long long n, float alpha, const float* prev, float* metrics, Workspace* ws,
+                           cudaStream_t s, float* cache = nullptr, bool cooperative = true) {
   int dev = 0, sms = 0, per_sm = 0, coop = 0;
-  if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev) == cudaSuccess && coop &&
+  if (cooperative && cudaGetDevice(&dev) == cudaSuccess &&
+      cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev) == cudaSuccess && coop &&
       cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess &&
       cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, meter_fused_kernel<Sampler>, 256, 0) == cudaSuccess && per_sm > 0) {
     long long want = (n + 256 * kMeterUnroll - 1) / (256 * kMeterUnroll);
     long long cap = (long long)per_sm * sms;
     if (cap > kMaxPartialBlocks / 2) cap = kMaxPartialBlocks / 2;
     int grid = (int)(want < 1 ? 1 : (want > cap ? cap : want));
-    void* args[] = {(void*)&smp, (void*)&n, (void*)&alpha, (void*)&metrics, (void*)&ws, (void*)&cache};
+    void* args[] = {(void*)&smp, (void*)&n, (void*)&alpha, (void*)&prev, (void*)&metrics, (void*)&ws, (void*)&cache};
     const cudaError_t e = cudaLaunchCooperativeKernel((const void*)meter_fused_kernel<Sampler>, dim3(grid), dim3(256), args, 0, s);
     if (e == cudaSuccess) return B200ISP_OK;
     (void)cudaGetLastError();         // fall through to the two-launch form
   }
   const int grid = meter_grid(n);
-  meter_phase1_kernel<Sampler><<<grid, 256, 0, s>>>(smp, n, alpha, metrics, ws, cache);
+  meter_phase1_kernel<Sampler><<<grid, 256, 0, s>>>(smp, n, alpha, prev, ws, cache);
   int st = cuda_status(cudaPeekAtLastError(), "meter_phase1_kernel");
   if (st) return st;
-  if (cache) meter_phase2_kernel<CachedSampler><<<grid, 256, 0, s>>>(CachedSampler{cache}, n, alpha, metrics, ws);
-  else meter_phase2_kernel<Sampler><<<grid, 256, 0, s>>>(smp, n, alpha, metrics, ws);
+  if (cache) meter_phase2_kernel<CachedSampler><<<grid, 256, 0, s>>>(CachedSampler{cache}, n, alpha, prev, metrics, ws);
+  else meter_phase2_kernel<Sampler><<<grid, 256, 0, s>>>(smp, n, alpha, prev, metrics, ws);
   return cuda_status(cudaPeekAtLastError(), "meter_phase2_kernel");
 }
 
@@ -362,8 +366,8 @@ inline int launch_metering_phase2(const Sampler& smp, long long n, const float* 
                                   Workspace* ws, cudaStream_t s, const float* cache, float* rec2) {
   meter_fold_bounds_kernel<<<1, 32, 0, s>>>(g1, world, alpha, prev, ws);
   const int grid = meter_grid(n);
-  if (cache) meter_phase2_kernel<CachedSampler><<<grid, 256, 0, s>>>(CachedSampler{cache}, n, alpha, nullptr, ws, rec2);
-  else meter_phase2_kernel<Sampler><<<grid, 256, 0, s>>>(smp, n, alpha, nullptr, ws, rec2);
+  if (cache) meter_phase2_kernel<CachedSampler><<<grid, 256, 0, s>>>(CachedSampler{cache}, n, alpha, nullptr, nullptr, ws, rec2);
+  else meter_phase2_kernel<Sampler><<<grid, 256, 0, s>>>(smp, n, alpha, nullptr, nullptr, ws, rec2);
   return cuda_status(cudaPeekAtLastError(), "meter_phase2_kernel");
 }
 

@@ -160,6 +160,27 @@ struct WarpCtx {
   uint32_t* stage;      // this warp's staging buffer, Epi::kStageWords words
 };
 
+// Output rows are written once and never re-read by the ISP: store them with the evict-first policy so that
+// they do not push the packed input rows (which the metering pass has just pulled into the 126 MB L2 and the
+// sweep is about to read) out of L2.
+#ifndef ISP_STREAMING_STORES
+#define ISP_STREAMING_STORES 1
+#endif
+__device__ __forceinline__ void st_out(uint4* p, const uint4& v) {
+#if ISP_STREAMING_STORES
+  __stcs(p, v);
+#else
+  *p = v;
+#endif
+}
+__device__ __forceinline__ void st_out(uint2* p, const uint2& v) {
+#if ISP_STREAMING_STORES
+  __stcs(p, v);
+#else
+  *p = v;
+#endif
+}
+
 template <int NW, bool FULL = false>       // FULL: all 32 lanes map to real thread columns (no store predicates)
 __device__ __forceinline__ void warp_store_row(const WarpCtx& wc, void* row_dst /* warp's first byte of the row */,
                                                const uint32_t (&w)[NW]) {
@@ -176,7 +197,7 @@ __device__ __forceinline__ void warp_store_row(const WarpCtx& wc, void* row_dst 
 #pragma unroll
     for (int i = 0; i < PER_LANE; ++i) {
       const int idx = i * 32 + wc.lane;
-      if (FULL || idx < nchunks) d[idx] = s[idx];
+      if (FULL || idx < nchunks) st_out(d + idx, s[idx]);
     }
   } else {
     uint2* s = reinterpret_cast<uint2*>(wc.stage);
@@ -187,7 +208,7 @@ __device__ __forceinline__ void warp_store_row(const WarpCtx& wc, void* row_dst 
 #pragma unroll
     for (int i = 0; i < PER_LANE; ++i) {
       const int idx = i * 32 + wc.lane;
-      if (FULL || idx < nchunks) d[idx] = s[idx];
+      if (FULL || idx < nchunks) st_out(d + idx, s[idx]);
     }
   }
 }

@@ -316,7 +316,7 @@ extern "C" int b200isp_metering_update(const void* const* images_host, int n_ima
     ImageSampler<T> smp;
     for (int i = 0; i < n_images; ++i) smp.img[i] = (const T*)images_host[i];
     smp.W = width; smp.stride = stride; smp.hs = hs; smp.ws_ = wsamp;
-    return launch_metering(smp, n, alpha, metrics, (Workspace*)workspace, (cudaStream_t)stream);
+    return launch_metering(smp, n, alpha, metrics, metrics, (Workspace*)workspace, (cudaStream_t)stream);
   });
   return B200ISP_OK;
 }

@@ -56,8 +56,8 @@ class CudaMeteringBackend:
     def phase2(self, source, gathered1: torch.Tensor, alpha: float) -> torch.Tensor:
         return self.isp.meter_phase2(source, gathered1, alpha)
 
-    def finalize(self, gathered1: torch.Tensor, gathered2: torch.Tensor, alpha: float) -> None:
-        self.isp.meter_finalize(gathered1, gathered2, alpha)
+    def finalize(self, gathered1: torch.Tensor, gathered2: torch.Tensor, alpha: float, out=None) -> None:
+        self.isp.meter_finalize(gathered1, gathered2, alpha, out)
 
 
 def exchange(record: torch.Tensor, group=None) -> torch.Tensor:
@@ -70,12 +70,17 @@ def exchange(record: torch.Tensor, group=None) -> torch.Tensor:
     return out.view(world, record.numel())
 
 
-def shared_metering(backend, source, group=None) -> None:
-    """One joint metering update over the frames of ALL ranks (each rank passes its own ``source``)."""
-    alpha = backend.begin()
+def shared_metering(backend, source, group=None, alpha: Optional[float] = None, out=None) -> None:
+    """One joint metering update over the frames of ALL ranks (each rank passes its own ``source``).
+    ``alpha`` / ``out``: given by the look-ahead pipeline (weight of the previous metrics, second metrics buffer)."""
+    if alpha is None:
+        alpha = backend.begin()
     g1 = exchange(backend.phase1(source), group)
     g2 = exchange(backend.phase2(source, g1, alpha), group)
-    backend.finalize(g1, g2, alpha)
+    if out is None:
+        backend.finalize(g1, g2, alpha)
+    else:
+        backend.finalize(g1, g2, alpha, out)
 
 
 class SharedExposure:
@@ -112,8 +117,10 @@ class SharedExposure:
         isp = self.isp
         frames = [f.to(isp.device) for f in frames]
         if all(isp._fused_ok(f, ids_format) for f in frames) and not isp._resizes:
-            shared_metering(self.backend, frames, self.group)
-            return isp.process_packed12(frames, tonemap=tonemap, ids_format=ids_format, update_metering=False, **kw)
+            # the ISP's look-ahead pipeline drives the joint metering: the exchange of batch k+1 (two tiny
+            # all-gathers) then runs on the side stream under the sweep of batch k
+            meter = lambda fs, alpha, out, cooperative: shared_metering(self.backend, fs, self.group, alpha, out)
+            return isp.process_packed12(frames, tonemap=tonemap, ids_format=ids_format, meter_fn=meter, **kw)
         images = [isp.load_packed12(f, ids_format) for f in frames]
         kw.pop("out", None); kw.pop("rows_per_task", None); kw.pop("profile_events", None)
         if tonemap == "linear":

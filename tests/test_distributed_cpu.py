@@ -106,8 +106,9 @@ PORT = _free_port()
 
 
 def test_shared_exposure_wrapper_forwards_and_skips_local_metering():
-    """single process (no process group): SharedExposure must meter through the backend exactly once per call and
-    tone-map with update_metering=False"""
+    """single process (no process group): SharedExposure must hand the ISP a metering function that runs the
+    exchange protocol through the backend exactly once per call (fused path), and tone-map with
+    update_metering=False on the eager path"""
     calls = []
 
     class FakeISP:
@@ -119,8 +120,9 @@ def test_shared_exposure_wrapper_forwards_and_skips_local_metering():
             return True
         _resizes = False
 
-        def process_packed12(self, frames, **kw):
-            calls.append(("process", kw.get("update_metering"), kw.get("tonemap")))
+        def process_packed12(self, frames, **kw):        # like ISP.process_packed12: meters through meter_fn, then sweeps
+            kw["meter_fn"](frames, None, None, True)      # alpha None: the backend decides (first call -> 0)
+            calls.append(("process", kw.get("tonemap")))
             return ["out"]
 
         def tonemap_linear(self, images, gamma, **kw):
@@ -139,7 +141,7 @@ def test_shared_exposure_wrapper_forwards_and_skips_local_metering():
     isp = SharedExposure(FakeISP(), backend=Backend())
     assert isp.answer == 42                                    # attribute forwarding
     assert isp.process_packed12([torch.zeros(4, 12, dtype=torch.uint8)], tonemap="linear") == ["out"]
-    assert calls == [("phase1", 1), ("phase2", (1, 2), 0.0), ("process", False, "linear")]
+    assert calls == [("phase1", 1), ("phase2", (1, 2), 0.0), ("process", "linear")]
     calls.clear()
     isp.tonemap_linear([torch.zeros(8, 8, 3)], 1.0)
     assert [c[0] for c in calls] == ["phase1", "phase2", "linear"] and calls[-1][1] is False

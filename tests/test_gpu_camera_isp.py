@@ -181,3 +181,24 @@ def test_isp_api_surface(cuda):
         camera_isp.Camera32("RGGB")          # beartype: pattern must be a BayerPattern
     with pytest.raises(AssertionError):
         camera_isp.Camera32(bayer.BayerPattern.RGGB, scale=0.5, resize_width=10)
+
+
+@pytest.mark.parametrize("dt", ["f16", "f32"])
+@pytest.mark.parametrize("tm", ["linear", "reinhard"])
+def test_lookahead_metering_is_equivalent(cuda, dt, tm):
+    """process_packed12(lookahead=next batch) -- metering of batch k+1 on a side stream under sweep k -- must give
+    the same outputs and the same metrics trajectory as strictly serial calls, also when the announcement is
+    wrong (the pending update is then discarded)"""
+    r = rng(41)
+    batches = [[to_cuda(f) for f in frames(r, 3, 40, 64)] for _ in range(5)]
+    serial, ahead = make_isp(dt, moving_alpha=0.2), make_isp(dt, moving_alpha=0.2)
+    for i, b in enumerate(batches):
+        ya = serial.process_packed12(b, tonemap=tm, gamma=0.9)
+        nxt = batches[i + 1] if i + 1 < len(batches) else None
+        if i == 2:
+            nxt = batches[0]                                  # wrong announcement: batch 3 follows, not batch 0
+        yb = ahead.process_packed12(b, tonemap=tm, gamma=0.9, lookahead=nxt)
+        torch.cuda.synchronize()
+        np.testing.assert_allclose(to_np(ahead.metrics), to_np(serial.metrics), rtol=2e-6, atol=1e-7)
+        for x, y in zip(ya, yb):
+            assert_close_int(to_np(x), to_np(y), 1, f"lookahead {dt} {tm} step {i}")
