@@ -191,6 +191,8 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=0, help="steps of the host-buffer pipeline leg (default: min(steps, 12))")
     ap.add_argument("--lookahead", type=int, default=1, help="announce the next batch so its metering (and exposure exchange) "
                     "runs on a side stream under this batch's sweep (camera-stream mode; 0 = strictly serial steps)")
+    ap.add_argument("--graph", type=int, default=1, help="replay the step (sweep k || metering k+1) as a CUDA graph "
+                    "(taichi_image_b200.graphed.GraphedStream); 0 = eager Python calls")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -209,7 +211,8 @@ def main():
     device = torch.device("cuda", local_rank)
     torch.cuda.set_device(device)
     if world > 1:
-        dist.init_process_group("nccl", device_id=device)
+        opts = dist.ProcessGroupNCCL.Options(is_high_priority_stream=True)   # the exposure exchange must not queue behind the sweep
+        dist.init_process_group("nccl", device_id=device, pg_options=opts)
     shared = (world > 1) if args.shared_exposure < 0 else bool(args.shared_exposure)
 
     n, h, w, isp_dt, tonemap, out_dt, tm, desc = WORKLOADS[args.workload]
@@ -224,7 +227,16 @@ def main():
     px_per_step = n * h * w
     alg_bytes = px_per_step * 1.5 + px_per_step * 3 * OUT_BYTES[out_dt]
 
+    graphed = None
+    if args.graph and args.lookahead:
+        from taichi_image_b200.graphed import GraphedStream
+        graphed = GraphedStream(isp, frames, outs, tonemap=tonemap, dtype=out_dt, rows_per_task=args.rows_per_task,
+                                profile=True, **tm)
+
     def step(events=None):
+        if graphed is not None:
+            graphed.step()
+            return
         isp.process_packed12(frames, tonemap=tonemap, dtype=out_dt, out=outs, rows_per_task=args.rows_per_task,
                              profile_events=events, lookahead=frames if args.lookahead else None, **tm)
 
@@ -254,7 +266,8 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         elapsed_ms = float(t.item())
     clocks = sampler.stop(t0, t1) if sampler else None
-    kern_ms = [a.elapsed_time(b) for a, b in evs]
+    # graph mode: the event pair is part of the two captured graphs -> device times of the last two timed steps
+    kern_ms = graphed.kernel_ms() if graphed is not None else [a.elapsed_time(b) for a, b in evs]
     kern_avg_ms = sum(kern_ms) / len(kern_ms)
     # Reinhard: the event pair brackets the write sweep of the first frame group only
     group = n if tonemap != "reinhard" else max(1, min(n, int((48 << 20) // (h * w * 3 // 2))))
@@ -322,6 +335,7 @@ def main():
         "vs_baseline": None, "dtype": isp_dt, "data": "synthetic",
         "config": {"workload": desc, "frames_per_gpu": n, "height": h, "width": w, "tonemap": tonemap, "out_dtype": out_dt,
                    "shared_exposure": bool(shared and world > 1), "lookahead_metering": bool(args.lookahead),
+                   "cuda_graph": graphed is not None,
                    "l2": f"inputs+outputs per step = {alg_bytes / 1e6:.0f} MB > 126 MB L2 (no flush needed)" if alg_bytes > 200e6
                          else "per-step working set fits L2: inputs are re-read from L2 between steps (stated, not flushed)"},
         "clocks": clocks,

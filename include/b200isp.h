@@ -193,6 +193,24 @@ int b200isp_meter_packed12_phase2(const uint8_t* const* packed_host, int n_frame
                                   const b200isp_fused_params* params, const float* gathered1, int world,
                                   const float* metrics_prev, float* rec2, void* workspace, b200isp_stream stream);
 
+/* ---- peer-memory exchange of the two records over NVLink (csrc/exchange.cu) ----
+ * One process per GPU.  Every rank owns a small mailbox in device memory (b200isp_mailbox_create), exports it
+ * with a 64-byte CUDA IPC handle, and opens the other ranks' mailboxes (b200isp_mailbox_open).  An exchange is
+ * two 1-warp kernels on the metering stream -- post: write the record into every rank's mailbox and publish a
+ * sequence number; wait: spin (bounded, ~2 s) until every rank's number has arrived, then copy the records to
+ * `gathered` in rank order -- no host call, no NCCL, capturable in a CUDA graph.  kind = 1 | 2 (record 1 | 2). */
+size_t b200isp_mailbox_bytes(int world);
+int b200isp_mailbox_create(int world, void** mailbox_out, void* ipc_handle_out64);
+int b200isp_mailbox_open(const void* ipc_handle64, void** mailbox_out);
+int b200isp_mailbox_close(void* mailbox, int is_owner);
+int b200isp_mailbox_post(const float* rec, int kind, void* const* peers_host, int world, int rank,
+                         b200isp_stream stream);
+int b200isp_mailbox_wait(void* mailbox, int kind, int world, float* gathered, b200isp_stream stream);
+int b200isp_mailbox_exchange(const float* rec, int kind, void* const* peers_host, int world, int rank,
+                             float* gathered, b200isp_stream stream);
+/* 1 if a bounded wait has expired on this mailbox (a peer never posted); synchronises `stream` */
+int b200isp_mailbox_error(const void* mailbox, int world, b200isp_stream stream);
+
 /* camera_isp.py:376-385 update_metering on its own, straight from packed12 frames (what
  * b200isp_process_packed12 runs first when params->update_metering is set), with separate input / output
  * metrics so that the update for the NEXT batch can run on a side stream while the sweep of the current

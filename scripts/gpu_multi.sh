@@ -1,7 +1,6 @@
 #!/bin/bash
-# usage: gpu_multi.sh N [workload]
-N=${1:-2}; WL=${2:-cfg2}
+# usage: gpu_multi.sh N [workload] [extra bench args]   -- every command under its own timeout (a hang costs N x GPU time)
+N=${1:-2}; WL=${2:-cfg2}; shift 2
 mkdir -p gpurun_out
-python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $N --steps 20 --warmup 5 --workload $WL > gpurun_out/bench_n${N}_$WL.json 2> gpurun_out/bench_n${N}_$WL.err; echo "rc=$?"
-cat gpurun_out/bench_n${N}_$WL.json; tail -5 gpurun_out/bench_n${N}_$WL.err
-python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus $N --steps 3 --warmup 1 --impl reference > gpurun_out/bench_ref_n${N}.json 2> gpurun_out/bench_ref_n${N}.err; echo "ref rc=$?"; cat gpurun_out/bench_ref_n${N}.json
+timeout 150 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $N --steps 30 --warmup 5 --workload $WL --no-e2e "$@" > gpurun_out/bench_n${N}_$WL.json 2> gpurun_out/bench_n${N}_$WL.err; echo "rc=$?"
+cat gpurun_out/bench_n${N}_$WL.json; grep -v "^\*\*\*\|OMP_NUM\|^$" gpurun_out/bench_n${N}_$WL.err | tail -8

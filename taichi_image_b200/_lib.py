@@ -60,11 +60,18 @@ SIGNATURES = {
     "b200isp_metering_phase2": [C.POINTER(_vp), _i, _i, _i, _i, _i, _vp, _i, _f, _vp, _vp, _vp, _vp],
     "b200isp_metering_finalize": [_vp, _vp, _i, _f, _vp, _vp, _vp],
     "b200isp_meter_packed12": [C.POINTER(_vp), _i, C.POINTER(FusedParams), _vp, _vp, _i, _vp, _vp],
+    "b200isp_mailbox_create": [_i, C.POINTER(_vp), _vp],
+    "b200isp_mailbox_open": [_vp, C.POINTER(_vp)],
+    "b200isp_mailbox_close": [_vp, _i],
+    "b200isp_mailbox_post": [_vp, _i, C.POINTER(_vp), _i, _i, _vp],
+    "b200isp_mailbox_wait": [_vp, _i, _i, _vp, _vp],
+    "b200isp_mailbox_exchange": [_vp, _i, C.POINTER(_vp), _i, _i, _vp, _vp],
+    "b200isp_mailbox_error": [_vp, _i, _vp],
     "b200isp_meter_packed12_phase1": [C.POINTER(_vp), _i, C.POINTER(FusedParams), _vp, _vp, _vp],
     "b200isp_meter_packed12_phase2": [C.POINTER(_vp), _i, C.POINTER(FusedParams), _vp, _i, _vp, _vp, _vp, _vp],
 }
 _SPECIAL = {"b200isp_version": ([], C.c_int), "b200isp_last_error": ([], C.c_char_p),
-            "b200isp_workspace_bytes": ([], C.c_size_t)}
+            "b200isp_workspace_bytes": ([], C.c_size_t), "b200isp_mailbox_bytes": ([_i], C.c_size_t)}
 EXPORTS = tuple(SIGNATURES) + tuple(_SPECIAL)
 
 

@@ -446,7 +446,9 @@ def camera_isp(name: str, dtype=f32):
                 if all(self._fused_ok(f, ids_format) for f in nxt):
                     with torch.cuda.device(self.device):
                         if self._side_stream is None:
-                            self._side_stream = torch.cuda.Stream(self.device)
+                            # high priority: the metering CTAs take SM slots ahead of the sweep's not-yet-dispatched
+                            # CTAs (an earlier-launched grid otherwise keeps every freed slot until its tail)
+                            self._side_stream = torch.cuda.Stream(self.device, priority=-1)
                         if self._metrics_alt is None:
                             self._metrics_alt = torch.zeros(9, dtype=torch.float32, device=self.device)
                         side = self._side_stream

@@ -824,7 +824,15 @@ static int run_pass(const FramePtrs& fp, IspConsts k, int frame0, int nframes, i
   Packed12Loader2<CAM16> ld;
   ld.fp = fp; ld.pitch_words = k.W * 3 / 8; ld.frame0 = frame0;
   int st = B200ISP_OK;
-  if (ev_start) cudaEventRecord((cudaEvent_t)ev_start, s);
+  // profile hooks: inside a stream capture the record must be an "external" event node to stay queryable
+  auto record = [&](void* ev) {
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(s, &cs) == cudaSuccess && cs == cudaStreamCaptureStatusActive)
+      cudaEventRecordWithFlags((cudaEvent_t)ev, s, cudaEventRecordExternal);
+    else
+      cudaEventRecord((cudaEvent_t)ev, s);
+  };
+  if (ev_start) record(ev_start);
   ISP_DISPATCH_PATTERN(k.pattern, P, {
     if constexpr (MODE == MODE_RGB) { EpiRgb2<CAM16, OutT> e{fp, k}; st = launch_stream2<P>(ld, e, g, s, "isp_stream<rgb>"); }
     else if constexpr (MODE == MODE_LINEAR) {
@@ -836,7 +844,7 @@ static int run_pass(const FramePtrs& fp, IspConsts k, int frame0, int nframes, i
     else if constexpr (MODE == MODE_RMAX) { EpiReinhardMax2<CAM16> e{k}; st = launch_stream2<P>(ld, e, g, s, "isp_stream<reinhard_max>"); }
     else { EpiReinhard2<CAM16, OutT> e{fp, k}; st = launch_stream2<P>(ld, e, g, s, "isp_stream<reinhard>"); }
   });
-  if (ev_stop) cudaEventRecord((cudaEvent_t)ev_stop, s);
+  if (ev_stop) record(ev_stop);
   return st;     // the 2-pixel image frame is renormalised inside the sweep (border_fix.cuh): no border kernel
 }
 

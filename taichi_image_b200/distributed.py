@@ -70,13 +70,72 @@ def exchange(record: torch.Tensor, group=None) -> torch.Tensor:
     return out.view(world, record.numel())
 
 
-def shared_metering(backend, source, group=None, alpha: Optional[float] = None, out=None) -> None:
+class PeerExchange:
+    """All-gather of the two shared-exposure records through peer-mapped mailboxes over NVLink (csrc/exchange.cu):
+    two 1-warp kernels per gather on the current stream, no host call on the data path, CUDA-graph capturable.
+    One process per GPU of ONE node; the CUDA IPC handles travel once through ``torch.distributed``.  Without a
+    process group (single rank) the mailbox is local and the exchange degenerates to a copy."""
+
+    def __init__(self, device, group=None):
+        import ctypes as C
+        from . import _lib
+        self._lib, self.device, self.group = _lib, torch.device(device), group
+        multi = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
+        self.world = dist.get_world_size(group) if multi else 1
+        self.rank = dist.get_rank(group) if multi else 0
+        assert self.world <= 32, "PeerExchange supports up to 32 ranks"
+        handle = (C.c_ubyte * 64)()
+        self._own = C.c_void_p()
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib.b200isp_mailbox_create(self.world, C.byref(self._own), handle), "mailbox_create")
+            handles = [bytes(handle)]
+            if multi:
+                handles = [None] * self.world
+                dist.all_gather_object(handles, bytes(handle), group=group)
+            self._peers = (C.c_void_p * self.world)()
+            for r, h in enumerate(handles):
+                if r == self.rank:
+                    self._peers[r] = self._own.value
+                else:
+                    p = C.c_void_p()
+                    buf = (C.c_ubyte * 64).from_buffer_copy(h)
+                    _lib.check(_lib.lib.b200isp_mailbox_open(buf, C.byref(p)), f"mailbox_open(rank {r})")
+                    self._peers[r] = p.value
+            self.gathered = {1: torch.empty((self.world, 2), dtype=torch.float32, device=self.device),
+                             2: torch.empty((self.world, 8), dtype=torch.float32, device=self.device)}
+            torch.cuda.synchronize(self.device)
+        if multi:
+            dist.barrier(group=group)            # every mailbox is open everywhere before anyone posts
+
+    def __call__(self, record: torch.Tensor, kind: int) -> torch.Tensor:
+        """kind 1: record of 2 floats, kind 2: 8 floats -> (world, 2 | 8) in rank order (a reused buffer: valid until
+        the next exchange of the same kind on this stream)"""
+        assert record.is_cuda and record.dtype == torch.float32 and record.numel() == (2 if kind == 1 else 8)
+        out = self.gathered[kind]
+        with torch.cuda.device(self.device):
+            self._lib.check(self._lib.lib.b200isp_mailbox_exchange(
+                record.data_ptr(), kind, self._peers, self.world, self.rank, out.data_ptr(),
+                self._lib.stream_ptr(self.device)), "mailbox_exchange")
+        return out
+
+    def check(self) -> None:
+        """raises if a bounded wait expired (a peer never posted); synchronises the current stream"""
+        with torch.cuda.device(self.device):
+            st = self._lib.lib.b200isp_mailbox_error(self._own, self.world, self._lib.stream_ptr(self.device))
+        if st == 1:
+            raise RuntimeError(f"rank {self.rank}: shared-exposure exchange timed out waiting for a peer")
+        self._lib.check(st, "mailbox_error")
+
+
+def shared_metering(backend, source, group=None, alpha: Optional[float] = None, out=None, peer: Optional[PeerExchange] = None) -> None:
     """One joint metering update over the frames of ALL ranks (each rank passes its own ``source``).
-    ``alpha`` / ``out``: given by the look-ahead pipeline (weight of the previous metrics, second metrics buffer)."""
+    ``alpha`` / ``out``: given by the look-ahead pipeline (weight of the previous metrics, second metrics buffer).
+    ``peer``: exchange through NVLink mailboxes instead of ``torch.distributed`` all-gathers."""
     if alpha is None:
         alpha = backend.begin()
-    g1 = exchange(backend.phase1(source), group)
-    g2 = exchange(backend.phase2(source, g1, alpha), group)
+    ex = (lambda rec, kind: peer(rec, kind)) if peer is not None else (lambda rec, kind: exchange(rec, group))
+    g1 = ex(backend.phase1(source), 1)
+    g2 = ex(backend.phase2(source, g1, alpha), 2)
     if out is None:
         backend.finalize(g1, g2, alpha)
     else:
@@ -88,10 +147,16 @@ class SharedExposure:
     ranks of ``group`` (rig-wide shared exposure).  Same call signatures as the wrapped ISP; everything
     else (``set``, ``load_*``, attributes) is forwarded."""
 
-    def __init__(self, isp, group=None, backend=None):
+    def __init__(self, isp, group=None, backend=None, exchange: str = "auto"):
+        """exchange: "peer" = NVLink mailboxes (PeerExchange; CUDA ranks of one node), "nccl" = two
+        ``torch.distributed`` all-gathers per update (any backend), "auto" = peer for the CUDA backend"""
         self.isp = isp
         self.group = group
         self.backend = backend if backend is not None else CudaMeteringBackend(isp)
+        if exchange == "auto":
+            exchange = "peer" if backend is None else "nccl"
+        assert exchange in ("peer", "nccl")
+        self.peer = PeerExchange(isp.device, group) if exchange == "peer" else None
 
     def __getattr__(self, name):
         return getattr(self.isp, name)
@@ -101,7 +166,7 @@ class SharedExposure:
         return self.isp.metrics
 
     def update_metering(self, images: Sequence[torch.Tensor]) -> None:
-        shared_metering(self.backend, images, self.group)
+        shared_metering(self.backend, images, self.group, peer=self.peer)
 
     def tonemap_reinhard(self, images, gamma: float = 1.0, intensity: float = 1.0, light_adapt: float = 1.0,
                          color_adapt: float = 0.0, **kw):
@@ -119,7 +184,7 @@ class SharedExposure:
         if all(isp._fused_ok(f, ids_format) for f in frames) and not isp._resizes:
             # the ISP's look-ahead pipeline drives the joint metering: the exchange of batch k+1 (two tiny
             # all-gathers) then runs on the side stream under the sweep of batch k
-            meter = lambda fs, alpha, out, cooperative: shared_metering(self.backend, fs, self.group, alpha, out)
+            meter = lambda fs, alpha, out, cooperative: shared_metering(self.backend, fs, self.group, alpha, out, self.peer)
             return isp.process_packed12(frames, tonemap=tonemap, ids_format=ids_format, meter_fn=meter, **kw)
         images = [isp.load_packed12(f, ids_format) for f in frames]
         kw.pop("out", None); kw.pop("rows_per_task", None); kw.pop("profile_events", None)

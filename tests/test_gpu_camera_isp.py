@@ -202,3 +202,44 @@ def test_lookahead_metering_is_equivalent(cuda, dt, tm):
         np.testing.assert_allclose(to_np(ahead.metrics), to_np(serial.metrics), rtol=2e-6, atol=1e-7)
         for x, y in zip(ya, yb):
             assert_close_int(to_np(x), to_np(y), 1, f"lookahead {dt} {tm} step {i}")
+
+
+@pytest.mark.parametrize("tm,out", [("linear", "u16"), ("reinhard", "u8")])
+def test_graphed_stream_matches_eager(cuda, tm, out):
+    """graphed.GraphedStream (CUDA-graph replay of sweep k || metering k+1 on fixed buffers) == eager calls"""
+    from taichi_image_b200.graphed import GraphedStream
+    from taichi_image_b200 import as_dtype
+    r = rng(43)
+    h, w, n = 40, 64, 3
+    host = [frames(r, n, h, w) for _ in range(4)]
+    bufs = [torch.empty((h, w * 3 // 2), dtype=torch.uint8, device="cuda") for _ in range(n)]
+    outs = [torch.empty((h, w, 3), dtype=as_dtype(out).torch, device="cuda") for _ in range(n)]
+    eager, gisp = make_isp("f32", moving_alpha=0.2), make_isp("f32", moving_alpha=0.2)
+    for b, f in zip(bufs, host[0]):
+        b.copy_(to_cuda(f))
+    gs = GraphedStream(gisp, bufs, outs, tonemap=tm, dtype=out, gamma=0.9)
+    for k in range(4):
+        exp = eager.process_packed12([to_cuda(f) for f in host[k]], tonemap=tm, gamma=0.9, dtype=out)
+        # single-buffered ingest: the step meters what is in the buffers when it runs, i.e. refill BEFORE the step
+        # with batch k+1 would change sweep k -> here the sweep and the look-ahead metering both see batch k, so the
+        # graphed stream is compared on a constant scene after the first step
+        got = [o.clone() for o in gs.step()]
+        torch.cuda.synchronize()
+        if k == 0:
+            for x, y in zip(exp, got):
+                assert_close_int(to_np(x), to_np(y), 1, f"graphed {tm} first step")
+    # steady state on a constant scene: both must converge to the same metrics trajectory
+    eager2, gisp2 = make_isp("f32", moving_alpha=0.2), make_isp("f32", moving_alpha=0.2)
+    cu = [to_cuda(f) for f in host[1]]
+    for b, f in zip(bufs, cu):
+        b.copy_(f)
+    gs2 = GraphedStream(gisp2, bufs, outs, tonemap=tm, dtype=out, gamma=0.9)
+    for k in range(4):
+        exp = eager2.process_packed12(cu, tonemap=tm, gamma=0.9, dtype=out)
+        got = [o.clone() for o in gs2.step()]
+        torch.cuda.synchronize()
+        for x, y in zip(exp, got):
+            assert_close_int(to_np(x), to_np(y), 1, f"graphed {tm} step {k}")
+    # after k steps isp.metrics already holds the update for step k+1
+    eager2.process_packed12(cu, tonemap=tm, gamma=0.9, dtype=out)
+    np.testing.assert_allclose(to_np(gisp2.metrics), to_np(eager2.metrics), rtol=2e-6, atol=1e-7)

@@ -70,3 +70,38 @@ def test_shared_exposure_world1_equals_plain(cuda):
         np.testing.assert_allclose(to_np(a.metrics), to_np(b.metrics), rtol=1e-6, atol=1e-7)
         for x, y in zip(ya, yb):
             assert_close_int(to_np(x), to_np(y), 1, "shared vs plain")
+
+
+def test_peer_exchange_world1_and_emulated_ranks(cuda):
+    """csrc/exchange.cu on one GPU: (a) PeerExchange without a process group is a local copy, repeatable (sequence
+    numbers / parity); (b) two mailboxes owned by this process emulate two ranks: both post, then both wait"""
+    import ctypes as C
+    from taichi_image_b200 import _lib
+    from taichi_image_b200.distributed import PeerExchange
+    px = PeerExchange(torch.device("cuda", 0))
+    for step in range(5):
+        r1 = torch.tensor([0.1 * step, 1.0 + step], device="cuda")
+        r2 = torch.arange(8, dtype=torch.float32, device="cuda") + step
+        assert torch.equal(px(r1, 1), r1.reshape(1, 2)) and torch.equal(px(r2, 2), r2.reshape(1, 8))
+    px.check()
+    # (b) two emulated ranks
+    world, boxes = 2, []
+    for _ in range(world):
+        p, h = C.c_void_p(), (C.c_ubyte * 64)()
+        _lib.check(_lib.lib.b200isp_mailbox_create(world, C.byref(p), h), "create")
+        boxes.append(p)
+    peers = (C.c_void_p * world)(*[b.value for b in boxes])
+    st = _lib.stream_ptr(torch.device("cuda", 0))
+    gathered = [torch.zeros((world, 8), device="cuda") for _ in range(world)]
+    for step in range(4):
+        recs = [torch.arange(8, dtype=torch.float32, device="cuda") * (r + 1) + 10 * step for r in range(world)]
+        for r in range(world):
+            _lib.check(_lib.lib.b200isp_mailbox_post(recs[r].data_ptr(), 2, peers, world, r, st), "post")
+        for r in range(world):
+            _lib.check(_lib.lib.b200isp_mailbox_wait(boxes[r], 2, world, gathered[r].data_ptr(), st), "wait")
+        torch.cuda.synchronize()
+        for r in range(world):
+            assert torch.equal(gathered[r], torch.stack(recs)), f"step {step} rank {r}"
+            assert _lib.lib.b200isp_mailbox_error(boxes[r], world, st) == 0
+    for b in boxes:
+        _lib.check(_lib.lib.b200isp_mailbox_close(b, 1), "close")
