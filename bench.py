@@ -44,6 +44,9 @@ WORKLOADS = {
              "BASELINE configs[2] shard: 6 cameras x 4096x3000 per GPU, script tone-map settings -> RGB8"),
 }
 OUT_BYTES = {"u8": 1, "u16": 2, "f16": 2}
+# dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel per launch, from the ncu --set full capture
+# summarised under profiles/ (r01_stream2_kernel_ncu.txt); None where no capture exists
+TRAFFIC = {"cfg2": 843.6e6}     # 180.8 MB read + 662.8 MB written (algorithmic: 179.7 + 718.6; the last ~56 MB of writes are still in L2 at kernel end)
 
 
 def synth_frames(n, h, w, seed=1234):
@@ -80,7 +83,7 @@ class ClockSampler:
         self.rows, self.proc = [], None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          "-lms", "20"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
         except Exception:
@@ -90,12 +93,15 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.rows.append((time.time(), [x.strip() for x in line.split(",")]))
 
+    def count(self, t0, t1):
+        return sum(1 for t, _ in self.rows if t0 <= t <= t1)
+
     def stop(self, t0, t1):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        time.sleep(0.05)
         self.proc.terminate()
-        rows = [r for t, r in self.rows if t0 - 0.05 <= t <= t1 + 0.15] or [r for _, r in self.rows]
+        rows = [r for t, r in self.rows if t0 <= t <= t1] or [r for _, r in self.rows]
         sm, mx, reasons = [], None, set()
         names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
         for r in rows:
@@ -169,17 +175,34 @@ def run_reference(args):
     value = args.steps * band_h * w / dt / 1e9
     sample = (f"each step = one {w}x{band_h} frame of the workload through oracle/c/isp_oracle.c "
               f"(OpenMP, {cores} threads); the reference's Taichi CPU backend is not installable here")
-    print(json.dumps({
+    emit({
         "impl": "reference", "metric": "Gpixel/s packed12->RGB ISP", "value": value, "unit": "Gpixel/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32" if isp_dt == "f32" else "f16", "data": "synthetic",
         "config": {"workload": desc, "sample": sample},
         "cpu_baseline": {"value": value, "unit": "Gpixel/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "Gpixel/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-    }))
+    })
+
+
+_REAL_STDOUT = None
+
+
+def emit(line: dict):
+    """the ONE JSON line on the real stdout (everything else -- NCCL's version banner, library chatter -- was
+    redirected to stderr at start-up)"""
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
 
 
 def main():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)                      # fd 1 -> stderr for native libraries and stray prints
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=30)
@@ -265,7 +288,29 @@ def main():
         t = torch.tensor([elapsed_ms], device=device)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         elapsed_ms = float(t.item())
+    # nvidia-smi cannot sample faster than ~20 ms: when the timed region was too short to contain a sample, the
+    # identical load keeps running (untimed, the same number of steps on every rank) for about half a second and
+    # the clocks are sampled there
+    clock_window = "timed region"
+    need_more = 1 if (sampler is not None and sampler.count(t0, t1) == 0) else 0
+    if world > 1:
+        f = torch.tensor([need_more], device=device)
+        dist.all_reduce(f, op=dist.ReduceOp.MAX)
+        need_more = int(f.item())
+    if need_more:
+        clock_window = "~0.5 s of the same steps right after the (too short) timed region"
+        extra = max(20, int(500.0 / max(elapsed_ms / args.steps, 1e-3)))
+        torch.cuda.synchronize()
+        t0 = time.time()
+        for _ in range(extra):
+            step(None)
+        torch.cuda.synchronize()
+        t1 = time.time()
+        if world > 1:
+            dist.barrier()
     clocks = sampler.stop(t0, t1) if sampler else None
+    if clocks is not None:
+        clocks["window"] = clock_window
     # graph mode: the event pair is part of the two captured graphs -> device times of the last two timed steps
     kern_ms = graphed.kernel_ms() if graphed is not None else [a.elapsed_time(b) for a, b in evs]
     kern_avg_ms = sum(kern_ms) / len(kern_ms)
@@ -273,19 +318,33 @@ def main():
     group = n if tonemap != "reinhard" else max(1, min(n, int((48 << 20) // (h * w * 3 // 2))))
     kern_bytes = alg_bytes * (group / n) if tonemap == "reinhard" else alg_bytes
     peak, peak_src = measured_peak()
+    in_step_ms = kern_avg_ms
+    # The dominant kernel timed ALONE (same process, same resident inputs, CUDA events on the launching stream):
+    # inside the timed region it shares the GPU with the look-ahead metering of the next batch, so its in-step
+    # duration measures the overlap, not the kernel.  Both are reported.
+    torch.cuda.synchronize()
+    base_isp = isp.isp if hasattr(isp, "isp") else isp
+    iso = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(10)]
+    for a, b in iso:
+        a.record(); b.record()
+    for a, b in iso:
+        base_isp._run_fused(frames, tonemap, tib.as_dtype(out_dt), outs, tm, update_metering=False,
+                            rows_per_task=args.rows_per_task, profile_events=(a, b))
+    torch.cuda.synchronize()
+    kern_avg_ms = sum(a.elapsed_time(b) for a, b in iso[2:]) / len(iso[2:])
     achieved = kern_bytes / (kern_avg_ms * 1e-3) / 1e9
     value = world * px_per_step * args.steps / (elapsed_ms * 1e-3) / 1e9
 
-    # launches of our kernels per step: metering 2 (shared exposure: + bounds fold + finalize) + sweeps + border kernels
-    if tonemap == "reinhard":
-        ngroups = (n + group - 1) // group
-        launches = 2 + 4 * ngroups
-    else:
-        launches = 2 + 2
+    # launches of OUR kernels per step (counted from the launch plan):
+    #   sweep: linear 1 (the image frame is renormalised inside the sweep), Reinhard 2 per L2-sized frame group
+    #   metering: 1 cooperative launch; as look-ahead on the side stream 2 ordinary launches; with shared exposure
+    #             phase1 + post + wait + bounds fold + phase2 + post + wait + finalize = 8
+    ngroups = (n + group - 1) // group if tonemap == "reinhard" else 1
+    launches = 2 * ngroups if tonemap == "reinhard" else 1
     if shared and world > 1:
-        launches += 2
-    if args.lookahead and not (shared and world > 1):
-        launches += 1          # look-ahead metering runs as two ordinary launches instead of one cooperative launch
+        launches += 8
+    else:
+        launches += 2 if args.lookahead else 1
 
     # ---------------- end to end through the public API with host buffers
     e2e = None
@@ -341,14 +400,21 @@ def main():
         "clocks": clocks,
         "gpu_launches": launches * args.steps,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": None, "kernel": f"isp::stream_kernel<{tonemap}> (fused packed12 sweep)",
+                     "kernel": f"isp::stream2_kernel<{tonemap}> (fused packed12 sweep, pair engine)",
                      "kernel_ms": kern_avg_ms, "algorithmic_bytes_per_launch": kern_bytes, "peak_source": peak_src,
-                     "bytes_per_pixel": 1.5 + 3 * OUT_BYTES[out_dt]},
+                     "bytes_per_pixel": 1.5 + 3 * OUT_BYTES[out_dt],
+                     "timing": "kernel timed alone: 8 launches after the timed region, CUDA events recorded by the library "
+                               "around the launch on the launching stream",
+                     "in_step": {"kernel_ms": in_step_ms, "achieved": kern_bytes / (in_step_ms * 1e-3) / 1e9,
+                                 "frac": kern_bytes / (in_step_ms * 1e-3) / 1e9 / peak,
+                                 "note": "same kernel inside the timed region, where it runs concurrently with the "
+                                         "look-ahead metering (and exposure exchange) of the next batch"},
+                     "traffic": TRAFFIC.get(args.workload)},
         "step_gbps": alg_bytes * args.steps / (elapsed_ms * 1e-3) / 1e9,
         "e2e": e2e,
         "cpu_baseline": cpu,
     }
-    print(json.dumps(line))
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 

@@ -131,6 +131,9 @@ inline Stream2Geom make_geom2(int H, int W, int nframes, int rows_per_task) {
   return s;
 }
 
+#ifndef ISP_S2_PF_ROWS
+#define ISP_S2_PF_ROWS 6        // L2 prefetch distance beyond the register fetch (rows row+4+PF, row+5+PF); 2 / 6 / 12 measured: 173.6 / 171.4 / 172.4 us
+#endif
 #ifndef ISP_S2_THREADS
 #define ISP_S2_THREADS 128      // 4 warps per CTA
 #endif
@@ -177,8 +180,11 @@ __device__ __forceinline__ void stream2_rows(const Loader& ld, const Epi& epi, t
   uint32_t mask = row_mask(r0 + 2);
   ld.template fetch<KIND>(cur, pn, raw0);
   ld.template fetch<KIND>(cur, pn + pitch, raw1);
-  ld.prefetch(cur, cur.p + (ptrdiff_t)clamped(r0 + 4) * pitch);
-  ld.prefetch(cur, cur.p + (ptrdiff_t)clamped(r0 + 4) * pitch + pitch);
+#pragma unroll
+  for (int d = 4; d < 4 + ISP_S2_PF_ROWS; d += 2) {
+    ld.prefetch(cur, cur.p + (ptrdiff_t)clamped(r0 + d) * pitch);
+    ld.prefetch(cur, cur.p + (ptrdiff_t)clamped(r0 + d) * pitch + pitch);
+  }
 
 #define ISP_STEP(U, ROW)                                                                                        \
   {                                                                                                             \
@@ -190,14 +196,14 @@ __device__ __forceinline__ void stream2_rows(const Loader& ld, const Epi& epi, t
     pn += in_ ? 2 * pitch : 0;                                                                                  \
     if (MASKED) mask = in_ ? kMask : 0u;                                                                        \
     ld.template fetch<KIND>(cur, pn, raw0);                                                                     \
-    if (row_ + 6 < g.H) ld.prefetch(cur, pn + 2 * pitch);                                                       \
+    if (row_ + 4 + ISP_S2_PF_ROWS < g.H) ld.prefetch(cur, pn + ISP_S2_PF_ROWS * pitch);                                                     \
     f2 R_[4], G_[4], B_[4];                                                                                     \
     malvar_row2<BROW0, GFIRST0>(W[(2 * (U)) % 6], W[(2 * (U) + 1) % 6], W[(2 * (U) + 2) % 6],                   \
                                 W[(2 * (U) + 3) % 6], W[(2 * (U) + 4) % 6], R_, G_, B_);                        \
     epi.template emit<BROW0, GFIRST0, KIND>(st, row_, R_, G_, B_);                                              \
     ld.template decode<KIND>(cur, raw1, m_, W[(2 * (U) + 5) % 6]);                                              \
     ld.template fetch<KIND>(cur, pn + pitch, raw1);                                                             \
-    if (row_ + 6 < g.H) ld.prefetch(cur, pn + 3 * pitch);                                                       \
+    if (row_ + 4 + ISP_S2_PF_ROWS < g.H) ld.prefetch(cur, pn + (ISP_S2_PF_ROWS + 1) * pitch);                                                     \
     malvar_row2<!BROW0, !GFIRST0>(W[(2 * (U) + 1) % 6], W[(2 * (U) + 2) % 6], W[(2 * (U) + 3) % 6],             \
                                   W[(2 * (U) + 4) % 6], W[(2 * (U) + 5) % 6], R_, G_, B_);                      \
     epi.template emit<!BROW0, !GFIRST0, KIND>(st, row_ + 1, R_, G_, B_);                                        \
