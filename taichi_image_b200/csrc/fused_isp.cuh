@@ -55,6 +55,10 @@ struct Packed12Loader2 {
   int pitch_words;       // W * 3 / 8
   int frame0;
   static constexpr uint32_t kRowMask = 0x007FF800u;
+#ifndef ISP_S2_RING
+#define ISP_S2_RING 0      // measured on cfg2 (see stream2.cuh): register fetch 172 us; ring + 3x unroll 229 us; ring + 1 step 185 us
+#endif
+  static constexpr bool kRing = ISP_S2_RING != 0;     // K_CORE stages its rows through the cp.async ring (stream2.cuh)
   struct Raw { uint32_t w[5]; };
   struct Cursor { const uint32_t* p; uint32_t mL, mR; bool left, right, pf; };
 
