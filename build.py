@@ -35,7 +35,7 @@ FUSED_OUT = {"u8": "uint8_t", "u16": "uint16_t", "f16": "__half", "f32": "float"
 
 def translation_units():
     """(object name, source, extra defines)"""
-    tus = [(n, CSRC / f"{n}.cu", []) for n in ("api", "pack", "demosaic", "tonemap", "resize", "fused_api", "exchange")]
+    tus = [(n, CSRC / f"{n}.cu", []) for n in ("api", "pack", "demosaic", "tonemap", "resize", "fused_api", "exchange", "yuv420")]
     for cam in (0, 1):
         tus.append((f"fused_rmax_cam{16 if cam else 32}", CSRC / "fused_inst.cu",
                     [f"-DISP_INST_CAM16={cam}", "-DISP_INST_RMAX"]))

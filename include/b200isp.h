@@ -85,6 +85,12 @@ int b200isp_bayer_to_rgb(const void* bayer, int in_dtype, void* rgb, int out_dty
                          int height, int width, int pattern, const float* ccm9_host,
                          b200isp_stream stream);
 
+/* EXTENSION (north_star "bilinear demosaic"; the reference has only Malvar): 3x3 bilinear CFA interpolation with the
+ * normalisation / CCM / clamp / cast rule of bayer.py:137-155 (mean of the in-bounds neighbours of each colour). */
+int b200isp_bayer_to_rgb_bilinear(const void* bayer, int in_dtype, void* rgb, int out_dtype,
+                                  int height, int width, int pattern, const float* ccm9_host,
+                                  b200isp_stream stream);
+
 /* ---- util.py / tonemap.py (stand-alone, per image) ---------------------- */
 /* util.py:49-60 bounds_func: min/max over n_elems values -> bounds_out[2] (device). */
 int b200isp_bounds(const void* src, int dtype, int64_t n_elems, float* bounds_out,
@@ -113,6 +119,15 @@ int b200isp_resize_area(const void* src, int in_dtype, int src_h, int src_w,
 /* interpolate.py:93-108 transform_kernel(dtype)(src,dst,transform); src is (H,W,3). */
 int b200isp_transform(const void* src, void* dst, int dtype, int src_h, int src_w,
                       int transform, b200isp_stream stream);
+
+/* ---- color/yuv_420.py -------------------------------- */
+/* yuv_420.py:38-64 rgb_yuv420_kernel(in, out)(src, y_image, uv_image): rgb (H,W,3) -> one (3H/2, W) plane = Y rows
+ * followed by the two (H/2, W/2) chroma planes.  matrix9_host = YCrCb_T_bgr (yuv_420.py:12-16), row-major, HOST. */
+int b200isp_rgb_yuv420(const void* rgb, int in_dtype, void* yuv, int out_dtype, int height, int width,
+                       const float* matrix9_host, b200isp_stream stream);
+/* yuv_420.py:66-90 yuv420_rgb_kernel(in, out)(y_image, uv_image, rgb_image); matrix9_host = bgr_T_YCrCb (:18). */
+int b200isp_yuv420_rgb(const void* yuv, int in_dtype, void* rgb, int out_dtype, int height, int width,
+                       const float* matrix9_host, b200isp_stream stream);
 
 /* ---- camera_isp.py (eager, per-stage; float RGB images of the ISP dtype) - */
 /* camera_isp.py:82-99 load_16u / load_32f / load_16f: element-wise convert.
@@ -161,6 +176,14 @@ typedef struct {
 int b200isp_process_packed12(const uint8_t* const* packed_host, void* const* out_host, int n_frames,
                              const b200isp_fused_params* params, float* metrics,
                              void* workspace, b200isp_stream stream);
+
+/* EXTENSION (north_star "percentile histogram"; no reference counterpart): luminance histogram of the metering
+ * samples (n_samples RGB float triples as written to fused_params.meter_cache), bin = min(bins-1, trunc(gray*bins)),
+ * and percentiles of it: out[k] = upper edge of the first bin whose cumulative count reaches percents[k] %.
+ * hist / percents / out are device pointers. */
+int b200isp_sample_histogram(const float* samples, int64_t n_samples, int bins, uint32_t* hist, b200isp_stream stream);
+int b200isp_histogram_percentiles(const uint32_t* hist, int bins, const float* percents, int n_percents, float* out,
+                                  b200isp_stream stream);
 
 /* ---- multi-GPU shared exposure (no reference counterpart: the reference is single-GPU) ----
  * The reference meters all cameras of a time step jointly (camera_isp.py:168-175).  With one camera

@@ -23,7 +23,7 @@ sys.path.insert(0, REFERENCE)
 import numpy as np          # noqa: E402
 import torch                # noqa: E402
 import taichi as ti         # noqa: E402  (the shim)
-from taichi_image import packed, bayer, tonemap, interpolate, camera_isp   # noqa: E402  (the reference)
+from taichi_image import packed, bayer, tonemap, interpolate, camera_isp, color   # noqa: E402  (the reference)
 
 OUT = os.path.join(ROOT, "tests", "golden")
 TI = {"u8": ti.u8, "u16": ti.u16, "i16": ti.i16, "f16": ti.f16, "f32": ti.f32}
@@ -131,6 +131,22 @@ def gen_interpolate():
     np.savez_compressed(os.path.join(OUT, "interpolate.npz"), **d)
 
 
+def gen_color():
+    """color/yuv_420.py: planar YUV 4:2:0 encode / decode"""
+    r = np.random.default_rng(105)
+    d = {}
+    for name in ("u8", "u16", "f16", "f32"):
+        # smooth-ish content keeps the chroma inside [0, 1]: the reference's "clamp" has no lower bound (yuv_420.py:57)
+        img = plane(r, (6, 10, 3), name)
+        d[f"rgb_{name}"] = img
+        enc = color.rgb_yuv420_image(img)
+        d[f"yuv_{name}"] = enc
+        d[f"rgb_back_{name}"] = color.yuv420_rgb_image(enc)
+    d["yuv_u8_to_f32"] = color.rgb_yuv420_image(d["rgb_u8"], ti.f32)
+    d["yuv_f32_to_u8"] = color.rgb_yuv420_image(d["rgb_f32"], ti.u8)
+    np.savez_compressed(os.path.join(OUT, "color.npz"), **d)
+
+
 def smooth(r, h, w):
     y, x = np.mgrid[0:h, 0:w].astype(np.float32)
     base = 0.5 + 0.35 * np.sin(x / w * 5.1 + 0.3) * np.cos(y / h * 3.7)
@@ -179,7 +195,7 @@ def gen_camera_isp():
 def main():
     os.makedirs(OUT, exist_ok=True)
     only = set(sys.argv[1:])
-    for fn in (gen_packed, gen_bayer, gen_tonemap, gen_interpolate, gen_camera_isp):
+    for fn in (gen_packed, gen_bayer, gen_tonemap, gen_interpolate, gen_camera_isp, gen_color):
         if only and fn.__name__[4:] not in only:
             continue
         fn()

@@ -506,3 +506,103 @@ class ISP:
         self.update_metering(images)
         outs = [isp_linear(im, self.metrics, gamma, out_dtype) for im in images]
         return [transform(o, self.transform) for o in outs]
+
+
+# --------------------------------------------------------------------------
+# color/yuv_420.py
+# --------------------------------------------------------------------------
+# yuv_420.py:12-16.  NB the reference applies this matrix to the BGR-swizzled vector (yuv_420.py:24-26), i.e.
+# Y = 0.299 B + 0.587 G + 0.114 R: reproduced as is.
+YCRCB_T_BGR = np.array([[0.299, 0.587, 0.114], [-0.168736, -0.331264, 0.5], [0.5, -0.418688, -0.081312]], np.float64)
+BGR_T_YCRCB = np.linalg.inv(YCRCB_T_BGR.astype(f32).astype(np.float64)).astype(f32)      # yuv_420.py:18 (Python-scope inverse)
+
+
+def _mat_vec(m, x):
+    """mat3 @ vec3 in f32, row dot products left to right"""
+    m = m.astype(f32)
+    return np.stack([(m[r, 0] * x[..., 0] + m[r, 1] * x[..., 1]) + m[r, 2] * x[..., 2] for r in range(3)], -1)
+
+
+def _ref_clamp01(v):
+    """tm.clamp(0, 1, v) as the reference writes it (yuv_420.py:57, 61, 88): Taichi's clamp is clamp(x, xmin, xmax),
+    so the call evaluates min(max(0, 1), v) = min(1, v) -- no lower clamp."""
+    return np.minimum(f32(1.0), v)
+
+
+def rgb_yuv420(src: np.ndarray, dtype: str | None = None) -> np.ndarray:
+    """yuv_420.py:38-64, :104-118: planar Y (H rows) followed by two (H/2, W/2) chroma planes; the second matrix
+    row goes to plane 1, the third to plane 0 (yuv_420.py:62-63)."""
+    in_name = dtype_name(src)
+    dtype = dtype or in_name
+    h, w, _ = src.shape
+    x = src.astype(f32) / f32(SCALE[in_name])
+    yuv = _mat_vec(YCRCB_T_BGR, x[..., ::-1]) + np.array([0, 0.5, 0.5], f32)
+    out = np.zeros(((h * 3) // 2, w), NP_DTYPE[dtype])
+    out[:h] = cast_to(_ref_clamp01(yuv[..., 0]) * f32(SCALE[dtype]), dtype)
+    he, we = h // 2 * 2, w // 2 * 2
+    uv = ((yuv[0:he:2, 0:we:2, 1:] + yuv[0:he:2, 1:we:2, 1:]) + yuv[1:he:2, 0:we:2, 1:]) + yuv[1:he:2, 1:we:2, 1:]
+    uvq = cast_to(_ref_clamp01(uv / f32(4.0)) * f32(SCALE[dtype]), dtype)
+    planes = out[h:].reshape(2, h // 2, w // 2)
+    planes[1] = uvq[..., 0]
+    planes[0] = uvq[..., 1]
+    return out
+
+
+def yuv420_rgb_unit(yuv: np.ndarray) -> np.ndarray:
+    """f32 RGB before the upper clamp and the cast.  Negative components are undefined behaviour in the reference
+    for integer outputs (no lower clamp, yuv_420.py:88); the product saturates them to 0."""
+    in_name = dtype_name(yuv)
+    h = yuv.shape[0] * 2 // 3
+    w = yuv.shape[1]
+    y = yuv[:h].astype(f32)
+    planes = yuv[h:].reshape(2, h // 2, w // 2).astype(f32)
+    ii, jj = np.arange(h) // 2, np.arange(w) // 2
+    v = np.stack([y, planes[1][ii][:, jj], planes[0][ii][:, jj]], -1) / f32(SCALE[in_name])
+    bgr = _mat_vec(BGR_T_YCRCB, v - np.array([0, 0.5, 0.5], f32))
+    return bgr[..., ::-1]
+
+
+def yuv420_rgb(yuv: np.ndarray, dtype: str | None = None) -> np.ndarray:
+    """yuv_420.py:66-90, :95-101, :120-131"""
+    dtype = dtype or dtype_name(yuv)
+    return cast_to(_ref_clamp01(yuv420_rgb_unit(yuv)) * f32(SCALE[dtype]), dtype)
+
+
+# --------------------------------------------------------------------------
+# EXTENSION: bilinear demosaic (no reference counterpart; rule of bayer.py:137-155 with 3x3 kernels)
+# --------------------------------------------------------------------------
+BILINEAR = {   # site kernel -> 3x3 taps (row-major) of (wR, wG, wB), x4
+    0: [(0, 0, 1), (0, 1, 0), (0, 0, 1), (0, 1, 0), (4, 0, 0), (0, 1, 0), (0, 0, 1), (0, 1, 0), (0, 0, 1)],
+    1: [(0, 0, 0), (2, 0, 0), (0, 0, 0), (0, 0, 2), (0, 4, 0), (0, 0, 2), (0, 0, 0), (2, 0, 0), (0, 0, 0)],
+    2: [(0, 0, 0), (0, 0, 2), (0, 0, 0), (2, 0, 0), (0, 4, 0), (2, 0, 0), (0, 0, 0), (0, 0, 2), (0, 0, 0)],
+    3: [(1, 0, 0), (0, 1, 0), (1, 0, 0), (0, 1, 0), (0, 0, 4), (0, 1, 0), (1, 0, 0), (0, 1, 0), (1, 0, 0)],
+}
+
+
+def bayer_to_rgb_bilinear(bayer: np.ndarray, pattern: str = "RGGB", ccm=None, dtype: str | None = None) -> np.ndarray:
+    dtype = dtype or dtype_name(bayer)
+    h, w = bayer.shape
+    in_scale = f32(SCALE[dtype_name(bayer)])
+    pad = np.zeros((h + 2, w + 2), f32)
+    pad[1:-1, 1:-1] = bayer.astype(f32)
+    valid = np.zeros((h + 2, w + 2), bool)
+    valid[1:-1, 1:-1] = True
+    out = np.zeros((h, w, 3), f32)
+    kidx = KERNEL_PATTERN[pattern]
+    for slot in range(4):
+        r0, c0 = slot & 1, slot >> 1
+        c = np.zeros((h // 2, w // 2, 3), f32)
+        t = np.zeros((h // 2, w // 2, 3), f32)
+        for i, wt in enumerate(BILINEAR[kidx[slot]]):
+            d0, d1 = i // 3 - 1, i % 3 - 1
+            v = pad[1 + r0 + d0: 1 + r0 + d0 + h: 2, 1 + c0 + d1: 1 + c0 + d1 + w: 2]
+            m = valid[1 + r0 + d0: 1 + r0 + d0 + h: 2, 1 + c0 + d1: 1 + c0 + d1 + w: 2]
+            wv = np.asarray(wt, f32)
+            c = c + np.where(m[..., None], v[..., None] * wv, f32(0))
+            t = t + np.where(m[..., None], wv, f32(0))
+        with np.errstate(all="ignore"):
+            c = np.where(t > 0, c / (in_scale * t), f32(0)).astype(f32)
+        if ccm is not None:
+            c = _ccm_apply(c, ccm)
+        out[r0::2, c0::2] = np.clip(c, f32(0), f32(1))
+    return cast_to(out * f32(SCALE[dtype]), dtype)

@@ -46,6 +46,7 @@ SIGNATURES = {
     "b200isp_decode16": [_vp, _i64, _vp, _i, _i, _vp],
     "b200isp_rgb_to_bayer": [_vp, _vp, _i, _i, _i, _i, _vp],
     "b200isp_bayer_to_rgb": [_vp, _i, _vp, _i, _i, _i, _i, C.POINTER(C.c_float), _vp],
+    "b200isp_bayer_to_rgb_bilinear": [_vp, _i, _vp, _i, _i, _i, _i, C.POINTER(C.c_float), _vp],
     "b200isp_bounds": [_vp, _i, _i64, _vp, _vp, _vp],
     "b200isp_linear": [_vp, _i, _vp, _i, _i64, _vp, _f, _vp],
     "b200isp_reinhard_standalone": [_vp, _i, _vp, _vp, _i, _i64, _f, _f, _f, _f, _vp, _vp],
@@ -60,6 +61,10 @@ SIGNATURES = {
     "b200isp_metering_phase2": [C.POINTER(_vp), _i, _i, _i, _i, _i, _vp, _i, _f, _vp, _vp, _vp, _vp],
     "b200isp_metering_finalize": [_vp, _vp, _i, _f, _vp, _vp, _vp],
     "b200isp_meter_packed12": [C.POINTER(_vp), _i, C.POINTER(FusedParams), _vp, _vp, _i, _vp, _vp],
+    "b200isp_sample_histogram": [_vp, _i64, _i, _vp, _vp],
+    "b200isp_histogram_percentiles": [_vp, _i, _vp, _i, _vp, _vp],
+    "b200isp_rgb_yuv420": [_vp, _i, _vp, _i, _i, _i, C.POINTER(C.c_float), _vp],
+    "b200isp_yuv420_rgb": [_vp, _i, _vp, _i, _i, _i, C.POINTER(C.c_float), _vp],
     "b200isp_mailbox_create": [_i, C.POINTER(_vp), _vp],
     "b200isp_mailbox_open": [_vp, C.POINTER(_vp)],
     "b200isp_mailbox_close": [_vp, _i],

@@ -111,8 +111,11 @@ def rgb_to_bayer(image, pattern: BayerPattern = BayerPattern.RGGB):
     return restore(bayer)
 
 
-def bayer_to_rgb(bayer, pattern: BayerPattern = BayerPattern.RGGB, correct_colors: Optional[np.ndarray] = None, dtype=None):
-    """bayer.py:202-219"""
+def bayer_to_rgb(bayer, pattern: BayerPattern = BayerPattern.RGGB, correct_colors: Optional[np.ndarray] = None, dtype=None,
+                 method: str = "malvar"):
+    """bayer.py:202-219.  ``method="bilinear"`` (EXTENSION, no reference counterpart): 3x3 bilinear interpolation with
+    the same border rule (mean of the in-bounds neighbours of each colour), ``b200isp_bayer_to_rgb_bilinear``."""
+    assert method in ("malvar", "bilinear")
     assert bayer.ndim == 2, "image must be mono bayer"
     assert bayer.shape[0] % 2 == 0 and bayer.shape[1] % 2 == 0, "image must be even size"
     dev, restore = types.to_device(bayer)
@@ -121,6 +124,12 @@ def bayer_to_rgb(bayer, pattern: BayerPattern = BayerPattern.RGGB, correct_color
     rgb = torch.empty(tuple(dev.shape) + (3,), dtype=out_dtype.torch, device=dev.device)
     if correct_colors is not None:
         correct_colors = tuple(np.asarray(correct_colors, dtype=np.float64).flatten().tolist())
-    if dev.numel():
+    if dev.numel() and method == "bilinear":
+        ccm = None if correct_colors is None else (ctypes.c_float * 9)(*correct_colors)
+        with torch.cuda.device(dev.device):
+            _lib.check(_lib.lib.b200isp_bayer_to_rgb_bilinear(dev.data_ptr(), in_dtype.code, rgb.data_ptr(), out_dtype.code,
+                                                              dev.shape[0], dev.shape[1], pattern.value, ccm,
+                                                              _lib.stream_ptr(dev.device)), "bayer_to_rgb_bilinear")
+    elif dev.numel():
         bayer_to_rgb_kernel(pattern, correct_colors, in_dtype, out_dtype)(dev, rgb)
     return restore(rgb)

@@ -304,6 +304,29 @@ def camera_isp(name: str, dtype=f32):
                     _lib.ptr_array(frames), len(frames), p, self.metrics.data_ptr(), out.data_ptr(), int(cooperative),
                     _lib.workspace(self.device).data_ptr(), _lib.stream_ptr(self.device)), "meter_packed12")
 
+        # ------------------------------------------------------------ percentile histogram (EXTENSION, north_star)
+        def metering_histogram(self, bins: int = 256) -> torch.Tensor:
+            """Luminance histogram (``bins`` int32 counts over [0, 1]) of the samples of the LAST fused metering
+            (``process_packed12`` / ``meter_packed12``): the same ``[::stride, ::stride]`` RGB samples of all frames the
+            reference's statistics are computed from (camera_isp.py:168-170).  No reference counterpart."""
+            cache, n = getattr(self, "_meter_cache", None), getattr(self, "_meter_n", 0)
+            assert cache is not None and n > 0, "no fused metering has run yet"
+            hist = torch.empty(bins, dtype=torch.int32, device=self.device)
+            with torch.cuda.device(self.device):
+                _lib.check(_lib.lib.b200isp_sample_histogram(cache.data_ptr(), n, int(bins), hist.data_ptr(),
+                                                             _lib.stream_ptr(self.device)), "sample_histogram")
+            return hist
+
+        def metering_percentiles(self, percents=(1.0, 50.0, 99.0), bins: int = 256) -> torch.Tensor:
+            """luminance percentiles (upper bin edges in [0, 1]) from ``metering_histogram``; stays on the device"""
+            hist = self.metering_histogram(bins)
+            pct = torch.tensor([float(p) for p in percents], dtype=torch.float32, device=self.device)
+            out = torch.empty(len(pct), dtype=torch.float32, device=self.device)
+            with torch.cuda.device(self.device):
+                _lib.check(_lib.lib.b200isp_histogram_percentiles(hist.data_ptr(), int(bins), pct.data_ptr(), len(pct), out.data_ptr(),
+                                                                  _lib.stream_ptr(self.device)), "histogram_percentiles")
+            return out
+
         # ------------------------------------------------------------ tone mapping (eager API)
         def tonemap_only(self, image, metrics, gamma, intensity, light_adapt, color_adapt):
             """camera_isp.py:387-390"""
@@ -361,6 +384,7 @@ def camera_isp(name: str, dtype=f32):
                 if cache is None or cache.numel() < need or cache.device != torch.device(self.device):
                     cache = self._meter_cache = torch.empty(need, dtype=torch.uint8, device=self.device)
                 p.meter_cache, p.meter_cache_bytes = cache.data_ptr(), cache.numel()
+                self._meter_n = need // 12
             if profile_events is not None:      # (start, stop) torch.cuda.Event pair, see bench.py
                 p.profile_start, p.profile_stop = profile_events[0].cuda_event, profile_events[1].cuda_event
             return p

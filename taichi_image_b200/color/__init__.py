@@ -6,6 +6,8 @@ from __future__ import annotations
 import numpy as np
 import torch
 
+from .yuv_420 import rgb_yuv420_image, yuv420_rgb_image, split_yuv_420, YCrCb_T_bgr, bgr_T_YCrCb  # noqa: F401  (color/__init__.py:4)
+
 GRAY_WEIGHTS = (0.299, 0.587, 0.114)     # color/__init__.py:7-10
 
 

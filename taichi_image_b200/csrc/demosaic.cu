@@ -220,6 +220,52 @@ static int run_demosaic_stream(const void* bayer, void* rgb, int H, int W, int p
   return run_demosaic_pixel<T, T>(bayer, rgb, H, W, pattern, ccm, true, s);
 }
 
+// ---------------------------------------------------------------- bilinear demosaic (EXTENSION)
+// north_star names "Malvar-He-Cutler / bilinear demosaic"; the reference has only Malvar.  Defined as the
+// classic 3x3 bilinear CFA interpolation evaluated with the SAME rule as bayer.py:137-155: per channel
+// c = sum of in-bounds (v * w), t = sum of in-bounds w, c / (in_scale * t), [CCM], clamp, cast(c * out_scale) --
+// i.e. the mean of the in-bounds neighbours of that colour.  Site kernels (x4; taps in row-major 3x3 order):
+//   K0 R site: R = centre, G = N,S,E,W, B = 4 diagonals       K3 B site: K0 with R <-> B
+//   K1 G site with R above/below: R = N,S, B = E,W            K2 G site with R left/right: R = E,W, B = N,S
+static __constant__ signed char c_bilinear[4][9][3] = {
+  {{0,0,1},{0,1,0},{0,0,1},{0,1,0},{4,0,0},{0,1,0},{0,0,1},{0,1,0},{0,0,1}},
+  {{0,0,0},{2,0,0},{0,0,0},{0,0,2},{0,4,0},{0,0,2},{0,0,0},{2,0,0},{0,0,0}},
+  {{0,0,0},{0,0,2},{0,0,0},{2,0,0},{0,4,0},{2,0,0},{0,0,0},{0,0,2},{0,0,0}},
+  {{1,0,0},{0,1,0},{1,0,0},{0,1,0},{0,0,4},{0,1,0},{1,0,0},{0,1,0},{1,0,0}}};
+
+template <typename InT, typename OutT>
+__global__ void __launch_bounds__(256) demosaic_bilinear_kernel(const InT* __restrict__ bayer, OutT* __restrict__ out,
+                                                                int H, int W, int pattern, int ccm, const float9 m) {
+  const int col = blockIdx.x * blockDim.x + threadIdx.x;
+  const int row = blockIdx.y;
+  if (col >= W || row >= H) return;
+  const int K = site_kernel(pattern, row, col);
+  float c[3] = {0.f, 0.f, 0.f}, t[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+  for (int i = 0; i < 9; ++i) {
+    const int rr = row + i / 3 - 1, cc = col + i % 3 - 1;
+    if (rr >= 0 && rr < H && cc >= 0 && cc < W) {
+      const float v = to_f32(bayer[(size_t)rr * W + cc]);
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        const float w = (float)c_bilinear[K][i][k];
+        c[k] = __fadd_rn(c[k], __fmul_rn(v, w));
+        t[k] += w;
+      }
+    }
+  }
+  constexpr float is = DT<InT>::scale, os = DT<OutT>::scale;
+  // a 2-pixel-wide image can leave a colour without any in-bounds neighbour (t = 0): define it as 0
+  float cr = t[0] > 0.f ? __fdiv_rn(c[0], __fmul_rn(is, t[0])) : 0.f;
+  float cg = t[1] > 0.f ? __fdiv_rn(c[1], __fmul_rn(is, t[1])) : 0.f;
+  float cb = t[2] > 0.f ? __fdiv_rn(c[2], __fmul_rn(is, t[2])) : 0.f;
+  if (ccm) ccm_apply(m.v, cr, cg, cb);
+  OutT* o = out + ((size_t)row * W + col) * 3;
+  o[0] = cast_from_f32<OutT>(__fmul_rn(clamp01(cr), os));
+  o[1] = cast_from_f32<OutT>(__fmul_rn(clamp01(cg), os));
+  o[2] = cast_from_f32<OutT>(__fmul_rn(clamp01(cb), os));
+}
+
 // ---------------------------------------------------------------- rgb_to_bayer (bayer.py:101-112)
 // pixel_orders (bayer.py:85-90): channel at ((r0,c0),(r0,c1),(r1,c0),(r1,c1)), 2 bits each
 template <typename T>
@@ -269,5 +315,26 @@ extern "C" int b200isp_bayer_to_rgb(const void* bayer, int in_dtype, void* rgb, 
   ISP_DISPATCH_DTYPE(in_dtype, InT, {
     ISP_DISPATCH_DTYPE(out_dtype, OutT, return (run_demosaic_pixel<InT, OutT>(bayer, rgb, height, width, pattern, ccm9_host, false, s)));
   });
+  return B200ISP_OK;
+}
+
+extern "C" int b200isp_bayer_to_rgb_bilinear(const void* bayer, int in_dtype, void* rgb, int out_dtype,
+                                             int height, int width, int pattern, const float* ccm9_host,
+                                             b200isp_stream stream) {
+  ISP_REQUIRE(height >= 0 && width >= 0 && height % 2 == 0 && width % 2 == 0, B200ISP_E_SHAPE,
+              "bayer_to_rgb_bilinear: image must be even size, got %dx%d", height, width);
+  ISP_REQUIRE(pattern >= 0 && pattern <= 3, B200ISP_E_ARG, "bayer_to_rgb_bilinear: unknown pattern %d", pattern);
+  ISP_REQUIRE(valid_dtype(in_dtype) && valid_dtype(out_dtype), B200ISP_E_DTYPE, "bayer_to_rgb_bilinear: bad dtype");
+  if (height == 0 || width == 0) return B200ISP_OK;
+  ISP_REQUIRE(bayer && rgb, B200ISP_E_ARG, "bayer_to_rgb_bilinear: null pointer");
+  float9 m;
+  for (int i = 0; i < 9; ++i) m.v[i] = ccm9_host ? ccm9_host[i] : 0.f;
+  const dim3 grid((width + 255) / 256, height);
+  cudaStream_t s = (cudaStream_t)stream;
+  ISP_DISPATCH_DTYPE(in_dtype, InT, {
+    ISP_DISPATCH_DTYPE(out_dtype, OutT, (demosaic_bilinear_kernel<InT, OutT><<<grid, 256, 0, s>>>(
+        (const InT*)bayer, (OutT*)rgb, height, width, pattern, ccm9_host != nullptr, m)));
+  });
+  ISP_LAUNCH_CHECK("demosaic_bilinear_kernel");
   return B200ISP_OK;
 }

@@ -398,3 +398,58 @@ extern "C" int b200isp_load_convert(const void* src, void* dst, int out_dtype, i
   ISP_LAUNCH_CHECK("load_convert_kernel");
   return B200ISP_OK;
 }
+
+// ---------------------------------------------------------------- luminance histogram + percentiles (EXTENSION)
+// north_star asks for a "percentile histogram" next to the reference's statistics; the reference has none
+// (SURVEY 2.4).  Defined on the SAME samples the metering uses (the [::stride, ::stride] RGB of all frames, as cached
+// by the metering pass): bin = min(bins-1, trunc(rgb_gray(sample) * bins)), luminance in [0,1].  Integer counts:
+// deterministic.  Percentile p = smallest bin edge (b+1)/bins whose cumulative count reaches p % of the samples.
+namespace isp {
+__global__ void __launch_bounds__(256) sample_histogram_kernel(const float* __restrict__ samples, long long n, int bins,
+                                                               unsigned int* __restrict__ hist) {
+  extern __shared__ unsigned int sh[];
+  for (int b = threadIdx.x; b < bins; b += blockDim.x) sh[b] = 0u;
+  __syncthreads();
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float g = rgb_gray(__ldcg(samples + 3 * i), __ldcg(samples + 3 * i + 1), __ldcg(samples + 3 * i + 2));
+    const int b = min(bins - 1, max(0, (int)__float2int_rz(__fmul_rn(g, (float)bins))));
+    atomicAdd(&sh[b], 1u);
+  }
+  __syncthreads();
+  for (int b = threadIdx.x; b < bins; b += blockDim.x)
+    if (sh[b]) atomicAdd(&hist[b], sh[b]);
+}
+
+__global__ void histogram_percentiles_kernel(const unsigned int* __restrict__ hist, int bins, const float* __restrict__ pct, int npct,
+                                             float* __restrict__ out) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  unsigned long long total = 0;
+  for (int b = 0; b < bins; ++b) total += hist[b];
+  for (int k = 0; k < npct; ++k) {
+    const double need = (double)pct[k] * 0.01 * (double)total;
+    unsigned long long cum = 0;
+    int b = 0;
+    for (; b < bins; ++b) { cum += hist[b]; if ((double)cum >= need) break; }
+    out[k] = (float)(min(b, bins - 1) + 1) / (float)bins;
+  }
+}
+}  // namespace isp
+
+extern "C" int b200isp_sample_histogram(const float* samples, int64_t n_samples, int bins, uint32_t* hist, b200isp_stream stream) {
+  ISP_REQUIRE(samples && hist && n_samples >= 0 && bins >= 1 && bins <= 4096, B200ISP_E_ARG, "sample_histogram: bad argument");
+  cudaStream_t s = (cudaStream_t)stream;
+  int st = cuda_status(cudaMemsetAsync(hist, 0, sizeof(uint32_t) * bins, s), "memset hist");
+  if (st) return st;
+  if (n_samples == 0) return B200ISP_OK;
+  sample_histogram_kernel<<<meter_grid(n_samples), 256, sizeof(unsigned int) * bins, s>>>(samples, n_samples, bins, hist);
+  ISP_LAUNCH_CHECK("sample_histogram_kernel");
+  return B200ISP_OK;
+}
+
+extern "C" int b200isp_histogram_percentiles(const uint32_t* hist, int bins, const float* percents, int n_percents, float* out,
+                                             b200isp_stream stream) {
+  ISP_REQUIRE(hist && percents && out && bins >= 1 && n_percents >= 1, B200ISP_E_ARG, "histogram_percentiles: bad argument");
+  histogram_percentiles_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(hist, bins, percents, n_percents, out);
+  ISP_LAUNCH_CHECK("histogram_percentiles_kernel");
+  return B200ISP_OK;
+}

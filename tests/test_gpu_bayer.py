@@ -108,3 +108,24 @@ def test_tables_match_reference_layout():
     for k in range(4):
         assert [tuple(w) for _, w in bayer.bayer_kernels[k]] == [tuple(w) for _, w in O.MALVAR[k]]
         assert [o for o, _ in bayer.bayer_kernels[k]] == O.DIAMOND_OFFSETS
+
+
+@pytest.mark.parametrize("name", ["u8", "u16", "f32"])
+@pytest.mark.parametrize("pattern", O.PATTERNS)
+def test_bilinear_demosaic_extension(cuda, name, pattern):
+    """EXTENSION (north_star; no reference counterpart): bit-exact against the oracle's restatement of the same rule,
+    constant images stay constant, and the CFA samples themselves are reproduced exactly"""
+    from taichi_image_b200 import bayer
+    r = rng(90)
+    cfa = random_plane(r, (38, 52), name)
+    got = to_np(bayer.bayer_to_rgb(to_cuda(cfa), bayer.BayerPattern[pattern], method="bilinear"))
+    ref = O.bayer_to_rgb_bilinear(cfa, pattern)
+    if name == "f32":
+        np.testing.assert_allclose(got, ref, rtol=1e-6, atol=1e-7)
+    else:
+        assert np.array_equal(got, ref)
+    assert np.array_equal(to_np(bayer.rgb_to_bayer(to_cuda(got), bayer.BayerPattern[pattern])), cfa) or name == "f32"
+    value = O.NP_DTYPE[name](0.25 if name == "f32" else 77)
+    const = np.full((8, 8), value)
+    out = to_np(bayer.bayer_to_rgb(to_cuda(const), bayer.BayerPattern[pattern], method="bilinear"))
+    assert np.all(out == value)

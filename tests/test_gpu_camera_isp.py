@@ -243,3 +243,25 @@ def test_graphed_stream_matches_eager(cuda, tm, out):
     # after k steps isp.metrics already holds the update for step k+1
     eager2.process_packed12(cu, tonemap=tm, gamma=0.9, dtype=out)
     np.testing.assert_allclose(to_np(gisp2.metrics), to_np(eager2.metrics), rtol=2e-6, atol=1e-7)
+
+
+@pytest.mark.parametrize("dt", ["f16", "f32"])
+def test_metering_histogram_and_percentiles(cuda, dt):
+    """EXTENSION (no reference counterpart): luminance histogram / percentiles of the metering samples, checked
+    against numpy on the oracle's samples; counts may move by one bin where gray * bins lands on an integer"""
+    r = rng(45)
+    fr = frames(r, 3, 48, 64)
+    isp, ref = make_isp(dt), O.ISP(dt)
+    isp.process_packed12([to_cuda(f) for f in fr], tonemap="linear")
+    hist = to_np(isp.metering_histogram(64))
+    samples = np.stack([ref.load_packed12(f)[::8, ::8] for f in fr]).astype(np.float32).reshape(-1, 3)
+    gray = O.rgb_gray(samples)
+    exp = np.bincount(np.minimum(63, (gray * np.float32(64)).astype(np.int64)), minlength=64)
+    assert hist.sum() == exp.sum() == samples.shape[0]
+    assert np.abs(np.cumsum(hist) - np.cumsum(exp)).max() <= max(2, samples.shape[0] // 200)
+    pct = to_np(isp.metering_percentiles((1.0, 50.0, 99.0), 64))
+    cum = np.cumsum(hist)
+    for p, v in zip((1.0, 50.0, 99.0), pct):
+        b = int(np.searchsorted(cum, p * 0.01 * cum[-1]))
+        assert abs(v - (min(b, 63) + 1) / 64.0) < 1e-6
+    assert pct[0] <= pct[1] <= pct[2]

@@ -125,3 +125,19 @@ def test_camera_isp_golden(cam, cfg):
                 checked += d.size
                 assert d.max() <= 1 and np.count_nonzero(d) <= 0.01 * d.size, (key, c, d.max())
     assert checked > 5000
+
+
+def test_color_yuv420_golden():
+    """color/yuv_420.py.  The decoder has no lower clamp (its tm.clamp arguments are swapped, yuv_420.py:88), so a
+    negative component is cast to an unsigned integer -- undefined behaviour in the reference: those pixels are
+    excluded for the integer dtypes (the oracle and the product saturate them to 0)."""
+    g = load("color")
+    for name in ("u8", "u16", "f16", "f32"):
+        assert same(O.rgb_yuv420(g[f"rgb_{name}"]), g[f"yuv_{name}"]), name
+        got, ref = O.yuv420_rgb(g[f"yuv_{name}"]), g[f"rgb_back_{name}"]
+        assert got.shape == ref.shape and got.dtype == ref.dtype
+        defined = (O.yuv420_rgb_unit(g[f"yuv_{name}"]) >= 0) | (name in ("f16", "f32"))
+        assert defined.mean() > 0.5
+        assert np.array_equal(got[defined], ref[defined]), name
+    assert same(O.rgb_yuv420(g["rgb_u8"], "f32"), g["yuv_u8_to_f32"])
+    assert same(O.rgb_yuv420(g["rgb_f32"], "u8"), g["yuv_f32_to_u8"])
