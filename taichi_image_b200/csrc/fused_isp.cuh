@@ -298,9 +298,10 @@ template <bool CAM16, bool GAMMA>
 __device__ __forceinline__ void reinhard_out(const ReinhardConsts& c, const float (&p)[3], float (&y)[3]) {
 #pragma unroll
   for (int k = 0; k < 3; ++k) {
-    float q = fmaxf(round_isp<CAM16>(p[k]) * c.out_scale_inv_max, 0.f);     // NaN / negative -> 0
-    if constexpr (GAMMA) q = fast_pow(q, c.inv_gamma);
-    y[k] = fminf(q, 1.0f);     // the reference does not clamp (q <= 1 + one f16 ulp); saturate for the RZ-FMA quantiser
+    // the reference does not clamp (q <= 1 + one f16 ulp); saturate for the RZ-FMA quantiser: one FMUL.SAT (NaN -> 0)
+    float q = __saturatef(round_isp<CAM16>(p[k]) * c.out_scale_inv_max);
+    if constexpr (GAMMA) q = __saturatef(fast_pow(q, c.inv_gamma));
+    y[k] = q;
   }
 }
 

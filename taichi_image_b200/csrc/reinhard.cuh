@@ -48,7 +48,14 @@ __device__ __forceinline__ void reinhard_map_exact(const ReinhardParams& p, cons
   }
 }
 
-__device__ __forceinline__ float fast_pow(float x, float y) { return exp2f(y * __log2f(x)); }   // MUFU.LG2 + MUFU.EX2
+// x^y through the two MUFU ops only (lg2.approx / ex2.approx, no range fix-ups: arguments are O(1) here; x <= 0
+// gives NaN / 0 like powf's domain error, which the callers saturate)
+__device__ __forceinline__ float fast_pow(float x, float y) {
+  float l, r;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l) : "f"(x));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(y * l));
+  return r;
+}
 __device__ __forceinline__ float fast_rcp(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 
 // s = scaled RGB (already (x - bmin) * inv_range).  CA0: color_adapt == 0 -> one shared adaptation level.
