@@ -276,7 +276,8 @@ __device__ __forceinline__ void linear_px(const LinearConsts& c, const float (&r
   }
 }
 
-struct ReinhardConsts { ReinhardParams p; float b; float out_scale_inv_max; float inv_gamma; int has_gamma; int ca0; };
+struct ReinhardConsts { ReinhardParams p; float b; float out_scale_inv_max; float inv_gamma; int has_gamma; int ca0;
+                        float kla, kml; /* ki * la, ki * mean * (1 - la): ki * adapt_mean = gray * kla + kml (color_adapt == 0) */ };
 
 template <bool CAM16, bool CA0>
 __device__ __forceinline__ void reinhard_p(const ReinhardConsts& c, const float (&rgb)[3], float (&p)[3]) {
@@ -310,6 +311,8 @@ __device__ __forceinline__ ReinhardConsts reinhard_consts(const IspConsts& k, in
   c.p = reinhard_params(k.metrics, k.intensity, k.la, k.ca);
   c.b = -c.p.bmin * c.p.inv_range;
   c.ca0 = k.ca == 0.f;
+  c.kla = c.p.ki * c.p.la;
+  c.kml = c.p.ki * c.p.mean[0] * (1.0f - c.p.la);
   c.inv_gamma = (float)(1.0 / (double)k.gamma);
   c.has_gamma = k.gamma != 1.0f;
   c.out_scale_inv_max = 0.f;
@@ -416,6 +419,83 @@ __device__ __forceinline__ void raw_to_rgb(const IspConsts& k, const float* x, f
     rgb[0] = __low2float(h); rgb[1] = __high2float(h); rgb[2] = __half2float(__float2half_rn(b));
   } else {
     rgb[0] = r; rgb[1] = g; rgb[2] = b;
+  }
+}
+
+// ---------------------------------------------------------------- packed (pair) form of the generic stages
+// raw pairs: demosaiced value normalised by 16 (unclamped, before CCM) of pixel pair j (pixels j, j+4), channel c
+template <bool CAM16, bool BROW, bool GFIRST>
+__device__ __forceinline__ void pairs_to_raw2(const f2 (&R)[4], const f2 (&G)[4], const f2 (&B)[4], f2 (&X)[4][3]) {
+  using SS = SiteScale2<BROW, GFIRST>;
+  constexpr float kn = 256.f * kInv4095;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    if constexpr (CAM16) {
+      X[j][0] = mul2(R[j], bc(SS::r(j) * 0.0625f)); X[j][1] = mul2(G[j], bc(SS::g(j) * 0.0625f)); X[j][2] = mul2(B[j], bc(SS::b(j) * 0.0625f));
+    } else {
+      X[j][0] = fma2k(SS::r(j) * kn, R[j], bc(-16.f * kn)); X[j][1] = fma2k(SS::g(j) * kn, G[j], bc(-16.f * kn));
+      X[j][2] = fma2k(SS::b(j) * kn, B[j], bc(-16.f * kn));
+    }
+  }
+}
+
+// frame columns of an interior row on the raw pairs, exact (division) form; edge != 0 only in the first / last thread column
+template <bool BROW, bool GFIRST>
+__device__ __forceinline__ void patch_cols_pairs(f2 (&X)[4][3], int edge) {
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    if (q >= 2 && q < 6) continue;
+    if ((q < 2 && (edge & 1)) || (q >= 6 && (edge & 2))) {
+      const int K = site_kernel_of(BROW, SiteScale2<BROW, GFIRST>::gsite(q & 3));
+      const float* t = c_border.t[K][2][q < 2 ? q : q - 3];
+#pragma unroll
+      for (int ch = 0; ch < 3; ++ch) {
+        float lo, hi;
+        upk(X[q & 3][ch], lo, hi);
+        if (q < 4) lo = frame_exact(lo, t[ch]); else hi = frame_exact(hi, t[ch]);
+        X[q & 3][ch] = pk(lo, hi);
+      }
+    }
+  }
+}
+
+// raw pair -> ISP RGB pair in [0,1]: CCM (kernel-uniform run-time flag), clamp (bayer.py:152-155), ISP dtype rounding
+template <bool CAM16>
+__device__ __forceinline__ void raw2_to_rgb2(const IspConsts& k, const f2 (&x)[3], f2 (&rgb)[3]) {
+  f2 y[3] = {x[0], x[1], x[2]};
+  if (k.ccm) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+      y[c] = fma2(x[2], bc(k.m[3 * c + 2]), fma2(x[1], bc(k.m[3 * c + 1]), mul2(x[0], bc(k.m[3 * c]))));
+  }
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    float lo, hi;
+    upk(y[c], lo, hi);
+    lo = clamp01(lo); hi = clamp01(hi);
+    if constexpr (CAM16) {
+      const __half2 h = __floats2half2_rn(lo, hi);
+      lo = __low2float(h); hi = __high2float(h);
+    }
+    rgb[c] = pk(lo, hi);
+  }
+}
+
+// camera_isp.py:200-210 for a pixel pair, color_adapt == 0 (one adaptation level per pixel): p = s / (adapt + s)
+template <bool CAM16>
+__device__ __forceinline__ void reinhard_p2(const ReinhardConsts& c, const f2 (&rgb)[3], f2 (&p)[3]) {
+  f2 s[3];
+#pragma unroll
+  for (int ch = 0; ch < 3; ++ch) s[ch] = fma2(rgb[ch], bc(c.p.inv_range), bc(c.b));
+  const f2 gray = fma2(s[2], bc(0.114f), fma2(s[1], bc(0.587f), mul2(s[0], bc(0.299f))));
+  float tl, th;
+  upk(fma2(gray, bc(c.kla), bc(c.kml)), tl, th);                  // ki * lerp(la, mean, gray)
+  const f2 adapt = pk(fast_pow(tl, c.p.map_key), fast_pow(th, c.p.map_key));
+#pragma unroll
+  for (int ch = 0; ch < 3; ++ch) {
+    float dl, dh;
+    upk(add2(adapt, s[ch]), dl, dh);
+    p[ch] = mul2(s[ch], pk(fast_rcp(dl), fast_rcp(dh)));
   }
 }
 
@@ -576,6 +656,26 @@ struct EpiReinhardMax2 {      // pass 1 without the write-back: frame-global max
   }
   template <bool BROW, bool GFIRST, int KIND>
   __device__ __forceinline__ void emit(State& st, int row, const f2 (&R)[4], const f2 (&G)[4], const f2 (&B)[4]) const {
+    if (KIND != K_GENERAL && st.c.ca0) {        // packed path (kernel-uniform condition)
+      f2 X[4][3];
+      pairs_to_raw2<CAM16, BROW, GFIRST>(R, G, B, X);
+      if (st.edge) patch_cols_pairs<BROW, GFIRST>(X, st.edge);
+      float mx = st.mx;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        f2 rgb[3], p[3];
+        raw2_to_rgb2<CAM16>(k, X[j], rgb);
+        reinhard_p2<CAM16>(st.c, rgb, p);
+#pragma unroll
+        for (int ch = 0; ch < 3; ++ch) {
+          float lo, hi;
+          upk(p[ch], lo, hi);
+          mx = fmaxf(mx, fmaxf(lo, hi));
+        }
+      }
+      st.mx = mx;
+      return;
+    }
     Vals24 x;
     raw_with_frame<CAM16, BROW, GFIRST, KIND>(R, G, B, row, k.H, st.edge, x);
     if (st.c.ca0) emit_t<true>(st, x);          // kernel-uniform, one branch per row
@@ -616,8 +716,50 @@ struct EpiReinhard2 {         // pass 2 recomputed from the packed frame: map, n
     store_row8<OutT>(st.wc, st.out, k.W, row, v);
   }
   __device__ __forceinline__ bool fast_kinds_ok(const State&) const { return true; }
+  // packed path: color_adapt == 0, any gamma (kernel-uniform)
+  template <bool BROW, bool GFIRST, bool GAMMA>
+  __device__ __forceinline__ void emit_pairs(const State& st, int row, const f2 (&R)[4], const f2 (&G)[4], const f2 (&B)[4]) const {
+    f2 X[4][3];
+    pairs_to_raw2<CAM16, BROW, GFIRST>(R, G, B, X);
+    if (st.edge) patch_cols_pairs<BROW, GFIRST>(X, st.edge);
+    uint32_t v[24];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      f2 rgb[3], p[3];
+      raw2_to_rgb2<CAM16>(k, X[j], rgb);
+      reinhard_p2<CAM16>(st.c, rgb, p);
+#pragma unroll
+      for (int ch = 0; ch < 3; ++ch) {                 // camera_isp.py:211-218
+        float lo, hi;
+        upk(p[ch], lo, hi);
+        if constexpr (CAM16) {
+          const __half2 h = __floats2half2_rn(lo, hi);
+          lo = __low2float(h); hi = __high2float(h);
+        }
+        lo = __saturatef(lo * st.c.out_scale_inv_max);
+        hi = __saturatef(hi * st.c.out_scale_inv_max);
+        if constexpr (GAMMA) { lo = fast_pow(lo, st.c.inv_gamma); hi = fast_pow(hi, st.c.inv_gamma); }
+        if constexpr (DT<OutT>::is_int) {
+          float ql, qh;
+          upk(fma2_rz(pk(lo, hi), bc(DT<OutT>::scale), bc(8388608.f)), ql, qh);
+          v[3 * j + ch] = __float_as_uint(ql);
+          v[3 * (j + 4) + ch] = __float_as_uint(qh);
+        } else {
+          v[3 * j + ch] = __float_as_uint(lo);
+          v[3 * (j + 4) + ch] = __float_as_uint(hi);
+        }
+      }
+    }
+    store_row8<OutT>(st.wc, st.out, k.W, row, v);
+  }
+
   template <bool BROW, bool GFIRST, int KIND>
   __device__ __forceinline__ void emit(State& st, int row, const f2 (&R)[4], const f2 (&G)[4], const f2 (&B)[4]) const {
+    if (KIND != K_GENERAL && st.c.ca0) {
+      if (st.c.has_gamma) emit_pairs<BROW, GFIRST, true>(st, row, R, G, B);
+      else emit_pairs<BROW, GFIRST, false>(st, row, R, G, B);
+      return;
+    }
     Vals24 x;
     raw_with_frame<CAM16, BROW, GFIRST, KIND>(R, G, B, row, k.H, st.edge, x);
     if (st.c.ca0) {                     // kernel-uniform flags, dispatched once per row
