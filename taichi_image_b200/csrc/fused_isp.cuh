@@ -512,6 +512,7 @@ struct EpiRgb2 {      // load_packed12: ISP-dtype float RGB out
   }
   __device__ __forceinline__ void finish(State&, int, int, bool) const {}
   static constexpr bool kSplitEdge = false;
+  static constexpr bool kCompactLoop = false;
   __device__ __forceinline__ bool fast_kinds_ok(const State&) const { return true; }
   template <bool BROW, bool GFIRST, int KIND>
   __device__ __forceinline__ void emit(State& st, int row, const f2 (&R)[4], const f2 (&G)[4], const f2 (&B)[4]) const {
@@ -549,6 +550,7 @@ struct EpiLinear2 {
   __device__ __forceinline__ void finish(State&, int, int, bool) const {}
 
   static constexpr bool kSplitEdge = FAST;
+  static constexpr bool kCompactLoop = false;
   template <bool GAMMA>
   __device__ __forceinline__ void emit_t(const State& st, int row, const Vals24& x) const {
     uint32_t v[24];
@@ -641,6 +643,7 @@ struct EpiReinhardMax2 {      // pass 1 without the write-back: frame-global max
     st.edge = edge_bits(tcol, k.W);
   }
   static constexpr bool kSplitEdge = false;
+  static constexpr bool kCompactLoop = true;
   __device__ __forceinline__ bool fast_kinds_ok(const State&) const { return true; }
   template <bool CA0>
   __device__ __forceinline__ void emit_t(State& st, const Vals24& x) const {
@@ -702,6 +705,7 @@ struct EpiReinhard2 {         // pass 2 recomputed from the packed frame: map, n
   }
   __device__ __forceinline__ void finish(State&, int, int, bool) const {}
   static constexpr bool kSplitEdge = false;
+  static constexpr bool kCompactLoop = true;
   template <bool CA0, bool GAMMA>
   __device__ __forceinline__ void emit_t(const State& st, int row, const Vals24& x) const {
     uint32_t v[24];

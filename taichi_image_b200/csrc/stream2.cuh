@@ -111,6 +111,7 @@ enum { K_CORE = 0, K_EDGE = 1, K_GENERAL = 2 };
 //   static constexpr int kStageWords
 //   struct State;  void init(State&, int frame, int tcol, const WarpCtx&);  void finish(State&, int frame, int lane, bool task_ok)
 //   static constexpr bool kSplitEdge                                false: no K_CORE instantiation, interior tasks run K_EDGE
+//   static constexpr bool kCompactLoop                              true: single-step loop body (register moves) for every kind
 //   bool fast_kinds_ok(const State&)                                false -> every task runs K_GENERAL
 //   template <bool BROW, bool GFIRST, int KIND> void emit(State&, int row, const f2 (&R)[4], const f2 (&G)[4], const f2 (&B)[4])
 //       scaled filter sums (SiteScale2); out-of-image taps contributed the zero sample; the epilogue renormalises
@@ -209,8 +210,9 @@ __device__ __forceinline__ void stream2_rows(const Loader& ld, const Epi& epi, t
     epi.template emit<!BROW0, !GFIRST0, KIND>(st, row_ + 1, R_, G_, B_);                                        \
   }
 
-  if constexpr (KIND == K_GENERAL) {
-    // cold kind: one copy of the step, the window slides by register moves
+  if constexpr (KIND == K_GENERAL || Epi::kCompactLoop) {
+    // cold kind, or an epilogue so large that three copies of the step overflow the instruction cache (Reinhard:
+    // 51 KB hot, no_instruction 3.1 cycles per issue): one copy of the step, the window slides by register moves
 #pragma unroll 1
     for (int row = r0; row < rend; row += 2) {
       ISP_STEP(0, row);
