@@ -642,7 +642,7 @@ struct EpiReinhardMax2 {      // pass 1 without the write-back: frame-global max
     st.mx = 0.f;
     st.edge = edge_bits(tcol, k.W);
   }
-  static constexpr bool kSplitEdge = false;
+  static constexpr bool kSplitEdge = false;     // measured: a separate K_CORE copy costs more (instruction cache) than its leaner code saves
   static constexpr bool kCompactLoop = true;
   __device__ __forceinline__ bool fast_kinds_ok(const State&) const { return true; }
   template <bool CA0>
@@ -662,7 +662,7 @@ struct EpiReinhardMax2 {      // pass 1 without the write-back: frame-global max
     if (KIND != K_GENERAL && st.c.ca0) {        // packed path (kernel-uniform condition)
       f2 X[4][3];
       pairs_to_raw2<CAM16, BROW, GFIRST>(R, G, B, X);
-      if (st.edge) patch_cols_pairs<BROW, GFIRST>(X, st.edge);
+      if (KIND == K_EDGE && st.edge) patch_cols_pairs<BROW, GFIRST>(X, st.edge);
       float mx = st.mx;
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
@@ -704,7 +704,7 @@ struct EpiReinhard2 {         // pass 2 recomputed from the packed frame: map, n
     st.edge = edge_bits(tcol, k.W);
   }
   __device__ __forceinline__ void finish(State&, int, int, bool) const {}
-  static constexpr bool kSplitEdge = false;
+  static constexpr bool kSplitEdge = false;     // measured: a separate K_CORE copy costs more (instruction cache) than its leaner code saves
   static constexpr bool kCompactLoop = true;
   template <bool CA0, bool GAMMA>
   __device__ __forceinline__ void emit_t(const State& st, int row, const Vals24& x) const {
@@ -721,11 +721,11 @@ struct EpiReinhard2 {         // pass 2 recomputed from the packed frame: map, n
   }
   __device__ __forceinline__ bool fast_kinds_ok(const State&) const { return true; }
   // packed path: color_adapt == 0, any gamma (kernel-uniform)
-  template <bool BROW, bool GFIRST, bool GAMMA>
+  template <bool BROW, bool GFIRST, bool GAMMA, int KIND>
   __device__ __forceinline__ void emit_pairs(const State& st, int row, const f2 (&R)[4], const f2 (&G)[4], const f2 (&B)[4]) const {
     f2 X[4][3];
     pairs_to_raw2<CAM16, BROW, GFIRST>(R, G, B, X);
-    if (st.edge) patch_cols_pairs<BROW, GFIRST>(X, st.edge);
+    if (KIND == K_EDGE && st.edge) patch_cols_pairs<BROW, GFIRST>(X, st.edge);
     uint32_t v[24];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
@@ -754,14 +754,14 @@ struct EpiReinhard2 {         // pass 2 recomputed from the packed frame: map, n
         }
       }
     }
-    store_row8<OutT>(st.wc, st.out, k.W, row, v);
+    store_row8<OutT, KIND == K_CORE>(st.wc, st.out, k.W, row, v);
   }
 
   template <bool BROW, bool GFIRST, int KIND>
   __device__ __forceinline__ void emit(State& st, int row, const f2 (&R)[4], const f2 (&G)[4], const f2 (&B)[4]) const {
     if (KIND != K_GENERAL && st.c.ca0) {
-      if (st.c.has_gamma) emit_pairs<BROW, GFIRST, true>(st, row, R, G, B);
-      else emit_pairs<BROW, GFIRST, false>(st, row, R, G, B);
+      if (st.c.has_gamma) emit_pairs<BROW, GFIRST, true, KIND>(st, row, R, G, B);
+      else emit_pairs<BROW, GFIRST, false, KIND>(st, row, R, G, B);
       return;
     }
     Vals24 x;
