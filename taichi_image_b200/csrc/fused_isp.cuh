@@ -550,7 +550,10 @@ struct EpiLinear2 {
   __device__ __forceinline__ void finish(State&, int, int, bool) const {}
 
   static constexpr bool kSplitEdge = FAST;
-  static constexpr bool kCompactLoop = false;
+#ifndef ISP_LINEAR_COMPACT
+#define ISP_LINEAR_COMPACT 1      // measured on cfg2: kernel alone 169 vs 171 us, step (sweep || metering) 197 vs 204 us
+#endif
+  static constexpr bool kCompactLoop = ISP_LINEAR_COMPACT != 0;
   template <bool GAMMA>
   __device__ __forceinline__ void emit_t(const State& st, int row, const Vals24& x) const {
     uint32_t v[24];
