@@ -265,3 +265,32 @@ def test_metering_histogram_and_percentiles(cuda, dt):
         b = int(np.searchsorted(cum, p * 0.01 * cum[-1]))
         assert abs(v - (min(b, 63) + 1) / 64.0) < 1e-6
     assert pct[0] <= pct[1] <= pct[2]
+
+
+@pytest.mark.parametrize("dt", ["f16", "f32"])
+@pytest.mark.parametrize("pattern", O.PATTERNS)
+@pytest.mark.parametrize("shape,rpt", [((30, 1288), 0), ((52, 768), 0), ((44, 1032), 6), ((40, 776), 2), ((64, 520), 24)])
+def test_fused_wide_frames_all_task_kinds(cuda, dt, pattern, shape, rpt):
+    """Frames wide enough for interior strips (K_CORE: W > 512), with exact and partial last strips, several row
+    chunks and chunk sizes that are not a multiple of the unrolled step -- every task kind of the pair engine
+    (stream2.cuh) against the oracle: load_packed12 (float RGB), linear -> u16 (packed fast path for Camera32) and
+    Reinhard -> u8 (packed Reinhard path)."""
+    h, w = shape
+    r = rng(50 + h)
+    fr = frames(r, 2, h, w, pattern)
+    cu = [to_cuda(f) for f in fr]
+    isp, ref = make_isp(dt, bayer_pattern=pattern), O.ISP(dt, pattern)
+    got = to_np(isp.load_packed12(cu[0]))
+    exp = ref.load_packed12(fr[0])
+    assert_close_float(got, exp, rtol=1e-3, atol=1e-3 if dt == "f16" else 2e-6, what=f"rgb {dt} {pattern} {shape}")
+    ims = [ref.load_packed12(f) for f in fr]
+    lin = isp.process_packed12(cu, tonemap="linear", dtype="u16", rows_per_task=rpt)
+    exp_lin = ref.tonemap_linear([im.copy() for im in ims], out_dtype="u16")
+    lsb = 1 if dt == "f32" else int(32.0 / float(ref.metrics[1] - ref.metrics[0])) + 2
+    for g, e in zip(lin, exp_lin):
+        assert_close_int(to_np(g), e, lsb, f"linear {dt} {pattern} {shape}")
+    isp2, ref2 = make_isp(dt, bayer_pattern=pattern), O.ISP(dt, pattern)
+    rei = isp2.process_packed12(cu, tonemap="reinhard", gamma=0.9, intensity=2.0, light_adapt=0.8, dtype="u8", rows_per_task=rpt)
+    exp_rei = ref2.tonemap_reinhard([ref2.load_packed12(f) for f in fr], gamma=0.9, intensity=2.0, light_adapt=0.8, out_dtype="u8")
+    for g, e in zip(rei, exp_rei):
+        assert_close_int(to_np(g), e, 1, f"reinhard {dt} {pattern} {shape}")
