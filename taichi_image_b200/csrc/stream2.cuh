@@ -210,7 +210,10 @@ __device__ __forceinline__ void stream2_rows(const Loader& ld, const Epi& epi, t
     epi.template emit<!BROW0, !GFIRST0, KIND>(st, row_ + 1, R_, G_, B_);                                        \
   }
 
-  if constexpr (KIND == K_GENERAL || Epi::kCompactLoop) {
+#ifndef ISP_S2_COMPACT_UNROLL
+#define ISP_S2_COMPACT_UNROLL 1     // measured: 1 step 607 / 147 Gpx/s (cfg2 / cfg3), 2 steps 585 / 120 -- code size beats moves
+#endif
+  if constexpr (KIND == K_GENERAL || (Epi::kCompactLoop && ISP_S2_COMPACT_UNROLL == 1)) {
     // cold kind, or an epilogue so large that three copies of the step overflow the instruction cache (Reinhard:
     // 51 KB hot, no_instruction 3.1 cycles per issue): one copy of the step, the window slides by register moves
 #pragma unroll 1
@@ -220,6 +223,16 @@ __device__ __forceinline__ void stream2_rows(const Loader& ld, const Epi& epi, t
       for (int k = 0; k < 4; ++k)
 #pragma unroll
         for (int i = 0; i < 8; ++i) W[k][i] = W[k + 2][i];
+    }
+  } else if constexpr (Epi::kCompactLoop) {
+    // two copies of the step: half the register moves of the single-step form, two thirds of the unrolled code
+#pragma unroll 1
+    for (int row = r0; row < rend; row += 4) {
+      ISP_STEP(0, row);
+      if (row + 2 >= rend) break;
+      ISP_STEP(1, row + 2);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { W[2][i] = W[0][i]; W[3][i] = W[1][i]; W[0][i] = W[4][i]; W[1][i] = W[5][i]; }
     }
   } else {
 #pragma unroll 1
