@@ -635,7 +635,9 @@ struct EpiLinear2 {
   }
 };
 
-template <bool CAM16>
+// CA0 (color_adapt == 0) and GAMMA (gamma != 1) are host-known: separate instantiations keep each kernel's code small
+// (the sweep is instruction-cache sensitive, see stream2.cuh)
+template <bool CAM16, bool CA0>
 struct EpiReinhardMax2 {      // pass 1 without the write-back: frame-global max of the mapped values
   IspConsts k;
   static constexpr int kStageWords = 0;
@@ -648,7 +650,6 @@ struct EpiReinhardMax2 {      // pass 1 without the write-back: frame-global max
   static constexpr bool kSplitEdge = false;     // measured: a separate K_CORE copy costs more (instruction cache) than its leaner code saves
   static constexpr bool kCompactLoop = true;
   __device__ __forceinline__ bool fast_kinds_ok(const State&) const { return true; }
-  template <bool CA0>
   __device__ __forceinline__ void emit_t(State& st, const Vals24& x) const {
     float mx = st.mx;
 #pragma unroll
@@ -662,7 +663,7 @@ struct EpiReinhardMax2 {      // pass 1 without the write-back: frame-global max
   }
   template <bool BROW, bool GFIRST, int KIND>
   __device__ __forceinline__ void emit(State& st, int row, const f2 (&R)[4], const f2 (&G)[4], const f2 (&B)[4]) const {
-    if (KIND != K_GENERAL && st.c.ca0) {        // packed path (kernel-uniform condition)
+    if constexpr (KIND != K_GENERAL && CA0) {        // packed path
       f2 X[4][3];
       pairs_to_raw2<CAM16, BROW, GFIRST>(R, G, B, X);
       if (KIND == K_EDGE && st.edge) patch_cols_pairs<BROW, GFIRST>(X, st.edge);
@@ -680,12 +681,11 @@ struct EpiReinhardMax2 {      // pass 1 without the write-back: frame-global max
         }
       }
       st.mx = mx;
-      return;
+    } else {
+      Vals24 x;
+      raw_with_frame<CAM16, BROW, GFIRST, KIND>(R, G, B, row, k.H, st.edge, x);
+      emit_t(st, x);
     }
-    Vals24 x;
-    raw_with_frame<CAM16, BROW, GFIRST, KIND>(R, G, B, row, k.H, st.edge, x);
-    if (st.c.ca0) emit_t<true>(st, x);          // kernel-uniform, one branch per row
-    else emit_t<false>(st, x);
   }
   __device__ __forceinline__ void finish(State& st, int frame, int lane, bool task_ok) const {
     const float m = warp_max(st.mx);
@@ -694,7 +694,7 @@ struct EpiReinhardMax2 {      // pass 1 without the write-back: frame-global max
   }
 };
 
-template <bool CAM16, typename OutT>
+template <bool CAM16, typename OutT, bool CA0, bool GAMMA>
 struct EpiReinhard2 {         // pass 2 recomputed from the packed frame: map, normalise by the max, gamma, quantise
   FramePtrs fp;
   IspConsts k;
@@ -709,7 +709,6 @@ struct EpiReinhard2 {         // pass 2 recomputed from the packed frame: map, n
   __device__ __forceinline__ void finish(State&, int, int, bool) const {}
   static constexpr bool kSplitEdge = false;     // measured: a separate K_CORE copy costs more (instruction cache) than its leaner code saves
   static constexpr bool kCompactLoop = true;
-  template <bool CA0, bool GAMMA>
   __device__ __forceinline__ void emit_t(const State& st, int row, const Vals24& x) const {
     uint32_t v[24];
 #pragma unroll
@@ -724,7 +723,7 @@ struct EpiReinhard2 {         // pass 2 recomputed from the packed frame: map, n
   }
   __device__ __forceinline__ bool fast_kinds_ok(const State&) const { return true; }
   // packed path: color_adapt == 0, any gamma (kernel-uniform)
-  template <bool BROW, bool GFIRST, bool GAMMA, int KIND>
+  template <bool BROW, bool GFIRST, int KIND>
   __device__ __forceinline__ void emit_pairs(const State& st, int row, const f2 (&R)[4], const f2 (&G)[4], const f2 (&B)[4]) const {
     f2 X[4][3];
     pairs_to_raw2<CAM16, BROW, GFIRST>(R, G, B, X);
@@ -762,17 +761,12 @@ struct EpiReinhard2 {         // pass 2 recomputed from the packed frame: map, n
 
   template <bool BROW, bool GFIRST, int KIND>
   __device__ __forceinline__ void emit(State& st, int row, const f2 (&R)[4], const f2 (&G)[4], const f2 (&B)[4]) const {
-    if (KIND != K_GENERAL && st.c.ca0) {
-      if (st.c.has_gamma) emit_pairs<BROW, GFIRST, true, KIND>(st, row, R, G, B);
-      else emit_pairs<BROW, GFIRST, false, KIND>(st, row, R, G, B);
-      return;
-    }
-    Vals24 x;
-    raw_with_frame<CAM16, BROW, GFIRST, KIND>(R, G, B, row, k.H, st.edge, x);
-    if (st.c.ca0) {                     // kernel-uniform flags, dispatched once per row
-      if (st.c.has_gamma) emit_t<true, true>(st, row, x); else emit_t<true, false>(st, row, x);
+    if constexpr (KIND != K_GENERAL && CA0) {
+      emit_pairs<BROW, GFIRST, KIND>(st, row, R, G, B);
     } else {
-      if (st.c.has_gamma) emit_t<false, true>(st, row, x); else emit_t<false, false>(st, row, x);
+      Vals24 x;
+      raw_with_frame<CAM16, BROW, GFIRST, KIND>(R, G, B, row, k.H, st.edge, x);
+      emit_t(st, row, x);
     }
   }
 };
@@ -970,6 +964,17 @@ struct Packed12FastSampler {
 };
 
 // ---------------------------------------------------------------- host orchestration
+// host dispatch of the Reinhard write sweep on (color_adapt == 0, gamma != 1)
+template <int P, bool CAM16, typename OutT>
+static int launch_reinhard(const Packed12Loader2<CAM16>& ld, const FramePtrs& fp, const IspConsts& k, const Stream2Geom& g, cudaStream_t s) {
+  const bool ca0 = k.ca == 0.f, gam = k.gamma != 1.0f;
+  if (ca0 && gam) { EpiReinhard2<CAM16, OutT, true, true> e{fp, k}; return launch_stream2<P>(ld, e, g, s, "isp_stream<reinhard>"); }
+  if (ca0) { EpiReinhard2<CAM16, OutT, true, false> e{fp, k}; return launch_stream2<P>(ld, e, g, s, "isp_stream<reinhard>"); }
+  if (gam) { EpiReinhard2<CAM16, OutT, false, true> e{fp, k}; return launch_stream2<P>(ld, e, g, s, "isp_stream<reinhard>"); }
+  EpiReinhard2<CAM16, OutT, false, false> e{fp, k};
+  return launch_stream2<P>(ld, e, g, s, "isp_stream<reinhard>");
+}
+
 template <bool CAM16, int MODE, typename OutT>
 static int run_pass(const FramePtrs& fp, IspConsts k, int frame0, int nframes, int rows_per_task, cudaStream_t s,
                     void* ev_start = nullptr, void* ev_stop = nullptr) {
@@ -995,8 +1000,12 @@ static int run_pass(const FramePtrs& fp, IspConsts k, int frame0, int nframes, i
       if constexpr (!CAM16) { if (fast) { EpiLinear2<false, OutT, true> e{fp, k}; st = launch_stream2<P>(ld, e, g, s, "isp_stream<linear,fast>"); } }
       if (!fast) { EpiLinear2<CAM16, OutT, false> e{fp, k}; st = launch_stream2<P>(ld, e, g, s, "isp_stream<linear>"); }
     }
-    else if constexpr (MODE == MODE_RMAX) { EpiReinhardMax2<CAM16> e{k}; st = launch_stream2<P>(ld, e, g, s, "isp_stream<reinhard_max>"); }
-    else { EpiReinhard2<CAM16, OutT> e{fp, k}; st = launch_stream2<P>(ld, e, g, s, "isp_stream<reinhard>"); }
+    else if constexpr (MODE == MODE_RMAX) {
+      if (k.ca == 0.f) { EpiReinhardMax2<CAM16, true> e{k}; st = launch_stream2<P>(ld, e, g, s, "isp_stream<reinhard_max>"); }
+      else { EpiReinhardMax2<CAM16, false> e{k}; st = launch_stream2<P>(ld, e, g, s, "isp_stream<reinhard_max>"); }
+    } else {
+      st = launch_reinhard<P, CAM16, OutT>(ld, fp, k, g, s);
+    }
   });
   if (ev_stop) record(ev_stop);
   return st;     // the 2-pixel image frame is renormalised inside the sweep (border_fix.cuh): no border kernel
