@@ -142,3 +142,40 @@ def test_packed_roundtrip_and_ids_quirk():
     exp[0::2] = (x[0::2] & 0xFF0) | (x[1::2] & 0xF)
     exp[1::2] = (x[1::2] & 0xFF0) | (x[0::2] & 0xF)
     assert np.array_equal(y, exp)
+
+
+def test_c_abi_rejects_bad_arguments_without_touching_the_gpu():
+    """Every entry point validates its arguments before the first CUDA call and reports through the status code +
+    b200isp_last_error (include/b200isp.h conventions): exercised on the CPU with arguments that must be refused."""
+    import ctypes as C
+    from taichi_image_b200 import _lib
+    lib = _lib.lib
+    E_ARG, E_DTYPE, E_SHAPE, E_FRAMES = -1, -2, -3, -6
+    dummy = C.c_void_p(0x1000)                                  # never dereferenced: validation fails first
+    f9 = (C.c_float * 9)()
+    assert lib.b200isp_bayer_to_rgb(dummy, 0, dummy, 0, 5, 8, 0, None, None) == E_SHAPE             # odd height
+    assert b"even size" in lib.b200isp_last_error()
+    assert lib.b200isp_bayer_to_rgb(dummy, 0, dummy, 0, 4, 8, 7, None, None) == E_ARG               # unknown pattern
+    assert lib.b200isp_bayer_to_rgb(dummy, 9, dummy, 0, 4, 8, 0, None, None) == E_DTYPE
+    assert lib.b200isp_bayer_to_rgb(None, 0, None, 0, 0, 0, 0, None, None) == 0                      # empty image: no-op
+    assert lib.b200isp_rgb_to_bayer(dummy, dummy, 0, 4, 4, 9, None) == E_ARG
+    assert lib.b200isp_rgb_yuv420(dummy, 0, dummy, 0, 5, 4, f9, None) == E_SHAPE
+    assert lib.b200isp_transform(dummy, dummy, 0, 4, 4, 42, None) == E_ARG
+    assert lib.b200isp_metering_update(None, 1, 4, 8, 8, 8, 0.0, None, None, None) == E_ARG
+    p = _lib.FusedParams()
+    p.height, p.width, p.pattern, p.isp_dtype, p.out_dtype, p.tonemap, p.gamma = 8, 16, 0, 4, 0, 0, 1.0
+    ptrs = (C.c_void_p * 1)(0x1000)
+    assert lib.b200isp_process_packed12(ptrs, ptrs, 0, p, dummy, dummy, None) == E_FRAMES           # no frames
+    assert lib.b200isp_process_packed12(ptrs, ptrs, 65, p, dummy, dummy, None) == E_FRAMES          # > B200ISP_MAX_FRAMES
+    p.width = 12
+    assert lib.b200isp_process_packed12(ptrs, ptrs, 1, p, dummy, dummy, None) == E_SHAPE            # width % 8 != 0
+    p.width, p.isp_dtype = 16, 0
+    assert lib.b200isp_process_packed12(ptrs, ptrs, 1, p, dummy, dummy, None) == E_DTYPE            # ISP dtype must be f16 / f32
+    p.isp_dtype, p.gamma = 4, 0.0
+    ptrs16 = (C.c_void_p * 1)(0x1000)
+    assert lib.b200isp_process_packed12(ptrs16, ptrs16, 1, p, dummy, dummy, None) == E_ARG          # gamma must be positive
+    assert lib.b200isp_mailbox_bytes(0) == 0 and lib.b200isp_mailbox_bytes(8) > 0
+    assert lib.b200isp_mailbox_exchange(dummy, 3, ptrs, 1, 0, dummy, None) == E_ARG                  # kind must be 1 | 2
+    assert lib.b200isp_sample_histogram(dummy, 10, 0, dummy, None) == E_ARG
+    with pytest.raises(_lib.B200ISPError, match="bad shape"):
+        _lib.check(E_SHAPE, "demo")
