@@ -52,7 +52,7 @@ RESIZE_WIDTH = {"cfg5": 1920}
 OUT_BYTES = {"u8": 1, "u16": 2, "f16": 2}
 # dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel per launch, from the ncu --set full capture
 # summarised under profiles/ (r01_stream2_kernel_ncu.txt); None where no capture exists
-TRAFFIC = {"cfg2": 843.6e6}     # 180.8 MB read + 662.8 MB written (algorithmic: 179.7 + 718.6; the last ~56 MB of writes are still in L2 at kernel end)
+TRAFFIC = {"cfg2": 843.8e6}     # 180.8 MB read + 663.0 MB written (algorithmic: 179.7 + 718.6; the last ~56 MB of writes are still in L2 at kernel end)
 
 
 def synth_frames(n, h, w, seed=1234):
