@@ -332,6 +332,10 @@ def main():
     # Reinhard: the event pair brackets the write sweep of the first frame group only
     group = n if tonemap != "reinhard" else max(1, min(n, int((48 << 20) // (h * w * 3 // 2))))
     kern_bytes = alg_bytes * (group / n) if tonemap == "reinhard" else alg_bytes
+    one_sweep = tonemap == "reinhard" and isp_dt == "f16"       # Camera16: store sweep over all frames + normalise pass
+    if one_sweep:
+        group = n
+        kern_bytes = px_per_step * (1.5 + 6.0)                  # packed in + f16 map out (the bracketed store sweep)
     peak, peak_src = measured_peak()
     in_step_ms = kern_avg_ms
     # The dominant kernel timed ALONE (same process, same resident inputs, CUDA events on the launching stream):
@@ -361,7 +365,7 @@ def main():
     #   metering: 1 cooperative launch; as look-ahead on the side stream 2 ordinary launches; with shared exposure
     #             phase1 + post + wait + bounds fold + phase2 + post + wait + finalize = 8
     ngroups = (n + group - 1) // group if tonemap == "reinhard" else 1
-    launches = 2 * ngroups if tonemap == "reinhard" else 1
+    launches = 2 * ngroups if tonemap == "reinhard" else 1      # (Camera16 Reinhard: store sweep + normalise pass = 2)
     if shared and world > 1:
         launches += 8
     else:

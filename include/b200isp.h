@@ -167,6 +167,8 @@ typedef struct {
   void* profile_stop;           /*   the dominant streaming kernel (bench.py's live roofline timing); NULL = off */
   void* meter_cache;            /* optional device scratch: >= n_frames*ceil(H/stride)*ceil(W/stride)*12 bytes; the second */
   size_t meter_cache_bytes;     /*   metering phase then re-reads the phase-1 samples instead of recomputing them */
+  void* reinhard_scratch;       /* optional device scratch, >= n_frames*H*W*3*2 bytes: Camera16 Reinhard then runs ONE sweep that */
+  size_t reinhard_scratch_bytes;/*   stores the f16 map (camera_isp.py:211) + an element-wise normalise / quantise pass */
 } b200isp_fused_params;
 
 /* camera_isp.py:333-340 load_packed12 + :376-385 update_metering + :394-413 tonemap_* over a

@@ -34,7 +34,8 @@ class FusedParams(C.Structure):
                 ("color_adapt", C.c_float), ("metering_stride", C.c_int), ("alpha", C.c_float),
                 ("update_metering", C.c_int), ("rows_per_task", C.c_int),
                 ("profile_start", C.c_void_p), ("profile_stop", C.c_void_p),
-                ("meter_cache", C.c_void_p), ("meter_cache_bytes", C.c_size_t)]
+                ("meter_cache", C.c_void_p), ("meter_cache_bytes", C.c_size_t),
+                ("reinhard_scratch", C.c_void_p), ("reinhard_scratch_bytes", C.c_size_t)]
 
 
 _vp, _i, _i64, _f = C.c_void_p, C.c_int, C.c_int64, C.c_float

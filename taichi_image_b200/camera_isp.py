@@ -385,6 +385,13 @@ def camera_isp(name: str, dtype=f32):
                     cache = self._meter_cache = torch.empty(need, dtype=torch.uint8, device=self.device)
                 p.meter_cache, p.meter_cache_bytes = cache.data_ptr(), cache.numel()
                 self._meter_n = need // 12
+            if tonemap == "reinhard" and isp_dtype == f16:
+                # Camera16: scratch for the f16 Reinhard map (one sweep + a light normalise pass, csrc/fused_isp.cuh)
+                need = len(frames) * h * w * 6
+                sc = getattr(self, "_reinhard_scratch", None)
+                if sc is None or sc.numel() < need or sc.device != torch.device(self.device):
+                    sc = self._reinhard_scratch = torch.empty(need, dtype=torch.uint8, device=self.device)
+                p.reinhard_scratch, p.reinhard_scratch_bytes = sc.data_ptr(), sc.numel()
             if profile_events is not None:      # (start, stop) torch.cuda.Event pair, see bench.py
                 p.profile_start, p.profile_stop = profile_events[0].cuda_event, profile_events[1].cuda_event
             return p

@@ -14,6 +14,7 @@
 //               stream<EpiReinhard>    + border   (second sweep re-reads the packed frame from L2)
 //   none        stream<EpiRgb> + border           (load_packed12 only: float RGB out)
 #pragma once
+#include <algorithm>
 #include "stream2.cuh"
 #include "border_fix.cuh"
 #include "pixel_ops.cuh"
@@ -637,29 +638,39 @@ struct EpiLinear2 {
 
 // CA0 (color_adapt == 0) and GAMMA (gamma != 1) are host-known: separate instantiations keep each kernel's code small
 // (the sweep is instruction-cache sensitive, see stream2.cuh)
-template <bool CAM16, bool CA0>
-struct EpiReinhardMax2 {      // pass 1 without the write-back: frame-global max of the mapped values
+// STORE (Camera16 only): also write the un-normalised map p, rounded through f16 exactly like the reference's in-place
+// write-back (camera_isp.py:211), to a scratch image -- the second pass then only normalises and quantises that
+// scratch (reinhard_scratch_out_kernel) instead of sweeping the packed frames again.
+template <bool CAM16, bool CA0, bool STORE = false>
+struct EpiReinhardMax2 {      // pass 1: frame-global max of the mapped values (+ the map itself when STORE)
+  FramePtrs fp;               // .out = scratch images (STORE only)
   IspConsts k;
-  static constexpr int kStageWords = 0;
-  struct State { ReinhardConsts c; float mx; int edge; };
-  __device__ __forceinline__ void init(State& st, int frame, int tcol, const WarpCtx&) const {
+  static_assert(!STORE || CAM16, "the f16 scratch is exact only for Camera16");
+  static constexpr int kStageWords = STORE ? 32 * Quant<__half>::kWords : 0;
+  struct State { ReinhardConsts c; float mx; int edge; __half* out; WarpCtx wc; };
+  __device__ __forceinline__ void init(State& st, int frame, int tcol, const WarpCtx& wc) const {
     st.c = reinhard_consts(k, frame, false);
     st.mx = 0.f;
     st.edge = edge_bits(tcol, k.W);
+    st.wc = wc;
+    st.out = STORE ? reinterpret_cast<__half*>(fp.out[k.frame0 + frame]) + 24 * wc.tcol0 : nullptr;
   }
   static constexpr bool kSplitEdge = false;     // measured: a separate K_CORE copy costs more (instruction cache) than its leaner code saves
   static constexpr bool kCompactLoop = true;
   __device__ __forceinline__ bool fast_kinds_ok(const State&) const { return true; }
-  __device__ __forceinline__ void emit_t(State& st, const Vals24& x) const {
+  __device__ __forceinline__ void emit_t(State& st, int row, const Vals24& x) const {
     float mx = st.mx;
+    uint32_t v[24];
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
       float rgb[3], p[3];
       raw_to_rgb<CAM16>(k, &x.v[3 * q], rgb);
       reinhard_p<CAM16, CA0>(st.c, rgb, p);
       mx = fmaxf(mx, fmaxf(p[0], fmaxf(p[1], p[2])));
+      v[3 * q] = __float_as_uint(p[0]); v[3 * q + 1] = __float_as_uint(p[1]); v[3 * q + 2] = __float_as_uint(p[2]);
     }
     st.mx = mx;
+    if constexpr (STORE) store_row8<__half>(st.wc, st.out, k.W, row, v);
   }
   template <bool BROW, bool GFIRST, int KIND>
   __device__ __forceinline__ void emit(State& st, int row, const f2 (&R)[4], const f2 (&G)[4], const f2 (&B)[4]) const {
@@ -668,6 +679,7 @@ struct EpiReinhardMax2 {      // pass 1 without the write-back: frame-global max
       pairs_to_raw2<CAM16, BROW, GFIRST>(R, G, B, X);
       if (KIND == K_EDGE && st.edge) patch_cols_pairs<BROW, GFIRST>(X, st.edge);
       float mx = st.mx;
+      uint32_t v[24];
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         f2 rgb[3], p[3];
@@ -678,13 +690,16 @@ struct EpiReinhardMax2 {      // pass 1 without the write-back: frame-global max
           float lo, hi;
           upk(p[ch], lo, hi);
           mx = fmaxf(mx, fmaxf(lo, hi));
+          v[3 * j + ch] = __float_as_uint(lo);
+          v[3 * (j + 4) + ch] = __float_as_uint(hi);
         }
       }
       st.mx = mx;
+      if constexpr (STORE) store_row8<__half>(st.wc, st.out, k.W, row, v);
     } else {
       Vals24 x;
       raw_with_frame<CAM16, BROW, GFIRST, KIND>(R, G, B, row, k.H, st.edge, x);
-      emit_t(st, x);
+      emit_t(st, row, x);
     }
   }
   __device__ __forceinline__ void finish(State& st, int frame, int lane, bool task_ok) const {
@@ -964,6 +979,15 @@ struct Packed12FastSampler {
 };
 
 // ---------------------------------------------------------------- host orchestration
+// profile hooks: inside a stream capture the record must be an "external" event node to stay queryable
+static inline void record_profile_event(void* ev, cudaStream_t s) {
+  cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(s, &cs) == cudaSuccess && cs == cudaStreamCaptureStatusActive)
+    cudaEventRecordWithFlags((cudaEvent_t)ev, s, cudaEventRecordExternal);
+  else
+    cudaEventRecord((cudaEvent_t)ev, s);
+}
+
 // host dispatch of the Reinhard write sweep on (color_adapt == 0, gamma != 1)
 template <int P, bool CAM16, typename OutT>
 static int launch_reinhard(const Packed12Loader2<CAM16>& ld, const FramePtrs& fp, const IspConsts& k, const Stream2Geom& g, cudaStream_t s) {
@@ -983,14 +1007,7 @@ static int run_pass(const FramePtrs& fp, IspConsts k, int frame0, int nframes, i
   Packed12Loader2<CAM16> ld;
   ld.fp = fp; ld.pitch_words = k.W * 3 / 8; ld.frame0 = frame0;
   int st = B200ISP_OK;
-  // profile hooks: inside a stream capture the record must be an "external" event node to stay queryable
-  auto record = [&](void* ev) {
-    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
-    if (cudaStreamIsCapturing(s, &cs) == cudaSuccess && cs == cudaStreamCaptureStatusActive)
-      cudaEventRecordWithFlags((cudaEvent_t)ev, s, cudaEventRecordExternal);
-    else
-      cudaEventRecord((cudaEvent_t)ev, s);
-  };
+  auto record = [&](void* ev) { record_profile_event(ev, s); };
   if (ev_start) record(ev_start);
   ISP_DISPATCH_PATTERN(k.pattern, P, {
     if constexpr (MODE == MODE_RGB) { EpiRgb2<CAM16, OutT> e{fp, k}; st = launch_stream2<P>(ld, e, g, s, "isp_stream<rgb>"); }
@@ -1001,14 +1018,75 @@ static int run_pass(const FramePtrs& fp, IspConsts k, int frame0, int nframes, i
       if (!fast) { EpiLinear2<CAM16, OutT, false> e{fp, k}; st = launch_stream2<P>(ld, e, g, s, "isp_stream<linear>"); }
     }
     else if constexpr (MODE == MODE_RMAX) {
-      if (k.ca == 0.f) { EpiReinhardMax2<CAM16, true> e{k}; st = launch_stream2<P>(ld, e, g, s, "isp_stream<reinhard_max>"); }
-      else { EpiReinhardMax2<CAM16, false> e{k}; st = launch_stream2<P>(ld, e, g, s, "isp_stream<reinhard_max>"); }
+      if (k.ca == 0.f) { EpiReinhardMax2<CAM16, true> e{fp, k}; st = launch_stream2<P>(ld, e, g, s, "isp_stream<reinhard_max>"); }
+      else { EpiReinhardMax2<CAM16, false> e{fp, k}; st = launch_stream2<P>(ld, e, g, s, "isp_stream<reinhard_max>"); }
     } else {
       st = launch_reinhard<P, CAM16, OutT>(ld, fp, k, g, s);
     }
   });
   if (ev_stop) record(ev_stop);
   return st;     // the 2-pixel image frame is renormalised inside the sweep (border_fix.cuh): no border kernel
+}
+
+// ---------------------------------------------------------------- Camera16 Reinhard in ONE sweep + a light second pass
+// pass A: the max sweep with STORE over all frames (scratch = f16 map); pass B: out = quantise((p / max)^(1/gamma))
+// element-wise on the scratch, all frames in one launch (blockIdx.y = frame).
+template <typename OutT>
+__global__ void __launch_bounds__(256) reinhard_scratch_out_kernel(const FramePtrs scratch /* .out = f16 maps */, const FramePtrs fp,
+                                                                   long long n_elems /* per frame, % 8 == 0 */, float gamma, const Workspace* ws) {
+  const int frame = blockIdx.y;
+  const __half* src = reinterpret_cast<const __half*>(scratch.out[frame]);
+  OutT* dst = reinterpret_cast<OutT*>(fp.out[frame]);
+  const float inv_max = __fdiv_rn(1.0f, fmaxf(1e-6f, __ldcg(&ws->frame_max[frame])));
+  const float inv_gamma = (float)(1.0 / (double)gamma);
+  const bool has_gamma = gamma != 1.0f;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_elems / 8; i += (long long)gridDim.x * blockDim.x) {
+    const uint4 w = __ldcs(reinterpret_cast<const uint4*>(src) + i);
+    const __half* t = reinterpret_cast<const __half*>(&w);
+    uint32_t v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float q = __saturatef(__half2float(t[j]) * inv_max);
+      if (has_gamma) q = fast_pow(q, inv_gamma);
+      v[j] = Quant<OutT>::q(q);
+    }
+    if constexpr (std::is_same<OutT, uint8_t>::value) {
+      uint2 o;
+      o.x = __byte_perm(__byte_perm(v[0], v[1], 0x0040), __byte_perm(v[2], v[3], 0x0040), 0x5410);
+      o.y = __byte_perm(__byte_perm(v[4], v[5], 0x0040), __byte_perm(v[6], v[7], 0x0040), 0x5410);
+      __stcs(reinterpret_cast<uint2*>(dst) + i, o);
+    } else if constexpr (std::is_same<OutT, uint16_t>::value) {
+      uint4 o = make_uint4(__byte_perm(v[0], v[1], 0x5410), __byte_perm(v[2], v[3], 0x5410), __byte_perm(v[4], v[5], 0x5410),
+                           __byte_perm(v[6], v[7], 0x5410));
+      __stcs(reinterpret_cast<uint4*>(dst) + i, o);
+    } else {
+      alignas(16) __half o[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = __float2half_rn(__uint_as_float(v[j]));
+      __stcs(reinterpret_cast<uint4*>(dst) + i, *reinterpret_cast<const uint4*>(o));
+    }
+  }
+}
+
+// pass A for frames [0, nframes): instantiated once (fused_inst.cu with ISP_INST_RMAX, Camera16)
+template <bool CAM16>
+int run_rstore(const FramePtrs& fp_scratch, IspConsts k, int nframes, int rows_per_task, cudaStream_t s, void* ev_start, void* ev_stop) {
+  if constexpr (!CAM16) {
+    return B200ISP_E_DTYPE;
+  } else {
+    k.frame0 = 0;
+    const Stream2Geom g = make_geom2(k.H, k.W, nframes, rows_per_task);
+    Packed12Loader2<true> ld;
+    ld.fp = fp_scratch; ld.pitch_words = k.W * 3 / 8; ld.frame0 = 0;
+    int st = B200ISP_OK;
+    if (ev_start) record_profile_event(ev_start, s);
+    ISP_DISPATCH_PATTERN(k.pattern, P, {
+      if (k.ca == 0.f) { EpiReinhardMax2<true, true, true> e{fp_scratch, k}; st = launch_stream2<P>(ld, e, g, s, "isp_stream<reinhard_store>"); }
+      else { EpiReinhardMax2<true, false, true> e{fp_scratch, k}; st = launch_stream2<P>(ld, e, g, s, "isp_stream<reinhard_store>"); }
+    });
+    if (ev_stop) record_profile_event(ev_stop, s);
+    return st;
+  }
 }
 
 // frame-global Reinhard max for frames [frame0, frame0 + nframes): independent of the output dtype,
@@ -1035,6 +1113,21 @@ int run_fused(const FramePtrs& fp, int n_frames, const b200isp_fused_params& p, 
     // per group of frames whose packed bytes stay well inside the 126 MB L2.
     int st = cuda_status(cudaMemsetAsync(k.ws->frame_max, 0, sizeof(float) * B200ISP_MAX_FRAMES, s), "memset frame_max");
     if (st) return st;
+    if constexpr (CAM16) {
+      // Camera16: the reference stores the map as f16 anyway -> one sweep writes it to the caller's scratch, a light
+      // element-wise pass normalises it (no second sweep, no L2 grouping)
+      const size_t need = (size_t)n_frames * k.H * k.W * 3 * sizeof(__half);
+      if (p.reinhard_scratch && p.reinhard_scratch_bytes >= need) {
+        FramePtrs sc = fp;
+        for (int f = 0; f < n_frames; ++f) sc.out[f] = (char*)p.reinhard_scratch + (size_t)f * k.H * k.W * 3 * sizeof(__half);
+        st = run_rstore<true>(sc, k, n_frames, rpt, s, p.profile_start, p.profile_stop);
+        if (st) return st;
+        const long long n_elems = (long long)k.H * k.W * 3;
+        const dim3 grid((unsigned)std::min<long long>((n_elems / 8 + 255) / 256, 4 * kNumSMs), (unsigned)n_frames);
+        reinhard_scratch_out_kernel<OutT><<<grid, 256, 0, s>>>(sc, fp, n_elems, k.gamma, k.ws);
+        return cuda_status(cudaPeekAtLastError(), "reinhard_scratch_out_kernel");
+      }
+    }
     const long long frame_bytes = (long long)k.H * k.W * 3 / 2;
     int group = (int)((48LL << 20) / (frame_bytes > 0 ? frame_bytes : 1));
     if (group < 1) group = 1;
@@ -1049,6 +1142,7 @@ int run_fused(const FramePtrs& fp, int n_frames, const b200isp_fused_params& p, 
   }
 }
 
+extern template int run_rstore<true>(const FramePtrs&, IspConsts, int, int, cudaStream_t, void*, void*);
 extern template int run_rmax<true>(const FramePtrs&, IspConsts, int, int, int, cudaStream_t);
 extern template int run_rmax<false>(const FramePtrs&, IspConsts, int, int, int, cudaStream_t);
 
