@@ -836,7 +836,7 @@ struct Packed12FastSampler {
   static constexpr bool kRowStructured = true;
 
   static __device__ __forceinline__ float dec(uint32_t shifted) {
-    const float b = __uint_as_float((shifted & 0x007FF800u) | 0x3F800000u);      // 1 + v/4096
+    const float b = biased_from_shifted(shifted, 0x007FF800u, 0x3F800000u);       // 1 + v/4096, one LOP3
     if constexpr (CAM16) {
       constexpr float kk = 4096.f * kInv4095;
       return __half2float(__float2half_rn(fmaf(b, kk, -kk)));
