@@ -70,6 +70,10 @@ def exchange(record: torch.Tensor, group=None) -> torch.Tensor:
     return out.view(world, record.numel())
 
 
+class PeerExchangeUnavailable(RuntimeError):
+    """raised on EVERY rank when at least one rank could not map its peers' mailboxes (no P2P / IPC between the GPUs)"""
+
+
 class PeerExchange:
     """All-gather of the two shared-exposure records through peer-mapped mailboxes over NVLink (csrc/exchange.cu):
     two 1-warp kernels per gather on the current stream, no host call on the data path, CUDA-graph capturable.
@@ -86,26 +90,40 @@ class PeerExchange:
         assert self.world <= 32, "PeerExchange supports up to 32 ranks"
         handle = (C.c_ubyte * 64)()
         self._own = C.c_void_p()
+        error = None
         with torch.cuda.device(self.device):
-            _lib.check(_lib.lib.b200isp_mailbox_create(self.world, C.byref(self._own), handle), "mailbox_create")
+            try:
+                _lib.check(_lib.lib.b200isp_mailbox_create(self.world, C.byref(self._own), handle), "mailbox_create")
+            except Exception as e:                # keep going: the collectives below must run on every rank
+                error = e
             handles = [bytes(handle)]
             if multi:
                 handles = [None] * self.world
                 dist.all_gather_object(handles, bytes(handle), group=group)
             self._peers = (C.c_void_p * self.world)()
             for r, h in enumerate(handles):
+                if error is not None:
+                    break
                 if r == self.rank:
                     self._peers[r] = self._own.value
                 else:
                     p = C.c_void_p()
                     buf = (C.c_ubyte * 64).from_buffer_copy(h)
-                    _lib.check(_lib.lib.b200isp_mailbox_open(buf, C.byref(p)), f"mailbox_open(rank {r})")
+                    try:
+                        _lib.check(_lib.lib.b200isp_mailbox_open(buf, C.byref(p)), f"mailbox_open(rank {r})")
+                    except Exception as e:
+                        error = e
                     self._peers[r] = p.value
             self.gathered = {1: torch.empty((self.world, 2), dtype=torch.float32, device=self.device),
                              2: torch.empty((self.world, 8), dtype=torch.float32, device=self.device)}
             torch.cuda.synchronize(self.device)
-        if multi:
-            dist.barrier(group=group)            # every mailbox is open everywhere before anyone posts
+            if multi:                             # agree: every mailbox is open everywhere before anyone posts
+                ok = torch.tensor([0 if error is not None else 1], device=self.device)
+                dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
+                if int(ok.item()) == 0:
+                    raise PeerExchangeUnavailable(f"rank {self.rank}: peer mailboxes unavailable ({error})")
+            elif error is not None:
+                raise error
 
     def __call__(self, record: torch.Tensor, kind: int) -> torch.Tensor:
         """kind 1: record of 2 floats, kind 2: 8 floats -> (world, 2 | 8) in rank order (a reused buffer: valid until
@@ -156,7 +174,12 @@ class SharedExposure:
         if exchange == "auto":
             exchange = "peer" if backend is None else "nccl"
         assert exchange in ("peer", "nccl")
-        self.peer = PeerExchange(isp.device, group) if exchange == "peer" else None
+        self.peer = None
+        if exchange == "peer":
+            try:
+                self.peer = PeerExchange(isp.device, group)
+            except PeerExchangeUnavailable:       # raised on every rank alike: all fall back to the all-gather exchange
+                self.peer = None
 
     def __getattr__(self, name):
         return getattr(self.isp, name)
