@@ -227,44 +227,50 @@ static int run_demosaic_stream(const void* bayer, void* rgb, int H, int W, int p
 // i.e. the mean of the in-bounds neighbours of that colour.  Site kernels (x4; taps in row-major 3x3 order):
 //   K0 R site: R = centre, G = N,S,E,W, B = 4 diagonals       K3 B site: K0 with R <-> B
 //   K1 G site with R above/below: R = N,S, B = E,W            K2 G site with R left/right: R = E,W, B = N,S
-static __constant__ signed char c_bilinear[4][9][3] = {
-  {{0,0,1},{0,1,0},{0,0,1},{0,1,0},{4,0,0},{0,1,0},{0,0,1},{0,1,0},{0,0,1}},
-  {{0,0,0},{2,0,0},{0,0,0},{0,0,2},{0,4,0},{0,0,2},{0,0,0},{2,0,0},{0,0,0}},
-  {{0,0,0},{0,0,2},{0,0,0},{2,0,0},{0,4,0},{2,0,0},{0,0,0},{0,0,2},{0,0,0}},
-  {{1,0,0},{0,1,0},{1,0,0},{0,1,0},{0,0,4},{0,1,0},{1,0,0},{0,1,0},{1,0,0}}};
+// accumulate tap i (weight W) into channel CH exactly like the generic loop: c += v * w (separately rounded), t += w
+#define ISP_BL_TAP(CH, I, Wt) { c[CH] = __fadd_rn(c[CH], __fmul_rn(v[I], Wt)); t[CH] += m[I] * Wt; }
 
 template <typename InT, typename OutT>
 __global__ void __launch_bounds__(256) demosaic_bilinear_kernel(const InT* __restrict__ bayer, OutT* __restrict__ out,
-                                                                int H, int W, int pattern, int ccm, const float9 m) {
+                                                                int H, int W, int pattern, int ccm, const float9 m9) {
   const int col = blockIdx.x * blockDim.x + threadIdx.x;
   const int row = blockIdx.y;
   if (col >= W || row >= H) return;
   const int K = site_kernel(pattern, row, col);
-  float c[3] = {0.f, 0.f, 0.f}, t[3] = {0.f, 0.f, 0.f};
+  // 3x3 neighbourhood, 0 outside the image (m = in-bounds indicator); taps in row-major order
+  float v[9], m[9];
 #pragma unroll
   for (int i = 0; i < 9; ++i) {
     const int rr = row + i / 3 - 1, cc = col + i % 3 - 1;
-    if (rr >= 0 && rr < H && cc >= 0 && cc < W) {
-      const float v = to_f32(bayer[(size_t)rr * W + cc]);
-#pragma unroll
-      for (int k = 0; k < 3; ++k) {
-        const float w = (float)c_bilinear[K][i][k];
-        c[k] = __fadd_rn(c[k], __fmul_rn(v, w));
-        t[k] += w;
-      }
-    }
+    const bool in = rr >= 0 && rr < H && cc >= 0 && cc < W;
+    v[i] = in ? to_f32(bayer[(size_t)rr * W + cc]) : 0.f;
+    m[i] = in ? 1.f : 0.f;
+  }
+  float c[3] = {0.f, 0.f, 0.f}, t[3] = {0.f, 0.f, 0.f};
+  // c_bilinear[K] with compile-time weights (zero-weight taps add exactly 0 and are skipped); same tap order
+  if (K == 0) {              // R site: R centre, G cross, B diagonals
+    ISP_BL_TAP(2, 0, 1.f) ISP_BL_TAP(1, 1, 1.f) ISP_BL_TAP(2, 2, 1.f) ISP_BL_TAP(1, 3, 1.f) ISP_BL_TAP(0, 4, 4.f)
+    ISP_BL_TAP(1, 5, 1.f) ISP_BL_TAP(2, 6, 1.f) ISP_BL_TAP(1, 7, 1.f) ISP_BL_TAP(2, 8, 1.f)
+  } else if (K == 3) {       // B site: the same with R <-> B
+    ISP_BL_TAP(0, 0, 1.f) ISP_BL_TAP(1, 1, 1.f) ISP_BL_TAP(0, 2, 1.f) ISP_BL_TAP(1, 3, 1.f) ISP_BL_TAP(2, 4, 4.f)
+    ISP_BL_TAP(1, 5, 1.f) ISP_BL_TAP(0, 6, 1.f) ISP_BL_TAP(1, 7, 1.f) ISP_BL_TAP(0, 8, 1.f)
+  } else if (K == 1) {       // G site, R above / below, B left / right
+    ISP_BL_TAP(0, 1, 2.f) ISP_BL_TAP(2, 3, 2.f) ISP_BL_TAP(1, 4, 4.f) ISP_BL_TAP(2, 5, 2.f) ISP_BL_TAP(0, 7, 2.f)
+  } else {                   // G site, R left / right, B above / below
+    ISP_BL_TAP(2, 1, 2.f) ISP_BL_TAP(0, 3, 2.f) ISP_BL_TAP(1, 4, 4.f) ISP_BL_TAP(0, 5, 2.f) ISP_BL_TAP(2, 7, 2.f)
   }
   constexpr float is = DT<InT>::scale, os = DT<OutT>::scale;
   // a 2-pixel-wide image can leave a colour without any in-bounds neighbour (t = 0): define it as 0
   float cr = t[0] > 0.f ? __fdiv_rn(c[0], __fmul_rn(is, t[0])) : 0.f;
   float cg = t[1] > 0.f ? __fdiv_rn(c[1], __fmul_rn(is, t[1])) : 0.f;
   float cb = t[2] > 0.f ? __fdiv_rn(c[2], __fmul_rn(is, t[2])) : 0.f;
-  if (ccm) ccm_apply(m.v, cr, cg, cb);
+  if (ccm) ccm_apply(m9.v, cr, cg, cb);
   OutT* o = out + ((size_t)row * W + col) * 3;
   o[0] = cast_from_f32<OutT>(__fmul_rn(clamp01(cr), os));
   o[1] = cast_from_f32<OutT>(__fmul_rn(clamp01(cg), os));
   o[2] = cast_from_f32<OutT>(__fmul_rn(clamp01(cb), os));
 }
+#undef ISP_BL_TAP
 
 // ---------------------------------------------------------------- rgb_to_bayer (bayer.py:101-112)
 // pixel_orders (bayer.py:85-90): channel at ((r0,c0),(r0,c1),(r1,c0),(r1,c1)), 2 bits each
