@@ -217,6 +217,8 @@ def main():
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
     ap.add_argument("--shared-exposure", type=int, default=-1, help="all-reduce the metering statistics across ranks (default: on for N > 1)")
     ap.add_argument("--rows-per-task", type=int, default=0)
+    ap.add_argument("--demosaic", default="malvar", choices=["malvar", "bilinear"],
+                    help="bilinear: the north_star's alternative demosaic inside the fused sweep (not the BASELINE configuration)")
     ap.add_argument("--e2e-steps", type=int, default=0, help="steps of the host-buffer pipeline leg (default: min(steps, 12))")
     ap.add_argument("--lookahead", type=int, default=1, help="announce the next batch so its metering (and exposure exchange) "
                     "runs on a side stream under this batch's sweep (camera-stream mode; 0 = strictly serial steps)")
@@ -247,7 +249,10 @@ def main():
     n, h, w, isp_dt, tonemap, out_dt, tm, desc = WORKLOADS[args.workload]
     cam = tib.camera_isp.Camera16 if isp_dt == "f16" else tib.camera_isp.Camera32
     resize_w = RESIZE_WIDTH.get(args.workload, 0)
-    isp = cam(tib.bayer.BayerPattern.RGGB, moving_alpha=0.1, device=device, resize_width=resize_w)
+    isp = cam(tib.bayer.BayerPattern.RGGB, moving_alpha=0.1, device=device, resize_width=resize_w, demosaic=args.demosaic)
+    if args.demosaic != "malvar":
+        desc += f" [demosaic = {args.demosaic}]"
+        args.no_cpu_baseline = True         # the CPU port implements the reference's (Malvar) path only
     if resize_w:                       # staged path: no fused sweep, no graph, no look-ahead, no e2e pipeline
         args.graph = args.lookahead = 0
         args.no_e2e = True

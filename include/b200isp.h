@@ -149,6 +149,7 @@ int b200isp_isp_reinhard(void* image, int dtype, void* output, int out_dtype, in
                          float color_adapt, void* workspace, b200isp_stream stream);
 
 /* ---- fused path: packed12 frames -> tone-mapped RGB in one sweep --------- */
+typedef enum { B200ISP_DEMOSAIC_MALVAR = 0, B200ISP_DEMOSAIC_BILINEAR = 1 } b200isp_demosaic_t;
 typedef struct {
   int height, width;            /* sensor size; width % 8 == 0, height % 2 == 0 */
   int pattern;                  /* b200isp_pattern */
@@ -163,6 +164,8 @@ typedef struct {
                                    1 - moving_alpha afterwards (camera_isp.py:376-385) */
   int update_metering;          /* 1: run the two metering phases on these frames first */
   int rows_per_task;            /* 0 = default */
+  int demosaic;                 /* b200isp_demosaic_t: 0 = Malvar-He-Cutler (bayer.py:30-55), 1 = bilinear (extension) */
+  int reserved;                 /* 0 */
   void* profile_start;          /* optional cudaEvent_t pair recorded on `stream` immediately before / after */
   void* profile_stop;           /*   the dominant streaming kernel (bench.py's live roofline timing); NULL = off */
   void* meter_cache;            /* optional device scratch: >= n_frames*ceil(H/stride)*ceil(W/stride)*12 bytes; the second */

@@ -446,8 +446,10 @@ class ISP:
 
     def __init__(self, dtype="f32", bayer_pattern="RGGB", scale=None, resize_width=0,
                  moving_alpha=0.1, correct_colors=False, white_balance=DEFAULT_WB,
-                 color_correction=DEFAULT_CC, transform="none", metering_stride=8):
+                 color_correction=DEFAULT_CC, transform="none", metering_stride=8, demosaic="malvar"):
         assert scale is None or resize_width == 0
+        assert demosaic in ("malvar", "bilinear")        # "bilinear": extension, bayer_to_rgb_bilinear below
+        self.demosaic = demosaic
         self.dtype, self.bayer_pattern = dtype, bayer_pattern
         self.scale, self.resize_width = scale, resize_width
         self.moving_alpha, self.correct_colors = moving_alpha, correct_colors
@@ -474,7 +476,8 @@ class ISP:
 
     def _process_image(self, cfa):                       # camera_isp.py:371-373
         ccm = self.color_correct_matrix
-        rgb = bayer_to_rgb(cfa, self.bayer_pattern, None if ccm is None else ccm.flatten().tolist())
+        demosaic = bayer_to_rgb_bilinear if self.demosaic == "bilinear" else bayer_to_rgb
+        rgb = demosaic(cfa, self.bayer_pattern, None if ccm is None else ccm.flatten().tolist())
         return self.resize_image(rgb)
 
     def load_packed12(self, data, ids_format=False):     # camera_isp.py:333-340

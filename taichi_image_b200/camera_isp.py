@@ -84,8 +84,13 @@ def camera_isp(name: str, dtype=f32):
                      color_correction: np.ndarray = default_cc,
                      transform: interpolate.ImageTransform = interpolate.ImageTransform.none,
                      device: torch.device = torch.device('cuda', 0),
-                     metering_stride: int = 8):
+                     metering_stride: int = 8,
+                     demosaic: str = "malvar"):
+            """camera_isp.py:237-268.  ``demosaic="bilinear"`` (EXTENSION, north_star): 3x3 bilinear interpolation
+            instead of Malvar-He-Cutler in every load / fused path of this object (``bayer_to_rgb(method=...)``)."""
             assert scale is None or resize_width == 0, "Cannot specify both scale and resize_width"
+            assert demosaic in ("malvar", "bilinear")
+            self.demosaic = demosaic
             self.bayer_pattern = bayer_pattern
             self.moving_alpha = moving_alpha
             self.scale = scale
@@ -205,7 +210,7 @@ def camera_isp(name: str, dtype=f32):
 
         def _process_image(self, cfa):
             """camera_isp.py:371-373 (with the configured pattern)"""
-            rgb = bayer.bayer_to_rgb(cfa, self.bayer_pattern, correct_colors=self.color_correct_matrix)
+            rgb = bayer.bayer_to_rgb(cfa, self.bayer_pattern, correct_colors=self.color_correct_matrix, method=self.demosaic)
             return self.resize_image(rgb)
 
         # ------------------------------------------------------------ metering
@@ -377,6 +382,7 @@ def camera_isp(name: str, dtype=f32):
             p.color_adapt = float(tm.get("color_adapt", 0.0))
             p.metering_stride, p.alpha = int(self.metering_stride), float(alpha)
             p.update_metering, p.rows_per_task = int(update_metering), int(rows_per_task)
+            p.demosaic = 1 if self.demosaic == "bilinear" else 0
             if update_metering:                  # scratch for the phase-1 samples (re-read by phase 2)
                 stride = max(int(self.metering_stride), 1)
                 need = len(frames) * (-(-h // stride)) * (-(-w // stride)) * 12

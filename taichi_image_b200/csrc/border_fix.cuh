@@ -10,22 +10,30 @@
 // column class of the pixel (0: first, 1: second, 2: interior, 3: second to last, 4: last), so it is a
 // 4 x 5 x 5 x 3 table, built at compile time from the tap table of bayer.py:30-55 (SURVEY Appendix A;
 // min |t| = 10, never 0).
+// Entries K = 4..7 are the same table for the BILINEAR demosaic (north_star extension; 3 x 3 taps written in
+// the 13-tap layout with weights x4, so they also sum to 16 and every formula above holds; min t = 4).
 #pragma once
 #include "common.cuh"
 
 namespace isp {
 
+constexpr int kBilinearBase = 4;     // site kernel K + kBilinearBase = the bilinear kernel of the same site
 struct BorderTable {
-  float t[4][5][5][3];   // t = sum of the in-bounds weights (bayer.py:147-149)
-  float f[4][5][5][3];   // 16 / t
+  float t[8][5][5][3];   // t = sum of the in-bounds weights (bayer.py:147-149)
+  float f[8][5][5][3];   // 16 / t
 };
 
 namespace border_detail {
-constexpr signed char kTaps[4][13][3] = {
+constexpr signed char kTaps[8][13][3] = {
   {{0,-2,-3},{0,0,4},{0,4,0},{0,0,4},{0,-2,-3},{0,4,0},{16,8,12},{0,4,0},{0,-2,-3},{0,0,4},{0,4,0},{0,0,4},{0,-2,-3}},
   {{-2,0,1},{-2,0,-2},{8,0,0},{-2,0,-2},{1,0,-2},{0,0,8},{10,16,10},{0,0,8},{1,0,-2},{-2,0,-2},{8,0,0},{-2,0,-2},{-2,0,1}},
   {{1,0,-2},{-2,0,-2},{0,0,8},{-2,0,-2},{-2,0,1},{8,0,0},{10,16,10},{8,0,0},{-2,0,1},{-2,0,-2},{0,0,8},{-2,0,-2},{1,0,-2}},
-  {{-3,-2,0},{4,0,0},{0,4,0},{4,0,0},{-3,-2,0},{0,4,0},{12,8,16},{0,4,0},{-3,-2,0},{4,0,0},{0,4,0},{4,0,0},{-3,-2,0}}};
+  {{-3,-2,0},{4,0,0},{0,4,0},{4,0,0},{-3,-2,0},{0,4,0},{12,8,16},{0,4,0},{-3,-2,0},{4,0,0},{0,4,0},{4,0,0},{-3,-2,0}},
+  // bilinear x4: R site (own centre, G cross, B diagonals); G site, R above / below; G site, R left / right; B site
+  {{0,0,0},{0,0,4},{0,4,0},{0,0,4},{0,0,0},{0,4,0},{16,0,0},{0,4,0},{0,0,0},{0,0,4},{0,4,0},{0,0,4},{0,0,0}},
+  {{0,0,0},{0,0,0},{8,0,0},{0,0,0},{0,0,0},{0,0,8},{0,16,0},{0,0,8},{0,0,0},{0,0,0},{8,0,0},{0,0,0},{0,0,0}},
+  {{0,0,0},{0,0,0},{0,0,8},{0,0,0},{0,0,0},{8,0,0},{0,16,0},{8,0,0},{0,0,0},{0,0,0},{0,0,8},{0,0,0},{0,0,0}},
+  {{0,0,0},{4,0,0},{0,4,0},{4,0,0},{0,0,0},{0,4,0},{0,0,16},{0,4,0},{0,0,0},{4,0,0},{0,4,0},{4,0,0},{0,0,0}}};
 constexpr int kD0[13] = {-2, -1, -1, -1, 0, 0, 0, 0, 0, 1, 1, 1, 2};
 constexpr int kD1[13] = {0, -1, 0, 1, -2, -1, 0, 1, 2, -1, 0, 1, 0};
 constexpr bool in_bounds(int cls, int d) {
@@ -33,7 +41,7 @@ constexpr bool in_bounds(int cls, int d) {
 }
 constexpr BorderTable make_table() {
   BorderTable t{};
-  for (int K = 0; K < 4; ++K)
+  for (int K = 0; K < 8; ++K)
     for (int rc = 0; rc < 5; ++rc)
       for (int cc = 0; cc < 5; ++cc)
         for (int ch = 0; ch < 3; ++ch) {

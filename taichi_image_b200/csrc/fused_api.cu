@@ -35,7 +35,10 @@ static int fused_setup(const char* what, const uint8_t* const* packed_host, void
   k.ccm = p.has_ccm ? 1 : 0;
   for (int i = 0; i < 9; ++i) k.m[i] = p.has_ccm ? p.ccm[i] : (i % 4 == 0 ? 1.f : 0.f);   // identity: see raw_to_rgb
   k.gamma = p.gamma; k.intensity = p.intensity; k.la = p.light_adapt; k.ca = p.color_adapt;
+  ISP_REQUIRE(p.demosaic == B200ISP_DEMOSAIC_MALVAR || p.demosaic == B200ISP_DEMOSAIC_BILINEAR, B200ISP_E_ARG,
+              "%s: unknown demosaic %d", what, p.demosaic);
   k.metrics = metrics; k.ws = (Workspace*)workspace; k.frame0 = 0;
+  k.kbase = p.demosaic == B200ISP_DEMOSAIC_BILINEAR ? kBilinearBase : 0;
   return B200ISP_OK;
 }
 

@@ -145,6 +145,7 @@ struct IspConsts {
   const float* metrics;      // device, 9 floats
   Workspace* ws;
   int frame0;
+  int kbase;                 // 0: Malvar-He-Cutler, kBilinearBase: bilinear demosaic (offset into c_taps / c_border)
 };
 
 // literal front end for one pixel (bayer.py:137-155 + ISP dtype rounding), used off the hot path
@@ -152,7 +153,7 @@ template <bool CAM16>
 __device__ __forceinline__ void isp_rgb_pixel(const Packed12Src<CAM16>& src, const IspConsts& k, int frame, int row, int col,
                                               float (&rgb)[3]) {
   float c[3], t[3];
-  malvar_pixel(src, frame, k.pattern, row, col, k.H, k.W, c, t);
+  malvar_pixel(src, frame, k.pattern, row, col, k.H, k.W, c, t, k.kbase);
   float r = __fdiv_rn(c[0], t[0]), g = __fdiv_rn(c[1], t[1]), b = __fdiv_rn(c[2], t[2]);   // in_scale = 1.0
   if (k.ccm) ccm_apply(k.m, r, g, b);
   rgb[0] = round_isp<CAM16>(clamp01(r));
@@ -348,12 +349,12 @@ __device__ __forceinline__ void pairs_to_raw(const f2 (&R)[4], const f2 (&G)[4],
 // Renormalisation of the frame columns of an interior row on the raw values, exact (division) form: pixels
 // 0,1 of the first thread column / 6,7 of the last (edge != 0 only there).
 template <bool BROW, bool GFIRST>
-__device__ __forceinline__ void patch_cols(Vals24& x, int edge) {
+__device__ __forceinline__ void patch_cols(Vals24& x, int edge, int kbase) {
 #pragma unroll
   for (int q = 0; q < 8; ++q) {
     if (q >= 2 && q < 6) continue;
     if ((q < 2 && (edge & 1)) || (q >= 6 && (edge & 2))) {
-      const int K = site_kernel_of(BROW, SiteScale2<BROW, GFIRST>::gsite(q & 3));
+      const int K = site_kernel_of(BROW, SiteScale2<BROW, GFIRST>::gsite(q & 3)) + kbase;
       const float* t = c_border.t[K][2][q < 2 ? q : q - 3];
       x.v[3 * q] = frame_exact(x.v[3 * q], t[0]);
       x.v[3 * q + 1] = frame_exact(x.v[3 * q + 1], t[1]);
@@ -367,7 +368,7 @@ __device__ __forceinline__ void patch_cols(Vals24& x, int edge) {
 // pixels that are not on the image frame.  brow / gfirst = row type at run time.
 struct Pairs12 { f2 R[4], G[4], B[4]; };
 template <bool CAM16>
-static __device__ __noinline__ Vals24 general_raw(Pairs12 s, int rc, int edge, int brow, int gfirst) {
+static __device__ __noinline__ Vals24 general_raw(Pairs12 s, int rc, int edge, int brow, int gfirst, int kbase) {
   Vals24 x;
   constexpr float kn = 256.f * kInv4095;
 #pragma unroll 1
@@ -376,7 +377,7 @@ static __device__ __noinline__ Vals24 general_raw(Pairs12 s, int rc, int edge, i
     const float sc[3] = {gsite ? -2.f : (brow ? 4.f : 16.f), gsite ? 16.f : -2.f, gsite ? -2.f : (brow ? 16.f : 4.f)};
     float v[3][2];
     upk(s.R[j], v[0][0], v[0][1]); upk(s.G[j], v[1][0], v[1][1]); upk(s.B[j], v[2][0], v[2][1]);
-    const int K = site_kernel_of(brow != 0, gsite);
+    const int K = site_kernel_of(brow != 0, gsite) + kbase;
 #pragma unroll 1
     for (int l = 0; l < 2; ++l) {
       const int q = j + 4 * l;
@@ -393,15 +394,15 @@ static __device__ __noinline__ Vals24 general_raw(Pairs12 s, int rc, int edge, i
 
 template <bool CAM16, bool BROW, bool GFIRST, int KIND>
 __device__ __forceinline__ void raw_with_frame(const f2 (&R)[4], const f2 (&G)[4], const f2 (&B)[4], int row, int H, int edge,
-                                               Vals24& x) {
+                                               int kbase, Vals24& x) {
   if constexpr (KIND == K_GENERAL) {
     Pairs12 s;
 #pragma unroll
     for (int j = 0; j < 4; ++j) { s.R[j] = R[j]; s.G[j] = G[j]; s.B[j] = B[j]; }
-    x = general_raw<CAM16>(s, edge_class(row, H), edge, BROW, GFIRST);
+    x = general_raw<CAM16>(s, edge_class(row, H), edge, BROW, GFIRST, kbase);
   } else {
     pairs_to_raw<CAM16, BROW, GFIRST>(R, G, B, x);
-    if (KIND == K_EDGE && edge) patch_cols<BROW, GFIRST>(x, edge);
+    if (KIND == K_EDGE && edge) patch_cols<BROW, GFIRST>(x, edge, kbase);
   }
 }
 
@@ -442,12 +443,12 @@ __device__ __forceinline__ void pairs_to_raw2(const f2 (&R)[4], const f2 (&G)[4]
 
 // frame columns of an interior row on the raw pairs, exact (division) form; edge != 0 only in the first / last thread column
 template <bool BROW, bool GFIRST>
-__device__ __forceinline__ void patch_cols_pairs(f2 (&X)[4][3], int edge) {
+__device__ __forceinline__ void patch_cols_pairs(f2 (&X)[4][3], int edge, int kbase) {
 #pragma unroll
   for (int q = 0; q < 8; ++q) {
     if (q >= 2 && q < 6) continue;
     if ((q < 2 && (edge & 1)) || (q >= 6 && (edge & 2))) {
-      const int K = site_kernel_of(BROW, SiteScale2<BROW, GFIRST>::gsite(q & 3));
+      const int K = site_kernel_of(BROW, SiteScale2<BROW, GFIRST>::gsite(q & 3)) + kbase;
       const float* t = c_border.t[K][2][q < 2 ? q : q - 3];
 #pragma unroll
       for (int ch = 0; ch < 3; ++ch) {
@@ -518,7 +519,7 @@ struct EpiRgb2 {      // load_packed12: ISP-dtype float RGB out
   template <bool BROW, bool GFIRST, int KIND>
   __device__ __forceinline__ void emit(State& st, int row, const f2 (&R)[4], const f2 (&G)[4], const f2 (&B)[4]) const {
     Vals24 x;
-    raw_with_frame<CAM16, BROW, GFIRST, KIND>(R, G, B, row, k.H, st.edge, x);
+    raw_with_frame<CAM16, BROW, GFIRST, KIND>(R, G, B, row, k.H, st.edge, k.kbase, x);
     uint32_t v[24];
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
@@ -570,7 +571,7 @@ struct EpiLinear2 {
   template <bool BROW, bool GFIRST, int KIND>
   __device__ __forceinline__ void emit_generic(const State& st, int row, const f2 (&R)[4], const f2 (&G)[4], const f2 (&B)[4]) const {
     Vals24 x;
-    raw_with_frame<CAM16, BROW, GFIRST, KIND>(R, G, B, row, k.H, st.edge, x);
+    raw_with_frame<CAM16, BROW, GFIRST, KIND>(R, G, B, row, k.H, st.edge, k.kbase, x);
     if (st.c.has_gamma) emit_t<true>(st, row, x);
     else emit_t<false>(st, row, x);
   }
@@ -597,7 +598,7 @@ struct EpiLinear2 {
         for (int q = 0; q < 8; ++q) {
           if (q >= 2 && q < 6) continue;
           if ((q < 2 && (st.edge & 1)) || (q >= 6 && (st.edge & 2))) {
-            const int K = site_kernel_of(BROW, SS::gsite(q & 3));
+            const int K = site_kernel_of(BROW, SS::gsite(q & 3)) + k.kbase;
             const float* f = c_border.f[K][2][q < 2 ? q : q - 3];
 #pragma unroll
             for (int ch = 0; ch < 3; ++ch) {
@@ -677,7 +678,7 @@ struct EpiReinhardMax2 {      // pass 1: frame-global max of the mapped values (
     if constexpr (KIND != K_GENERAL && CA0) {        // packed path
       f2 X[4][3];
       pairs_to_raw2<CAM16, BROW, GFIRST>(R, G, B, X);
-      if (KIND == K_EDGE && st.edge) patch_cols_pairs<BROW, GFIRST>(X, st.edge);
+      if (KIND == K_EDGE && st.edge) patch_cols_pairs<BROW, GFIRST>(X, st.edge, k.kbase);
       float mx = st.mx;
       uint32_t v[24];
 #pragma unroll
@@ -698,7 +699,7 @@ struct EpiReinhardMax2 {      // pass 1: frame-global max of the mapped values (
       if constexpr (STORE) store_row8<__half>(st.wc, st.out, k.W, row, v);
     } else {
       Vals24 x;
-      raw_with_frame<CAM16, BROW, GFIRST, KIND>(R, G, B, row, k.H, st.edge, x);
+      raw_with_frame<CAM16, BROW, GFIRST, KIND>(R, G, B, row, k.H, st.edge, k.kbase, x);
       emit_t(st, row, x);
     }
   }
@@ -742,7 +743,7 @@ struct EpiReinhard2 {         // pass 2 recomputed from the packed frame: map, n
   __device__ __forceinline__ void emit_pairs(const State& st, int row, const f2 (&R)[4], const f2 (&G)[4], const f2 (&B)[4]) const {
     f2 X[4][3];
     pairs_to_raw2<CAM16, BROW, GFIRST>(R, G, B, X);
-    if (KIND == K_EDGE && st.edge) patch_cols_pairs<BROW, GFIRST>(X, st.edge);
+    if (KIND == K_EDGE && st.edge) patch_cols_pairs<BROW, GFIRST>(X, st.edge, k.kbase);
     uint32_t v[24];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
@@ -780,7 +781,7 @@ struct EpiReinhard2 {         // pass 2 recomputed from the packed frame: map, n
       emit_pairs<BROW, GFIRST, KIND>(st, row, R, G, B);
     } else {
       Vals24 x;
-      raw_with_frame<CAM16, BROW, GFIRST, KIND>(R, G, B, row, k.H, st.edge, x);
+      raw_with_frame<CAM16, BROW, GFIRST, KIND>(R, G, B, row, k.H, st.edge, k.kbase, x);
       emit_t(st, row, x);
     }
   }
@@ -863,13 +864,15 @@ struct Packed12FastSampler {
     gsite = gfirst0 != ((row & 1) != 0);
     if (!gsite) {
       float g2, opp4;
-      malvar_csite(C, NS, EW, NNSS, EEWW, D, g2, opp4);
+      if (k.kbase) { g2 = 2.f * (NS + EW); opp4 = D; }              // bilinear (kernel-uniform): same scales, see bilinear_row2
+      else malvar_csite(C, NS, EW, NNSS, EEWW, D, g2, opp4);
       S[1] = g2; sc[1] = 2.f;
       S[0] = brow ? opp4 : C; sc[0] = brow ? 4.f : 16.f;
       S[2] = brow ? C : opp4; sc[2] = brow ? 16.f : 4.f;
     } else {
       float h2, v2;
-      malvar_gsite(C, NS, EW, NNSS, EEWW, D, h2, v2);
+      if (k.kbase) { h2 = 4.f * EW; v2 = 4.f * NS; }
+      else malvar_gsite(C, NS, EW, NNSS, EEWW, D, h2, v2);
       S[1] = C; sc[1] = 16.f;
       S[0] = brow ? v2 : h2; sc[0] = 2.f;
       S[2] = brow ? h2 : v2; sc[2] = 2.f;
@@ -903,7 +906,7 @@ struct Packed12FastSampler {
     float S[3], sc[3];
     bool brow, gsite;
     sums_from_words(a0, bm, b0, cm, c0, c1, dm, d0, e0, row, S, sc, brow, gsite);
-    const float* t = c_border.t[site_kernel_of(brow, gsite)][edge_class(row, k.H)][edge_class(col, k.W)];
+    const float* t = c_border.t[site_kernel_of(brow, gsite) + k.kbase][edge_class(row, k.H)][edge_class(col, k.W)];
     constexpr float kn = 256.f * kInv4095;
     float x[3];
 #pragma unroll
@@ -992,11 +995,11 @@ static inline void record_profile_event(void* ev, cudaStream_t s) {
 template <int P, bool CAM16, typename OutT>
 static int launch_reinhard(const Packed12Loader2<CAM16>& ld, const FramePtrs& fp, const IspConsts& k, const Stream2Geom& g, cudaStream_t s) {
   const bool ca0 = k.ca == 0.f, gam = k.gamma != 1.0f;
-  if (ca0 && gam) { EpiReinhard2<CAM16, OutT, true, true> e{fp, k}; return launch_stream2<P>(ld, e, g, s, "isp_stream<reinhard>"); }
-  if (ca0) { EpiReinhard2<CAM16, OutT, true, false> e{fp, k}; return launch_stream2<P>(ld, e, g, s, "isp_stream<reinhard>"); }
-  if (gam) { EpiReinhard2<CAM16, OutT, false, true> e{fp, k}; return launch_stream2<P>(ld, e, g, s, "isp_stream<reinhard>"); }
+  if (ca0 && gam) { EpiReinhard2<CAM16, OutT, true, true> e{fp, k}; return launch_stream2<P>(ld, e, g, s, "isp_stream<reinhard>", k.kbase != 0); }
+  if (ca0) { EpiReinhard2<CAM16, OutT, true, false> e{fp, k}; return launch_stream2<P>(ld, e, g, s, "isp_stream<reinhard>", k.kbase != 0); }
+  if (gam) { EpiReinhard2<CAM16, OutT, false, true> e{fp, k}; return launch_stream2<P>(ld, e, g, s, "isp_stream<reinhard>", k.kbase != 0); }
   EpiReinhard2<CAM16, OutT, false, false> e{fp, k};
-  return launch_stream2<P>(ld, e, g, s, "isp_stream<reinhard>");
+  return launch_stream2<P>(ld, e, g, s, "isp_stream<reinhard>", k.kbase != 0);
 }
 
 template <bool CAM16, int MODE, typename OutT>
@@ -1010,16 +1013,16 @@ static int run_pass(const FramePtrs& fp, IspConsts k, int frame0, int nframes, i
   auto record = [&](void* ev) { record_profile_event(ev, s); };
   if (ev_start) record(ev_start);
   ISP_DISPATCH_PATTERN(k.pattern, P, {
-    if constexpr (MODE == MODE_RGB) { EpiRgb2<CAM16, OutT> e{fp, k}; st = launch_stream2<P>(ld, e, g, s, "isp_stream<rgb>"); }
+    if constexpr (MODE == MODE_RGB) { EpiRgb2<CAM16, OutT> e{fp, k}; st = launch_stream2<P>(ld, e, g, s, "isp_stream<rgb>", k.kbase != 0); }
     else if constexpr (MODE == MODE_LINEAR) {
       bool fast = false;
       if constexpr (!CAM16) fast = !k.ccm && k.gamma == 1.0f;
-      if constexpr (!CAM16) { if (fast) { EpiLinear2<false, OutT, true> e{fp, k}; st = launch_stream2<P>(ld, e, g, s, "isp_stream<linear,fast>"); } }
-      if (!fast) { EpiLinear2<CAM16, OutT, false> e{fp, k}; st = launch_stream2<P>(ld, e, g, s, "isp_stream<linear>"); }
+      if constexpr (!CAM16) { if (fast) { EpiLinear2<false, OutT, true> e{fp, k}; st = launch_stream2<P>(ld, e, g, s, "isp_stream<linear,fast>", k.kbase != 0); } }
+      if (!fast) { EpiLinear2<CAM16, OutT, false> e{fp, k}; st = launch_stream2<P>(ld, e, g, s, "isp_stream<linear>", k.kbase != 0); }
     }
     else if constexpr (MODE == MODE_RMAX) {
-      if (k.ca == 0.f) { EpiReinhardMax2<CAM16, true> e{fp, k}; st = launch_stream2<P>(ld, e, g, s, "isp_stream<reinhard_max>"); }
-      else { EpiReinhardMax2<CAM16, false> e{fp, k}; st = launch_stream2<P>(ld, e, g, s, "isp_stream<reinhard_max>"); }
+      if (k.ca == 0.f) { EpiReinhardMax2<CAM16, true> e{fp, k}; st = launch_stream2<P>(ld, e, g, s, "isp_stream<reinhard_max>", k.kbase != 0); }
+      else { EpiReinhardMax2<CAM16, false> e{fp, k}; st = launch_stream2<P>(ld, e, g, s, "isp_stream<reinhard_max>", k.kbase != 0); }
     } else {
       st = launch_reinhard<P, CAM16, OutT>(ld, fp, k, g, s);
     }
@@ -1081,8 +1084,8 @@ int run_rstore(const FramePtrs& fp_scratch, IspConsts k, int nframes, int rows_p
     int st = B200ISP_OK;
     if (ev_start) record_profile_event(ev_start, s);
     ISP_DISPATCH_PATTERN(k.pattern, P, {
-      if (k.ca == 0.f) { EpiReinhardMax2<true, true, true> e{fp_scratch, k}; st = launch_stream2<P>(ld, e, g, s, "isp_stream<reinhard_store>"); }
-      else { EpiReinhardMax2<true, false, true> e{fp_scratch, k}; st = launch_stream2<P>(ld, e, g, s, "isp_stream<reinhard_store>"); }
+      if (k.ca == 0.f) { EpiReinhardMax2<true, true, true> e{fp_scratch, k}; st = launch_stream2<P>(ld, e, g, s, "isp_stream<reinhard_store>", k.kbase != 0); }
+      else { EpiReinhardMax2<true, false, true> e{fp_scratch, k}; st = launch_stream2<P>(ld, e, g, s, "isp_stream<reinhard_store>", k.kbase != 0); }
     });
     if (ev_stop) record_profile_event(ev_stop, s);
     return st;

@@ -7,12 +7,17 @@
 
 namespace isp {
 
-// bayer.py:30-55 expanded: [site kernel][tap][channel]
-static __constant__ signed char c_taps[4][13][3] = {
+// bayer.py:30-55 expanded: [site kernel][tap][channel]; entries 4..7: the bilinear demosaic
+// (extension) in the same layout, weights x4 (c / t is unchanged bit for bit by the power of two)
+static __constant__ signed char c_taps[8][13][3] = {
   {{0,-2,-3},{0,0,4},{0,4,0},{0,0,4},{0,-2,-3},{0,4,0},{16,8,12},{0,4,0},{0,-2,-3},{0,0,4},{0,4,0},{0,0,4},{0,-2,-3}},
   {{-2,0,1},{-2,0,-2},{8,0,0},{-2,0,-2},{1,0,-2},{0,0,8},{10,16,10},{0,0,8},{1,0,-2},{-2,0,-2},{8,0,0},{-2,0,-2},{-2,0,1}},
   {{1,0,-2},{-2,0,-2},{0,0,8},{-2,0,-2},{-2,0,1},{8,0,0},{10,16,10},{8,0,0},{-2,0,1},{-2,0,-2},{0,0,8},{-2,0,-2},{1,0,-2}},
-  {{-3,-2,0},{4,0,0},{0,4,0},{4,0,0},{-3,-2,0},{0,4,0},{12,8,16},{0,4,0},{-3,-2,0},{4,0,0},{0,4,0},{4,0,0},{-3,-2,0}}};
+  {{-3,-2,0},{4,0,0},{0,4,0},{4,0,0},{-3,-2,0},{0,4,0},{12,8,16},{0,4,0},{-3,-2,0},{4,0,0},{0,4,0},{4,0,0},{-3,-2,0}},
+  {{0,0,0},{0,0,4},{0,4,0},{0,0,4},{0,0,0},{0,4,0},{16,0,0},{0,4,0},{0,0,0},{0,0,4},{0,4,0},{0,0,4},{0,0,0}},
+  {{0,0,0},{0,0,0},{8,0,0},{0,0,0},{0,0,0},{0,0,8},{0,16,0},{0,0,8},{0,0,0},{0,0,0},{8,0,0},{0,0,0},{0,0,0}},
+  {{0,0,0},{0,0,0},{0,0,8},{0,0,0},{0,0,0},{8,0,0},{0,16,0},{8,0,0},{0,0,0},{0,0,0},{0,0,8},{0,0,0},{0,0,0}},
+  {{0,0,0},{4,0,0},{0,4,0},{4,0,0},{0,0,0},{0,4,0},{0,0,16},{0,4,0},{0,0,0},{4,0,0},{0,4,0},{4,0,0},{0,0,0}}};
 static __constant__ signed char c_d0[13] = {-2, -1, -1, -1, 0, 0, 0, 0, 0, 1, 1, 1, 2};
 static __constant__ signed char c_d1[13] = {0, -1, 0, 1, -2, -1, 0, 1, 2, -1, 0, 1, 0};
 
@@ -28,8 +33,8 @@ __device__ __forceinline__ int site_kernel(int pattern, int row, int col) {
 // returns c = sum(w*v) and t = sum(w) over the in-bounds taps.
 template <class Src>
 __device__ __forceinline__ void malvar_pixel(const Src& src, int frame, int pattern, int row, int col,
-                                             int H, int W, float (&c)[3], float (&t)[3]) {
-  const int K = site_kernel(pattern, row, col);
+                                             int H, int W, float (&c)[3], float (&t)[3], int kbase = 0) {
+  const int K = site_kernel(pattern, row, col) + kbase;
   c[0] = c[1] = c[2] = 0.f;
   t[0] = t[1] = t[2] = 0.f;
 #pragma unroll

@@ -87,6 +87,35 @@ __device__ __forceinline__ void malvar_row2(const f2 (&m2)[8], const f2 (&m1)[8]
   }
 }
 
+// Bilinear demosaic (north_star extension) in the same output convention, so every epilogue is shared: with the
+// 3 x 3 weights scaled by 4 the channel sums are again x16 sums whose weights total 16 (bias and frame
+// renormalisation as for Malvar, border_fix.cuh K = 4..7):
+//   R/B site:  own = C (x16)   G' = -2 (NS + EW) (x -2)   opposite = D (x4)
+//   G site:    G = C (x16)     H' = -4 EW (x -2)          V' = -4 NS (x -2)
+template <bool BROW, bool GFIRST>
+__device__ __forceinline__ void bilinear_row2(const f2 (&m1)[8], const f2 (&z)[8], const f2 (&p1)[8], f2 (&R)[4], f2 (&G)[4],
+                                              f2 (&B)[4]) {
+  f2 ns[8];
+#pragma unroll
+  for (int i = 1; i <= 6; ++i) ns[i] = add2(m1[i], p1[i]);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const f2 C = z[j + 2];
+    const f2 EW = add2(z[j + 1], z[j + 3]);
+    if (!SiteScale2<BROW, GFIRST>::gsite(j)) {
+      const f2 opp = add2(ns[j + 1], ns[j + 3]);
+      G[j] = mul2(bc(-2.f), add2(ns[j + 2], EW));
+      R[j] = BROW ? opp : C;
+      B[j] = BROW ? C : opp;
+    } else {
+      const f2 hn = mul2(bc(-4.f), EW), vn = mul2(bc(-4.f), ns[j + 2]);
+      G[j] = C;
+      R[j] = BROW ? vn : hn;
+      B[j] = BROW ? hn : vn;
+    }
+  }
+}
+
 // Task kinds.  The image rows 2 .. H-3 are cut into chunks of rows_per_task rows ("interior tasks": no row of
 // their window is ever outside the image); the four border rows of every frame form two extra 2-row tasks per
 // strip.  One warp per task; interior tasks first.  Each kind is its own instantiation of the row loop, chosen
@@ -144,7 +173,7 @@ inline Stream2Geom make_geom2(int H, int W, int nframes, int rows_per_task) {
 constexpr int kS2Warps = ISP_S2_THREADS / 32;
 
 // rows [r0, rend) of one strip of one frame; r0 even, rend - r0 even
-template <bool BROW0, bool GFIRST0, int KIND, class Loader, class Epi>
+template <bool BROW0, bool GFIRST0, int KIND, bool BL, class Loader, class Epi>
 __device__ __forceinline__ void stream2_rows(const Loader& ld, const Epi& epi, typename Epi::State& st, const StreamGeom& g,
                                              int frame, int tcol, int r0, int rend) {
   constexpr uint32_t kMask = Loader::kRowMask;
@@ -199,21 +228,23 @@ __device__ __forceinline__ void stream2_rows(const Loader& ld, const Epi& epi, t
     ld.template fetch<KIND>(cur, pn, raw0);                                                                     \
     if (row_ + 4 + ISP_S2_PF_ROWS < g.H) ld.prefetch(cur, pn + ISP_S2_PF_ROWS * pitch);                                                     \
     f2 R_[4], G_[4], B_[4];                                                                                     \
-    malvar_row2<BROW0, GFIRST0>(W[(2 * (U)) % 6], W[(2 * (U) + 1) % 6], W[(2 * (U) + 2) % 6],                   \
-                                W[(2 * (U) + 3) % 6], W[(2 * (U) + 4) % 6], R_, G_, B_);                        \
+    if constexpr (BL) bilinear_row2<BROW0, GFIRST0>(W[(2 * (U) + 1) % 6], W[(2 * (U) + 2) % 6], W[(2 * (U) + 3) % 6], R_, G_, B_); \
+    else malvar_row2<BROW0, GFIRST0>(W[(2 * (U)) % 6], W[(2 * (U) + 1) % 6], W[(2 * (U) + 2) % 6],              \
+                                     W[(2 * (U) + 3) % 6], W[(2 * (U) + 4) % 6], R_, G_, B_);                   \
     epi.template emit<BROW0, GFIRST0, KIND>(st, row_, R_, G_, B_);                                              \
     ld.template decode<KIND>(cur, raw1, m_, W[(2 * (U) + 5) % 6]);                                              \
     ld.template fetch<KIND>(cur, pn + pitch, raw1);                                                             \
     if (row_ + 4 + ISP_S2_PF_ROWS < g.H) ld.prefetch(cur, pn + (ISP_S2_PF_ROWS + 1) * pitch);                                                     \
-    malvar_row2<!BROW0, !GFIRST0>(W[(2 * (U) + 1) % 6], W[(2 * (U) + 2) % 6], W[(2 * (U) + 3) % 6],             \
-                                  W[(2 * (U) + 4) % 6], W[(2 * (U) + 5) % 6], R_, G_, B_);                      \
+    if constexpr (BL) bilinear_row2<!BROW0, !GFIRST0>(W[(2 * (U) + 2) % 6], W[(2 * (U) + 3) % 6], W[(2 * (U) + 4) % 6], R_, G_, B_); \
+    else malvar_row2<!BROW0, !GFIRST0>(W[(2 * (U) + 1) % 6], W[(2 * (U) + 2) % 6], W[(2 * (U) + 3) % 6],        \
+                                       W[(2 * (U) + 4) % 6], W[(2 * (U) + 5) % 6], R_, G_, B_);                 \
     epi.template emit<!BROW0, !GFIRST0, KIND>(st, row_ + 1, R_, G_, B_);                                        \
   }
 
 #ifndef ISP_S2_COMPACT_UNROLL
 #define ISP_S2_COMPACT_UNROLL 1     // measured: 1 step 607 / 147 Gpx/s (cfg2 / cfg3), 2 steps 585 / 120 -- code size beats moves
 #endif
-  if constexpr (KIND == K_GENERAL || (Epi::kCompactLoop && ISP_S2_COMPACT_UNROLL == 1)) {
+  if constexpr (KIND == K_GENERAL || BL || (Epi::kCompactLoop && ISP_S2_COMPACT_UNROLL == 1)) {
     // cold kind, or an epilogue so large that three copies of the step overflow the instruction cache (Reinhard:
     // 51 KB hot, no_instruction 3.1 cycles per issue): one copy of the step, the window slides by register moves
 #pragma unroll 1
@@ -379,7 +410,9 @@ __device__ __forceinline__ void stream2_rows_ring(const Loader& ld, const Epi& e
 template <class Loader, class = void> struct has_ring { static constexpr bool value = false; };
 template <class Loader> struct has_ring<Loader, std::enable_if_t<Loader::kRing>> { static constexpr bool value = true; };
 
-template <int PATTERN, class Loader, class Epi>
+// BL: bilinear demosaic instead of Malvar-He-Cutler.  The bilinear kernels have no K_CORE copy of the loop and use
+// the single-step body (their binary stays small; the arithmetic saved is hidden behind the same DRAM traffic).
+template <int PATTERN, bool BL, class Loader, class Epi>
 __global__ void __launch_bounds__(ISP_S2_THREADS, ISP_S2_MINBLOCKS) stream2_kernel(const Loader ld, const Epi epi, const Stream2Geom sg) {
   constexpr bool BROW0 = (PATTERN == B200ISP_GBRG || PATTERN == B200ISP_BGGR);
   constexpr bool GFIRST0 = (PATTERN == B200ISP_GRBG || PATTERN == B200ISP_GBRG);
@@ -414,7 +447,8 @@ __global__ void __launch_bounds__(ISP_S2_THREADS, ISP_S2_MINBLOCKS) stream2_kern
   wc.nvalid = min(32, g.ntcols - strip * 32);
   wc.stage = stage[threadIdx.x >> 5];
 
-  constexpr bool kUseRing = has_ring<Loader>::value && Epi::kSplitEdge;
+  constexpr bool kSplit = Epi::kSplitEdge && !BL;
+  constexpr bool kUseRing = has_ring<Loader>::value && kSplit;
   __shared__ __align__(16) uint32_t ring[kUseRing ? kS2Warps * kRingStages * 2 * kRowSlotWords : 1];
 
   typename Epi::State st;
@@ -422,27 +456,29 @@ __global__ void __launch_bounds__(ISP_S2_THREADS, ISP_S2_MINBLOCKS) stream2_kern
   if (task_ok) {
     // Epi::kSplitEdge = false: the epilogue does not want a separate K_CORE copy of the loop (K_EDGE covers it)
     const int kind = (border || !epi.fast_kinds_ok(st)) ? K_GENERAL
-                     : ((!Epi::kSplitEdge || strip == 0 || strip == g.warps_per_row - 1) ? K_EDGE : K_CORE);
-    if constexpr (Epi::kSplitEdge) {
+                     : ((!kSplit || strip == 0 || strip == g.warps_per_row - 1) ? K_EDGE : K_CORE);
+    if constexpr (kSplit) {
       if (kind == K_CORE) {
         if constexpr (kUseRing)
           stream2_rows_ring<BROW0, GFIRST0>(ld, epi, st, g, frame, tcol, r0, rend,
                                             ring + (threadIdx.x >> 5) * (kRingStages * 2 * kRowSlotWords));
         else
-          stream2_rows<BROW0, GFIRST0, K_CORE>(ld, epi, st, g, frame, tcol, r0, rend);
+          stream2_rows<BROW0, GFIRST0, K_CORE, BL>(ld, epi, st, g, frame, tcol, r0, rend);
       }
     }
-    if (kind == K_EDGE) stream2_rows<BROW0, GFIRST0, K_EDGE>(ld, epi, st, g, frame, tcol, r0, rend);
-    else if (kind == K_GENERAL) stream2_rows<BROW0, GFIRST0, K_GENERAL>(ld, epi, st, g, frame, tcol, r0, rend);
+    if (kind == K_EDGE) stream2_rows<BROW0, GFIRST0, K_EDGE, BL>(ld, epi, st, g, frame, tcol, r0, rend);
+    else if (kind == K_GENERAL) stream2_rows<BROW0, GFIRST0, K_GENERAL, BL>(ld, epi, st, g, frame, tcol, r0, rend);
   }
   epi.finish(st, frame, lane, task_ok);
 }
 
 template <int PATTERN, class Loader, class Epi>
-inline int launch_stream2(const Loader& ld, const Epi& epi, const Stream2Geom& sg, cudaStream_t s, const char* what) {
+inline int launch_stream2(const Loader& ld, const Epi& epi, const Stream2Geom& sg, cudaStream_t s, const char* what,
+                          bool bilinear = false) {
   if (sg.total_tasks == 0) return B200ISP_OK;
   const long long blocks = (sg.total_tasks + kS2Warps - 1) / kS2Warps;
-  stream2_kernel<PATTERN, Loader, Epi><<<(unsigned)blocks, ISP_S2_THREADS, 0, s>>>(ld, epi, sg);
+  if (bilinear) stream2_kernel<PATTERN, true, Loader, Epi><<<(unsigned)blocks, ISP_S2_THREADS, 0, s>>>(ld, epi, sg);
+  else stream2_kernel<PATTERN, false, Loader, Epi><<<(unsigned)blocks, ISP_S2_THREADS, 0, s>>>(ld, epi, sg);
   return cuda_status(cudaPeekAtLastError(), what);
 }
 
