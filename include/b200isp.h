@@ -148,6 +148,13 @@ int b200isp_isp_reinhard(void* image, int dtype, void* output, int out_dtype, in
                          const float* metrics, float gamma, float intensity, float light_adapt,
                          float color_adapt, void* workspace, b200isp_stream stream);
 
+/* camera_isp.py:394-403: the same for a list of n_images same-size images (host arrays of device pointers),
+ * one launch per pass for the whole list. */
+int b200isp_isp_reinhard_batch(void* const* images_host, void* const* outputs_host, int n_images, int dtype,
+                               int out_dtype, int64_t n_pixels, const float* metrics, float gamma,
+                               float intensity, float light_adapt, float color_adapt, void* workspace,
+                               b200isp_stream stream);
+
 /* ---- fused path: packed12 frames -> tone-mapped RGB in one sweep --------- */
 typedef enum { B200ISP_DEMOSAIC_MALVAR = 0, B200ISP_DEMOSAIC_BILINEAR = 1 } b200isp_demosaic_t;
 typedef struct {

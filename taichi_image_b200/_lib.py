@@ -57,6 +57,7 @@ SIGNATURES = {
     "b200isp_load_convert": [_vp, _vp, _i, _i64, _i, _vp],
     "b200isp_metering_update": [C.POINTER(_vp), _i, _i, _i, _i, _i, _f, _vp, _vp, _vp],
     "b200isp_isp_reinhard": [_vp, _i, _vp, _i, _i64, _vp, _f, _f, _f, _f, _vp, _vp],
+    "b200isp_isp_reinhard_batch": [_vp, _vp, _i, _i, _i, _i64, _vp, _f, _f, _f, _f, _vp, _vp],
     "b200isp_process_packed12": [C.POINTER(_vp), C.POINTER(_vp), _i, C.POINTER(FusedParams), _vp, _vp, _vp],
     "b200isp_metering_phase1": [C.POINTER(_vp), _i, _i, _i, _i, _i, _vp, _vp, _vp],
     "b200isp_metering_phase2": [C.POINTER(_vp), _i, _i, _i, _i, _i, _vp, _i, _f, _vp, _vp, _vp, _vp],

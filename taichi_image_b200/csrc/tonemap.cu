@@ -236,11 +236,15 @@ template <typename T> __device__ __forceinline__ void store24(T* p, const float 
 // camera_isp.py:200-213 (pass 1): the un-normalised map written back in the ISP dtype + its frame-global max.
 // Eight pixels per thread with 16-byte accesses; the map uses the MUFU evaluation of the fused sweep (relative error
 // ~1e-6, inside the <= 1 LSB contract; the literal IEEE order costs ~10x more instructions for the same output).
+// blockIdx.y = image of the batch (one launch per pass for all frames of a time step; frame_max[blockIdx.y])
+struct ImagePtrs { void* image[B200ISP_MAX_FRAMES]; void* out[B200ISP_MAX_FRAMES]; };
+
 template <typename T>
-__global__ void __launch_bounds__(256) isp_reinhard_pass1_kernel(T* __restrict__ image, long long n_px,
+__global__ void __launch_bounds__(256) isp_reinhard_pass1_kernel(const ImagePtrs ptrs, long long n_px,
                                                                  const float* __restrict__ metrics, float intensity,
                                                                  float la, float ca, Workspace* ws) {
   __shared__ float smem[8];
+  T* __restrict__ image = reinterpret_cast<T*>(ptrs.image[blockIdx.y]);
   const ReinhardParams p = reinhard_params(metrics, intensity, la, ca);
   const float b = -p.bmin * p.inv_range;
   const bool ca0 = ca == 0.f;
@@ -274,16 +278,17 @@ __global__ void __launch_bounds__(256) isp_reinhard_pass1_kernel(T* __restrict__
   if (threadIdx.x < 32) {
     mx = threadIdx.x < (blockDim.x >> 5) ? smem[threadIdx.x] : 0.f;
     mx = warp_max(mx);
-    if (threadIdx.x == 0 && mx > 0.f) atomicMax(reinterpret_cast<unsigned int*>(&ws->frame_max[0]), __float_as_uint(mx));
+    if (threadIdx.x == 0 && mx > 0.f) atomicMax(reinterpret_cast<unsigned int*>(&ws->frame_max[blockIdx.y]), __float_as_uint(mx));
   }
 }
 
 // camera_isp.py:215-218 (pass 2): out = cast(scale * (x' / max_out)^(1/gamma)), x' = the stored map; no clamp in the
 // reference (values <= 1 + one f16 ulp) -- the integer casts saturate.
 template <typename T, typename OutT>
-__global__ void __launch_bounds__(256) isp_reinhard_pass2_kernel(const T* __restrict__ image, OutT* __restrict__ out,
-                                                                 long long n_elems, float gamma, Workspace* ws) {
-  const float inv_max = __fdiv_rn(1.0f, fmaxf(1e-6f, __ldcg(&ws->frame_max[0])));
+__global__ void __launch_bounds__(256) isp_reinhard_pass2_kernel(const ImagePtrs ptrs, long long n_elems, float gamma, Workspace* ws) {
+  const T* __restrict__ image = reinterpret_cast<const T*>(ptrs.image[blockIdx.y]);
+  OutT* __restrict__ out = reinterpret_cast<OutT*>(ptrs.out[blockIdx.y]);
+  const float inv_max = __fdiv_rn(1.0f, fmaxf(1e-6f, __ldcg(&ws->frame_max[blockIdx.y])));
   const float inv_gamma = (float)(1.0 / (double)gamma);     // python double 1.0 / gamma -> f32 constant (:217)
   const bool has_gamma = gamma != 1.0f;
   constexpr int PER = 16 / (int)sizeof(T);
@@ -423,27 +428,43 @@ extern "C" int b200isp_metering_phase2(const void* const* images_host, int n_ima
   });
 }
 
-extern "C" int b200isp_isp_reinhard(void* image, int dtype, void* output, int out_dtype, int64_t n_pixels,
-                                    const float* metrics, float gamma, float intensity, float light_adapt,
-                                    float color_adapt, void* workspace, b200isp_stream stream) {
-  ISP_REQUIRE(image && output && metrics && workspace && n_pixels > 0, B200ISP_E_ARG, "isp_reinhard: bad argument");
+// camera_isp.py:394-403 for a list of same-size images: one launch per pass for the whole list
+extern "C" int b200isp_isp_reinhard_batch(void* const* images_host, void* const* outputs_host, int n_images, int dtype,
+                                          int out_dtype, int64_t n_pixels, const float* metrics, float gamma, float intensity,
+                                          float light_adapt, float color_adapt, void* workspace, b200isp_stream stream) {
+  ISP_REQUIRE(images_host && outputs_host && metrics && workspace && n_pixels > 0, B200ISP_E_ARG, "isp_reinhard: bad argument");
+  ISP_REQUIRE(n_images >= 1 && n_images <= B200ISP_MAX_FRAMES, B200ISP_E_FRAMES, "isp_reinhard: %d images (1..%d per call)",
+              n_images, B200ISP_MAX_FRAMES);
   ISP_REQUIRE(dtype == B200ISP_F16 || dtype == B200ISP_F32, B200ISP_E_DTYPE, "isp_reinhard: ISP dtype must be f16 or f32");
   ISP_REQUIRE(gamma > 0.f, B200ISP_E_ARG, "isp_reinhard: gamma must be positive");
+  ImagePtrs ptrs;
+  for (int i = 0; i < n_images; ++i) {
+    ISP_REQUIRE(images_host[i] && outputs_host[i], B200ISP_E_ARG, "isp_reinhard: null image %d", i);
+    ptrs.image[i] = images_host[i];
+    ptrs.out[i] = outputs_host[i];
+  }
   Workspace* ws = (Workspace*)workspace;
   cudaStream_t s = (cudaStream_t)stream;
-  const int grid = meter_grid(n_pixels);
+  const dim3 grid((unsigned)meter_grid(n_pixels), (unsigned)n_images);
   {
-    const int st = cuda_status(cudaMemsetAsync(&ws->frame_max[0], 0, sizeof(float), s), "memset frame_max");
+    const int st = cuda_status(cudaMemsetAsync(&ws->frame_max[0], 0, sizeof(float) * n_images, s), "memset frame_max");
     if (st) return st;
   }
   ISP_DISPATCH_DTYPE(dtype, T, {
-    isp_reinhard_pass1_kernel<T><<<grid, 256, 0, s>>>((T*)image, n_pixels, metrics, intensity, light_adapt, color_adapt, ws);
+    isp_reinhard_pass1_kernel<T><<<grid, 256, 0, s>>>(ptrs, n_pixels, metrics, intensity, light_adapt, color_adapt, ws);
     ISP_LAUNCH_CHECK("isp_reinhard_pass1_kernel");
-    ISP_DISPATCH_DTYPE(out_dtype, OutT,
-      (isp_reinhard_pass2_kernel<T, OutT><<<grid, 256, 0, s>>>((const T*)image, (OutT*)output, n_pixels * 3, gamma, ws)));
+    ISP_DISPATCH_DTYPE(out_dtype, OutT, (isp_reinhard_pass2_kernel<T, OutT><<<grid, 256, 0, s>>>(ptrs, n_pixels * 3, gamma, ws)));
   });
   ISP_LAUNCH_CHECK("isp_reinhard_pass2_kernel");
   return B200ISP_OK;
+}
+
+extern "C" int b200isp_isp_reinhard(void* image, int dtype, void* output, int out_dtype, int64_t n_pixels,
+                                    const float* metrics, float gamma, float intensity, float light_adapt,
+                                    float color_adapt, void* workspace, b200isp_stream stream) {
+  ISP_REQUIRE(image && output, B200ISP_E_ARG, "isp_reinhard: bad argument");
+  return b200isp_isp_reinhard_batch(&image, &output, 1, dtype, out_dtype, n_pixels, metrics, gamma, intensity, light_adapt,
+                                    color_adapt, workspace, stream);
 }
 
 extern "C" int b200isp_load_convert(const void* src, void* dst, int out_dtype, int64_t n_elems, int mode,
