@@ -112,4 +112,30 @@ __device__ __forceinline__ float warp_sum(float v) {
 inline bool valid_dtype(int dt) { return dt >= B200ISP_U8 && dt <= B200ISP_F32; }
 inline size_t dtype_size(int dt) { return dt == B200ISP_U8 ? 1 : (dt == B200ISP_F32 ? 4 : 2); }
 
+// NB bytes between global memory and a 16-byte aligned local buffer with the widest access NB allows (16 / 8 / 4)
+template <int NB> __device__ __forceinline__ void ld_bytes(const void* g, void* local) {
+  if constexpr (NB % 16 == 0) {
+#pragma unroll
+    for (int i = 0; i < NB / 16; ++i) reinterpret_cast<uint4*>(local)[i] = __ldg(reinterpret_cast<const uint4*>(g) + i);
+  } else if constexpr (NB % 8 == 0) {
+#pragma unroll
+    for (int i = 0; i < NB / 8; ++i) reinterpret_cast<uint2*>(local)[i] = __ldg(reinterpret_cast<const uint2*>(g) + i);
+  } else {
+#pragma unroll
+    for (int i = 0; i < NB / 4; ++i) reinterpret_cast<uint32_t*>(local)[i] = __ldg(reinterpret_cast<const uint32_t*>(g) + i);
+  }
+}
+template <int NB> __device__ __forceinline__ void st_bytes(void* g, const void* local) {
+  if constexpr (NB % 16 == 0) {
+#pragma unroll
+    for (int i = 0; i < NB / 16; ++i) reinterpret_cast<uint4*>(g)[i] = reinterpret_cast<const uint4*>(local)[i];
+  } else if constexpr (NB % 8 == 0) {
+#pragma unroll
+    for (int i = 0; i < NB / 8; ++i) reinterpret_cast<uint2*>(g)[i] = reinterpret_cast<const uint2*>(local)[i];
+  } else {
+#pragma unroll
+    for (int i = 0; i < NB / 4; ++i) reinterpret_cast<uint32_t*>(g)[i] = reinterpret_cast<const uint32_t*>(local)[i];
+  }
+}
+
 }  // namespace isp

@@ -131,6 +131,68 @@ __global__ void __launch_bounds__(256) transform_kernel(const T* __restrict__ sr
   }
 }
 
+// ---------------------------------------------------------------- word-granular transform (the fast path)
+// Same tiling idea, but the global accesses are 4-byte words on both sides and the tile is addressed as raw bytes:
+// a pixel is PB = 3 * sizeof(T) bytes, moved in granules of G = gcd(PB, 4) bytes (1 for u8, 2 for u16 / f16, 4 for
+// f32).  Phase 1 copies the source tile row segments (word-aligned start rounded down, `boff` = the bytes skipped)
+// into shared memory; phase 2 assembles every destination word from its 4 / G granules through the affine map
+// destination (y, x) -> source (sy, sx) of the transform (tile-local).  Needs 4-byte aligned bases and row pitches
+// (W * PB and wd * PB multiples of 4); everything else takes transform_kernel above.  The padded row pitch is an
+// odd number of words, so the column-wise reads of the transposing transforms are bank-conflict free.
+template <int PB, int TILE>
+__global__ void __launch_bounds__(256) transform_words_kernel(const uint32_t* __restrict__ src, uint32_t* __restrict__ dst,
+                                                              int H, int W, int hd, int wd, int t) {
+  constexpr int G = (PB % 4 == 0) ? 4 : ((PB % 2 == 0) ? 2 : 1);
+  constexpr int ROW_WORDS = TILE * PB / 4 + 1;                       // + 1 word for a misaligned start; odd pitch
+  static_assert(ROW_WORDS % 2 == 1, "odd smem pitch");
+  __shared__ uint32_t tile[TILE][ROW_WORDS];
+  const int dr0 = blockIdx.y * TILE, dc0 = blockIdx.x * TILE;
+  const int nr = min(TILE, hd - dr0), nc = min(TILE, wd - dc0);     // destination tile extent
+  // affine map in global coordinates: corners -> source tile origin and extent
+  int sra, sca, srb, scb;
+  transformed(t, dr0, dc0, H, W, sra, sca);
+  transformed(t, dr0 + nr - 1, dc0 + nc - 1, H, W, srb, scb);
+  const int sr0 = min(sra, srb), sc0 = min(sca, scb);
+  const int snr = abs(srb - sra) + 1, snc = abs(scb - sca) + 1;      // source tile extent
+  // phase 1: source rows sr0 .. sr0+snr-1, bytes [sc0 * PB, (sc0 + snc) * PB) of each, as aligned words
+  const int src_pitch_w = W * PB / 4;
+  const int b0 = sc0 * PB, w0 = b0 >> 2, boff = b0 & 3;
+  const int nwords = ((b0 + snc * PB + 3) >> 2) - w0;
+  for (int i = threadIdx.x; i < snr * nwords; i += 256) {
+    const int y = i / nwords, w = i - y * nwords;
+    tile[y][w] = __ldg(src + (size_t)(sr0 + y) * src_pitch_w + w0 + w);
+  }
+  __syncthreads();
+  // tile-local affine map: (sy, sx) = (oy + ayy * y + ayx * x, ox + axy * y + axx * x)
+  int s00r, s00c, s10r, s10c, s01r, s01c;
+  transformed(t, dr0, dc0, H, W, s00r, s00c);
+  transformed(t, dr0 + 1, dc0, H, W, s10r, s10c);
+  transformed(t, dr0, dc0 + 1, H, W, s01r, s01c);
+  const int oy = s00r - sr0, ox = s00c - sc0;
+  const int ayy = s10r - s00r, axy = s10c - s00c, ayx = s01r - s00r, axx = s01c - s00c;
+  const unsigned char* tb = reinterpret_cast<const unsigned char*>(&tile[0][0]);
+  const int dst_pitch_w = wd * PB / 4;
+  const int db0 = dc0 * PB, dw0 = db0 >> 2, dboff = db0 & 3;         // dboff == 0 whenever TILE * PB % 4 == 0 (always)
+  const int dwords = (nc * PB + dboff + 3) >> 2;
+  for (int i = threadIdx.x; i < nr * dwords; i += 256) {
+    const int y = i / dwords, w = i - y * dwords;
+    uint32_t word = 0;
+#pragma unroll
+    for (int g = 0; g < 4 / G; ++g) {
+      const int b = 4 * w + g * G - dboff;                           // byte within the destination tile row
+      const int x = b / PB, k = b - x * PB;
+      const int sy = oy + ayy * y + ayx * x, sx = ox + axy * y + axx * x;
+      const unsigned char* q = tb + (size_t)sy * (ROW_WORDS * 4) + boff + sx * PB + k;
+      uint32_t v;
+      if constexpr (G == 4) v = *reinterpret_cast<const uint32_t*>(q);
+      else if constexpr (G == 2) v = *reinterpret_cast<const unsigned short*>(q);
+      else v = *q;
+      if (x < nc) word |= v << (8 * g * G);
+    }
+    dst[(size_t)(dr0 + y) * dst_pitch_w + dw0 + w] = word;
+  }
+}
+
 }  // namespace isp
 
 using namespace isp;
@@ -180,8 +242,27 @@ extern "C" int b200isp_transform(const void* src, void* dst, int dtype, int src_
   const bool swaps = (transform == B200ISP_T_ROT90 || transform == B200ISP_T_ROT270 ||
                       transform == B200ISP_T_TRANSPOSE || transform == B200ISP_T_TRANSVERSE);
   const int hd = swaps ? src_w : src_h, wd = swaps ? src_h : src_w;
-  const dim3 grid((wd + 31) / 32, (hd + 31) / 32);
   cudaStream_t s = (cudaStream_t)stream;
+  const int esz = dtype == B200ISP_U8 ? 1 : (dtype == B200ISP_F32 ? 4 : 2), pb = 3 * esz;
+  const bool words = ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 3u) == 0 &&
+                     ((size_t)src_w * pb) % 4 == 0 && ((size_t)wd * pb) % 4 == 0;
+  if (words) {
+    const uint32_t* sw = (const uint32_t*)src;
+    uint32_t* dw = (uint32_t*)dst;
+    if (pb == 3) {
+      const dim3 grid((wd + 63) / 64, (hd + 63) / 64);
+      transform_words_kernel<3, 64><<<grid, 256, 0, s>>>(sw, dw, src_h, src_w, hd, wd, transform);
+    } else if (pb == 6) {
+      const dim3 grid((wd + 63) / 64, (hd + 63) / 64);
+      transform_words_kernel<6, 64><<<grid, 256, 0, s>>>(sw, dw, src_h, src_w, hd, wd, transform);
+    } else {
+      const dim3 grid((wd + 31) / 32, (hd + 31) / 32);
+      transform_words_kernel<12, 32><<<grid, 256, 0, s>>>(sw, dw, src_h, src_w, hd, wd, transform);
+    }
+    ISP_LAUNCH_CHECK("transform_words_kernel");
+    return B200ISP_OK;
+  }
+  const dim3 grid((wd + 31) / 32, (hd + 31) / 32);
   ISP_DISPATCH_DTYPE(dtype, T, (transform_kernel<T><<<grid, 256, 0, s>>>((const T*)src, (T*)dst, src_h, src_w, hd, wd, transform)));
   ISP_LAUNCH_CHECK("transform_kernel");
   return B200ISP_OK;

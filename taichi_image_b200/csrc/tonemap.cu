@@ -124,6 +124,40 @@ static int launch_linear(const InT* src, OutT* dst, long long n, const float* bo
   return cuda_status(cudaPeekAtLastError(), "linear_kernel");
 }
 
+// 24 consecutive elements (8 RGB pixels) with 16-byte accesses (8-byte accesses for 1-byte types)
+template <typename T> __device__ __forceinline__ void load24(const T* p, float (&v)[24]) {
+  if constexpr (sizeof(T) == 1) {
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      const uint2 w = reinterpret_cast<const uint2*>(p)[i];
+      const T* t = reinterpret_cast<const T*>(&w);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[i * 8 + j] = to_f32(t[j]);
+    }
+  } else {
+    constexpr int PER = 16 / (int)sizeof(T);               // elements per 16 bytes
+    const uint4* q = reinterpret_cast<const uint4*>(p);
+#pragma unroll
+    for (int i = 0; i < 24 / PER; ++i) {
+      const uint4 w = q[i];
+      const T* t = reinterpret_cast<const T*>(&w);
+#pragma unroll
+      for (int j = 0; j < PER; ++j) v[i * PER + j] = to_f32(t[j]);
+    }
+  }
+}
+template <typename T> __device__ __forceinline__ void store24(T* p, const float (&v)[24]) {
+  constexpr int PER = 16 / (int)sizeof(T);
+  uint4* q = reinterpret_cast<uint4*>(p);
+#pragma unroll
+  for (int i = 0; i < 24 / PER; ++i) {
+    alignas(16) T t[PER];
+#pragma unroll
+    for (int j = 0; j < PER; ++j) t[j] = cast_from_f32<T>(v[i * PER + j]);
+    q[i] = *reinterpret_cast<const uint4*>(t);
+  }
+}
+
 // ---------------------------------------------------------------- stand-alone Reinhard (tonemap.py:134-168)
 // pass A: temp = clamp((src - min) / range, 0, 1) as f32 (linear_func gamma 1, scale 1) fused with
 //         metering_func(temp, Bounds(0,1)) (tonemap.py:77-103): log-gray min/max, sums.
@@ -134,17 +168,32 @@ __global__ void __launch_bounds__(256) sa_normalise_meter_kernel(const InT* __re
   const float bmin = b[0];
   const float inv_range = __fdiv_rn(1.0f, __fsub_rn(b[1], bmin));
   float v[7] = {INFINITY, -INFINITY, 0.f, 0.f, 0.f, 0.f, 0.f};
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_px; i += (long long)gridDim.x * blockDim.x) {
+  auto accum = [&](const float* s) {
+    const float gray = rgb_gray(s[0], s[1], s[2]);     // (temp - 0) / (1 - 0) == temp
+    const float lg = logf(fmaxf(gray, 1e-4f));
+    v[0] = fminf(v[0], lg); v[1] = fmaxf(v[1], lg);
+    v[2] += lg; v[3] += gray; v[4] += s[0]; v[5] += s[1]; v[6] += s[2];
+  };
+  // eight pixels per thread with 16-byte accesses when both images allow it, the tail (and unaligned images) per pixel
+  const bool vec = ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(temp)) & 15u) == 0;
+  const long long n8 = vec ? n_px / 8 : 0;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (long long)gridDim.x * blockDim.x) {
+    float x[24];
+    load24(src + 24 * i, x);
+#pragma unroll
+    for (int e = 0; e < 24; ++e) x[e] = clamp01(__fmul_rn(__fsub_rn(x[e], bmin), inv_range));
+    store24(temp + 24 * i, x);
+#pragma unroll
+    for (int q = 0; q < 8; ++q) accum(x + 3 * q);
+  }
+  for (long long i = 8 * n8 + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_px; i += (long long)gridDim.x * blockDim.x) {
     float s[3];
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
       s[k] = clamp01(__fmul_rn(__fsub_rn(to_f32(src[3 * i + k]), bmin), inv_range));
       temp[3 * i + k] = s[k];
     }
-    const float gray = rgb_gray(s[0], s[1], s[2]);     // (temp - 0) / (1 - 0) == temp
-    const float lg = logf(fmaxf(gray, 1e-4f));
-    v[0] = fminf(v[0], lg); v[1] = fmaxf(v[1], lg);
-    v[2] += lg; v[3] += gray; v[4] += s[0]; v[5] += s[1]; v[6] += s[2];
+    accum(s);
   }
   const int op[7] = {0, 1, 2, 2, 2, 2, 2};
   block_fold<7>(v, op, smem);
@@ -180,15 +229,30 @@ __global__ void __launch_bounds__(256) sa_reinhard_kernel(float* __restrict__ te
   __shared__ float smem[8 * 2];
   const ReinhardParams p = reinhard_params(ws->scratch + 8, intensity, la, ca);
   float v[2] = {INFINITY, -INFINITY};
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_px; i += (long long)gridDim.x * blockDim.x) {
+  const bool ca0 = ca == 0.f;
+  // bmin = 0, range = 1: the scaled value is x itself.  MUFU evaluation of the map like the ISP kernels below
+  // (relative error ~1e-6, inside the <= 1 LSB contract)
+  auto map_px = [&](const float* x, float* o) {
+    const float sc[3] = {x[0], x[1], x[2]};
+    float r[3];
+    if (ca0) reinhard_map_fast<true>(p, sc, r); else reinhard_map_fast<false>(p, sc, r);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { o[k] = r[k]; v[0] = fminf(v[0], r[k]); v[1] = fmaxf(v[1], r[k]); }
+  };
+  const long long n8 = (reinterpret_cast<uintptr_t>(temp) & 15u) == 0 ? n_px / 8 : 0;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (long long)gridDim.x * blockDim.x) {
+    float x[24], o[24];
+    load24(temp + 24 * i, x);
+#pragma unroll
+    for (int q = 0; q < 8; ++q) map_px(x + 3 * q, o + 3 * q);
+    store24(temp + 24 * i, o);
+  }
+  for (long long i = 8 * n8 + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_px; i += (long long)gridDim.x * blockDim.x) {
     const float x[3] = {temp[3 * i], temp[3 * i + 1], temp[3 * i + 2]};
     float o[3];
-    reinhard_map_exact(p, x, o);      // bmin = 0, range = 1: (x - 0) / 1 == x
+    map_px(x, o);
 #pragma unroll
-    for (int k = 0; k < 3; ++k) {
-      temp[3 * i + k] = o[k];
-      v[0] = fminf(v[0], o[k]); v[1] = fmaxf(v[1], o[k]);
-    }
+    for (int k = 0; k < 3; ++k) temp[3 * i + k] = o[k];
   }
   const int op[2] = {0, 1};
   block_fold<2>(v, op, smem);
@@ -209,30 +273,6 @@ __global__ void __launch_bounds__(256) sa_reinhard_kernel(float* __restrict__ te
 
 // ---------------------------------------------------------------- ISP Reinhard (camera_isp.py:177-218)
 // pass 1: p -> image (ISP dtype), max over f32 p.  pass 2: (image / max_out)^(1/gamma) * scale -> out.
-// 24 consecutive elements (8 RGB pixels) with 16-byte accesses
-template <typename T> __device__ __forceinline__ void load24(const T* p, float (&v)[24]) {
-  constexpr int PER = 16 / (int)sizeof(T);               // elements per 16 bytes
-  const uint4* q = reinterpret_cast<const uint4*>(p);
-#pragma unroll
-  for (int i = 0; i < 24 / PER; ++i) {
-    const uint4 w = q[i];
-    const T* t = reinterpret_cast<const T*>(&w);
-#pragma unroll
-    for (int j = 0; j < PER; ++j) v[i * PER + j] = to_f32(t[j]);
-  }
-}
-template <typename T> __device__ __forceinline__ void store24(T* p, const float (&v)[24]) {
-  constexpr int PER = 16 / (int)sizeof(T);
-  uint4* q = reinterpret_cast<uint4*>(p);
-#pragma unroll
-  for (int i = 0; i < 24 / PER; ++i) {
-    alignas(16) T t[PER];
-#pragma unroll
-    for (int j = 0; j < PER; ++j) t[j] = cast_from_f32<T>(v[i * PER + j]);
-    q[i] = *reinterpret_cast<const uint4*>(t);
-  }
-}
-
 // camera_isp.py:200-213 (pass 1): the un-normalised map written back in the ISP dtype + its frame-global max.
 // Eight pixels per thread with 16-byte accesses; the map uses the MUFU evaluation of the fused sweep (relative error
 // ~1e-6, inside the <= 1 LSB contract; the literal IEEE order costs ~10x more instructions for the same output).

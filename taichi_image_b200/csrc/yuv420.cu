@@ -65,6 +65,78 @@ __global__ void __launch_bounds__(256) yuv420_rgb_kernel(const InT* __restrict__
   dst[2] = cast_from_f32<OutT>(__fmul_rn(fminf(1.0f, o[0]), os));
 }
 
+// ---------------------------------------------------------------- vector forms (W % 8 == 0, 16-byte aligned bases)
+// The same arithmetic in the same order, eight pixels (four quads) per thread and row with 8 / 16-byte accesses:
+// the scalar kernels above issue one 1..4-byte request per element and are request-bound (13-15 % of HBM peak).
+template <typename InT, typename OutT>
+__global__ void __launch_bounds__(256) rgb_yuv420_vec_kernel(const InT* __restrict__ rgb, OutT* __restrict__ yuv, int H, int W, Mat3 M) {
+  const int gx = blockIdx.x * blockDim.x + threadIdx.x;     // group of four quads = pixel columns 8 gx .. 8 gx + 7
+  const int qy = blockIdx.y;
+  if (gx >= W / 8) return;
+  constexpr float is = DT<InT>::scale, os = DT<OutT>::scale;
+  alignas(16) InT px[2][24];
+  alignas(16) OutT yrow[2][8];
+  alignas(16) OutT cu4[4], cv4[4];
+#pragma unroll
+  for (int dy = 0; dy < 2; ++dy) ld_bytes<24 * sizeof(InT)>(rgb + ((size_t)(2 * qy + dy) * W + 8 * gx) * 3, px[dy]);
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    float u = 0.f, v = 0.f;
+#pragma unroll
+    for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+      for (int dx = 0; dx < 2; ++dx) {                      // (0,0), (0,1), (1,0), (1,1) like the scalar kernel
+        const InT* p = &px[dy][3 * (2 * q + dx)];
+        const float R = __fdiv_rn(to_f32(p[0]), is), G = __fdiv_rn(to_f32(p[1]), is), B = __fdiv_rn(to_f32(p[2]), is);
+        float o[3];
+        mat_vec(M, B, G, R, o);
+        const float cu = __fadd_rn(o[1], 0.5f), cv = __fadd_rn(o[2], 0.5f);
+        yrow[dy][2 * q + dx] = cast_from_f32<OutT>(__fmul_rn(fminf(1.0f, o[0]), os));
+        if (dy == 0 && dx == 0) { u = cu; v = cv; } else { u = __fadd_rn(u, cu); v = __fadd_rn(v, cv); }
+      }
+    cu4[q] = cast_from_f32<OutT>(__fmul_rn(fminf(1.0f, __fdiv_rn(u, 4.0f)), os));
+    cv4[q] = cast_from_f32<OutT>(__fmul_rn(fminf(1.0f, __fdiv_rn(v, 4.0f)), os));
+  }
+#pragma unroll
+  for (int dy = 0; dy < 2; ++dy) st_bytes<8 * sizeof(OutT)>(yuv + (size_t)(2 * qy + dy) * W + 8 * gx, yrow[dy]);
+  OutT* planes = yuv + (size_t)H * W;
+  const size_t plane = (size_t)(H / 2) * (W / 2), idx = (size_t)qy * (W / 2) + 4 * gx;
+  st_bytes<4 * sizeof(OutT)>(planes + plane + idx, cu4);      // plane 1 <- second matrix row
+  st_bytes<4 * sizeof(OutT)>(planes + idx, cv4);              // plane 0 <- third matrix row
+}
+
+template <typename InT, typename OutT>
+__global__ void __launch_bounds__(256) yuv420_rgb_vec_kernel(const InT* __restrict__ yuv, OutT* __restrict__ rgb, int H, int W, Mat3 Minv) {
+  const int gx = blockIdx.x * blockDim.x + threadIdx.x;     // pixel columns 8 gx .. 8 gx + 7 of row r
+  const int r = blockIdx.y;
+  if (gx >= W / 8) return;
+  constexpr float is = DT<InT>::scale, os = DT<OutT>::scale;
+  const InT* planes = yuv + (size_t)H * W;
+  const size_t plane = (size_t)(H / 2) * (W / 2), idx = (size_t)(r / 2) * (W / 2) + 4 * gx;
+  alignas(16) InT y8[8];
+  alignas(16) InT cu4[4], cv4[4];
+  alignas(16) OutT out[24];
+  ld_bytes<8 * sizeof(InT)>(yuv + (size_t)r * W + 8 * gx, y8);
+  ld_bytes<4 * sizeof(InT)>(planes + plane + idx, cu4);
+  ld_bytes<4 * sizeof(InT)>(planes + idx, cv4);
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    const float y = __fdiv_rn(to_f32(y8[c]), is);
+    const float cu = __fsub_rn(__fdiv_rn(to_f32(cu4[c >> 1]), is), 0.5f);
+    const float cv = __fsub_rn(__fdiv_rn(to_f32(cv4[c >> 1]), is), 0.5f);
+    float o[3];
+    mat_vec(Minv, y, cu, cv, o);                            // = bgr
+    out[3 * c] = cast_from_f32<OutT>(__fmul_rn(fminf(1.0f, o[2]), os));
+    out[3 * c + 1] = cast_from_f32<OutT>(__fmul_rn(fminf(1.0f, o[1]), os));
+    out[3 * c + 2] = cast_from_f32<OutT>(__fmul_rn(fminf(1.0f, o[0]), os));
+  }
+  st_bytes<24 * sizeof(OutT)>(rgb + ((size_t)r * W + 8 * gx) * 3, out);
+}
+
+static inline bool vec_ok(const void* a, const void* b, int width) {
+  return width % 8 == 0 && ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b)) & 15u) == 0;
+}
+
 }  // namespace isp
 
 using namespace isp;
@@ -78,11 +150,18 @@ extern "C" int b200isp_rgb_yuv420(const void* rgb, int in_dtype, void* yuv, int 
   ISP_REQUIRE(valid_dtype(in_dtype) && valid_dtype(out_dtype), B200ISP_E_DTYPE, "rgb_yuv420: bad dtype");
   Mat3 M;
   for (int i = 0; i < 9; ++i) M.m[i] = matrix9_host[i];
-  const dim3 grid((width / 2 + 255) / 256, height / 2);
   cudaStream_t s = (cudaStream_t)stream;
-  ISP_DISPATCH_DTYPE(in_dtype, InT, {
-    ISP_DISPATCH_DTYPE(out_dtype, OutT, (rgb_yuv420_kernel<InT, OutT><<<grid, 256, 0, s>>>((const InT*)rgb, (OutT*)yuv, height, width, M)));
-  });
+  if (vec_ok(rgb, yuv, width)) {
+    const dim3 grid((width / 8 + 127) / 128, height / 2);
+    ISP_DISPATCH_DTYPE(in_dtype, InT, {
+      ISP_DISPATCH_DTYPE(out_dtype, OutT, (rgb_yuv420_vec_kernel<InT, OutT><<<grid, 128, 0, s>>>((const InT*)rgb, (OutT*)yuv, height, width, M)));
+    });
+  } else {
+    const dim3 grid((width / 2 + 255) / 256, height / 2);
+    ISP_DISPATCH_DTYPE(in_dtype, InT, {
+      ISP_DISPATCH_DTYPE(out_dtype, OutT, (rgb_yuv420_kernel<InT, OutT><<<grid, 256, 0, s>>>((const InT*)rgb, (OutT*)yuv, height, width, M)));
+    });
+  }
   ISP_LAUNCH_CHECK("rgb_yuv420_kernel");
   return B200ISP_OK;
 }
@@ -94,11 +173,18 @@ extern "C" int b200isp_yuv420_rgb(const void* yuv, int in_dtype, void* rgb, int 
   ISP_REQUIRE(valid_dtype(in_dtype) && valid_dtype(out_dtype), B200ISP_E_DTYPE, "yuv420_rgb: bad dtype");
   Mat3 M;
   for (int i = 0; i < 9; ++i) M.m[i] = matrix9_host[i];
-  const dim3 grid((width + 255) / 256, height);
   cudaStream_t s = (cudaStream_t)stream;
-  ISP_DISPATCH_DTYPE(in_dtype, InT, {
-    ISP_DISPATCH_DTYPE(out_dtype, OutT, (yuv420_rgb_kernel<InT, OutT><<<grid, 256, 0, s>>>((const InT*)yuv, (OutT*)rgb, height, width, M)));
-  });
+  if (vec_ok(rgb, yuv, width)) {
+    const dim3 grid((width / 8 + 127) / 128, height);
+    ISP_DISPATCH_DTYPE(in_dtype, InT, {
+      ISP_DISPATCH_DTYPE(out_dtype, OutT, (yuv420_rgb_vec_kernel<InT, OutT><<<grid, 128, 0, s>>>((const InT*)yuv, (OutT*)rgb, height, width, M)));
+    });
+  } else {
+    const dim3 grid((width + 255) / 256, height);
+    ISP_DISPATCH_DTYPE(in_dtype, InT, {
+      ISP_DISPATCH_DTYPE(out_dtype, OutT, (yuv420_rgb_kernel<InT, OutT><<<grid, 256, 0, s>>>((const InT*)yuv, (OutT*)rgb, height, width, M)));
+    });
+  }
   ISP_LAUNCH_CHECK("yuv420_rgb_kernel");
   return B200ISP_OK;
 }

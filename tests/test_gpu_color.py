@@ -34,6 +34,19 @@ def test_yuv420_dtype_conversion_and_numpy(cuda):
     assert np.array_equal(color.rgb_yuv420_image(g["rgb_f32"], u8), g["yuv_f32_to_u8"])
 
 
+@pytest.mark.parametrize("name", ["u8", "u16", "f16", "f32"])
+@pytest.mark.parametrize("shape", [(34, 72), (6, 20), (2, 8), (66, 1032)])     # vector kernels (W % 8 == 0) and element-wise
+def test_yuv420_shapes_vs_oracle(cuda, name, shape):
+    from taichi_image_b200 import color
+    rgb = random_plane(rng(81), shape + (3,), name)
+    ref = O.rgb_yuv420(rgb)
+    enc = to_np(color.rgb_yuv420_image(to_cuda(rgb)))
+    assert np.array_equal(np.ascontiguousarray(enc).view(np.uint8), np.ascontiguousarray(ref).view(np.uint8))
+    dec = to_np(color.yuv420_rgb_image(to_cuda(ref)))
+    ok = _defined(ref, name)
+    assert np.array_equal(dec[ok], O.yuv420_rgb(ref)[ok])
+
+
 @pytest.mark.parametrize("name", ["u8", "u16", "f32"])
 def test_yuv420_large_vs_oracle(cuda, name):
     from taichi_image_b200 import color

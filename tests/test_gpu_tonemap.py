@@ -72,16 +72,17 @@ def test_resize_width_and_per_axis(cuda):
     assert_close_int(got, ref, 0, "f32->u8")
 
 
-@pytest.mark.parametrize("name", ["u8", "f16", "f32"])
+@pytest.mark.parametrize("name", ["u8", "u16", "f16", "f32"])
 @pytest.mark.parametrize("tname", O.TRANSFORMS)
-@pytest.mark.parametrize("shape", [(5, 9), (64, 33), (70, 130)])
+@pytest.mark.parametrize("shape", [(5, 9), (64, 33), (70, 130),                   # element-wise kernel (unaligned row pitch for u8)
+                                   (4, 4), (64, 128), (72, 132), (100, 260), (8, 68)])   # word kernel: full and partial tiles
 def test_transform(cuda, name, tname, shape):
     import torch
     from taichi_image_b200 import interpolate
     img = random_plane(rng(24), shape + (3,), name)
     got = to_np(interpolate.transform(to_cuda(img), interpolate.ImageTransform[tname]))
     ref = O.transform(img, tname)
-    assert got.shape == ref.shape and np.array_equal(got.view(np.uint8), ref.view(np.uint8)), tname
+    assert got.shape == ref.shape and np.array_equal(np.ascontiguousarray(got).view(np.uint8), np.ascontiguousarray(ref).view(np.uint8)), tname
     if tname == "rotate_90":      # clockwise == torch.rot90(k=3)  
         assert np.array_equal(got, torch.rot90(torch.from_numpy(img), 3, (0, 1)).numpy())
 
