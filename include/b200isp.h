@@ -71,6 +71,9 @@ int b200isp_encode12(const void* values, int in_dtype, int64_t n_values, uint8_t
 /* packed.py:122-131 decode12_kernel(out_type, scaled, ids_format)(encoded, out). */
 int b200isp_decode12(const uint8_t* encoded, int64_t n_values, void* out, int out_dtype,
                      int scaled, int ids_format, b200isp_stream stream);
+/* packed.py:36-44 then :12-20: re-pack IDS-layout 12-bit data into the standard layout (byte stream to byte
+ * stream, n_bytes % 3 == 0) so that IDS frames can take b200isp_process_packed12. */
+int b200isp_repack12_ids(const uint8_t* ids, uint8_t* standard, int64_t n_bytes, b200isp_stream stream);
 /* packed.py:163-172 decode16_kernel(out_type, scaled)(encoded, out). */
 int b200isp_decode16(const uint8_t* encoded, int64_t n_values, void* out, int out_dtype,
                      int scaled, b200isp_stream stream);

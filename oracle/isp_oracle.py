@@ -100,6 +100,11 @@ def decode12(enc: np.ndarray, dtype: str = "u16", scaled: bool = False,
     return out.reshape(shape[:-1] + (shape[-1] * 2 // 3,))
 
 
+def repack12_ids(enc: np.ndarray) -> np.ndarray:
+    """IDS layout -> standard layout (extension of the framework): packed.py:36-44 followed by :12-20"""
+    return encode12(decode12_raw(enc, ids_format=True), ids_format=False).reshape(enc.shape)
+
+
 def decode16(enc: np.ndarray, dtype: str = "u16", scaled: bool = False) -> np.ndarray:
     """packed.py:134-172, :200-210 (the ids_format kwarg bug, SURVEY Q2, is not reproduced)."""
     shape = enc.shape

@@ -200,10 +200,21 @@ def camera_isp(name: str, dtype=f32):
             return (not ids_format and h >= 4 and h % 2 == 0 and w >= 8 and w % 8 == 0
                     and image_data.is_contiguous() and image_data.data_ptr() % 4 == 0)
 
+        def _ids_to_standard(self, frames):
+            """IDS-layout frames that the fused sweep could otherwise take -> standard layout in a persistent scratch
+            (one extra 1.5 + 1.5 B/px pass instead of the staged decode / demosaic / tone-map kernels)"""
+            scratch = getattr(self, "_ids_scratch", None)
+            if (scratch is None or len(scratch) < len(frames) or scratch[0].shape != frames[0].shape
+                    or scratch[0].device != frames[0].device):
+                scratch = self._ids_scratch = [torch.empty_like(frames[0]) for _ in frames]
+            return [packed.repack12_ids(f, out=s) for f, s in zip(frames, scratch)]
+
         def load_packed12(self, image_data, ids_format=False):
             """camera_isp.py:333-340: decode12(scaled) + demosaic (+CCM) (+resize) -> float RGB of the ISP dtype"""
             assert image_data.dtype == torch.uint8 and image_data.ndim == 2
             image_data = image_data.to(self.device)
+            if ids_format and self._fused_ok(image_data, False):
+                image_data, ids_format = self._ids_to_standard([image_data])[0], False
             if self._fused_ok(image_data, ids_format):
                 rgb = self._run_fused([image_data], "none", isp_dtype, None, {})[0]
                 return self.resize_image(rgb)
@@ -479,6 +490,10 @@ def camera_isp(name: str, dtype=f32):
             assert 1 <= len(frames) <= _lib.MAX_FRAMES, f"1..{_lib.MAX_FRAMES} frames per call"
             shape = frames[0].shape
             assert all(f.shape == shape and f.dtype == torch.uint8 and f.ndim == 2 for f in frames)
+            if ids_format and all(self._fused_ok(f, False) for f in frames):
+                # IDS layout: re-pack into the standard layout (scratch reused by every call, hence no look-ahead)
+                frames, ids_format, lookahead = self._ids_to_standard(frames), False, None
+                self._lookahead = None
             fused = all(self._fused_ok(f, ids_format) for f in frames) and not self._resizes
             if not fused:
                 if self._resizes and all(self._fused_ok(f, ids_format) for f in frames):

@@ -201,7 +201,60 @@ static int launch_encode12(const T* values, uint8_t* enc, int64_t n_values, floa
 
 }  // namespace isp
 
+namespace isp {
+// IDS 12-bit layout -> standard layout, byte stream to byte stream (packed.py:36-44 followed by :12-20 without
+// leaving registers): lets IDS frames take the fused sweep, whose row loader reads the standard layout.
+//   IDS:       p0 = b0 << 4 | (b2 & 0xF),  p1 = b1 << 4 | b2 >> 4
+//   standard:  c0 = p0 & 0xFF,  c1 = (p1 & 0xF) << 4 | p0 >> 8,  c2 = p1 >> 4
+__device__ __forceinline__ void ids_to_std3(uint32_t b0, uint32_t b1, uint32_t b2, uint32_t& c0, uint32_t& c1, uint32_t& c2) {
+  const uint32_t p0 = (b0 << 4) | (b2 & 0xFu), p1 = (b1 << 4) | (b2 >> 4);
+  c0 = p0 & 0xFFu; c1 = ((p1 & 0xFu) << 4) | (p0 >> 8); c2 = p1 >> 4;
+}
+
+// 12 bytes (4 triplets = 8 pixels) per thread as three aligned words; the tail triplets byte-wise
+__global__ void __launch_bounds__(256) repack12_ids_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst,
+                                                           long long n_triplets, bool words) {
+  const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x, nth = (long long)gridDim.x * blockDim.x;
+  const long long n4 = words ? n_triplets / 4 : 0;
+  for (long long i = tid; i < n4; i += nth) {
+    const uint32_t* p = reinterpret_cast<const uint32_t*>(src) + 3 * i;
+    const uint32_t w[3] = {__ldg(p), __ldg(p + 1), __ldg(p + 2)};
+    uint32_t o[3] = {0u, 0u, 0u};
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      uint32_t b[3], c[3];
+#pragma unroll
+      for (int k = 0; k < 3; ++k) b[k] = (w[(3 * t + k) >> 2] >> (8 * ((3 * t + k) & 3))) & 0xFFu;
+      ids_to_std3(b[0], b[1], b[2], c[0], c[1], c[2]);
+#pragma unroll
+      for (int k = 0; k < 3; ++k) o[(3 * t + k) >> 2] |= c[k] << (8 * ((3 * t + k) & 3));
+    }
+    uint32_t* q = reinterpret_cast<uint32_t*>(dst) + 3 * i;
+    q[0] = o[0]; q[1] = o[1]; q[2] = o[2];
+  }
+  for (long long i = 4 * n4 + tid; i < n_triplets; i += nth) {
+    uint32_t c0, c1, c2;
+    ids_to_std3(src[3 * i], src[3 * i + 1], src[3 * i + 2], c0, c1, c2);
+    dst[3 * i] = (uint8_t)c0; dst[3 * i + 1] = (uint8_t)c1; dst[3 * i + 2] = (uint8_t)c2;
+  }
+}
+}  // namespace isp
+
 using namespace isp;
+
+extern "C" int b200isp_repack12_ids(const uint8_t* ids, uint8_t* standard, int64_t n_bytes, b200isp_stream stream) {
+  ISP_REQUIRE(n_bytes >= 0 && n_bytes % 3 == 0, B200ISP_E_SHAPE, "repack12_ids: byte count must be a multiple of 3, got %lld", (long long)n_bytes);
+  if (n_bytes == 0) return B200ISP_OK;
+  ISP_REQUIRE(ids && standard, B200ISP_E_ARG, "repack12_ids: null pointer");
+  const long long n = n_bytes / 3;
+  const bool words = ((reinterpret_cast<uintptr_t>(ids) | reinterpret_cast<uintptr_t>(standard)) & 3u) == 0;
+  long long blocks = (n / 4 + 255) / 256;
+  if (blocks < 1) blocks = 1;
+  if (blocks > 8 * kNumSMs) blocks = 8 * kNumSMs;
+  repack12_ids_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(ids, standard, n, words);
+  ISP_LAUNCH_CHECK("repack12_ids_kernel");
+  return B200ISP_OK;
+}
 
 extern "C" int b200isp_decode12(const uint8_t* encoded, int64_t n_values, void* out, int out_dtype,
                                 int scaled, int ids_format, b200isp_stream stream) {

@@ -94,6 +94,24 @@ def decode12(values, dtype=u16, scaled=False, ids_format=False):
     return restore(decoded.reshape(shape[:-1] + (shape[-1] * 2 // 3,)))
 
 
+def repack12_ids(values, out=None):
+    """EXTENSION: IDS-layout 12-bit data -> the standard layout, i.e. ``encode12(decode12(values, ids_format=True))``
+    (packed.py:36-44 followed by :12-20) without leaving the packed domain.  Used by ``camera_isp`` so that IDS frames
+    take the fused sweep.  ``out``: optional preallocated uint8 tensor of the same shape (CUDA)."""
+    shape = tuple(values.shape)
+    assert types.ti_type(values) is u8
+    assert shape[-1] % 3 == 0, f"last dimension must be a factor of 3 for 12-bit data got: {shape}"
+    dev, restore = types.to_device(values)
+    dev = dev.contiguous()
+    res = torch.empty_like(dev) if out is None else out
+    assert res.dtype == torch.uint8 and tuple(res.shape) == shape and res.is_contiguous() and res.device == dev.device
+    if dev.numel():
+        with torch.cuda.device(dev.device):
+            _lib.check(_lib.lib.b200isp_repack12_ids(dev.data_ptr(), res.data_ptr(), dev.numel(), _lib.stream_ptr(dev.device)),
+                       "repack12_ids")
+    return res if out is not None else restore(res)
+
+
 def decode16(values, dtype=u16, scaled=False, ids_format=False):
     """packed.py:200-210.  ``ids_format`` is accepted and ignored: the reference forwards it to a
     kernel factory that has no such parameter and always raises."""

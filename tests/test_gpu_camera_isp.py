@@ -5,7 +5,7 @@ import pytest
 import torch
 
 from oracle import isp_oracle as O
-from tests.util import rng, packed_frame, to_cuda, to_np, assert_close_int, assert_close_float
+from tests.util import rng, packed_frame, smooth_rgb, to_cuda, to_np, assert_close_int, assert_close_float
 
 pytestmark = pytest.mark.gpu
 CAMS = {"f16": "Camera16", "f32": "Camera32"}
@@ -294,3 +294,34 @@ def test_fused_wide_frames_all_task_kinds(cuda, dt, pattern, shape, rpt):
     exp_rei = ref2.tonemap_reinhard([ref2.load_packed12(f) for f in fr], gamma=0.9, intensity=2.0, light_adapt=0.8, out_dtype="u8")
     for g, e in zip(rei, exp_rei):
         assert_close_int(to_np(g), e, 1, f"reinhard {dt} {pattern} {shape}")
+
+
+# ---------------------------------------------------------------- IDS layout through the fused sweep
+@pytest.mark.parametrize("n_bytes", [0, 3, 9, 12, 36, 3 * 1001, 48 * 64])
+def test_repack12_ids_bit_exact(cuda, n_bytes):
+    from taichi_image_b200 import packed
+    ids = rng(90).integers(0, 256, size=(n_bytes,)).astype(np.uint8)
+    got = to_np(packed.repack12_ids(to_cuda(ids)))
+    assert np.array_equal(got, O.repack12_ids(ids))
+    if n_bytes:      # the re-packed stream decodes (standard layout) to what the IDS stream decodes to
+        assert np.array_equal(O.decode12_raw(got), O.decode12_raw(ids, ids_format=True))
+    view = to_cuda(np.concatenate([np.zeros(1, np.uint8), ids]))[1:]           # unaligned base: byte-wise kernel path
+    assert np.array_equal(to_np(packed.repack12_ids(view)), O.repack12_ids(ids))
+
+
+@pytest.mark.parametrize("dt", ["f16", "f32"])
+@pytest.mark.parametrize("tonemap", ["linear", "reinhard"])
+def test_fused_ids_format(cuda, dt, tonemap):
+    """IDS frames: re-packed on the device, then the fused sweep -- same results as the reference's staged order"""
+    r = rng(91)
+    isp, ref = make_isp(dt, bayer_pattern="GBRG"), O.ISP(dt, "GBRG")
+    for step in range(2):
+        fr = [O.encode12(O.rgb_to_bayer(smooth_rgb(r, 36, 72), "GBRG"), scaled=True, ids_format=True) for _ in range(2)]
+        got = isp.process_packed12([to_cuda(f) for f in fr], tonemap=tonemap, gamma=0.8, ids_format=True)
+        imgs = [ref.load_packed12(f, ids_format=True) for f in fr]
+        exp = ref.tonemap_linear(imgs, gamma=0.8) if tonemap == "linear" else ref.tonemap_reinhard(imgs, gamma=0.8)
+        for g, e in zip(got, exp):
+            assert_close_int(to_np(g), e, 1, f"ids {dt} {tonemap} step {step}")
+    one = O.encode12(O.rgb_to_bayer(smooth_rgb(r, 36, 72), "GBRG"), scaled=True, ids_format=True)
+    assert_close_float(to_np(isp.load_packed12(to_cuda(one), ids_format=True)), ref.load_packed12(one, ids_format=True),
+                       rtol=1e-3, atol=1e-3 if dt == "f16" else 2e-6)
