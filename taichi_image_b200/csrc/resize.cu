@@ -172,24 +172,32 @@ __global__ void __launch_bounds__(256) transform_words_kernel(const uint32_t* __
   const int ayy = s10r - s00r, axy = s10c - s00c, ayx = s01r - s00r, axx = s01c - s00c;
   const unsigned char* tb = reinterpret_cast<const unsigned char*>(&tile[0][0]);
   const int dst_pitch_w = wd * PB / 4;
-  const int db0 = dc0 * PB, dw0 = db0 >> 2, dboff = db0 & 3;         // dboff == 0 whenever TILE * PB % 4 == 0 (always)
-  const int dwords = (nc * PB + dboff + 3) >> 2;
-  for (int i = threadIdx.x; i < nr * dwords; i += 256) {
-    const int y = i / dwords, w = i - y * dwords;
-    uint32_t word = 0;
+  // phase 2: 12-byte groups (4 / 2 / 1 pixels = 3 words): one affine map per pixel, compile-time byte positions.
+  // The destination tile starts word-aligned (TILE * PB % 4 == 0); nc * PB is a multiple of 4 because the row pitch
+  // is, and for PB = 3 / 6 / 12 that makes it a multiple of 12 as well (nc % 4 == 0 / nc % 2 == 0 / any nc).
+  constexpr int PPG = 12 / PB;
+  const int dw0 = dc0 * PB / 4;
+  const int groups = nc / PPG;
+  for (int i = threadIdx.x; i < nr * groups; i += 256) {
+    const int y = i / groups, gi = i - y * groups;
+    uint32_t o[3] = {0u, 0u, 0u};
 #pragma unroll
-    for (int g = 0; g < 4 / G; ++g) {
-      const int b = 4 * w + g * G - dboff;                           // byte within the destination tile row
-      const int x = b / PB, k = b - x * PB;
+    for (int j = 0; j < PPG; ++j) {
+      const int x = gi * PPG + j;
       const int sy = oy + ayy * y + ayx * x, sx = ox + axy * y + axx * x;
-      const unsigned char* q = tb + (size_t)sy * (ROW_WORDS * 4) + boff + sx * PB + k;
-      uint32_t v;
-      if constexpr (G == 4) v = *reinterpret_cast<const uint32_t*>(q);
-      else if constexpr (G == 2) v = *reinterpret_cast<const unsigned short*>(q);
-      else v = *q;
-      if (x < nc) word |= v << (8 * g * G);
+      const unsigned char* q = tb + (size_t)sy * (ROW_WORDS * 4) + boff + sx * PB;
+#pragma unroll
+      for (int g = 0; g < PB / G; ++g) {
+        uint32_t v;
+        if constexpr (G == 4) v = *reinterpret_cast<const uint32_t*>(q + 4 * g);
+        else if constexpr (G == 2) v = *reinterpret_cast<const unsigned short*>(q + 2 * g);
+        else v = q[g];
+        const int bpos = j * PB + g * G;                             // byte within the 12-byte group (compile time)
+        o[bpos >> 2] |= v << (8 * (bpos & 3));
+      }
     }
-    dst[(size_t)(dr0 + y) * dst_pitch_w + dw0 + w] = word;
+    uint32_t* d = dst + (size_t)(dr0 + y) * dst_pitch_w + dw0 + 3 * gi;
+    d[0] = o[0]; d[1] = o[1]; d[2] = o[2];
   }
 }
 
