@@ -175,7 +175,8 @@ typedef struct {
   int update_metering;          /* 1: run the two metering phases on these frames first */
   int rows_per_task;            /* 0 = default */
   int demosaic;                 /* b200isp_demosaic_t: 0 = Malvar-He-Cutler (bayer.py:30-55), 1 = bilinear (extension) */
-  int reserved;                 /* 0 */
+  int out_yuv420;               /* 1: every output is a planar YUV 4:2:0 image, (3H/2, W) u8 (color/yuv_420.py:95-118), instead
+                                   of RGB -- Camera16 + Reinhard + u8 with reinhard_scratch only; other combinations fail */
   void* profile_start;          /* optional cudaEvent_t pair recorded on `stream` immediately before / after */
   void* profile_stop;           /*   the dominant streaming kernel (bench.py's live roofline timing); NULL = off */
   void* meter_cache;            /* optional device scratch: >= n_frames*ceil(H/stride)*ceil(W/stride)*12 bytes; the second */

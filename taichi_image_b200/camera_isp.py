@@ -412,7 +412,7 @@ def camera_isp(name: str, dtype=f32):
 
         # ------------------------------------------------------------ fused path
         def _fused_params(self, frames, tonemap, out_dtype, tm, update_metering=False, alpha=0.0, rows_per_task=0,
-                          profile_events=None):
+                          profile_events=None, yuv420=False):
             """b200isp_fused_params for a list of same-shape packed12 frames (include/b200isp.h)"""
             h, w3 = frames[0].shape
             w = w3 * 2 // 3
@@ -430,6 +430,7 @@ def camera_isp(name: str, dtype=f32):
             p.metering_stride, p.alpha = int(self.metering_stride), float(alpha)
             p.update_metering, p.rows_per_task = int(update_metering), int(rows_per_task)
             p.demosaic = 1 if self.demosaic == "bilinear" else 0
+            p.out_yuv420 = int(bool(yuv420))
             if update_metering:                  # scratch for the phase-1 samples (re-read by phase 2)
                 stride = max(int(self.metering_stride), 1)
                 need = len(frames) * (-(-h // stride)) * (-(-w // stride)) * 12
@@ -450,16 +451,17 @@ def camera_isp(name: str, dtype=f32):
             return p
 
         def _run_fused(self, frames, tonemap, out_dtype, out, tm, update_metering=False, alpha=0.0, rows_per_task=0,
-                       profile_events=None):
+                       profile_events=None, yuv420=False):
             h, w3 = frames[0].shape
             w = w3 * 2 // 3
-            p = self._fused_params(frames, tonemap, out_dtype, tm, update_metering, alpha, rows_per_task, profile_events)
+            p = self._fused_params(frames, tonemap, out_dtype, tm, update_metering, alpha, rows_per_task, profile_events, yuv420)
+            oshape = (h * 3 // 2, w) if yuv420 else (h, w, 3)       # planar YUV 4:2:0: color/yuv_420.py:95-118
             if out is None:
-                out = [torch.empty((h, w, 3), dtype=out_dtype.torch, device=self.device) for _ in frames]
+                out = [torch.empty(oshape, dtype=out_dtype.torch, device=self.device) for _ in frames]
             else:
                 assert len(out) == len(frames)
                 for o in out:
-                    assert tuple(o.shape) == (h, w, 3) and o.dtype == out_dtype.torch and o.is_contiguous() and o.is_cuda
+                    assert tuple(o.shape) == oshape and o.dtype == out_dtype.torch and o.is_contiguous() and o.is_cuda
             metrics_ptr = 0 if self.metrics is None else self.metrics.data_ptr()
             with torch.cuda.device(self.device):
                 _lib.check(_lib.lib.b200isp_process_packed12(
@@ -471,7 +473,7 @@ def camera_isp(name: str, dtype=f32):
                              intensity: float = 1.0, light_adapt: float = 1.0, color_adapt: float = 0.0,
                              dtype=u8, ids_format: bool = False, out: Optional[list] = None,
                              rows_per_task: int = 0, profile_events=None, update_metering: bool = True,
-                             lookahead: Optional[Sequence[torch.Tensor]] = None, meter_fn=None):
+                             lookahead: Optional[Sequence[torch.Tensor]] = None, meter_fn=None, yuv420: bool = False):
             """Fused equivalent of ``[load_packed12(f) for f in frames]`` followed by
             ``tonemap_reinhard`` / ``tonemap_linear`` (camera_isp.py:333-340, :376-413): joint metering of
             all frames with the moving-average update of ``self.metrics``, then one sweep per frame.
@@ -483,9 +485,17 @@ def camera_isp(name: str, dtype=f32):
             while this batch is processed).  Their metering update -- which only depends on this call's metrics --
             is then issued on a side stream and runs under this batch's sweep; the next call finds it done.  The
             announced tensors must not be modified before that call.  Results are identical to calling without it.
-            ``meter_fn(frames, alpha, out, cooperative)``: replaces the local metering (distributed.SharedExposure)."""
+            ``meter_fn(frames, alpha, out, cooperative)``: replaces the local metering (distributed.SharedExposure).
+
+            ``yuv420=True`` (Camera16 + Reinhard + u8, fused frames only): every output is the planar YUV 4:2:0 image
+            ``color.rgb_yuv420_image`` would make of the RGB8 result -- ``(3H/2, W)`` u8, bit-identical -- written
+            directly by the normalise pass (1.5 instead of 3 bytes per pixel, no second kernel)."""
             assert tonemap in ("linear", "reinhard")
             out_dtype = as_dtype(dtype)
+            if yuv420:
+                assert isp_dtype == f16 and tonemap == "reinhard" and out_dtype == u8, \
+                    "yuv420 output is implemented for Camera16 + Reinhard + u8"
+                assert self.transform == interpolate.ImageTransform.none, "yuv420 output cannot be transformed"
             frames = [f.to(self.device) for f in frames]
             assert 1 <= len(frames) <= _lib.MAX_FRAMES, f"1..{_lib.MAX_FRAMES} frames per call"
             shape = frames[0].shape
@@ -495,6 +505,7 @@ def camera_isp(name: str, dtype=f32):
                 frames, ids_format, lookahead = self._ids_to_standard(frames), False, None
                 self._lookahead = None
             fused = all(self._fused_ok(f, ids_format) for f in frames) and not self._resizes
+            assert fused or not yuv420, "yuv420 output needs frames the fused sweep accepts (no resize, width % 8 == 0)"
             if not fused:
                 if self._resizes and all(self._fused_ok(f, ids_format) for f in frames):
                     images = self._load_packed12_resized(frames)
@@ -511,8 +522,8 @@ def camera_isp(name: str, dtype=f32):
                 alpha = self._metrics_and_alpha() if update_metering else 0.0
                 assert self.metrics is not None, "update_metering=False needs metrics from an earlier call"
                 outputs = self._run_fused(frames, tonemap, out_dtype, out, tm, update_metering=update_metering, alpha=alpha,
-                                          rows_per_task=rows_per_task, profile_events=profile_events)
-                return [interpolate.transform(o, self.transform) for o in outputs]
+                                          rows_per_task=rows_per_task, profile_events=profile_events, yuv420=yuv420)
+                return outputs if yuv420 else [interpolate.transform(o, self.transform) for o in outputs]
 
             # ---- look-ahead pipeline: metering(k+1) on the side stream under sweep(k)
             meter = meter_fn if meter_fn is not None else self.meter_packed12
@@ -529,7 +540,7 @@ def camera_isp(name: str, dtype=f32):
                 ready = torch.cuda.Event()
                 ready.record(main)
             outputs = self._run_fused(frames, tonemap, out_dtype, out, tm, update_metering=False,
-                                      rows_per_task=rows_per_task, profile_events=profile_events)
+                                      rows_per_task=rows_per_task, profile_events=profile_events, yuv420=yuv420)
             ev_sweep = torch.cuda.Event()
             ev_sweep.record(main)
             if lookahead is not None:
@@ -552,7 +563,7 @@ def camera_isp(name: str, dtype=f32):
                             done.record(side)
                     self._lookahead = dict(key=key(nxt), event=done, out=self._metrics_alt, frames=nxt)
             self._ev_prev_sweep = ev_sweep
-            return [interpolate.transform(o, self.transform) for o in outputs]
+            return outputs if yuv420 else [interpolate.transform(o, self.transform) for o in outputs]
 
     ISP.reinhard_kernel = staticmethod(_reinhard_kernel)     # camera_isp.py:415-416
     ISP.linear_kernel = staticmethod(_linear_kernel)

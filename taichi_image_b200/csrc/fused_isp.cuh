@@ -1071,6 +1071,68 @@ __global__ void __launch_bounds__(256) reinhard_scratch_out_kernel(const FramePt
   }
 }
 
+// pass B with planar YUV 4:2:0 output (for video encoders): the u8 RGB of reinhard_scratch_out_kernel
+// is formed in registers and converted with the arithmetic of color/yuv_420.py:47-64 (csrc/yuv420.cu: x / 255, the
+// BT.601 matrix applied to the BGR-swizzled pixel, chroma = mean of the 2x2 quad, one-sided clamp) -- bit-identical
+// to rgb_yuv420_image(process_packed12(...)) without writing or re-reading the RGB image: 1.5 B/px out instead of 3.
+// Thread = 8 pixel columns x 2 rows (four quads); out = (3H/2, W) u8: H rows of Y, then chroma plane 0 (third
+// matrix row) and plane 1 (second matrix row).
+static __global__ void __launch_bounds__(128) reinhard_scratch_yuv_kernel(const FramePtrs scratch, const FramePtrs fp, int H, int W, float gamma,
+                                                                   const Workspace* ws) {
+  // x / 255 (correctly rounded, yuv_420.py:50) for the 256 possible inputs: a table instead of three IEEE divisions per pixel
+  __shared__ float unit[256];
+  for (int i = threadIdx.x; i < 256; i += blockDim.x) unit[i] = __fdiv_rn((float)i, 255.0f);
+  __syncthreads();
+  const int gx = blockIdx.x * blockDim.x + threadIdx.x, qy = blockIdx.y, frame = blockIdx.z;
+  if (gx >= W / 8) return;
+  const __half* src = reinterpret_cast<const __half*>(scratch.out[frame]);
+  uint8_t* yuv = reinterpret_cast<uint8_t*>(fp.out[frame]);
+  const float inv_max = __fdiv_rn(1.0f, fmaxf(1e-6f, __ldcg(&ws->frame_max[frame])));
+  const float inv_gamma = (float)(1.0 / (double)gamma);
+  const bool has_gamma = gamma != 1.0f;
+  constexpr float M[9] = {0.299f, 0.587f, 0.114f, -0.168736f, -0.331264f, 0.5f, 0.5f, -0.418688f, -0.081312f};   // yuv_420.py:12-16
+  float rgb[2][24];
+#pragma unroll
+  for (int dy = 0; dy < 2; ++dy) {
+    alignas(16) __half h[24];
+    ld_bytes<48>(src + ((size_t)(2 * qy + dy) * W + 8 * gx) * 3, h);
+#pragma unroll
+    for (int e = 0; e < 24; ++e) {
+      float q = __saturatef(__half2float(h[e]) * inv_max);
+      if (has_gamma) q = fast_pow(q, inv_gamma);
+      rgb[dy][e] = unit[Quant<uint8_t>::q(q) & 0xFFu];                          // the u8 value the RGB path stores, / in_scale
+    }
+  }
+  alignas(8) uint8_t yrow[2][8];
+  alignas(4) uint8_t cu4[4], cv4[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    float u = 0.f, v = 0.f;
+#pragma unroll
+    for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+      for (int dx = 0; dx < 2; ++dx) {
+        const float* p = &rgb[dy][3 * (2 * q + dx)];
+        float o[3];
+#pragma unroll
+        for (int r = 0; r < 3; ++r)      // M @ (B, G, R), products and sums rounded separately, left to right
+          o[r] = __fadd_rn(__fadd_rn(__fmul_rn(M[3 * r], p[2]), __fmul_rn(M[3 * r + 1], p[1])), __fmul_rn(M[3 * r + 2], p[0]));
+        const float cu = __fadd_rn(o[1], 0.5f), cv = __fadd_rn(o[2], 0.5f);
+        yrow[dy][2 * q + dx] = cast_from_f32<uint8_t>(__fmul_rn(fminf(1.0f, o[0]), 255.0f));
+        if (dy == 0 && dx == 0) { u = cu; v = cv; } else { u = __fadd_rn(u, cu); v = __fadd_rn(v, cv); }
+      }
+    // u / 4.0 (yuv_420.py:62-63): a power-of-two divisor, the product with 0.25 is the same correctly rounded value
+    cu4[q] = cast_from_f32<uint8_t>(__fmul_rn(fminf(1.0f, __fmul_rn(u, 0.25f)), 255.0f));
+    cv4[q] = cast_from_f32<uint8_t>(__fmul_rn(fminf(1.0f, __fmul_rn(v, 0.25f)), 255.0f));
+  }
+#pragma unroll
+  for (int dy = 0; dy < 2; ++dy) st_bytes<8>(yuv + (size_t)(2 * qy + dy) * W + 8 * gx, yrow[dy]);
+  uint8_t* planes = yuv + (size_t)H * W;
+  const size_t plane = (size_t)(H / 2) * (W / 2), idx = (size_t)qy * (W / 2) + 4 * gx;
+  st_bytes<4>(planes + plane + idx, cu4);
+  st_bytes<4>(planes + idx, cv4);
+}
+
 // pass A for frames [0, nframes): instantiated once (fused_inst.cu with ISP_INST_RMAX, Camera16)
 template <bool CAM16>
 int run_rstore(const FramePtrs& fp_scratch, IspConsts k, int nframes, int rows_per_task, cudaStream_t s, void* ev_start, void* ev_stop) {
@@ -1102,6 +1164,14 @@ int run_rmax(const FramePtrs& fp, IspConsts k, int frame0, int nframes, int rows
 template <bool CAM16, typename OutT>
 int run_fused(const FramePtrs& fp, int n_frames, const b200isp_fused_params& p, IspConsts k, cudaStream_t s) {
   const int rpt = p.rows_per_task;
+  if (p.out_yuv420) {
+    const bool ok = CAM16 && std::is_same<OutT, uint8_t>::value && p.tonemap == B200ISP_TM_REINHARD && p.reinhard_scratch &&
+                    p.reinhard_scratch_bytes >= (size_t)n_frames * k.H * k.W * 3 * sizeof(__half);
+    if (!ok) {
+      set_error("process_packed12: YUV 4:2:0 output needs Camera16 (f16), Reinhard, u8 and the reinhard_scratch buffer");
+      return B200ISP_E_ARG;
+    }
+  }
   constexpr bool kIspOut = (CAM16 && std::is_same<OutT, __half>::value) || (!CAM16 && std::is_same<OutT, float>::value);
   if (p.tonemap == B200ISP_TM_NONE) {
     if constexpr (kIspOut) return run_pass<CAM16, MODE_RGB, OutT>(fp, k, 0, n_frames, rpt, s, p.profile_start, p.profile_stop);
@@ -1125,6 +1195,11 @@ int run_fused(const FramePtrs& fp, int n_frames, const b200isp_fused_params& p, 
         for (int f = 0; f < n_frames; ++f) sc.out[f] = (char*)p.reinhard_scratch + (size_t)f * k.H * k.W * 3 * sizeof(__half);
         st = run_rstore<true>(sc, k, n_frames, rpt, s, p.profile_start, p.profile_stop);
         if (st) return st;
+        if (p.out_yuv420) {
+          const dim3 grid((unsigned)((k.W / 8 + 127) / 128), (unsigned)(k.H / 2), (unsigned)n_frames);
+          reinhard_scratch_yuv_kernel<<<grid, 128, 0, s>>>(sc, fp, k.H, k.W, k.gamma, k.ws);
+          return cuda_status(cudaPeekAtLastError(), "reinhard_scratch_yuv_kernel");
+        }
         const long long n_elems = (long long)k.H * k.W * 3;
         const dim3 grid((unsigned)std::min<long long>((n_elems / 8 + 255) / 256, 4 * kNumSMs), (unsigned)n_frames);
         reinhard_scratch_out_kernel<OutT><<<grid, 256, 0, s>>>(sc, fp, n_elems, k.gamma, k.ws);

@@ -65,3 +65,50 @@ def test_yuv420_large_vs_oracle(cuda, name):
     back = to_np(color.yuv420_rgb_image(color.rgb_yuv420_image(to_cuda(grey))))
     tol = {"u8": 2, "u16": 300, "f32": 5e-3}[name]
     assert np.abs(back.astype(np.float64) - grey.astype(np.float64)).max() <= tol
+
+
+# ---------------------------------------------------------------- YUV 4:2:0 straight from the fused path
+@pytest.mark.parametrize("pattern", ["RGGB", "GBRG"])
+@pytest.mark.parametrize("gamma", [1.0, 0.7])
+@pytest.mark.parametrize("shape", [(36, 72), (20, 520)])
+def test_fused_yuv420_output(cuda, pattern, gamma, shape):
+    """process_packed12(yuv420=True) == rgb_yuv420_image(process_packed12(...)) bit for bit, and the RGB it is made
+    from is within 1 LSB of the oracle ISP"""
+    from taichi_image_b200 import bayer, camera_isp, color
+    from tests.util import packed_frame, assert_close_int
+    r = rng(82)
+    a = camera_isp.Camera16(bayer.BayerPattern[pattern])
+    b = camera_isp.Camera16(bayer.BayerPattern[pattern])
+    ref = O.ISP("f16", pattern)
+    for step in range(2):
+        fr = [packed_frame(r, *shape, pattern) for _ in range(3)]
+        cu = [to_cuda(f) for f in fr]
+        yuv = a.process_packed12(cu, tonemap="reinhard", gamma=gamma, intensity=2.0, light_adapt=0.8, yuv420=True)
+        rgb = b.process_packed12(cu, tonemap="reinhard", gamma=gamma, intensity=2.0, light_adapt=0.8)
+        exp = ref.tonemap_reinhard([ref.load_packed12(f) for f in fr], gamma=gamma, intensity=2.0, light_adapt=0.8)
+        for y, g, e in zip(yuv, rgb, exp):
+            assert tuple(y.shape) == (shape[0] * 3 // 2, shape[1]) and y.dtype == g.dtype
+            assert np.array_equal(to_np(y), to_np(color.rgb_yuv420_image(g))), f"step {step}"
+            assert np.array_equal(to_np(y), O.rgb_yuv420(to_np(g)))
+            assert_close_int(to_np(g), e, 1, "rgb behind the yuv")
+
+
+def test_fused_yuv420_unsupported_configurations_fail(cuda):
+    from taichi_image_b200 import bayer, camera_isp
+    from tests.util import packed_frame
+    fr = [to_cuda(packed_frame(rng(83), 16, 32))]
+    with pytest.raises(AssertionError):
+        camera_isp.Camera32(bayer.BayerPattern.RGGB).process_packed12(fr, tonemap="reinhard", yuv420=True)
+    with pytest.raises(AssertionError):
+        camera_isp.Camera16(bayer.BayerPattern.RGGB).process_packed12(fr, tonemap="linear", yuv420=True)
+    # the C layer refuses as well (no silent RGB output into a YUV-sized buffer)
+    from taichi_image_b200 import _lib
+    import torch
+    isp = camera_isp.Camera32(bayer.BayerPattern.RGGB)
+    p = isp._fused_params(fr, "reinhard", isp.dtype, {}, update_metering=True, yuv420=True)
+    p.out_dtype = 0
+    out = torch.empty((24, 32), dtype=torch.uint8, device="cuda")
+    m = torch.zeros(9, dtype=torch.float32, device="cuda")
+    rc = _lib.lib.b200isp_process_packed12(_lib.ptr_array(fr), _lib.ptr_array([out]), 1, p, m.data_ptr(),
+                                           _lib.workspace(isp.device).data_ptr(), _lib.stream_ptr(isp.device))
+    assert rc != 0 and b"YUV" in _lib.lib.b200isp_last_error()
