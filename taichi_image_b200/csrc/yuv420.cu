@@ -7,6 +7,7 @@
 // signature is clamp(x, xmin, xmax) (no lower clamp; negative values saturate to 0 in the integer casts here).
 // Encode: one thread per 2x2 quad (4 pixels in, 4 Y + 2 chroma out); decode: one thread per 2 horizontally
 // adjacent pixels (one chroma pair in, 6 values out).  Both are HBM-bound: 3 s_in + 1.5 s_out bytes per pixel.
+#include <type_traits>
 #include "common.cuh"
 
 namespace isp {
@@ -68,12 +69,33 @@ __global__ void __launch_bounds__(256) yuv420_rgb_kernel(const InT* __restrict__
 // ---------------------------------------------------------------- vector forms (W % 8 == 0, 16-byte aligned bases)
 // The same arithmetic in the same order, eight pixels (four quads) per thread and row with 8 / 16-byte accesses:
 // the scalar kernels above issue one 1..4-byte request per element and are request-bound (13-15 % of HBM peak).
+// to_f32(x) / in_scale (yuv_420.py:50, :80).  For u8 there are only 256 inputs: a shared-memory table of the correctly
+// rounded quotients replaces the IEEE division (the kernels are instruction-bound, not HBM-bound, with it).
+template <typename InT> struct UnitScale {
+  static constexpr bool kTable = std::is_same<InT, uint8_t>::value;
+  float* lut;
+  __device__ __forceinline__ void init(float* smem) {
+    lut = smem;
+    if constexpr (kTable) {
+      for (int i = threadIdx.x; i < 256; i += blockDim.x) smem[i] = __fdiv_rn((float)i, 255.0f);
+      __syncthreads();
+    }
+  }
+  __device__ __forceinline__ float operator()(InT x) const {
+    if constexpr (kTable) return lut[x];
+    else return __fdiv_rn(to_f32(x), DT<InT>::scale);
+  }
+};
+
 template <typename InT, typename OutT>
 __global__ void __launch_bounds__(256) rgb_yuv420_vec_kernel(const InT* __restrict__ rgb, OutT* __restrict__ yuv, int H, int W, Mat3 M) {
+  __shared__ float smem_lut[UnitScale<InT>::kTable ? 256 : 1];
+  UnitScale<InT> unit;
+  unit.init(smem_lut);
   const int gx = blockIdx.x * blockDim.x + threadIdx.x;     // group of four quads = pixel columns 8 gx .. 8 gx + 7
   const int qy = blockIdx.y;
   if (gx >= W / 8) return;
-  constexpr float is = DT<InT>::scale, os = DT<OutT>::scale;
+  constexpr float os = DT<OutT>::scale;
   alignas(16) InT px[2][24];
   alignas(16) OutT yrow[2][8];
   alignas(16) OutT cu4[4], cv4[4];
@@ -87,15 +109,16 @@ __global__ void __launch_bounds__(256) rgb_yuv420_vec_kernel(const InT* __restri
 #pragma unroll
       for (int dx = 0; dx < 2; ++dx) {                      // (0,0), (0,1), (1,0), (1,1) like the scalar kernel
         const InT* p = &px[dy][3 * (2 * q + dx)];
-        const float R = __fdiv_rn(to_f32(p[0]), is), G = __fdiv_rn(to_f32(p[1]), is), B = __fdiv_rn(to_f32(p[2]), is);
+        const float R = unit(p[0]), G = unit(p[1]), B = unit(p[2]);
         float o[3];
         mat_vec(M, B, G, R, o);
         const float cu = __fadd_rn(o[1], 0.5f), cv = __fadd_rn(o[2], 0.5f);
         yrow[dy][2 * q + dx] = cast_from_f32<OutT>(__fmul_rn(fminf(1.0f, o[0]), os));
         if (dy == 0 && dx == 0) { u = cu; v = cv; } else { u = __fadd_rn(u, cu); v = __fadd_rn(v, cv); }
       }
-    cu4[q] = cast_from_f32<OutT>(__fmul_rn(fminf(1.0f, __fdiv_rn(u, 4.0f)), os));
-    cv4[q] = cast_from_f32<OutT>(__fmul_rn(fminf(1.0f, __fdiv_rn(v, 4.0f)), os));
+    // u / 4.0: power-of-two divisor, the product with 0.25 is the same correctly rounded value
+    cu4[q] = cast_from_f32<OutT>(__fmul_rn(fminf(1.0f, __fmul_rn(u, 0.25f)), os));
+    cv4[q] = cast_from_f32<OutT>(__fmul_rn(fminf(1.0f, __fmul_rn(v, 0.25f)), os));
   }
 #pragma unroll
   for (int dy = 0; dy < 2; ++dy) st_bytes<8 * sizeof(OutT)>(yuv + (size_t)(2 * qy + dy) * W + 8 * gx, yrow[dy]);
@@ -107,10 +130,13 @@ __global__ void __launch_bounds__(256) rgb_yuv420_vec_kernel(const InT* __restri
 
 template <typename InT, typename OutT>
 __global__ void __launch_bounds__(256) yuv420_rgb_vec_kernel(const InT* __restrict__ yuv, OutT* __restrict__ rgb, int H, int W, Mat3 Minv) {
+  __shared__ float smem_lut[UnitScale<InT>::kTable ? 256 : 1];
+  UnitScale<InT> unit;
+  unit.init(smem_lut);
   const int gx = blockIdx.x * blockDim.x + threadIdx.x;     // pixel columns 8 gx .. 8 gx + 7 of row r
   const int r = blockIdx.y;
   if (gx >= W / 8) return;
-  constexpr float is = DT<InT>::scale, os = DT<OutT>::scale;
+  constexpr float os = DT<OutT>::scale;
   const InT* planes = yuv + (size_t)H * W;
   const size_t plane = (size_t)(H / 2) * (W / 2), idx = (size_t)(r / 2) * (W / 2) + 4 * gx;
   alignas(16) InT y8[8];
@@ -121,9 +147,9 @@ __global__ void __launch_bounds__(256) yuv420_rgb_vec_kernel(const InT* __restri
   ld_bytes<4 * sizeof(InT)>(planes + idx, cv4);
 #pragma unroll
   for (int c = 0; c < 8; ++c) {
-    const float y = __fdiv_rn(to_f32(y8[c]), is);
-    const float cu = __fsub_rn(__fdiv_rn(to_f32(cu4[c >> 1]), is), 0.5f);
-    const float cv = __fsub_rn(__fdiv_rn(to_f32(cv4[c >> 1]), is), 0.5f);
+    const float y = unit(y8[c]);
+    const float cu = __fsub_rn(unit(cu4[c >> 1]), 0.5f);
+    const float cv = __fsub_rn(unit(cv4[c >> 1]), 0.5f);
     float o[3];
     mat_vec(Minv, y, cu, cv, o);                            // = bgr
     out[3 * c] = cast_from_f32<OutT>(__fmul_rn(fminf(1.0f, o[2]), os));
