@@ -5,7 +5,7 @@
 //   IDS      (packed.py:36-55): p0 = b0<<4 | (b2 & 0xF),     p1 = b1<<4 | b2>>4   (decode)
 //                               b0 = p0>>4, b1 = p1>>4, b2 = (p0&0xF)<<4 | (p1&0xF) (encode; as
 //                               written the reference's IDS encode is NOT the inverse of its decode)
-// Vector path: one thread converts 32 pixels = 48 packed bytes = 3 x 16-byte loads.
+// Vector path: one thread converts kPackNpx pixels (8: 12 packed bytes, three words).
 #include "common.cuh"
 
 namespace isp {
@@ -73,24 +73,33 @@ template <typename T, int N> __device__ __forceinline__ void load_items(const T*
 }
 
 // ---------------------------------------------------------------- decode12
+// NPX pixels per thread (ISP_PACK_NPX, a multiple of 8): 8 keeps a warp's stores contiguous (one STG.128 per thread
+// for u16 / f16 outputs) -- measured against 32 (three 16-byte loads, but stores 64..128 bytes apart per thread).
+#ifndef ISP_PACK_NPX
+#define ISP_PACK_NPX 8
+#endif
+constexpr int kPackNpx = ISP_PACK_NPX;
+static_assert(kPackNpx % 8 == 0, "whole 12-byte groups");
+
 template <typename T, bool SCALED, bool IDS>
 __global__ void __launch_bounds__(256) decode12_vec_kernel(const uint8_t* __restrict__ enc, T* __restrict__ out,
                                                            int64_t n_groups, float k) {
+  constexpr int NW = kPackNpx * 3 / 8;
   const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (g >= n_groups) return;
-  alignas(16) uint32_t w[12];
-  load_items<uint32_t, 12>(reinterpret_cast<const uint32_t*>(enc + g * 48), w);
-  alignas(16) T v[32];
+  alignas(16) uint32_t w[NW];
+  ld_bytes<4 * NW>(enc + g * (4 * NW), w);
+  alignas(16) T v[kPackNpx];
 #pragma unroll
-  for (int i = 0; i < 16; ++i) {
+  for (int i = 0; i < kPackNpx / 2; ++i) {
     const int k0 = (3 * i) / 4, off = (24 * i) % 32;
-    const uint32_t x = (off == 0 ? w[k0] : (off == 8 ? (w[k0] >> 8) : __funnelshift_r(w[k0], w[k0 + 1], off))) & 0xFFFFFFu;
+    const uint32_t x = (off == 0 ? w[k0] : (off == 8 ? (w[k0] >> 8) : __funnelshift_r(w[k0], w[k0 + 1 < NW ? k0 + 1 : k0], off))) & 0xFFFFFFu;
     uint32_t p0, p1;
     decode_pair<IDS>(x, p0, p1);
     v[2 * i] = decoded_value<T, SCALED>(p0, k);
     v[2 * i + 1] = decoded_value<T, SCALED>(p1, k);
   }
-  store_items<T, 32>(out + g * 32, v);
+  st_bytes<kPackNpx * (int)sizeof(T)>(out + g * kPackNpx, v);
 }
 
 template <typename T, bool SCALED, bool IDS>
@@ -110,21 +119,22 @@ __global__ void __launch_bounds__(256) decode12_pair_kernel(const uint8_t* __res
 template <typename T, bool SCALED, bool IDS>
 __global__ void __launch_bounds__(256) encode12_vec_kernel(const T* __restrict__ values, uint8_t* __restrict__ enc,
                                                            int64_t n_groups, float k) {
+  constexpr int NW = kPackNpx * 3 / 8;
   const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (g >= n_groups) return;
-  alignas(16) T v[32];
-  load_items<T, 32>(values + g * 32, v);
-  alignas(16) uint32_t w[12];
+  alignas(16) T v[kPackNpx];
+  ld_bytes<kPackNpx * (int)sizeof(T)>(values + g * kPackNpx, v);
+  alignas(16) uint32_t w[NW];
 #pragma unroll
-  for (int i = 0; i < 12; ++i) w[i] = 0u;
+  for (int i = 0; i < NW; ++i) w[i] = 0u;
 #pragma unroll
-  for (int i = 0; i < 16; ++i) {
+  for (int i = 0; i < kPackNpx / 2; ++i) {
     const uint32_t x = encode_pair<IDS>(value_to_u12<T, SCALED>(v[2 * i], k), value_to_u12<T, SCALED>(v[2 * i + 1], k));
     const int k0 = (3 * i) / 4, off = (24 * i) % 32;
     w[k0] |= x << off;
-    if (off > 8) w[k0 + 1] |= x >> (32 - off);
+    if (off > 8) w[k0 + 1 < NW ? k0 + 1 : k0] |= x >> (32 - off);
   }
-  store_items<uint32_t, 12>(reinterpret_cast<uint32_t*>(enc + g * 48), w);
+  st_bytes<4 * NW>(enc + g * (4 * NW), w);
 }
 
 template <typename T, bool SCALED, bool IDS>
@@ -170,14 +180,14 @@ static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t
 template <typename T, bool SCALED, bool IDS>
 static int launch_decode12(const uint8_t* enc, T* out, int64_t n_values, float k, cudaStream_t s) {
   const int64_t n_pairs = n_values / 2;
-  int64_t n_groups = (aligned16(enc) && aligned16(out)) ? n_values / 32 : 0;
+  int64_t n_groups = (aligned16(enc) && aligned16(out)) ? n_values / kPackNpx : 0;
   if (n_groups > 0) {
     decode12_vec_kernel<T, SCALED, IDS><<<(unsigned)((n_groups + 255) / 256), 256, 0, s>>>(enc, out, n_groups, k);
     ISP_LAUNCH_CHECK("decode12_vec_kernel");
   }
-  const int64_t rest = n_pairs - n_groups * 16;
+  const int64_t rest = n_pairs - n_groups * (kPackNpx / 2);
   if (rest > 0) {
-    decode12_pair_kernel<T, SCALED, IDS><<<(unsigned)((rest + 255) / 256), 256, 0, s>>>(enc, out, n_groups * 16, n_pairs, k);
+    decode12_pair_kernel<T, SCALED, IDS><<<(unsigned)((rest + 255) / 256), 256, 0, s>>>(enc, out, n_groups * (kPackNpx / 2), n_pairs, k);
     ISP_LAUNCH_CHECK("decode12_pair_kernel");
   }
   return B200ISP_OK;
@@ -186,14 +196,14 @@ static int launch_decode12(const uint8_t* enc, T* out, int64_t n_values, float k
 template <typename T, bool SCALED, bool IDS>
 static int launch_encode12(const T* values, uint8_t* enc, int64_t n_values, float k, cudaStream_t s) {
   const int64_t n_pairs = n_values / 2;
-  int64_t n_groups = (aligned16(enc) && aligned16(values)) ? n_values / 32 : 0;
+  int64_t n_groups = (aligned16(enc) && aligned16(values)) ? n_values / kPackNpx : 0;
   if (n_groups > 0) {
     encode12_vec_kernel<T, SCALED, IDS><<<(unsigned)((n_groups + 255) / 256), 256, 0, s>>>(values, enc, n_groups, k);
     ISP_LAUNCH_CHECK("encode12_vec_kernel");
   }
-  const int64_t rest = n_pairs - n_groups * 16;
+  const int64_t rest = n_pairs - n_groups * (kPackNpx / 2);
   if (rest > 0) {
-    encode12_pair_kernel<T, SCALED, IDS><<<(unsigned)((rest + 255) / 256), 256, 0, s>>>(values, enc, n_groups * 16, n_pairs, k);
+    encode12_pair_kernel<T, SCALED, IDS><<<(unsigned)((rest + 255) / 256), 256, 0, s>>>(values, enc, n_groups * (kPackNpx / 2), n_pairs, k);
     ISP_LAUNCH_CHECK("encode12_pair_kernel");
   }
   return B200ISP_OK;
