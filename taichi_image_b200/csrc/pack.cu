@@ -54,24 +54,6 @@ template <typename T, bool SCALED> __device__ __forceinline__ uint32_t value_to_
   }
 }
 
-template <typename T, int N> __device__ __forceinline__ void store_items(T* dst, const T (&v)[N]) {
-  constexpr int kBytes = N * (int)sizeof(T);
-  static_assert(kBytes % 16 == 0, "vector store needs 16-byte multiples");
-  const uint4* s = reinterpret_cast<const uint4*>(v);
-  uint4* d = reinterpret_cast<uint4*>(dst);
-#pragma unroll
-  for (int i = 0; i < kBytes / 16; ++i) d[i] = s[i];
-}
-
-template <typename T, int N> __device__ __forceinline__ void load_items(const T* src, T (&v)[N]) {
-  constexpr int kBytes = N * (int)sizeof(T);
-  static_assert(kBytes % 16 == 0, "vector load needs 16-byte multiples");
-  uint4* d = reinterpret_cast<uint4*>(v);
-  const uint4* s = reinterpret_cast<const uint4*>(src);
-#pragma unroll
-  for (int i = 0; i < kBytes / 16; ++i) d[i] = __ldg(s + i);
-}
-
 // ---------------------------------------------------------------- decode12
 // NPX pixels per thread (ISP_PACK_NPX, a multiple of 8): 8 keeps a warp's stores contiguous (one STG.128 per thread
 // for u16 / f16 outputs) -- measured against 32 (three 16-byte loads, but stores 64..128 bytes apart per thread).
