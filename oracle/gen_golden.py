@@ -192,10 +192,39 @@ def gen_camera_isp():
     np.savez_compressed(os.path.join(OUT, "camera_isp.npz"), **d)
 
 
+def gen_camera_isp_wide():
+    """One wide case (20 x 776: four 256-pixel strips, the last one partial; with rows_per_task = 6 three row
+    chunks): the interior-strip kind (K_CORE), the partial last strip and multi-chunk tasks of the CUDA sweep are
+    pinned to the reference source too, not only to the oracle.  Two time steps x two cameras, script Reinhard
+    settings -> u8 and linear gamma 1 -> u8, Camera16 and Camera32.  Takes ~10 minutes on the emulation."""
+    r = np.random.default_rng(106)
+    d = {}
+    h, w = 20, 776
+    frames = [[packed.encode12(bayer.rgb_to_bayer(smooth(r, h, w)), scaled=True) for _ in range(2)] for _ in range(2)]
+    for s, fs in enumerate(frames):
+        for c, f in enumerate(fs):
+            d[f"frame_s{s}_c{c}"] = f
+    tms = {"script": dict(gamma=0.9, intensity=3.0, light_adapt=0.9, color_adapt=0.0), "linear1": dict(gamma=1.0)}
+    for cam_name, cam in (("f16", camera_isp.Camera16), ("f32", camera_isp.Camera32)):
+        isps = {k: cam(bayer.BayerPattern.RGGB, device=torch.device("cpu")) for k in tms}
+        for s, fs in enumerate(frames):
+            images = [isps["script"].load_packed12(torch.from_numpy(f.copy())) for f in fs]
+            for c, im in enumerate(images):
+                d[f"{cam_name}_rgb_s{s}_c{c}"] = im.numpy().copy()
+            for tm_name, tm in tms.items():
+                ims = [im.clone() for im in images]           # tonemap_reinhard overwrites its inputs (SURVEY Q6)
+                outs = isps[tm_name].tonemap_linear(ims, **tm) if tm_name.startswith("linear") else isps[tm_name].tonemap_reinhard(ims, **tm)
+                key = f"{cam_name}_{tm_name}_s{s}"
+                d[key + "_metrics"] = isps[tm_name].metrics.numpy().copy()
+                for c, o in enumerate(outs):
+                    d[key + f"_c{c}"] = o.numpy().copy()
+    np.savez_compressed(os.path.join(OUT, "camera_isp_wide.npz"), **d)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     only = set(sys.argv[1:])
-    for fn in (gen_packed, gen_bayer, gen_tonemap, gen_interpolate, gen_camera_isp, gen_color):
+    for fn in (gen_packed, gen_bayer, gen_tonemap, gen_interpolate, gen_camera_isp, gen_color, gen_camera_isp_wide):
         if only and fn.__name__[4:] not in only:
             continue
         fn()

@@ -436,6 +436,8 @@ def camera_isp(name: str, dtype=f32):
                 need = len(frames) * (-(-h // stride)) * (-(-w // stride)) * 12
                 cache = getattr(self, "_meter_cache", None)
                 if cache is None or cache.numel() < need or cache.device != torch.device(self.device):
+                    if cache is not None:
+                        torch.cuda.synchronize(self.device)      # a look-ahead metering on the side stream may still use it
                     cache = self._meter_cache = torch.empty(need, dtype=torch.uint8, device=self.device)
                 p.meter_cache, p.meter_cache_bytes = cache.data_ptr(), cache.numel()
                 self._meter_n = need // 12
@@ -511,11 +513,22 @@ def camera_isp(name: str, dtype=f32):
                     images = self._load_packed12_resized(frames)
                 else:
                     images = [self.load_packed12(f, ids_format) for f in frames]
+                if meter_fn is not None and update_metering:      # distributed.SharedExposure: joint metering of all ranks
+                    meter_fn(images, None, None, True)
+                    update_metering = False
                 if tonemap == "linear":
-                    return self.tonemap_linear(images, gamma=float(gamma), dtype=out_dtype, update_metering=update_metering)
-                return self.tonemap_reinhard(images, gamma=float(gamma), intensity=float(intensity),
-                                             light_adapt=float(light_adapt), color_adapt=float(color_adapt), dtype=out_dtype,
-                                             update_metering=update_metering)
+                    res = self.tonemap_linear(images, gamma=float(gamma), dtype=out_dtype, update_metering=update_metering)
+                else:
+                    res = self.tonemap_reinhard(images, gamma=float(gamma), intensity=float(intensity),
+                                                light_adapt=float(light_adapt), color_adapt=float(color_adapt),
+                                                dtype=out_dtype, update_metering=update_metering)
+                if out is not None:                # staged kernels allocate their own results: honour the caller's buffers
+                    assert len(out) == len(res) and all(o.shape == r.shape and o.dtype == r.dtype for o, r in zip(out, res)), \
+                        "out= buffers must have the shape / dtype of the (resized, transformed) results"
+                    for o, r in zip(out, res):
+                        o.copy_(r)
+                    return list(out)
+                return res
             tm = dict(gamma=gamma, intensity=intensity, light_adapt=light_adapt, color_adapt=color_adapt)
             pipelined = update_metering and (lookahead is not None or self._lookahead is not None or meter_fn is not None)
             if not pipelined:
@@ -528,6 +541,16 @@ def camera_isp(name: str, dtype=f32):
             # ---- look-ahead pipeline: metering(k+1) on the side stream under sweep(k)
             meter = meter_fn if meter_fn is not None else self.meter_packed12
             main = torch.cuda.current_stream(self.device)
+            with torch.cuda.device(self.device):
+                # Everything the side stream touches exists BEFORE any work of this call is enqueued: a buffer
+                # created later would be initialised on the main stream behind the sweep, i.e. after the side-stream
+                # metering that writes it.  (torch.empty: the metering kernels write all nine floats.)
+                if self._side_stream is None:
+                    # high priority: the metering CTAs take SM slots ahead of the sweep's not-yet-dispatched
+                    # CTAs (an earlier-launched grid otherwise keeps every freed slot until its tail)
+                    self._side_stream = torch.cuda.Stream(self.device, priority=-1)
+                if self._metrics_alt is None:
+                    self._metrics_alt = torch.empty(9, dtype=torch.float32, device=self.device)
             key = lambda fs: tuple((f.data_ptr(), tuple(f.shape)) for f in fs)
             pending, self._lookahead = self._lookahead, None
             if pending is not None and pending["key"] == key(frames):
@@ -535,6 +558,10 @@ def camera_isp(name: str, dtype=f32):
                 self.metrics, self._metrics_alt = pending["out"], self.metrics
                 ready = pending["event"]
             else:
+                if pending is not None:
+                    # wrong announcement: the stale side-stream metering shares the sample cache, the workspace and
+                    # (shared exposure) the mailbox sequence with the metering issued now -> let it drain first
+                    main.wait_event(pending["event"])
                 alpha = self._metrics_and_alpha()
                 meter(frames, alpha, None, True)                       # in place, on the main stream
                 ready = torch.cuda.Event()
@@ -547,12 +574,6 @@ def camera_isp(name: str, dtype=f32):
                 nxt = [f.to(self.device) for f in lookahead]
                 if all(self._fused_ok(f, ids_format) for f in nxt):
                     with torch.cuda.device(self.device):
-                        if self._side_stream is None:
-                            # high priority: the metering CTAs take SM slots ahead of the sweep's not-yet-dispatched
-                            # CTAs (an earlier-launched grid otherwise keeps every freed slot until its tail)
-                            self._side_stream = torch.cuda.Stream(self.device, priority=-1)
-                        if self._metrics_alt is None:
-                            self._metrics_alt = torch.zeros(9, dtype=torch.float32, device=self.device)
                         side = self._side_stream
                         side.wait_event(ready)                         # needs this batch's metrics ...
                         if self._ev_prev_sweep is not None:

@@ -10,7 +10,8 @@
 //          the records to a local buffer in rank order -- every rank folds them identically afterwards.
 // Mailboxes are double-buffered on the parity of the sequence number: a rank cannot run more than one step ahead
 // of the slowest rank (it needs that rank's record to finish its own step), so a slot is never overwritten while
-// a peer still reads it.  The spin is bounded (~2 s): on expiry the error word is set and the wait returns.
+// a peer still reads it.  The spin is bounded (~2 s): on expiry the error word is set, the late rank's record is
+// delivered as NaN and the wait returns.
 //
 // One process per GPU: the mailbox is cudaMalloc'ed by its owner, exported with cudaIpcGetMemHandle and opened by
 // the peers (cudaIpcOpenMemHandle enables peer access lazily); the handles travel once through torch.distributed.
@@ -63,13 +64,18 @@ __global__ void mailbox_wait_kernel(uint32_t* __restrict__ mine, int kind, int w
     const uint32_t* f = mine + L.flag(kind, par, lane);
     uint32_t v = 0;
     long long spins = 0;
+    bool late = false;
     while (true) {
       asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
       if ((int)(v - seq) >= 0) break;
-      if (++spins > (1LL << 24)) { atomicExch(mine + L.err(), 1u); break; }     // ~2 s at 128 ns per probe
+      // a probe = one system-scope load of local memory (~1 us) + the sleep: 2^21 probes are roughly 2 s
+      if (++spins > (1LL << 21)) { atomicExch(mine + L.err(), 1u); late = true; break; }
       __nanosleep(128);
     }
-    for (int i = 0; i < nf; ++i) gathered[lane * nf + i] = __uint_as_float(mine[L.data(kind, par, lane) + i]);
+    // a peer that never posted must not be folded in as a stale / zero record: NaN poisons this rank's metrics
+    // visibly (and PeerExchange.check() raises) instead of silently shifting the exposure
+    for (int i = 0; i < nf; ++i)
+      gathered[lane * nf + i] = late ? __int_as_float(0x7fc00000) : __uint_as_float(mine[L.data(kind, par, lane) + i]);
   }
 }
 

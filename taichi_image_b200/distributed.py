@@ -175,6 +175,7 @@ class SharedExposure:
             exchange = "peer" if backend is None else "nccl"
         assert exchange in ("peer", "nccl")
         self.peer = None
+        self.check_every = 256                    # process_packed12 calls between two PeerExchange.check() (a stream sync)
         if exchange == "peer":
             try:
                 self.peer = PeerExchange(isp.device, group)
@@ -202,15 +203,11 @@ class SharedExposure:
 
     def process_packed12(self, frames, tonemap: str = "reinhard", ids_format: bool = False, **kw):
         """fused path: the joint statistics come straight from the packed frames of every rank"""
-        isp = self.isp
-        frames = [f.to(isp.device) for f in frames]
-        if all(isp._fused_ok(f, ids_format) for f in frames) and not isp._resizes:
-            # the ISP's look-ahead pipeline drives the joint metering: the exchange of batch k+1 (two tiny
-            # all-gathers) then runs on the side stream under the sweep of batch k
-            meter = lambda fs, alpha, out, cooperative: shared_metering(self.backend, fs, self.group, alpha, out, self.peer)
-            return isp.process_packed12(frames, tonemap=tonemap, ids_format=ids_format, meter_fn=meter, **kw)
-        images = [isp.load_packed12(f, ids_format) for f in frames]
-        kw.pop("out", None); kw.pop("rows_per_task", None); kw.pop("profile_events", None)
-        if tonemap == "linear":
-            return self.tonemap_linear(images, kw.pop("gamma", 1.0), **kw)
-        return self.tonemap_reinhard(images, **kw)
+        # the ISP's look-ahead pipeline drives the joint metering: the exchange of batch k+1 then runs on the side stream
+        # under the sweep of batch k.  Frames the fused sweep cannot take (resize, ragged width) go through the ISP's
+        # staged kernels, which call the same ``meter_fn`` on the demosaiced (resized) images.
+        meter = lambda fs, alpha, out, cooperative: shared_metering(self.backend, fs, self.group, alpha, out, self.peer)
+        self._steps = getattr(self, "_steps", 0) + 1
+        if self.peer is not None and self._steps % self.check_every == 0:
+            self.peer.check()                     # a bounded mailbox wait expired on this rank: raise instead of drifting
+        return self.isp.process_packed12(frames, tonemap=tonemap, ids_format=ids_format, meter_fn=meter, **kw)

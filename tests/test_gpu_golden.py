@@ -76,7 +76,7 @@ def test_tonemap_golden(cuda):
                 if out == "f32":
                     assert_close_float(got, ref, rtol=1e-3, atol=1e-5)
                 else:
-                    assert np.abs(got.astype(np.int64) - ref.astype(np.int64)).max() <= (1 if out == "u8" else 4), (src, out, key)
+                    assert np.abs(got.astype(np.int64) - ref.astype(np.int64)).max() <= 1, (src, out, key)     # u8 and u16 (measured: r02_error_histogram)
 
 
 def test_interpolate_golden(cuda):
