@@ -177,6 +177,9 @@ typedef struct {
   int demosaic;                 /* b200isp_demosaic_t: 0 = Malvar-He-Cutler (bayer.py:30-55), 1 = bilinear (extension) */
   int out_yuv420;               /* 1: every output is a planar YUV 4:2:0 image, (3H/2, W) u8 (color/yuv_420.py:95-118), instead
                                    of RGB -- Camera16 + Reinhard + u8 with reinhard_scratch only; other combinations fail */
+  int reinhard_group;           /* Camera32 Reinhard (max sweep + write sweep per group of frames): frames per group;
+                                   0 = default (all frames of the call in one pair of launches) */
+  int reserved0;                /* keeps the pointers below 8-byte aligned; must be 0 */
   void* profile_start;          /* optional cudaEvent_t pair recorded on `stream` immediately before / after */
   void* profile_stop;           /*   the dominant streaming kernel (bench.py's live roofline timing); NULL = off */
   void* meter_cache;            /* optional device scratch: >= n_frames*ceil(H/stride)*ceil(W/stride)*12 bytes; the second */

@@ -431,6 +431,7 @@ def camera_isp(name: str, dtype=f32):
             p.update_metering, p.rows_per_task = int(update_metering), int(rows_per_task)
             p.demosaic = 1 if self.demosaic == "bilinear" else 0
             p.out_yuv420 = int(bool(yuv420))
+            p.reinhard_group = int(os.environ.get("B200ISP_REINHARD_GROUP", "0"))      # tuning knob (0 = library default)
             if update_metering:                  # scratch for the phase-1 samples (re-read by phase 2)
                 stride = max(int(self.metering_stride), 1)
                 need = len(frames) * (-(-h // stride)) * (-(-w // stride)) * 12
@@ -441,7 +442,7 @@ def camera_isp(name: str, dtype=f32):
                     cache = self._meter_cache = torch.empty(need, dtype=torch.uint8, device=self.device)
                 p.meter_cache, p.meter_cache_bytes = cache.data_ptr(), cache.numel()
                 self._meter_n = need // 12
-            if tonemap == "reinhard" and isp_dtype == f16:
+            if tonemap == "reinhard" and isp_dtype == f16 and os.environ.get("B200ISP_CAM16_RECOMPUTE", "0") != "1":
                 # Camera16: scratch for the f16 Reinhard map (one sweep + a light normalise pass, csrc/fused_isp.cuh)
                 need = len(frames) * h * w * 6
                 sc = getattr(self, "_reinhard_scratch", None)

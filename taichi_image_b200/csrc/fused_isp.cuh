@@ -278,7 +278,7 @@ __device__ __forceinline__ void linear_px(const LinearConsts& c, const float (&r
   }
 }
 
-struct ReinhardConsts { ReinhardParams p; float b; float out_scale_inv_max; float inv_gamma; int has_gamma; int ca0;
+struct ReinhardConsts { ReinhardParams p; float b; float out_scale_inv_max; float max_out; float inv_gamma; int has_gamma; int ca0;
                         float kla, kml; /* ki * la, ki * mean * (1 - la): ki * adapt_mean = gray * kla + kml (color_adapt == 0) */ };
 
 template <bool CAM16, bool CA0>
@@ -318,7 +318,11 @@ __device__ __forceinline__ ReinhardConsts reinhard_consts(const IspConsts& k, in
   c.inv_gamma = (float)(1.0 / (double)k.gamma);
   c.has_gamma = k.gamma != 1.0f;
   c.out_scale_inv_max = 0.f;
-  if (with_max) c.out_scale_inv_max = __fdiv_rn(1.0f, fmaxf(1e-6f, __ldcg(&k.ws->frame_max[k.frame0 + frame])));
+  c.max_out = 1.0f;
+  if (with_max) {
+    c.max_out = fmaxf(1e-6f, __ldcg(&k.ws->frame_max[k.frame0 + frame]));      // camera_isp.py:190, :213
+    c.out_scale_inv_max = __fdiv_rn(1.0f, c.max_out);
+  }
   return c;
 }
 
@@ -483,22 +487,69 @@ __device__ __forceinline__ void raw2_to_rgb2(const IspConsts& k, const f2 (&x)[3
   }
 }
 
-// camera_isp.py:200-210 for a pixel pair, color_adapt == 0 (one adaptation level per pixel): p = s / (adapt + s)
-template <bool CAM16>
-__device__ __forceinline__ void reinhard_p2(const ReinhardConsts& c, const f2 (&rgb)[3], f2 (&p)[3]) {
-  f2 s[3];
+// camera_isp.py:200-210 for a pixel pair, color_adapt == 0 (one adaptation level per pixel): p = s / (adapt + s).
+// MUFU diet (profiles/r01_reinhard_sweep_ncu.txt: the sweep was MUFU-bound at 11 MUFU per pixel):
+//  * s = (x - min) * (1 / range) with the subtraction rounded on its own (exact near x == min, where a folded
+//    FMA loses all relative accuracy and gamma > 1 amplifies it: r02_error_histogram, 16 LSB of u16 before);
+//  * ONE reciprocal per pixel instead of three: with d_c = adapt + s_c,  p_c = s_c * (d_x * d_y) / (d_r * d_g * d_b),
+//    five packed multiplies more, two MUFU less; `post` scales the denominator (the write sweep passes max_out, so
+//    the normalisation p / max_out costs no instruction of its own).
+__device__ __forceinline__ void reinhard_s2(const ReinhardConsts& c, const f2 (&rgb)[3], f2 (&s)[3]) {
 #pragma unroll
-  for (int ch = 0; ch < 3; ++ch) s[ch] = fma2(rgb[ch], bc(c.p.inv_range), bc(c.b));
+  for (int ch = 0; ch < 3; ++ch) s[ch] = mul2(add2(rgb[ch], bc(-c.p.bmin)), bc(c.p.inv_range));
+}
+
+__device__ __forceinline__ f2 reinhard_adapt2(const ReinhardConsts& c, const f2 (&s)[3]) {
   const f2 gray = fma2(s[2], bc(0.114f), fma2(s[1], bc(0.587f), mul2(s[0], bc(0.299f))));
   float tl, th;
   upk(fma2(gray, bc(c.kla), bc(c.kml)), tl, th);                  // ki * lerp(la, mean, gray)
-  const f2 adapt = pk(fast_pow(tl, c.p.map_key), fast_pow(th, c.p.map_key));
+  return pk(fast_pow(tl, c.p.map_key), fast_pow(th, c.p.map_key));
+}
+
+// numerators n_c and the shared reciprocal r:  p_c / post = n_c * r
+__device__ __forceinline__ void reinhard_nr2(const ReinhardConsts& c, const f2 (&rgb)[3], f2 post, f2 (&n)[3], f2& r) {
+  f2 s[3];
+  reinhard_s2(c, rgb, s);
+  const f2 adapt = reinhard_adapt2(c, s);
+  const f2 dr = add2(adapt, s[0]), dg = add2(adapt, s[1]), db = add2(adapt, s[2]);
+  const f2 gb = mul2(dg, db);
+  n[0] = mul2(s[0], gb);
+  n[1] = mul2(s[1], mul2(dr, db));
+  n[2] = mul2(s[2], mul2(dr, dg));
+  float pl, ph;
+  upk(mul2(mul2(dr, post), gb), pl, ph);
+  r = pk(fast_rcp(pl), fast_rcp(ph));
+}
+
+template <bool CAM16>
+__device__ __forceinline__ void reinhard_p2(const ReinhardConsts& c, const f2 (&rgb)[3], f2 (&p)[3]) {
+  f2 n[3], r;
+  reinhard_nr2(c, rgb, bc(1.0f), n, r);
 #pragma unroll
-  for (int ch = 0; ch < 3; ++ch) {
-    float dl, dh;
-    upk(add2(adapt, s[ch]), dl, dh);
-    p[ch] = mul2(s[ch], pk(fast_rcp(dl), fast_rcp(dh)));
-  }
+  for (int ch = 0; ch < 3; ++ch) p[ch] = mul2(n[ch], r);
+}
+
+// max over the three channels of p for a pixel pair: p = s / (adapt + s) is increasing in s_c as long as every
+// denominator is positive, so the largest channel carries it -- one reciprocal and no per-channel quotient (the max
+// sweep only needs the frame maximum).  A channel far BELOW the metered minimum (s_c < -adapt; possible because the
+// bounds come from the strided samples only) makes its denominator negative and its quotient large and positive --
+// the reference takes that value into max_out too (camera_isp.py:213).  dmin tracks the smallest denominator; the
+// caller re-evaluates the row exactly when it ever is negative (cold path).
+__device__ __forceinline__ f2 reinhard_pmax2(const ReinhardConsts& c, const f2 (&rgb)[3], float& dmin) {
+  f2 s[3];
+#pragma unroll
+  for (int ch = 0; ch < 3; ++ch) s[ch] = fma2(rgb[ch], bc(c.p.inv_range), bc(c.b));
+  const f2 adapt = reinhard_adapt2(c, s);
+  float l[3], h[3];
+#pragma unroll
+  for (int ch = 0; ch < 3; ++ch) upk(s[ch], l[ch], h[ch]);
+  const f2 sm = pk(fmaxf(l[0], fmaxf(l[1], l[2])), fmaxf(h[0], fmaxf(h[1], h[2])));
+  const f2 sn = pk(fminf(l[0], fminf(l[1], l[2])), fminf(h[0], fminf(h[1], h[2])));
+  float dl, dh, el, eh;
+  upk(add2(adapt, sm), dl, dh);
+  upk(add2(adapt, sn), el, eh);
+  dmin = fminf(dmin, fminf(el, eh));
+  return mul2(sm, pk(fast_rcp(dl), fast_rcp(dh)));
 }
 
 template <bool CAM16, typename OutT>
@@ -680,23 +731,45 @@ struct EpiReinhardMax2 {      // pass 1: frame-global max of the mapped values (
       pairs_to_raw2<CAM16, BROW, GFIRST>(R, G, B, X);
       if (KIND == K_EDGE && st.edge) patch_cols_pairs<BROW, GFIRST>(X, st.edge, k.kbase);
       float mx = st.mx;
-      uint32_t v[24];
+      if constexpr (STORE) {
+        uint32_t v[24];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        f2 rgb[3], p[3];
-        raw2_to_rgb2<CAM16>(k, X[j], rgb);
-        reinhard_p2<CAM16>(st.c, rgb, p);
+        for (int j = 0; j < 4; ++j) {
+          f2 rgb[3], p[3];
+          raw2_to_rgb2<CAM16>(k, X[j], rgb);
+          reinhard_p2<CAM16>(st.c, rgb, p);
 #pragma unroll
-        for (int ch = 0; ch < 3; ++ch) {
+          for (int ch = 0; ch < 3; ++ch) {
+            float lo, hi;
+            upk(p[ch], lo, hi);
+            mx = fmaxf(mx, fmaxf(lo, hi));
+            v[3 * j + ch] = __float_as_uint(lo);
+            v[3 * (j + 4) + ch] = __float_as_uint(hi);
+          }
+        }
+        store_row8<__half>(st.wc, st.out, k.W, row, v);
+      } else {
+        float dmin = 0.f;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          f2 rgb[3];
+          raw2_to_rgb2<CAM16>(k, X[j], rgb);
           float lo, hi;
-          upk(p[ch], lo, hi);
+          upk(reinhard_pmax2(st.c, rgb, dmin), lo, hi);
           mx = fmaxf(mx, fmaxf(lo, hi));
-          v[3 * j + ch] = __float_as_uint(lo);
-          v[3 * (j + 4) + ch] = __float_as_uint(hi);
+        }
+        if (dmin < 0.f) {                      // some channel's denominator is negative: all three quotients, exactly
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            f2 rgb[3], p[3];
+            raw2_to_rgb2<CAM16>(k, X[j], rgb);
+            reinhard_p2<CAM16>(st.c, rgb, p);
+#pragma unroll
+            for (int ch = 0; ch < 3; ++ch) mx = fmaxf(mx, fmaxf(lo_of(p[ch]), hi_of(p[ch])));
+          }
         }
       }
       st.mx = mx;
-      if constexpr (STORE) store_row8<__half>(st.wc, st.out, k.W, row, v);
     } else {
       Vals24 x;
       raw_with_frame<CAM16, BROW, GFIRST, KIND>(R, G, B, row, k.H, st.edge, k.kbase, x);
@@ -747,19 +820,24 @@ struct EpiReinhard2 {         // pass 2 recomputed from the packed frame: map, n
     uint32_t v[24];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      f2 rgb[3], p[3];
+      f2 rgb[3], n[3], r;
       raw2_to_rgb2<CAM16>(k, X[j], rgb);
-      reinhard_p2<CAM16>(st.c, rgb, p);
+      // Camera32: q = p / max_out straight from the shared reciprocal; Camera16: p is rounded through f16 first
+      reinhard_nr2(st.c, rgb, bc(CAM16 ? 1.0f : st.c.max_out), n, r);
+      float rl, rh;
+      upk(r, rl, rh);
 #pragma unroll
       for (int ch = 0; ch < 3; ++ch) {                 // camera_isp.py:211-218
         float lo, hi;
-        upk(p[ch], lo, hi);
+        upk(n[ch], lo, hi);
         if constexpr (CAM16) {
-          const __half2 h = __floats2half2_rn(lo, hi);
-          lo = __low2float(h); hi = __high2float(h);
+          const __half2 h = __floats2half2_rn(lo * rl, hi * rh);
+          lo = __saturatef(__low2float(h) * st.c.out_scale_inv_max);
+          hi = __saturatef(__high2float(h) * st.c.out_scale_inv_max);
+        } else {
+          lo = __saturatef(lo * rl);                   // the reference does not clamp; NaN / negative -> 0
+          hi = __saturatef(hi * rh);
         }
-        lo = __saturatef(lo * st.c.out_scale_inv_max);
-        hi = __saturatef(hi * st.c.out_scale_inv_max);
         if constexpr (GAMMA) { lo = fast_pow(lo, st.c.inv_gamma); hi = fast_pow(hi, st.c.inv_gamma); }
         if constexpr (DT<OutT>::is_int) {
           float ql, qh;
@@ -1206,9 +1284,10 @@ int run_fused(const FramePtrs& fp, int n_frames, const b200isp_fused_params& p, 
         return cuda_status(cudaPeekAtLastError(), "reinhard_scratch_out_kernel");
       }
     }
-    const long long frame_bytes = (long long)k.H * k.W * 3 / 2;
-    int group = (int)((48LL << 20) / (frame_bytes > 0 ? frame_bytes : 1));
-    if (group < 1) group = 1;
+    // Camera32 (or no scratch): max sweep, then the write sweep recomputes the map.  Both sweeps are bound by
+    // instruction issue, not by DRAM, so the second read of the packed frames (1.5 B/px) is cheaper than cutting the
+    // call into L2-sized groups whose short launches end in idle tails (measured, profiles/r02_reinhard_diet.txt).
+    int group = p.reinhard_group > 0 ? p.reinhard_group : n_frames;
     for (int f = 0; f < n_frames; f += group) {
       const int n = (n_frames - f < group) ? n_frames - f : group;
       st = run_rmax<CAM16>(fp, k, f, n, rpt, s);

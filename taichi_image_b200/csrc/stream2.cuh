@@ -152,8 +152,23 @@ struct Stream2Geom {
   long long total_tasks;    // + nframes * 2 * warps_per_row
 };
 
+// rows_per_task <= 0: 24 rows per task (4 halo rows = 17 % extra loads, all L2 hits), shrunk for small jobs until
+// the tasks fill one wave of 148 SMs x 16 resident warps.  Measured (scripts/rpt_sweep.py, profiles/r02_rpt_sweep.txt):
+// the sweep time is flat within 3 % between 16 and 32 rows for 1 x 4096x3000, 6 x 4096x3000 and 6 x 5472x3648; chunks
+// of 48+ rows lose 10-50 % (the tail of the last wave is one whole task long), a wave-count model predicts nothing
+// finer than that.
+inline int auto_rows_per_task2(int H, int W, int nframes) {
+  const int interior = H - 4;
+  if (interior <= 0) return 2;
+  const long long wpr = ((W + 7) / 8 + 31) / 32;
+  int rpt = 24;
+  while (rpt > 8 && (long long)nframes * wpr * ((interior + rpt - 1) / rpt + 2) < (long long)(0.9 * 16 * kNumSMs)) rpt -= 2;
+  return rpt;
+}
+
 inline Stream2Geom make_geom2(int H, int W, int nframes, int rows_per_task) {
   Stream2Geom s;
+  if (rows_per_task <= 0) rows_per_task = auto_rows_per_task2(H, W, nframes);
   s.g = make_geom(H - 4 > 0 ? H - 4 : 0, W, nframes, rows_per_task);      // chunking of the interior rows
   s.g.H = H;
   s.interior_tasks = (H > 4) ? s.g.total_tasks : 0;

@@ -126,3 +126,31 @@ def test_camera_isp_golden(cuda, cam, cfg, fused):
                     defined_mask(g[f"{cam}_{cfg}_rgb_s{s}_c{c}"], g[key + "_metrics"], tm)
                 d = np.abs(to_np(o).astype(np.int64) - ref.astype(np.int64))[mask]
                 assert d.max() <= 1, (key, c, int(d.max()), int(np.count_nonzero(d)))
+
+
+@pytest.mark.parametrize("cam", ["f16", "f32"])
+@pytest.mark.parametrize("rpt", [0, 6])
+def test_camera_isp_wide_golden(cuda, cam, rpt):
+    """The fused sweep against the reference SOURCE at a width that reaches its interior-strip kind (K_CORE), the
+    partial last strip and (rows_per_task = 6) several row chunks per strip: 20 x 776, two time steps x two cameras."""
+    from taichi_image_b200 import camera_isp, bayer
+    from tests.test_oracle_golden import WIDE_TMS
+    g = load("camera_isp_wide")
+    cls = camera_isp.Camera16 if cam == "f16" else camera_isp.Camera32
+    for tm_name, tm in WIDE_TMS.items():
+        isp = cls(bayer.BayerPattern.RGGB)
+        for s in range(2):
+            frames = [to_cuda(g[f"frame_s{s}_c{c}"]) for c in range(2)]
+            if tm_name == "script":
+                for c, f in enumerate(frames):
+                    assert_close_float(to_np(isp.load_packed12(f)), g[f"{cam}_rgb_s{s}_c{c}"], rtol=1e-3,
+                                       atol=1e-3 if cam == "f16" else 2e-6)
+            linear = tm_name.startswith("linear")
+            outs = isp.process_packed12(frames, tonemap="linear" if linear else "reinhard", rows_per_task=rpt, **tm)
+            key = f"{cam}_{tm_name}_s{s}"
+            assert_close_float(to_np(isp.metrics), g[key + "_metrics"], rtol=2e-5, atol=2e-6, what=key)
+            for c, o in enumerate(outs):
+                ref = g[key + f"_c{c}"]
+                mask = np.ones(ref.shape[:2], bool) if linear else defined_mask(g[f"{cam}_rgb_s{s}_c{c}"], g[key + "_metrics"], tm)
+                d = np.abs(to_np(o).astype(np.int64) - ref.astype(np.int64))[mask]
+                assert d.max() <= 1, (key, c, int(d.max()), int(np.count_nonzero(d)))

@@ -141,3 +141,29 @@ def test_color_yuv420_golden():
         assert np.array_equal(got[defined], ref[defined]), name
     assert same(O.rgb_yuv420(g["rgb_u8"], "f32"), g["yuv_u8_to_f32"])
     assert same(O.rgb_yuv420(g["rgb_f32"], "u8"), g["yuv_f32_to_u8"])
+
+
+WIDE_TMS = {"script": dict(gamma=0.9, intensity=3.0, light_adapt=0.9, color_adapt=0.0), "linear1": dict(gamma=1.0)}
+
+
+@pytest.mark.parametrize("cam", ["f16", "f32"])
+def test_camera_isp_wide_golden(cam):
+    """the 20 x 776 golden case (oracle/gen_golden.py gen_camera_isp_wide): wide enough for interior strips of the
+    CUDA sweep -- here it pins the oracle at that size"""
+    g = load("camera_isp_wide")
+    for tm_name, tm in WIDE_TMS.items():
+        isp = O.ISP(cam)
+        for s in range(2):
+            frames = [g[f"frame_s{s}_c{c}"] for c in range(2)]
+            images = [isp.load_packed12(f) for f in frames]
+            for c, im in enumerate(images):
+                assert same(im, g[f"{cam}_rgb_s{s}_c{c}"]), (cam, s, c)
+            linear = tm_name.startswith("linear")
+            outs = isp.tonemap_linear(images, **tm) if linear else isp.tonemap_reinhard(images, **tm)
+            key = f"{cam}_{tm_name}_s{s}"
+            assert np.allclose(isp.metrics, g[key + "_metrics"], rtol=2e-6, atol=2e-6), key
+            for c, o in enumerate(outs):
+                ref = g[key + f"_c{c}"]
+                mask = np.ones(o.shape[:2], bool) if linear else defined_mask(g[f"{cam}_rgb_s{s}_c{c}"], isp.metrics, tm)
+                d = np.abs(o.astype(np.int64) - ref.astype(np.int64))[mask]
+                assert d.max() <= 1 and np.count_nonzero(d) <= 0.01 * d.size, (key, c, d.max())
