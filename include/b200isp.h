@@ -179,7 +179,10 @@ typedef struct {
                                    of RGB -- Camera16 + Reinhard + u8 with reinhard_scratch only; other combinations fail */
   int reinhard_group;           /* Camera32 Reinhard (max sweep + write sweep per group of frames): frames per group;
                                    0 = default (all frames of the call in one pair of launches) */
-  int reserved0;                /* keeps the pointers below 8-byte aligned; must be 0 */
+  int out_height, out_width;    /* > 0: bilinear resize of the demosaiced image BEFORE metering / tone map (camera_isp.py:302-315,
+                                   :371-373; interpolate.py:59-66) fused into the pass: outputs are (out_height, out_width, 3) */
+  float scale_r, scale_c;       /* source position of output (ro, co) = (ro / scale_r, co / scale_c) in f32, interpolate.py:60 */
+  int resize_gather;            /* 1: force the per-output-pixel gather instead of the resizing sweep (testing / profiling) */
   void* profile_start;          /* optional cudaEvent_t pair recorded on `stream` immediately before / after */
   void* profile_stop;           /*   the dominant streaming kernel (bench.py's live roofline timing); NULL = off */
   void* meter_cache;            /* optional device scratch: >= n_frames*ceil(H/stride)*ceil(W/stride)*12 bytes; the second */

@@ -7,6 +7,7 @@
  * (paths relative to /root/reference/taichi_image):
  *   decode12 scaled          packed.py:23-31, :98-100, :108-117
  *   Malvar demosaic + CCM    bayer.py:30-55 (tables), :137-155 (filter_at), :158-175
+ *   bilinear resize          interpolate.py:19-34, :59-66 via camera_isp.py:302-315 (before metering / tone map)
  *   metering + moving avg    camera_isp.py:102-175
  *   Reinhard                 camera_isp.py:177-218
  *   linear                   tonemap.py:11-17 via camera_isp.py:220-227
@@ -73,6 +74,29 @@ static void demosaic_frame(const float* cfa, float* rgb, int H, int W, int patte
       o[0] = round_isp(clamp01(x), cam16);
       o[1] = round_isp(clamp01(y), cam16);
       o[2] = round_isp(clamp01(z), cam16);
+    }
+  }
+}
+
+/* interpolate.py:59-66: p = I / scale, p1 = trunc(p), clamp-to-edge taps, mix along dim 0 first, cast to the ISP dtype */
+static inline float mixf(float a, float b, float t) { return a * (1.0f - t) + b * t; }
+static void resize_frame(const float* src, float* dst, int H, int W, int Ho, int Wo, float scale_r, float scale_c, int cam16) {
+#pragma omp parallel for schedule(static)
+  for (int r = 0; r < Ho; ++r) {
+    const float pr = (float)r / scale_r;
+    const int r1 = (int)pr;
+    const float fr = pr - (float)r1;
+    const int ra = r1 < 0 ? 0 : (r1 > H - 1 ? H - 1 : r1), rb = r1 + 1 < 0 ? 0 : (r1 + 1 > H - 1 ? H - 1 : r1 + 1);
+    for (int c = 0; c < Wo; ++c) {
+      const float pc = (float)c / scale_c;
+      const int c1 = (int)pc;
+      const float fc = pc - (float)c1;
+      const int ca = c1 < 0 ? 0 : (c1 > W - 1 ? W - 1 : c1), cb = c1 + 1 < 0 ? 0 : (c1 + 1 > W - 1 ? W - 1 : c1 + 1);
+      for (int k = 0; k < 3; ++k) {
+        const float y1 = mixf(src[((long)ra * W + ca) * 3 + k], src[((long)rb * W + ca) * 3 + k], fr);
+        const float y2 = mixf(src[((long)ra * W + cb) * 3 + k], src[((long)rb * W + cb) * 3 + k], fr);
+        dst[((long)r * Wo + c) * 3 + k] = round_isp(mixf(y1, y2, fc), cam16);
+      }
     }
   }
 }
@@ -160,9 +184,10 @@ static void tonemap_reinhard(float* rgb, void* out, long npx, const float* m, fl
 }
 
 /* returns 0 on success.  metrics: 9 floats in/out; alpha = weight of the previous metrics. */
-int isp_oracle_process(const uint8_t* const* packed, void* const* out, int n_frames, int H, int W, int pattern,
-                       int cam16, int out_u16, int reinhard, const float* ccm, float gamma, float intensity,
-                       float la, float ca, int stride, float alpha, float* metrics, int nthreads) {
+static int process_impl(const uint8_t* const* packed, void* const* out, int n_frames, int H, int W, int pattern,
+                        int cam16, int out_u16, int reinhard, const float* ccm, float gamma, float intensity,
+                        float la, float ca, int stride, float alpha, float* metrics, int nthreads,
+                        int Ho, int Wo, float scale_r, float scale_c) {
 #ifdef _OPENMP
   if (nthreads > 0) omp_set_num_threads(nthreads);
 #endif
@@ -174,7 +199,15 @@ int isp_oracle_process(const uint8_t* const* packed, void* const* out, int n_fra
     if (!rgb[f]) return -1;
     decode_frame(packed[f], cfa, H, W, cam16);
     demosaic_frame(cfa, rgb[f], H, W, pattern, ccm, cam16);
+    if (Ho > 0 && Wo > 0) {                 /* camera_isp.py:371-373: resize BEFORE metering / tone map */
+      float* small = (float*)malloc(sizeof(float) * (size_t)Ho * Wo * 3);
+      if (!small) return -1;
+      resize_frame(rgb[f], small, H, W, Ho, Wo, scale_r, scale_c, cam16);
+      free(rgb[f]);
+      rgb[f] = small;
+    }
   }
+  if (Ho > 0 && Wo > 0) { H = Ho; W = Wo; }
   metering(rgb, n_frames, H, W, stride, alpha, metrics);
   for (int f = 0; f < n_frames; ++f) {
     if (reinhard) tonemap_reinhard(rgb[f], out[f], (long)H * W, metrics, gamma, intensity, la, ca, cam16, out_u16);
@@ -184,6 +217,22 @@ int isp_oracle_process(const uint8_t* const* packed, void* const* out, int n_fra
   free(rgb);
   free(cfa);
   return 0;
+}
+
+int isp_oracle_process(const uint8_t* const* packed, void* const* out, int n_frames, int H, int W, int pattern,
+                       int cam16, int out_u16, int reinhard, const float* ccm, float gamma, float intensity,
+                       float la, float ca, int stride, float alpha, float* metrics, int nthreads) {
+  return process_impl(packed, out, n_frames, H, W, pattern, cam16, out_u16, reinhard, ccm, gamma, intensity, la, ca, stride, alpha,
+                      metrics, nthreads, 0, 0, 1.f, 1.f);
+}
+
+/* the same with the ISP's bilinear resize to (Ho, Wo); out buffers are (Ho, Wo, 3) */
+int isp_oracle_process_resized(const uint8_t* const* packed, void* const* out, int n_frames, int H, int W, int pattern,
+                               int cam16, int out_u16, int reinhard, const float* ccm, float gamma, float intensity,
+                               float la, float ca, int stride, float alpha, float* metrics, int nthreads,
+                               int Ho, int Wo, float scale_r, float scale_c) {
+  return process_impl(packed, out, n_frames, H, W, pattern, cam16, out_u16, reinhard, ccm, gamma, intensity, la, ca, stride, alpha,
+                      metrics, nthreads, Ho, Wo, scale_r, scale_c);
 }
 
 int isp_oracle_max_threads(void) {

@@ -98,11 +98,16 @@ def camera_isp(name: str, dtype=f32):
                      transform: interpolate.ImageTransform = interpolate.ImageTransform.none,
                      device: torch.device = torch.device('cuda', 0),
                      metering_stride: int = 8,
-                     demosaic: str = "malvar"):
+                     demosaic: str = "malvar",
+                     resize_size: Optional[tuple] = None):
             """camera_isp.py:237-268.  ``demosaic="bilinear"`` (EXTENSION, north_star): 3x3 bilinear interpolation
             instead of Malvar-He-Cutler in every load / fused path of this object (``bayer_to_rgb(method=...)``)."""
             assert scale is None or resize_width == 0, "Cannot specify both scale and resize_width"
+            assert resize_size is None or (scale is None and resize_width == 0), "resize_size excludes scale / resize_width"
             assert demosaic in ("malvar", "bilinear")
+            # EXTENSION (BASELINE configs[4] "resize to 1920x1080"): explicit (width, height) target with per-axis scales
+            # (SURVEY Q9); the reference only knows the aspect-preserving ``scale`` / ``resize_width``
+            self.resize_size = None if resize_size is None else (int(resize_size[0]), int(resize_size[1]))
             self.demosaic = demosaic
             self.bayer_pattern = bayer_pattern
             self.moving_alpha = moving_alpha
@@ -134,9 +139,11 @@ def camera_isp(name: str, dtype=f32):
             if resize_width is not None:
                 self.resize_width = resize_width
                 self.scale = None
+                self.resize_size = None
             if scale is not None:
                 self.scale = scale
                 self.resize_width = 0
+                self.resize_size = None
             if transform is not None:
                 self.transform = transform
             if correct_colors is not None:
@@ -156,19 +163,28 @@ def camera_isp(name: str, dtype=f32):
                 return cc
             return None
 
-        def resize_image(self, image):
-            """camera_isp.py:302-315"""
-            w, h = image.shape[1], image.shape[0]
+        def _resize_plan(self, h, w):
+            """((width, height), (scale_row, scale_col)) of camera_isp.py:302-315 for an (h, w) image, or None"""
             if self.resize_width > 0:
                 scale = self.resize_width / w
-                return interpolate.resize_bilinear(image, (self.resize_width, round(h * scale)), scale)
+                return (self.resize_width, round(h * scale)), (scale, scale)
             if self.scale is not None:
-                return interpolate.resize_bilinear(image, (round(w * self.scale), round(h * self.scale)), self.scale)
-            return image
+                return (round(w * self.scale), round(h * self.scale)), (self.scale, self.scale)
+            if self.resize_size is not None:
+                wo, ho = self.resize_size
+                return (wo, ho), (ho / h, wo / w)
+            return None
+
+        def resize_image(self, image):
+            """camera_isp.py:302-315"""
+            plan = self._resize_plan(image.shape[0], image.shape[1])
+            if plan is None:
+                return image
+            return interpolate.resize_bilinear(image, plan[0], plan[1])
 
         @property
         def _resizes(self) -> bool:
-            return self.resize_width > 0 or self.scale is not None
+            return self.resize_width > 0 or self.scale is not None or self.resize_size is not None
 
         # ------------------------------------------------------------ loaders (eager API)
         def _convert(self, image, mode):
@@ -216,30 +232,11 @@ def camera_isp(name: str, dtype=f32):
             if ids_format and self._fused_ok(image_data, False):
                 image_data, ids_format = self._ids_to_standard([image_data])[0], False
             if self._fused_ok(image_data, ids_format):
-                rgb = self._run_fused([image_data], "none", isp_dtype, None, {})[0]
-                return self.resize_image(rgb)
+                return self._run_fused([image_data], "none", isp_dtype, None, {})[0]      # resize included (resize_isp.cuh)
             w, h = (image_data.shape[1] * 2 // 3, image_data.shape[0])
             cfa = torch.empty(h, w, dtype=torch_dtype, device=self.device)
             packed.decode12_kernel(isp_dtype, scaled=True, ids_format=ids_format)(image_data.contiguous().view(-1), cfa.view(-1))
             return self._process_image(cfa)
-
-        def _load_packed12_resized(self, frames, group: int = 0):
-            """``[load_packed12(f) for f in frames]`` for an ISP that resizes: the demosaic sweep runs over ``group``
-            frames per launch (one frame alone cannot fill 148 SMs) into a persistent full-resolution scratch, then the
-            gather resize per frame.  Same kernels, same results.  Measured on cfg5 (8 x 4096x3000 -> width 1920):
-            group 1 / 2 / 4 / 8 = 169 / 169 / 175 / 186 Gpixel/s."""
-            group = group or int(os.environ.get("B200ISP_RESIZE_GROUP", "8"))
-            h, w = frames[0].shape[0], frames[0].shape[1] * 2 // 3
-            need = min(group, len(frames))
-            scratch = getattr(self, "_fullres_scratch", None)
-            if scratch is None or len(scratch) < need or tuple(scratch[0].shape) != (h, w, 3) or scratch[0].device != torch.device(self.device):
-                scratch = self._fullres_scratch = [torch.empty((h, w, 3), dtype=torch_dtype, device=self.device) for _ in range(need)]
-            images = []
-            for i in range(0, len(frames), group):
-                chunk = frames[i:i + group]
-                full = self._run_fused(chunk, "none", isp_dtype, scratch[:len(chunk)], {})
-                images += [self.resize_image(rgb) for rgb in full]
-            return images
 
         def load_packed16(self, image_data):
             """camera_isp.py:342-347"""
@@ -432,9 +429,15 @@ def camera_isp(name: str, dtype=f32):
             p.demosaic = 1 if self.demosaic == "bilinear" else 0
             p.out_yuv420 = int(bool(yuv420))
             p.reinhard_group = int(os.environ.get("B200ISP_REINHARD_GROUP", "0"))      # tuning knob (0 = library default)
+            plan = self._resize_plan(h, w)
+            ho, wo = h, w
+            if plan is not None:                 # resize fused into the pass (demosaic + bilinear gather)
+                (wo, ho), (sr, sc) = plan
+                p.out_height, p.out_width, p.scale_r, p.scale_c = int(ho), int(wo), float(sr), float(sc)
+                p.resize_gather = int(os.environ.get("B200ISP_RESIZE_GATHER", "0"))        # testing / profiling knob
             if update_metering:                  # scratch for the phase-1 samples (re-read by phase 2)
                 stride = max(int(self.metering_stride), 1)
-                need = len(frames) * (-(-h // stride)) * (-(-w // stride)) * 12
+                need = len(frames) * (-(-ho // stride)) * (-(-wo // stride)) * 12
                 cache = getattr(self, "_meter_cache", None)
                 if cache is None or cache.numel() < need or cache.device != torch.device(self.device):
                     if cache is not None:
@@ -442,9 +445,10 @@ def camera_isp(name: str, dtype=f32):
                     cache = self._meter_cache = torch.empty(need, dtype=torch.uint8, device=self.device)
                 p.meter_cache, p.meter_cache_bytes = cache.data_ptr(), cache.numel()
                 self._meter_n = need // 12
-            if tonemap == "reinhard" and isp_dtype == f16 and os.environ.get("B200ISP_CAM16_RECOMPUTE", "0") != "1":
-                # Camera16: scratch for the f16 Reinhard map (one sweep + a light normalise pass, csrc/fused_isp.cuh)
-                need = len(frames) * h * w * 6
+            if tonemap == "reinhard" and (plan is not None or (isp_dtype == f16 and os.environ.get("B200ISP_CAM16_RECOMPUTE", "0") != "1")):
+                # scratch for the un-normalised Reinhard map in the ISP dtype: Camera16 (one sweep + a light normalise
+                # pass, csrc/fused_isp.cuh) and every resizing ISP (output resolution, csrc/fused_resize.cu)
+                need = len(frames) * ho * wo * 3 * isp_dtype.itemsize
                 sc = getattr(self, "_reinhard_scratch", None)
                 if sc is None or sc.numel() < need or sc.device != torch.device(self.device):
                     sc = self._reinhard_scratch = torch.empty(need, dtype=torch.uint8, device=self.device)
@@ -458,6 +462,9 @@ def camera_isp(name: str, dtype=f32):
             h, w3 = frames[0].shape
             w = w3 * 2 // 3
             p = self._fused_params(frames, tonemap, out_dtype, tm, update_metering, alpha, rows_per_task, profile_events, yuv420)
+            plan = self._resize_plan(h, w)
+            if plan is not None:
+                w, h = plan[0]
             oshape = (h * 3 // 2, w) if yuv420 else (h, w, 3)       # planar YUV 4:2:0: color/yuv_420.py:95-118
             if out is None:
                 out = [torch.empty(oshape, dtype=out_dtype.torch, device=self.device) for _ in frames]
@@ -481,7 +488,8 @@ def camera_isp(name: str, dtype=f32):
             ``tonemap_reinhard`` / ``tonemap_linear`` (camera_isp.py:333-340, :376-413): joint metering of
             all frames with the moving-average update of ``self.metrics``, then one sweep per frame.
             Returns the list of tone-mapped (H, W, 3) images (transformed if ``self.transform`` is set).
-            Falls back to the staged CUDA kernels when the frames need resizing, use the IDS layout or
+            A resizing ISP runs the fused demosaic + bilinear-resize gather (csrc/fused_resize.cu: the metering and the tone
+            map then see the resized image, like the reference).  Falls back to the staged CUDA kernels when the frames
             have a width that is not a multiple of 8 -- never to the CPU.
 
             ``lookahead``: the frames of the NEXT call (a camera stream knows them: they are being captured / copied
@@ -507,13 +515,10 @@ def camera_isp(name: str, dtype=f32):
                 # IDS layout: re-pack into the standard layout (scratch reused by every call, hence no look-ahead)
                 frames, ids_format, lookahead = self._ids_to_standard(frames), False, None
                 self._lookahead = None
-            fused = all(self._fused_ok(f, ids_format) for f in frames) and not self._resizes
-            assert fused or not yuv420, "yuv420 output needs frames the fused sweep accepts (no resize, width % 8 == 0)"
+            fused = all(self._fused_ok(f, ids_format) for f in frames)
+            assert (fused and not self._resizes) or not yuv420, "yuv420 output needs frames the fused sweep accepts (no resize, width % 8 == 0)"
             if not fused:
-                if self._resizes and all(self._fused_ok(f, ids_format) for f in frames):
-                    images = self._load_packed12_resized(frames)
-                else:
-                    images = [self.load_packed12(f, ids_format) for f in frames]
+                images = [self.load_packed12(f, ids_format) for f in frames]
                 if meter_fn is not None and update_metering:      # distributed.SharedExposure: joint metering of all ranks
                     meter_fn(images, None, None, True)
                     update_metering = False

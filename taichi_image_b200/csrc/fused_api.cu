@@ -1,5 +1,6 @@
 // C entry point of the fused packed12 sweep + the sparse metering launch (see fused_isp.cuh).
 #include "fused_isp.cuh"
+#include "resize_isp.cuh"
 
 namespace isp {
 extern template int run_fused<true, uint8_t>(const FramePtrs&, int, const b200isp_fused_params&, IspConsts, cudaStream_t);
@@ -47,10 +48,17 @@ static int fused_setup(const char* what, const uint8_t* const* packed_host, void
 template <class F>
 static int with_packed12_sampler(const FramePtrs& fp, const b200isp_fused_params& p, const IspConsts& k, int n_frames, F f) {
   const int stride = p.metering_stride > 0 ? p.metering_stride : 8;
+  const bool cam16 = p.isp_dtype == B200ISP_F16;
+  if (resizes(p)) {                     // the reference meters what _process_image returns: the RESIZED image
+    const int hs = (p.out_height + stride - 1) / stride, wsamp = (p.out_width + stride - 1) / stride;
+    const long long n = (long long)n_frames * hs * wsamp;
+    float* cache = (p.meter_cache && p.meter_cache_bytes >= (size_t)n * 3 * sizeof(float)) ? (float*)p.meter_cache : nullptr;
+    if (cam16) return f(ResizedSampler<true>{make_resize_src<true>(fp, k, p), stride, hs, wsamp}, n, cache);
+    return f(ResizedSampler<false>{make_resize_src<false>(fp, k, p), stride, hs, wsamp}, n, cache);
+  }
   const int hs = (p.height + stride - 1) / stride, wsamp = (p.width + stride - 1) / stride;
   const long long n = (long long)n_frames * hs * wsamp;
   float* cache = (p.meter_cache && p.meter_cache_bytes >= (size_t)n * 3 * sizeof(float)) ? (float*)p.meter_cache : nullptr;
-  const bool cam16 = p.isp_dtype == B200ISP_F16;
   if (stride % 8 == 0) {
     if (cam16) return f(Packed12FastSampler<true>{Packed12Src<true>{fp, p.width * 3 / 2}, k, stride, hs, wsamp, p.width * 3 / 8}, n, cache);
     return f(Packed12FastSampler<false>{Packed12Src<false>{fp, p.width * 3 / 2}, k, stride, hs, wsamp, p.width * 3 / 8}, n, cache);
@@ -135,6 +143,11 @@ extern "C" int b200isp_process_packed12(const uint8_t* const* packed_host, void*
     if (st) return st;
   }
 
+  if (resizes(p)) {
+    ISP_REQUIRE(p.scale_r > 0.f && p.scale_c > 0.f, B200ISP_E_ARG, "process_packed12: resize scales must be positive");
+    ISP_REQUIRE(!p.out_yuv420, B200ISP_E_ARG, "process_packed12: YUV 4:2:0 output is not available with resize");
+    return run_resize(fp, n_frames, p, k, s);
+  }
 #define RUN(CAM, T) return run_fused<CAM, T>(fp, n_frames, p, k, s)
   if (cam16) {
     switch (p.out_dtype) {

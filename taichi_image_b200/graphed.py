@@ -39,8 +39,8 @@ class GraphedStream:
         self.double_buffered = next_frames is not None
         self.F = [list(frames), list(next_frames) if next_frames is not None else list(frames)]
         self.O = [list(outs), list(next_outs) if next_outs is not None else list(outs)]
-        assert all(base._fused_ok(f, False) for f in self.F[0] + self.F[1]) and not base._resizes, \
-            "GraphedStream needs frames the fused sweep accepts (standard layout, width % 8 == 0, no resize)"
+        assert all(base._fused_ok(f, False) for f in self.F[0] + self.F[1]), \
+            "GraphedStream needs frames the fused sweep accepts (standard layout, width % 8 == 0)"
         self.tonemap, self.out_dtype, self.tm = tonemap, as_dtype(dtype), dict(tonemap_args)
         self.rows_per_task = rows_per_task
         dev = base.device
