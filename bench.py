@@ -1,20 +1,23 @@
 #!/usr/bin/env python
-"""Benchmark of the camera-ISP hot path (BASELINE.json metric: Gpixel/s packed12 -> RGB ISP, achieved HBM
-GB/s vs peak).
+"""Benchmark of the camera-ISP hot path (BASELINE.json metric: Gpixel/s packed12 -> RGB8/RGB16 ISP at 1/2/4/8 B200,
+achieved HBM GB/s vs peak).
 
-    python bench.py --gpus N --steps K --warmup W [--impl reference] [--workload cfg2|cfg1|cfg1_16]
+    python bench.py --gpus N --steps K --warmup W [--impl reference] [--workload cfg2|cfg1|cfg1_16|cfg3|cfg5]
+                    [--cameras C]
 
-A step = one pass of the hot path over one batch of synthetic packed12 frames already resident in HBM:
-joint metering of the batch (moving-average update of the 9-float metrics) + the fused
-packed12 -> demosaic -> tone map -> quantise sweep (``Camera32/16.process_packed12``).
-Default workload (N = 1) = BASELINE.json configs[1]: 6 x 5472x3648 packed12 frames -> linear tone map
--> RGB16.  With N > 1 (torchrun, one rank per GPU) every rank runs the same per-GPU batch on its own
-camera streams (weak scaling, no pixel traffic between GPUs) and, with --shared-exposure (default for
-N > 1), the ranks all-reduce the metering statistics over NCCL so that all cameras share one exposure.
+A step = one pass of the hot path over one batch of synthetic packed12 frames already resident in HBM: the fused
+packed12 -> demosaic -> tone map -> quantise sweep of batch k (``Camera32/16.process_packed12``) while the joint
+metering of batch k+1 (moving-average update of the 9-float metrics) runs on a side stream -- one CUDA-graph replay
+(``graphed.GraphedStream``, double-buffered ingest).  Default workload (N = 1) = BASELINE.json configs[1]: 6 x 5472x3648
+packed12 frames -> linear tone map -> RGB16.  With N > 1 (torchrun, one rank per GPU) every rank runs the same per-GPU
+batch on its own camera streams (weak scaling, no pixel traffic between GPUs) and the ranks exchange the metering
+records over NVLink mailboxes so that all cameras share one exposure (``--shared-exposure``, default for N > 1).
+``--cameras C`` instead shards C camera streams over the ranks (BASELINE configs[2]: 12 cameras; strong scaling).
 
-Prints ONE JSON line (see the keys at the bottom).  `--impl reference` times the CPU restatement of
-the reference path (oracle/c/isp_oracle.c, OpenMP on all host cores) on a bounded sample of the same
-workload: Taichi, and therefore the reference's own CPU backend, is not installable in this image.
+Prints ONE JSON line (keys at the bottom of main()).  The default N = 1 run also times the other BASELINE
+configurations (>= 0.5 s each) into ``configs``.  ``--impl reference`` times the CPU restatement of the reference path
+(oracle/c/isp_oracle.c, OpenMP on all host cores): Taichi, and therefore the reference's own CPU backend, is not
+installable in this image.
 """
 from __future__ import annotations
 
@@ -32,6 +35,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+METRIC = "Gpixel/s packed12->RGB8/RGB16 ISP"
 WORKLOADS = {
     # name: (frames, H, W, isp dtype, tonemap, out dtype, tonemap kwargs, description)
     "cfg2": (6, 3648, 5472, "f32", "linear", "u16", dict(gamma=1.0),
@@ -41,23 +45,24 @@ WORKLOADS = {
     "cfg1_16": (6, 3000, 4096, "f16", "reinhard", "u8", dict(gamma=0.6),
                 "reference bench/camera_isp.py: 6 x 4096x3000 -> Camera16 -> Reinhard gamma 0.6 -> RGB8"),
     "cfg3": (6, 3000, 4096, "f32", "reinhard", "u8", dict(gamma=0.9, intensity=3.0, light_adapt=0.9, color_adapt=0.0),
-             "BASELINE configs[2] shard: 6 cameras x 4096x3000 per GPU, script tone-map settings -> RGB8"),
+             "BASELINE configs[2] shard: 6 cameras x 4096x3000 per GPU, script tone-map settings -> RGB8 (Camera32)"),
     # BASELINE configs[4] per-GPU shard: 8 x 4096x3000 -> full ISP (Camera16, Reinhard script settings) -> bilinear resize
     # to width 1920 (aspect-preserving 1920x1406, the reference-pinned path) -> fp16 output.  Resize runs
-    # BEFORE metering / tone map like the reference (camera_isp.py:371-373), through the staged CUDA kernels.
+    # BEFORE metering / tone map like the reference (camera_isp.py:371-373), inside the sweep (csrc/resize_sweep.cuh).
     "cfg5": (8, 3000, 4096, "f16", "reinhard", "f16", dict(gamma=0.9, intensity=3.0, light_adapt=0.9, color_adapt=0.0),
-             "BASELINE configs[4] shard: 8 x 4096x3000 -> ISP + bilinear resize_width 1920 -> Reinhard -> fp16 (staged kernels)"),
+             "BASELINE configs[4] shard: 8 x 4096x3000 -> ISP + bilinear resize_width 1920 (fused into the sweep) -> Reinhard -> fp16"),
 }
 RESIZE_WIDTH = {"cfg5": 1920}
-OUT_BYTES = {"u8": 1, "u16": 2, "f16": 2}
-# dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel per launch, from the ncu --set full capture
-# summarised under profiles/ (r01_stream2_kernel_ncu.txt); None where no capture exists
-TRAFFIC = {"cfg2": 843.8e6}     # 180.8 MB read + 663.0 MB written (algorithmic: 179.7 + 718.6; the last ~56 MB of writes are still in L2 at kernel end)
+OUT_BYTES = {"u8": 1, "u16": 2, "f16": 2, "f32": 4}
+# dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel per launch, from the ncu --set full captures
+# summarised under profiles/ (None where no capture exists); the source file is named next to the number
+TRAFFIC = {"cfg2": (843.8e6, "profiles/r01_stream2_kernel_ncu.txt (180.8 MB read + 663.0 MB written; the last ~56 MB of writes still in L2)"),
+           "cfg3": (282.1e6, "profiles/r02_reinhard_write_ncu.txt (111.1 MB read + 171.0 MB written)"),
+           "cfg5": (243.2e6, "profiles/r02_resize_sweep_ncu.txt (148.4 MB read + 94.8 MB written)")}
 
 
-def synth_frames(n, h, w, seed=1234):
-    """SURVEY 8d generator, made cheap: smooth HDR-ish RGB field x channel gains + 2 % noise, mosaiced
-    (RGGB), quantised to 12 bit, packed with the standard layout.  Built with numpy on the host."""
+def synth_frames_np(n, h, w, seed=1234):
+    """SURVEY 8d generator on the host (numpy): the frames of the CPU arm"""
     frames = []
     yy, xx = np.mgrid[0:h, 0:w].astype(np.float32)
     for i in range(n):
@@ -80,6 +85,27 @@ def synth_frames(n, h, w, seed=1234):
     return frames
 
 
+def synth_frames(n, h, w, seed, device):
+    """SURVEY 8d generator on the device: smooth HDR-ish field x channel gains + 2 % noise, mosaiced (RGGB), 12 bit,
+    packed with the standard layout (packed.encode12, bit-exact against the golden vectors).  Deterministic in
+    (seed, camera index), so that rank 0 can rebuild every rank's frames for the N > 1 parity check."""
+    import torch
+    from taichi_image_b200 import packed
+    yy = torch.arange(h, device=device, dtype=torch.float32)[:, None] / h
+    xx = torch.arange(w, device=device, dtype=torch.float32)[None, :] / w
+    gains = ((0, 0, 0.9), (0, 1, 1.0), (1, 0, 1.0), (1, 1, 0.7))
+    frames = []
+    for i in range(n):
+        g = torch.Generator(device=device).manual_seed(seed + i)
+        base = 0.5 + 0.35 * torch.sin(xx * (5.1 + (seed + i) % 7) + 0.3 * ((seed + i) % 11)) * torch.cos(yy * 3.7)
+        cfa = torch.empty((h, w), device=device)
+        for dy, dx, gain in gains:
+            cfa[dy::2, dx::2] = base[dy::2, dx::2] * gain
+        cfa += 0.05 + 0.02 * (torch.rand((h, w), generator=g, device=device) - 0.5)
+        frames.append(packed.encode12(torch.round(cfa.clamp(0, 1) * 4095).to(torch.int32).to(torch.uint16)))
+    return frames
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
@@ -99,15 +125,10 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.rows.append((time.time(), [x.strip() for x in line.split(",")]))
 
-    def count(self, t0, t1):
-        return sum(1 for t, _ in self.rows if t0 <= t <= t1)
-
-    def stop(self, t0, t1):
+    def window(self, t0, t1):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.05)
-        self.proc.terminate()
-        rows = [r for t, r in self.rows if t0 <= t <= t1] or [r for _, r in self.rows]
+        rows = [r for t, r in self.rows if t0 <= t <= t1]
         sm, mx, reasons = [], None, set()
         names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
         for r in rows:
@@ -119,6 +140,11 @@ class ClockSampler:
                 if val.lower().startswith("active"):
                     reasons.add(nme)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+    def stop(self):
+        if self.proc is not None:
+            time.sleep(0.05)
+            self.proc.terminate()
 
 
 def measured_peak():
@@ -137,16 +163,25 @@ def host_threads() -> int:
         return max(1, os.cpu_count() or 1)
 
 
-def cpu_baseline(workload, budget_s=20.0, threads=0):
-    """C/OpenMP restatement of the reference path on the host cores, on a bounded sample: a horizontal
-    band of one frame of the workload (same width, same tone map, same dtype)."""
-    from oracle import c_oracle
+def _oracle_kwargs(workload, threads):
     n, h, w, isp_dt, tonemap, out_dt, tm, _ = WORKLOADS[workload]
-    band_h = h                                    # one whole frame of the workload per repetition
-    frame = synth_frames(1, band_h, w)[0]
-    threads = threads or host_threads()
     kw = dict(pattern="RGGB", cam16=isp_dt == "f16", out_dtype="u16" if out_dt == "u16" else "u8", tonemap=tonemap,
               stride=8, nthreads=threads, **tm)
+    rw = RESIZE_WIDTH.get(workload, 0)
+    if rw:
+        s = rw / w
+        kw["resize"] = ((rw, round(h * s)), (s, s))
+    return kw
+
+
+def cpu_baseline(workload, budget_s=20.0, threads=0):
+    """C/OpenMP restatement of the reference path on the host cores, on a bounded sample: whole frames of the workload
+    (same size, same tone map, same dtype), one per repetition."""
+    from oracle import c_oracle
+    n, h, w, isp_dt, tonemap, out_dt, tm, _ = WORKLOADS[workload]
+    frame = synth_frames_np(1, h, w)[0]
+    threads = threads or host_threads()
+    kw = _oracle_kwargs(workload, threads)
     c_oracle.process([frame], **kw)                 # warm-up (page faults, thread pool)
     t0 = time.perf_counter()
     reps = 0
@@ -156,9 +191,9 @@ def cpu_baseline(workload, budget_s=20.0, threads=0):
         if time.perf_counter() - t0 > budget_s or reps >= 50:
             break
     dt = (time.perf_counter() - t0) / reps
-    return {"value": band_h * w / dt / 1e9, "unit": "Gpixel/s", "cores": threads, "kind": "port",
-            "sample": f"{reps} x one {w}x{band_h} frame of the workload through oracle/c/isp_oracle.c "
-                      f"(literal 13-tap demosaic, metering, {tonemap}, {out_dt}); Taichi CPU backend not installable"}, dt
+    return {"value": h * w / dt / 1e9, "unit": "Gpixel/s", "cores": threads, "kind": "port",
+            "sample": f"{reps} x one {w}x{h} frame of the workload through oracle/c/isp_oracle.c "
+                      f"(literal 13-tap demosaic, metering, {tonemap}, {out_dt}); Taichi CPU backend not installable"}
 
 
 def run_reference(args):
@@ -167,23 +202,22 @@ def run_reference(args):
         return
     n, h, w, isp_dt, tonemap, out_dt, tm, desc = WORKLOADS[args.workload]
     from oracle import c_oracle
-    band_h = h                                    # each step = one whole frame of the workload
-    frame = synth_frames(1, band_h, w)[0]
+    frame = synth_frames_np(1, h, w)[0]
     cores = host_threads()
-    kw = dict(pattern="RGGB", cam16=isp_dt == "f16", out_dtype="u16" if out_dt == "u16" else "u8", tonemap=tonemap, stride=8,
-              nthreads=cores, **tm)
-    for _ in range(args.warmup):
+    kw = _oracle_kwargs(args.workload, cores)
+    steps = min(args.steps, 60)                     # bounded: one frame takes ~0.1 s on the host cores
+    for _ in range(min(args.warmup, 5)):
         c_oracle.process([frame], **kw)
     t0 = time.perf_counter()
-    for _ in range(args.steps):
+    for _ in range(steps):
         c_oracle.process([frame], **kw)
     dt = time.perf_counter() - t0
-    value = args.steps * band_h * w / dt / 1e9
-    sample = (f"each step = one {w}x{band_h} frame of the workload through oracle/c/isp_oracle.c "
+    value = steps * h * w / dt / 1e9
+    sample = (f"each step = one {w}x{h} frame of the workload through oracle/c/isp_oracle.c "
               f"(OpenMP, {cores} threads); the reference's Taichi CPU backend is not installable here")
     emit({
-        "impl": "reference", "metric": "Gpixel/s packed12->RGB ISP", "value": value, "unit": "Gpixel/s", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "Gpixel/s", "n_gpus": args.gpus,
+        "steps": steps, "warmup": min(args.warmup, 5), "ms_per_step": dt / steps * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32" if isp_dt == "f32" else "f16", "data": "synthetic",
         "config": {"workload": desc, "sample": sample},
         "cpu_baseline": {"value": value, "unit": "Gpixel/s", "cores": cores, "kind": "port", "sample": sample},
@@ -204,6 +238,281 @@ def emit(line: dict):
         os.write(_REAL_STDOUT, data)
 
 
+class Ctx:
+    """per-process state shared by the workloads"""
+
+    def __init__(self, args):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist, self.args = torch, dist, args
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+        self.device = torch.device("cuda", self.local_rank)
+        torch.cuda.set_device(self.device)
+        if self.world > 1:
+            dist.init_process_group("nccl", device_id=self.device)     # rendezvous, mailbox handles, timing reductions only
+        self.peak, self.peak_src = measured_peak()
+        self.sampler = ClockSampler(self.local_rank) if self.rank == 0 else None
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+
+    def max_over_ranks(self, x: float) -> float:
+        if self.world == 1:
+            return x
+        t = self.torch.tensor([x], device=self.device, dtype=self.torch.float64)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+
+def launches_per_step(tonemap, isp_dt, resize, shared, lookahead):
+    """launches of OUR kernels per step, counted from the launch plan:
+    sweep: linear 1; Reinhard Camera32 max sweep + write sweep = 2; Camera16 store sweep + normalise = 2;
+    resizing ISP: sweep + orphan columns (+ normalise for Reinhard) = 2 / 3;
+    metering: cooperative 1; as look-ahead on the side stream 2; shared exposure 2 (exchange inside the kernels)"""
+    sweep = (3 if tonemap == "reinhard" else 2) if resize else (2 if tonemap == "reinhard" else 1)
+    return sweep + (2 if (shared or lookahead) else 1)
+
+
+def run_workload(ctx: Ctx, name: str, steps: int, warmup: int, min_seconds: float = 0.0, shared=None, cameras: int = 0,
+                 isolate: bool = True):
+    """Times `steps` steps of workload `name` (max over ranks, CUDA events), then -- when min_seconds > 0 -- keeps the same
+    steps running for at least that long (timed the same way: the sustained figure with the clocks sampled under it).
+    Returns a dict of results plus the live objects the caller may reuse (isp, frames)."""
+    torch = ctx.torch
+    import taichi_image_b200 as tib
+    from taichi_image_b200.graphed import GraphedStream
+    args = ctx.args
+    n, h, w, isp_dt, tonemap, out_dt, tm, desc = WORKLOADS[name]
+    world, rank, device = ctx.world, ctx.rank, ctx.device
+    cam_ids = list(range(rank * n, rank * n + n))
+    if cameras:                       # strong scaling: `cameras` streams sharded over the ranks
+        from taichi_image_b200.distributed import shard_cameras
+        assert cameras >= world, "every rank needs at least one camera stream (it takes part in the exposure exchange)"
+        cam_ids = list(shard_cameras(cameras, world, rank))
+        n = len(cam_ids)
+    shared = (world > 1) if shared is None else shared
+    cam = tib.camera_isp.Camera16 if isp_dt == "f16" else tib.camera_isp.Camera32
+    resize_w = RESIZE_WIDTH.get(name, 0)
+    base = cam(tib.bayer.BayerPattern.RGGB, moving_alpha=0.1, device=device, resize_width=resize_w, demosaic=args.demosaic)
+    isp = base
+    if shared:
+        from taichi_image_b200.distributed import SharedExposure
+        isp = SharedExposure(base)
+    # per-camera seeds: camera c of the rig always gets the same frame, whichever rank owns it
+    frames = [synth_frames(1, h, w, 1234 + 17 * c, device)[0] for c in cam_ids]
+    frames_b = [f.clone() for f in frames]                       # second ingest buffer set (double-buffered stream)
+    plan = base._resize_plan(h, w)
+    ho, wo = (h, w) if plan is None else (plan[0][1], plan[0][0])
+    outs = [torch.empty((ho, wo, 3), dtype=tib.as_dtype(out_dt).torch, device=device) for _ in range(n)]
+    px_per_step = n * h * w
+    alg_bytes = px_per_step * 1.5 + n * ho * wo * 3 * OUT_BYTES[out_dt]
+
+    graphed = None
+    if args.graph and args.lookahead and n > 0:
+        graphed = GraphedStream(isp, frames, outs, tonemap=tonemap, dtype=out_dt, next_frames=frames_b,
+                                rows_per_task=args.rows_per_task, **tm)
+
+    def step():
+        if n == 0:
+            return
+        if graphed is not None:
+            graphed.step()
+        else:
+            isp.process_packed12(frames, tonemap=tonemap, dtype=out_dt, out=outs, rows_per_task=args.rows_per_task,
+                                 lookahead=frames if args.lookahead else None, **tm)
+
+    def timed(k):
+        start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        ctx.barrier()
+        t0 = time.time()
+        start.record()
+        for _ in range(k):
+            step()
+        stop.record()
+        torch.cuda.synchronize()
+        t1 = time.time()
+        ctx.barrier()
+        return ctx.max_over_ranks(start.elapsed_time(stop)), t0, t1
+
+    # The dominant kernel timed ALONE (same process, same resident inputs, CUDA events recorded by the library on the
+    # launching stream right before / after the launch): inside the timed region it shares the GPU with the look-ahead
+    # metering of the next batch.  Timed once right after the warm-up (the conditions MEASURED_PEAKS.json's burst copy
+    # bandwidth was taken under) and once more after the sustained window.
+    def kernel_alone():
+        iso = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(10)]
+        for a, b in iso:
+            a.record(); b.record()
+        torch.cuda.synchronize()
+        for a, b in iso:
+            base._run_fused(frames, tonemap, tib.as_dtype(out_dt), outs, tm, update_metering=False,
+                            rows_per_task=args.rows_per_task, profile_events=(a, b))
+        torch.cuda.synchronize()
+        return sum(a.elapsed_time(b) for a, b in iso[2:]) / len(iso[2:])
+
+    def roofline_of(kern_ms):
+        if resize_w:
+            kern, kern_bytes = "isp::stream2_resize_kernel (sweep + bilinear down-scaling) + orphan columns", \
+                px_per_step * 1.5 + n * ho * wo * 3 * (OUT_BYTES[isp_dt] if tonemap == "reinhard" else OUT_BYTES[out_dt])
+        elif tonemap == "reinhard" and isp_dt == "f16":
+            kern, kern_bytes = "isp::stream2_kernel<EpiReinhardMax2, STORE> (map sweep: packed in, f16 map out)", px_per_step * (1.5 + 6.0)
+        elif tonemap == "reinhard":
+            kern, kern_bytes = "isp::stream2_kernel<EpiReinhard2> (write sweep of the max + write pair)", alg_bytes
+        else:
+            kern, kern_bytes = "isp::stream2_kernel<EpiLinear2> (fused packed12 sweep, pair engine)", alg_bytes
+        achieved = kern_bytes / (kern_ms * 1e-3) / 1e9
+        traffic = TRAFFIC.get(name)
+        return {"bound": "hbm", "achieved": achieved, "peak": ctx.peak, "unit": "GB/s", "frac": achieved / ctx.peak,
+                "kernel": kern, "kernel_ms": kern_ms, "algorithmic_bytes_per_launch": kern_bytes,
+                "peak_source": ctx.peak_src, "bytes_per_pixel": kern_bytes / px_per_step,
+                "timing": "kernel timed alone right after the warm-up: 8 launches, CUDA events recorded by the library "
+                          "around the launch on the launching stream",
+                "traffic": traffic[0] if traffic else None, "traffic_source": traffic[1] if traffic else None}
+
+    for _ in range(max(warmup, 3)):
+        step()
+    kern_ms_cool = kernel_alone() if (isolate and n > 0) else None
+    total_px = world * px_per_step if not cameras else cameras * h * w
+    ms, t0, t1 = timed(steps)
+    res = {"workload": desc, "value": total_px * steps / (ms * 1e-3) / 1e9, "ms_per_step": ms / steps, "steps": steps,
+           "frames_per_gpu": n, "height": h, "width": w, "tonemap": tonemap, "out_dtype": out_dt, "isp_dtype": isp_dt}
+    clocks = ctx.sampler.window(t0, t1) if ctx.sampler else None
+    if clocks is not None:
+        clocks["window"] = "timed region"
+    if min_seconds > 0:
+        k2 = max(steps, int(min_seconds * 1e3 / max(ms / steps, 1e-3)) + 1)
+        k2 = int(ctx.max_over_ranks(float(k2)))
+        ms2, t0s, t1s = timed(k2)
+        res["sustained"] = {"value": total_px * k2 / (ms2 * 1e-3) / 1e9, "ms_per_step": ms2 / k2, "steps": k2,
+                            "seconds": ms2 * 1e-3}
+        if ctx.sampler:
+            res["sustained"]["clocks"] = ctx.sampler.window(t0s, t1s)
+            if clocks is not None and not clocks.get("samples"):
+                clocks = dict(res["sustained"]["clocks"], window=f"the {ms2 * 1e-3:.2f} s sustained window right after the (too short) timed region")
+    res["clocks"] = clocks
+
+    if isolate and n > 0:
+        hot_ms = kernel_alone()
+        res["roofline"] = roofline_of(kern_ms_cool)
+        res["roofline"]["after_sustained_window"] = {"kernel_ms": hot_ms, "frac": res["roofline"]["algorithmic_bytes_per_launch"] / (hot_ms * 1e-3) / 1e9 / ctx.peak,
+                                                     "note": "the same isolated timing repeated right after the sustained window (power-capped clocks)"}
+        res["step_gbps"] = alg_bytes / (res["ms_per_step"] * 1e-3) / 1e9
+        res["step_frac_of_peak"] = res["step_gbps"] / ctx.peak
+    res["gpu_launches_per_step"] = launches_per_step(tonemap, isp_dt, bool(resize_w), shared, bool(args.lookahead))
+    res["_live"] = dict(isp=isp, base=base, frames=frames, outs=outs, n=n, cam_ids=cam_ids, shared=shared, tm=tm)
+    return res
+
+
+def parity_across_ranks(ctx: Ctx, name: str, live, cameras: int):
+    """N > 1: every rank's metrics must be bit-identical, and equal to (a) the same split reduction emulated on rank 0
+    over ALL ranks' frames (bit-exact) and (b) the single-call joint metering of all frames (reduction order aside)."""
+    torch, dist = ctx.torch, ctx.dist
+    import taichi_image_b200 as tib
+    from taichi_image_b200.distributed import shard_cameras
+    n, h, w, isp_dt, tonemap, out_dt, tm, _ = WORKLOADS[name]
+    base = live["base"]
+    mine = base.metrics.detach().clone().reshape(1, 9)
+    allm = torch.empty((ctx.world, 9), dtype=torch.float32, device=ctx.device)
+    dist.all_gather_into_tensor(allm, mine)
+    out = {"ranks_bit_identical": bool((allm.view(torch.int32) == allm[0:1].view(torch.int32)).all().item())}
+    if ctx.rank == 0:
+        per_rank = [list(shard_cameras(cameras, ctx.world, r)) for r in range(ctx.world)] if cameras else \
+                   [list(range(r * n, r * n + n)) for r in range(ctx.world)]
+        cam = tib.camera_isp.Camera16 if isp_dt == "f16" else tib.camera_isp.Camera32
+        rw = RESIZE_WIDTH.get(name, 0)
+        shards = [[synth_frames(1, h, w, 1234 + 17 * c, ctx.device)[0] for c in ids] for ids in per_rank]
+        # (a) the split reduction of every rank, emulated here: phase1 / phase2 per shard, folded in rank order.  With
+        # constant frames the moving average is stationary after the first update (lerp of identical values), so one
+        # update from zero metrics reproduces the ranks' state.
+        emu = [cam(tib.bayer.BayerPattern.RGGB, moving_alpha=0.1, device=ctx.device, resize_width=rw) for _ in shards]
+        for e in emu:
+            e._metrics_and_alpha()
+        live_shards = [(e, s) for e, s in zip(emu, shards) if s]
+        g1 = torch.stack([e.meter_phase1(s) for e, s in live_shards]).contiguous()
+        g2 = torch.stack([e.meter_phase2(s, g1, 0.0) for e, s in live_shards]).contiguous()
+        emu[0].meter_finalize(g1, g2, 0.0)
+        # (b) one joint call over all cameras
+        joint = cam(tib.bayer.BayerPattern.RGGB, moving_alpha=0.1, device=ctx.device, resize_width=rw)
+        flat = [f for s in shards for f in s]
+        joint._metrics_and_alpha()
+        joint.meter_packed12(flat, 0.0)
+        torch.cuda.synchronize()
+        m0 = allm[0].cpu().numpy()
+        out["equals_emulated_split_bit_exact"] = bool(np.array_equal(m0, emu[0].metrics.cpu().numpy()))
+        out["max_rel_diff_vs_joint_single_gpu"] = float(np.max(np.abs(m0 - joint.metrics.cpu().numpy()) / np.maximum(np.abs(m0), 1e-6)))
+        out["cameras_total"] = len(flat)
+        ok = out["ranks_bit_identical"] and out["max_rel_diff_vs_joint_single_gpu"] < 5e-6
+        out["status"] = "ok" if ok else "MISMATCH"
+    return out
+
+
+def host_copy_ceiling(ctx: Ctx, seconds=0.25, mbytes=256):
+    """pinned-memory H2D || D2H memcpy rate of this process while every rank does the same: the ceiling of the e2e leg"""
+    torch = ctx.torch
+    nb = mbytes << 20
+    h_in, h_out = torch.empty(nb, dtype=torch.uint8, pin_memory=True), torch.empty(nb, dtype=torch.uint8, pin_memory=True)
+    d_in, d_out = torch.empty(nb, dtype=torch.uint8, device=ctx.device), torch.empty(nb, dtype=torch.uint8, device=ctx.device)
+    s1, s2 = torch.cuda.Stream(ctx.device), torch.cuda.Stream(ctx.device)
+    torch.cuda.synchronize()
+    ctx.barrier()
+    t0 = time.perf_counter()
+    reps = 0
+    while time.perf_counter() - t0 < seconds:
+        with torch.cuda.stream(s1):
+            d_in.copy_(h_in, non_blocking=True)
+        with torch.cuda.stream(s2):
+            h_out.copy_(d_out, non_blocking=True)
+        reps += 1
+        if reps % 4 == 0:
+            torch.cuda.synchronize()
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    ctx.barrier()
+    each = reps * nb / dt / 1e9
+    tot = each * 2
+    if ctx.world > 1:
+        t = torch.tensor([tot], device=ctx.device, dtype=torch.float64)
+        ctx.dist.all_reduce(t)
+        tot = float(t.item())
+    return {"h2d_gbs_per_rank": each, "d2h_gbs_per_rank": each, "all_ranks_both_directions_gbs": tot,
+            "how": f"{mbytes} MB pinned buffers, H2D and D2H on two streams concurrently, all ranks at once, {seconds} s"}
+
+
+def run_e2e(ctx: Ctx, name: str, live, ksteps: int, yuv420=False):
+    """end to end through the public API with HOST buffers: pinned host -> H2D -> fused ISP -> D2H -> pinned host"""
+    torch = ctx.torch
+    from taichi_image_b200.pipeline import RigPipeline
+    n, h, w, isp_dt, tonemap, out_dt, tm, desc = WORKLOADS[name]
+    n = live["n"]
+    if n == 0:
+        return None
+    pipe = RigPipeline(live["isp"], n, h, w, tonemap=tonemap, dtype=out_dt, depth=2, yuv420=yuv420, **live["tm"])
+    pinned = [f.cpu().pin_memory() for f in live["frames"]]
+    for _ in range(3):
+        pipe.process(pinned)
+    torch.cuda.synchronize()
+    ctx.barrier()
+    t_a = time.perf_counter()
+    tickets, checksum = [], 0
+    for i in range(ksteps):
+        tickets.append(pipe.submit(pinned))
+        if len(tickets) == 2:
+            checksum += int(pipe.result(tickets.pop(0))[0].reshape(-1)[0])
+    while tickets:
+        checksum += int(pipe.result(tickets.pop(0))[0].reshape(-1)[0])
+    torch.cuda.synchronize()
+    dt = ctx.max_over_ranks(time.perf_counter() - t_a)
+    px = ctx.world * n * h * w
+    return {"value": px * ksteps / dt / 1e9, "unit": "Gpixel/s", "h2d_bytes_per_step": pipe.h2d_bytes_per_step,
+            "d2h_bytes_per_step": pipe.d2h_bytes_per_step, "steps": ksteps, "workload": desc + (" -> planar YUV 4:2:0" if yuv420 else ""),
+            "host_gbs": ctx.world * (pipe.h2d_bytes_per_step + pipe.d2h_bytes_per_step) * ksteps / dt / 1e9,
+            "pipeline": "pinned host -> H2D -> fused ISP -> D2H -> pinned host, 2 slots, 3 streams", "checksum": checksum}
+
+
 def main():
     global _REAL_STDOUT
     sys.stdout.flush()
@@ -211,237 +520,112 @@ def main():
     os.dup2(2, 1)                      # fd 1 -> stderr for native libraries and stray prints
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
-    ap.add_argument("--shared-exposure", type=int, default=-1, help="all-reduce the metering statistics across ranks (default: on for N > 1)")
+    ap.add_argument("--cameras", type=int, default=0, help="shard this many camera streams over the ranks (strong scaling; "
+                    "BASELINE configs[2]: --workload cfg3 --cameras 12)")
+    ap.add_argument("--shared-exposure", type=int, default=-1, help="exchange the metering records across ranks (default: on for N > 1)")
     ap.add_argument("--rows-per-task", type=int, default=0)
     ap.add_argument("--demosaic", default="malvar", choices=["malvar", "bilinear"],
                     help="bilinear: the north_star's alternative demosaic inside the fused sweep (not the BASELINE configuration)")
-    ap.add_argument("--e2e-steps", type=int, default=0, help="steps of the host-buffer pipeline leg (default: min(steps, 12))")
-    ap.add_argument("--lookahead", type=int, default=1, help="announce the next batch so its metering (and exposure exchange) "
-                    "runs on a side stream under this batch's sweep (camera-stream mode; 0 = strictly serial steps)")
-    ap.add_argument("--graph", type=int, default=1, help="replay the step (sweep k || metering k+1) as a CUDA graph "
-                    "(taichi_image_b200.graphed.GraphedStream); 0 = eager Python calls")
+    ap.add_argument("--e2e-steps", type=int, default=12)
+    ap.add_argument("--lookahead", type=int, default=1, help="meter the next batch on a side stream under this batch's sweep "
+                    "(camera-stream mode; 0 = strictly serial steps)")
+    ap.add_argument("--graph", type=int, default=1, help="replay the step (sweep k || metering k+1) as a CUDA graph; 0 = eager calls")
+    ap.add_argument("--configs", type=int, default=-1, help="also time the other BASELINE configurations into `configs` "
+                    "(default: on for the plain N = 1 run of the default workload)")
+    ap.add_argument("--min-seconds", type=float, default=0.5, help="length of the sustained window after the K timed steps")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
 
-    import torch
-    import torch.distributed as dist
-    import taichi_image_b200 as tib
-    from taichi_image_b200.pipeline import RigPipeline
-
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
-    device = torch.device("cuda", local_rank)
-    torch.cuda.set_device(device)
-    if world > 1:
-        opts = dist.ProcessGroupNCCL.Options(is_high_priority_stream=True)   # the exposure exchange must not queue behind the sweep
-        dist.init_process_group("nccl", device_id=device, pg_options=opts)
+    ctx = Ctx(args)
+    world, rank = ctx.world, ctx.rank
     shared = (world > 1) if args.shared_exposure < 0 else bool(args.shared_exposure)
+    name = args.workload
+    top = run_workload(ctx, name, args.steps, args.warmup, min_seconds=args.min_seconds, shared=shared, cameras=args.cameras)
+    live = top.pop("_live")
+    n, h, w, isp_dt, tonemap, out_dt, tm, desc = WORKLOADS[name]
 
-    n, h, w, isp_dt, tonemap, out_dt, tm, desc = WORKLOADS[args.workload]
-    cam = tib.camera_isp.Camera16 if isp_dt == "f16" else tib.camera_isp.Camera32
-    resize_w = RESIZE_WIDTH.get(args.workload, 0)
-    isp = cam(tib.bayer.BayerPattern.RGGB, moving_alpha=0.1, device=device, resize_width=resize_w, demosaic=args.demosaic)
-    if args.demosaic != "malvar":
-        desc += f" [demosaic = {args.demosaic}]"
-        args.no_cpu_baseline = True         # the CPU port implements the reference's (Malvar) path only
-    if resize_w:                       # staged path: no fused sweep, no graph, no look-ahead, no e2e pipeline
-        args.graph = args.lookahead = 0
-        args.no_e2e = True
-        shared = False
-    if shared and world > 1:
-        from taichi_image_b200.distributed import SharedExposure
-        isp = SharedExposure(isp)
-    host = synth_frames(n, h, w, seed=1234 + 100 * rank)
-    frames = [torch.from_numpy(f).to(device) for f in host]
-    outs = None if resize_w else [torch.empty((h, w, 3), dtype=tib.as_dtype(out_dt).torch, device=device) for _ in range(n)]
-    px_per_step = n * h * w
-    out_frac = (resize_w * round(h * resize_w / w)) / (h * w) if resize_w else 1.0
-    alg_bytes = px_per_step * 1.5 + px_per_step * out_frac * 3 * OUT_BYTES[out_dt]
+    parity = None
+    if world > 1 and shared:
+        parity = parity_across_ranks(ctx, name, live, args.cameras)
 
-    graphed = None
-    if args.graph and args.lookahead:
-        from taichi_image_b200.graphed import GraphedStream
-        graphed = GraphedStream(isp, frames, outs, tonemap=tonemap, dtype=out_dt, rows_per_task=args.rows_per_task, **tm)
-
-    def step(events=None):
-        if graphed is not None:
-            graphed.step()
-            return
-        if resize_w:
-            isp.process_packed12(frames, tonemap=tonemap, dtype=out_dt, **tm)
-            return
-        isp.process_packed12(frames, tonemap=tonemap, dtype=out_dt, out=outs, rows_per_task=args.rows_per_task,
-                             profile_events=events, lookahead=frames if args.lookahead else None, **tm)
-
-    for _ in range(max(args.warmup, 3)):
-        step()
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    for a, b in evs:            # torch creates the cudaEvent lazily on the first record(); the library re-records it
-        a.record(); b.record()
-    start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    sampler = ClockSampler(local_rank) if rank == 0 else None
-    torch.cuda.synchronize()
-    t0 = time.time()
-    start.record()
-    for i in range(args.steps):
-        step(evs[i])
-    stop.record()
-    torch.cuda.synchronize()
-    t1 = time.time()
-    if world > 1:
-        dist.barrier()
-    elapsed_ms = start.elapsed_time(stop)
-    if world > 1:
-        t = torch.tensor([elapsed_ms], device=device)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        elapsed_ms = float(t.item())
-    # nvidia-smi cannot sample faster than ~20 ms: when the timed region was too short to contain a sample, the
-    # identical load keeps running (untimed, the same number of steps on every rank) for about half a second and
-    # the clocks are sampled there
-    clock_window = "timed region"
-    need_more = 1 if (sampler is not None and sampler.count(t0, t1) == 0) else 0
-    if world > 1:
-        f = torch.tensor([need_more], device=device)
-        dist.all_reduce(f, op=dist.ReduceOp.MAX)
-        need_more = int(f.item())
-    if need_more:
-        clock_window = "~0.5 s of the same steps right after the (too short) timed region"
-        extra = max(20, int(500.0 / max(elapsed_ms / args.steps, 1e-3)))
-        torch.cuda.synchronize()
-        t0 = time.time()
-        for _ in range(extra):
-            step(None)
-        torch.cuda.synchronize()
-        t1 = time.time()
-        if world > 1:
-            dist.barrier()
-    clocks = sampler.stop(t0, t1) if sampler else None
-    if clocks is not None:
-        clocks["window"] = clock_window
-    # graph mode: the event pair is part of the two captured graphs -> device times of the last two timed steps
-    kern_ms = [0.0] if graphed is not None else [a.elapsed_time(b) for a, b in evs]
-    kern_avg_ms = sum(kern_ms) / len(kern_ms)
-    # Reinhard: the event pair brackets the write sweep of the first frame group only
-    group = n if tonemap != "reinhard" else max(1, min(n, int((48 << 20) // (h * w * 3 // 2))))
-    kern_bytes = alg_bytes * (group / n) if tonemap == "reinhard" else alg_bytes
-    one_sweep = tonemap == "reinhard" and isp_dt == "f16"       # Camera16: store sweep over all frames + normalise pass
-    if one_sweep:
-        group = n
-        kern_bytes = px_per_step * (1.5 + 6.0)                  # packed in + f16 map out (the bracketed store sweep)
-    peak, peak_src = measured_peak()
-    in_step_ms = kern_avg_ms
-    # The dominant kernel timed ALONE (same process, same resident inputs, CUDA events on the launching stream):
-    # inside the timed region it shares the GPU with the look-ahead metering of the next batch, so its in-step
-    # duration measures the overlap, not the kernel.  Both are reported.
-    torch.cuda.synchronize()
-    base_isp = isp.isp if hasattr(isp, "isp") else isp
-    if resize_w:
-        # staged path (demosaic sweep -> resize -> metering -> tone map kernels): no single dominant fused kernel yet;
-        # the roofline entry is the whole step against the compulsory bytes
-        kern_bytes = alg_bytes
-        kern_avg_ms = in_step_ms = elapsed_ms / args.steps
-    else:
-        iso = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(10)]
-        for a, b in iso:
-            a.record(); b.record()
-        for a, b in iso:
-            base_isp._run_fused(frames, tonemap, tib.as_dtype(out_dt), outs, tm, update_metering=False,
-                                rows_per_task=args.rows_per_task, profile_events=(a, b))
-        torch.cuda.synchronize()
-        kern_avg_ms = sum(a.elapsed_time(b) for a, b in iso[2:]) / len(iso[2:])
-    achieved = kern_bytes / (kern_avg_ms * 1e-3) / 1e9
-    value = world * px_per_step * args.steps / (elapsed_ms * 1e-3) / 1e9
-
-    # launches of OUR kernels per step (counted from the launch plan):
-    #   sweep: linear 1 (the image frame is renormalised inside the sweep), Reinhard 2 per L2-sized frame group
-    #   metering: 1 cooperative launch; as look-ahead on the side stream 2 ordinary launches; with shared exposure
-    #             phase1 + post + wait + bounds fold + phase2 + post + wait + finalize = 8
-    ngroups = (n + group - 1) // group if tonemap == "reinhard" else 1
-    launches = 2 * ngroups if tonemap == "reinhard" else 1      # (Camera16 Reinhard: store sweep + normalise pass = 2)
-    if shared and world > 1:
-        launches += 8
-    else:
-        launches += 2 if args.lookahead else 1
-
-    # ---------------- end to end through the public API with host buffers
     e2e = None
     if not args.no_e2e:
-        ksteps = args.e2e_steps or min(args.steps, 12)
-        pipe = RigPipeline(isp, n, h, w, tonemap=tonemap, dtype=out_dt, depth=2, **tm)
-        pinned = RigPipeline.pin(host)
-        for _ in range(3):
-            pipe.process(pinned)
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        t_a = time.perf_counter()
-        tickets = []
-        checksum = 0
-        for i in range(ksteps):
-            tickets.append(pipe.submit(pinned))
-            if len(tickets) == 2:
-                res = pipe.result(tickets.pop(0))
-                checksum += int(res[0][0, 0, 0])
-        while tickets:
-            res = pipe.result(tickets.pop(0))
-            checksum += int(res[0][0, 0, 0])
-        torch.cuda.synchronize()
-        dt_e2e = time.perf_counter() - t_a
-        if world > 1:
-            t = torch.tensor([dt_e2e], device=device)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            dt_e2e = float(t.item())
-        e2e = {"value": world * px_per_step * ksteps / dt_e2e / 1e9, "unit": "Gpixel/s",
-               "h2d_bytes_per_step": pipe.h2d_bytes_per_step, "d2h_bytes_per_step": pipe.d2h_bytes_per_step,
-               "steps": ksteps, "pipeline": "pinned host -> H2D -> fused ISP -> D2H -> pinned host, 2 slots, 3 streams",
-               "checksum": checksum}
+        e2e = run_e2e(ctx, name, live, args.e2e_steps)
+        if e2e is not None:
+            e2e["host_ceiling"] = host_copy_ceiling(ctx)
 
+    # the shared-exposure step at N = 1 (exchange with itself: same kernels, same launch count as N > 1), so that the
+    # scaling run compares like with like
+    shared_n1 = None
+    if world == 1 and not shared and not args.cameras and args.configs != 0:
+        r = run_workload(ctx, name, max(args.steps, 50), args.warmup, min_seconds=0.3, shared=True, isolate=False)
+        r.pop("_live")
+        shared_n1 = {"value": r["value"], "ms_per_step": r["ms_per_step"], "sustained": r.get("sustained"),
+                     "note": "the same step with the shared-exposure exchange on (world 1: the rank exchanges with itself)"}
+
+    configs, e2e_variants = None, None
+    want_configs = (world == 1 and name == "cfg2" and not args.cameras) if args.configs < 0 else bool(args.configs)
+    if want_configs:
+        configs = []
+        for other in ("cfg1", "cfg3", "cfg1_16", "cfg5"):
+            if other == name:
+                continue
+            r = run_workload(ctx, other, 50, args.warmup, min_seconds=args.min_seconds)
+            lv = r.pop("_live")
+            item = {"workload": r["workload"], "value": r["sustained"]["value"], "ms_per_step": r["sustained"]["ms_per_step"],
+                    "timed_seconds": r["sustained"]["seconds"], "steps": r["sustained"]["steps"],
+                    "roofline": {k: r["roofline"][k] for k in ("frac", "kernel", "kernel_ms", "achieved", "bytes_per_pixel", "traffic", "traffic_source", "after_sustained_window")},
+                    "step_frac_of_peak": r["step_frac_of_peak"], "clocks": r["sustained"].get("clocks")}
+            if not args.no_e2e and other in ("cfg3", "cfg1_16"):
+                # the metric's own dtype (RGB8) and the 1.5 B/px planar YUV 4:2:0 output end to end
+                e2e_variants = e2e_variants or []
+                e2e_variants.append(run_e2e(ctx, other, lv, args.e2e_steps))
+                if other == "cfg1_16":
+                    e2e_variants.append(run_e2e(ctx, other, lv, args.e2e_steps, yuv420=True))
+            configs.append(item)
+            del lv
+
+    if ctx.sampler:
+        ctx.sampler.stop()
     if rank != 0:
         if world > 1:
-            dist.destroy_process_group()
+            ctx.dist.destroy_process_group()
         return
 
     cpu = None
     if not args.no_cpu_baseline and world == 1:
-        cpu, _ = cpu_baseline(args.workload)
+        cpu = cpu_baseline(name)
 
+    scaling = "strong" if args.cameras else "weak"
+    config = {"workload": desc, "frames_per_gpu": top["frames_per_gpu"], "height": h, "width": w, "tonemap": tonemap, "out_dtype": out_dt,
+              "shared_exposure": bool(shared), "lookahead_metering": bool(args.lookahead),
+              "cuda_graph": bool(args.graph and args.lookahead), "ingest": "double-buffered (two input buffer sets alternate)",
+              "l2": "inputs+outputs per step exceed the 126 MB L2 (no flush needed)" if n * h * w * 4.5 > 200e6
+                    else "per-step working set near L2 size: stated, not flushed; two input sets alternate"}
+    if args.cameras:
+        from taichi_image_b200.distributed import max_cameras_per_rank
+        config.update({"cameras_total": args.cameras, "cameras_on_busiest_rank": max_cameras_per_rank(args.cameras, world),
+                       "ideal_speedup_cap": args.cameras / max_cameras_per_rank(args.cameras, world)})
     line = {
-        "metric": "Gpixel/s packed12->RGB ISP", "value": value, "unit": "Gpixel/s", "n_gpus": world, "steps": args.steps,
-        "warmup": max(args.warmup, 3), "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": isp_dt, "data": "synthetic",
-        "config": {"workload": desc, "frames_per_gpu": n, "height": h, "width": w, "tonemap": tonemap, "out_dtype": out_dt,
-                   "shared_exposure": bool(shared and world > 1), "lookahead_metering": bool(args.lookahead),
-                   "cuda_graph": graphed is not None,
-                   "l2": f"inputs+outputs per step = {alg_bytes / 1e6:.0f} MB > 126 MB L2 (no flush needed)" if alg_bytes > 200e6
-                         else "per-step working set fits L2: inputs are re-read from L2 between steps (stated, not flushed)"},
-        "clocks": clocks,
-        "gpu_launches": launches * args.steps,
-        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "kernel": f"isp::stream2_kernel<{tonemap}> (fused packed12 sweep, pair engine)",
-                     "kernel_ms": kern_avg_ms, "algorithmic_bytes_per_launch": kern_bytes, "peak_source": peak_src,
-                     "bytes_per_pixel": 1.5 + out_frac * 3 * OUT_BYTES[out_dt],
-                     "timing": "kernel timed alone: 8 launches after the timed region, CUDA events recorded by the library "
-                               "around the launch on the launching stream",
-                     "traffic": TRAFFIC.get(args.workload)},
-        "step_gbps": alg_bytes * args.steps / (elapsed_ms * 1e-3) / 1e9,
-        "e2e": e2e,
-        "cpu_baseline": cpu,
+        "metric": METRIC, "value": top["value"], "unit": "Gpixel/s", "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": top["ms_per_step"], "higher_is_better": True, "scaling": scaling,
+        "vs_baseline": None, "dtype": isp_dt, "data": "synthetic", "config": config, "clocks": top["clocks"],
+        "sustained": top.get("sustained"),
+        "gpu_launches": top["gpu_launches_per_step"] * args.steps,
+        "roofline": top.get("roofline"), "step_gbps": top.get("step_gbps"), "step_frac_of_peak": top.get("step_frac_of_peak"),
+        "e2e": e2e, "e2e_variants": e2e_variants, "cpu_baseline": cpu, "configs": configs,
+        "shared_exposure_at_n1": shared_n1, "parity_nranks": parity,
     }
     emit(line)
     if world > 1:
-        dist.destroy_process_group()
+        ctx.dist.destroy_process_group()
 
 
 if __name__ == "__main__":

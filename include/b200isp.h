@@ -256,6 +256,14 @@ int b200isp_mailbox_exchange(const float* rec, int kind, void* const* peers_host
 /* 1 if a bounded wait has expired on this mailbox (a peer never posted); synchronises `stream` */
 int b200isp_mailbox_error(const void* mailbox, int world, b200isp_stream stream);
 
+/* The whole joint metering update (camera_isp.py:376-385 over the frames of ALL ranks) in two launches: the two
+ * metering kernels run the record exchanges themselves (last block: post to every rank's mailbox, wait for every
+ * rank's record, fold).  peers_host = the `world` mailbox pointers (entry `rank` = own).  params as for
+ * b200isp_meter_packed12; every rank must call it once per time step, in the same order. */
+int b200isp_meter_packed12_shared(const uint8_t* const* packed_host, int n_frames,
+                                  const b200isp_fused_params* params, void* const* peers_host, int world, int rank,
+                                  const float* metrics_prev, float* metrics_out, void* workspace, b200isp_stream stream);
+
 /* camera_isp.py:376-385 update_metering on its own, straight from packed12 frames (what
  * b200isp_process_packed12 runs first when params->update_metering is set), with separate input / output
  * metrics so that the update for the NEXT batch can run on a side stream while the sweep of the current

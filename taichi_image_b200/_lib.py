@@ -77,6 +77,7 @@ SIGNATURES = {
     "b200isp_mailbox_wait": [_vp, _i, _i, _vp, _vp],
     "b200isp_mailbox_exchange": [_vp, _i, C.POINTER(_vp), _i, _i, _vp, _vp],
     "b200isp_mailbox_error": [_vp, _i, _vp],
+    "b200isp_meter_packed12_shared": [C.POINTER(_vp), _i, C.POINTER(FusedParams), C.POINTER(_vp), _i, _i, _vp, _vp, _vp, _vp],
     "b200isp_meter_packed12_phase1": [C.POINTER(_vp), _i, C.POINTER(FusedParams), _vp, _vp, _vp],
     "b200isp_meter_packed12_phase2": [C.POINTER(_vp), _i, C.POINTER(FusedParams), _vp, _i, _vp, _vp, _vp, _vp],
 }

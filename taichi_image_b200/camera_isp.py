@@ -348,6 +348,16 @@ def camera_isp(name: str, dtype=f32):
                     _lib.ptr_array(frames), len(frames), p, self.metrics.data_ptr(), out.data_ptr(), int(cooperative),
                     _lib.workspace(self.device).data_ptr(), _lib.stream_ptr(self.device)), "meter_packed12")
 
+        def meter_packed12_shared(self, frames, alpha: float, peer, out: Optional[torch.Tensor] = None):
+            """``meter_packed12`` jointly with the other ranks of ``peer`` (distributed.PeerExchange): two launches, the
+            record exchanges over NVLink run inside the metering kernels; all ranks end with bit-identical metrics"""
+            out = self.metrics if out is None else out
+            p = self._fused_params(frames, "linear", u8, {}, update_metering=True, alpha=alpha)
+            with torch.cuda.device(self.device):
+                _lib.check(_lib.lib.b200isp_meter_packed12_shared(
+                    _lib.ptr_array(frames), len(frames), p, peer._peers, peer.world, peer.rank, self.metrics.data_ptr(),
+                    out.data_ptr(), _lib.workspace(self.device).data_ptr(), _lib.stream_ptr(self.device)), "meter_packed12_shared")
+
         # ------------------------------------------------------------ percentile histogram (EXTENSION, north_star)
         def metering_histogram(self, bins: int = 256) -> torch.Tensor:
             """Luminance histogram (``bins`` int32 counts over [0, 1]) of the samples of the LAST fused metering

@@ -16,67 +16,17 @@
 // One process per GPU: the mailbox is cudaMalloc'ed by its owner, exported with cudaIpcGetMemHandle and opened by
 // the peers (cudaIpcOpenMemHandle enables peer access lazily); the handles travel once through torch.distributed.
 #include <string.h>
-#include "common.cuh"
+#include "exchange.cuh"
 
 namespace isp {
 
-constexpr int kMaxRanks = 64;
-constexpr int kRecFloats[2] = {B200ISP_REC1, B200ISP_REC2};
-
-// layout in 32-bit words, per kind k (0: record 1, 1: record 2) and parity p:
-//   data [k][p][world][8]      flags [k][p][world]      then  seq[2] (this rank's own counters), err
-struct MailboxLayout {
-  int world;
-  __host__ __device__ int data(int k, int p, int r) const { return ((k * 2 + p) * world + r) * 8; }
-  __host__ __device__ int flag(int k, int p, int r) const { return 4 * world * 8 + (k * 2 + p) * world + r; }
-  __host__ __device__ int seq(int k) const { return 4 * world * 8 + 4 * world + k; }
-  __host__ __device__ int err() const { return 4 * world * 8 + 4 * world + 2; }
-  __host__ __device__ int words() const { return 4 * world * 8 + 4 * world + 3; }
-};
-
-struct PeerPtrs { uint32_t* p[kMaxRanks]; };
-
 __global__ void mailbox_post_kernel(const float* __restrict__ rec, int kind, const PeerPtrs peers, int world, int rank) {
-  const MailboxLayout L{world};
-  uint32_t* mine = peers.p[rank];
-  // this rank's sequence number of this kind: advanced here, read back by the wait kernel that follows in stream order
-  const uint32_t seq = mine[L.seq(kind)] + 1u;
-  const int par = (int)(seq & 1u);
-  const int nf = kind == 0 ? B200ISP_REC1 : B200ISP_REC2;
-  const int lane = threadIdx.x;
-  if (lane < world) {
-    uint32_t* dst = peers.p[lane];
-    for (int i = 0; i < nf; ++i) dst[L.data(kind, par, rank) + i] = __float_as_uint(rec[i]);
-    __threadfence_system();
-    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(dst + L.flag(kind, par, rank)), "r"(seq) : "memory");
-  }
-  __syncwarp();
-  if (lane == 0) mine[L.seq(kind)] = seq;
+  mailbox_post_warp(peers.p, world, rank, kind, rec, kind == 0 ? B200ISP_REC1 : B200ISP_REC2);
 }
 
 __global__ void mailbox_wait_kernel(uint32_t* __restrict__ mine, int kind, int world, float* __restrict__ gathered) {
   const MailboxLayout L{world};
-  const uint32_t seq = mine[L.seq(kind)];
-  const int par = (int)(seq & 1u);
-  const int nf = kind == 0 ? B200ISP_REC1 : B200ISP_REC2;
-  const int lane = threadIdx.x;
-  if (lane < world) {
-    const uint32_t* f = mine + L.flag(kind, par, lane);
-    uint32_t v = 0;
-    long long spins = 0;
-    bool late = false;
-    while (true) {
-      asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
-      if ((int)(v - seq) >= 0) break;
-      // a probe = one system-scope load of local memory (~1 us) + the sleep: 2^21 probes are roughly 2 s
-      if (++spins > (1LL << 21)) { atomicExch(mine + L.err(), 1u); late = true; break; }
-      __nanosleep(128);
-    }
-    // a peer that never posted must not be folded in as a stale / zero record: NaN poisons this rank's metrics
-    // visibly (and PeerExchange.check() raises) instead of silently shifting the exposure
-    for (int i = 0; i < nf; ++i)
-      gathered[lane * nf + i] = late ? __int_as_float(0x7fc00000) : __uint_as_float(mine[L.data(kind, par, lane) + i]);
-  }
+  mailbox_wait_warp(mine, world, kind, mine[L.seq(kind)], gathered, kind == 0 ? B200ISP_REC1 : B200ISP_REC2);
 }
 
 }  // namespace isp

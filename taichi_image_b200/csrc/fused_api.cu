@@ -115,6 +115,29 @@ extern "C" int b200isp_meter_packed12(const uint8_t* const* packed_host, int n_f
   });
 }
 
+// camera_isp.py:376-385 jointly over the frames of ALL ranks (each rank passes its own), with both record exchanges inside
+// the two metering kernels (metering.cuh meter_phase1x / meter_phase2x, exchange.cuh): every rank ends with bit-identical
+// metrics_out = lerp(alpha, joint statistics, metrics_prev).  peers_host: the world mailbox pointers of
+// b200isp_mailbox_create / _open (entry `rank` = this rank's own).
+extern "C" int b200isp_meter_packed12_shared(const uint8_t* const* packed_host, int n_frames, const b200isp_fused_params* params,
+                                             void* const* peers_host, int world, int rank, const float* metrics_prev,
+                                             float* metrics_out, void* workspace, b200isp_stream stream) {
+  FramePtrs fp; IspConsts k;
+  const int st = fused_setup("meter_packed12_shared", packed_host, nullptr, n_frames, params, nullptr, workspace, fp, k);
+  if (st) return st;
+  ISP_REQUIRE(metrics_prev && metrics_out && peers_host, B200ISP_E_ARG, "meter_packed12_shared: null pointer");
+  ISP_REQUIRE(world >= 1 && world <= kXchgRanks && rank >= 0 && rank < world, B200ISP_E_ARG, "meter_packed12_shared: world %d rank %d", world, rank);
+  PeerXchg xc;
+  xc.world = world; xc.rank = rank;
+  for (int r = 0; r < kXchgRanks; ++r) xc.p[r] = r < world ? (uint32_t*)peers_host[r] : nullptr;
+  for (int r = 0; r < world; ++r) ISP_REQUIRE(xc.p[r], B200ISP_E_ARG, "meter_packed12_shared: null mailbox of rank %d", r);
+  cudaStream_t s = (cudaStream_t)stream;
+  const float alpha = params->alpha;
+  return with_packed12_sampler(fp, *params, k, n_frames, [&](const auto& smp, long long n, float* cache) {
+    return launch_metering_shared(smp, n, alpha, metrics_prev, metrics_out, k.ws, s, cache, xc);
+  });
+}
+
 extern "C" int b200isp_process_packed12(const uint8_t* const* packed_host, void* const* out_host, int n_frames,
                                         const b200isp_fused_params* params, float* metrics, void* workspace,
                                         b200isp_stream stream) {

@@ -11,6 +11,7 @@
 // `alpha` is the weight of the PREVIOUS value: lerp(t,a,b) = a + t*(b-a) (util.py:82-84).
 #pragma once
 #include "common.cuh"
+#include "exchange.cuh"
 
 namespace isp {
 
@@ -209,6 +210,99 @@ static __global__ void meter_finalize_kernel(const float* __restrict__ g1, const
   }
 }
 
+// ---------------------------------------------------------------- shared exposure with the exchange INSIDE the kernels
+// Same two reductions, but the last block to finish a phase also runs that phase's cross-rank exchange (one warp:
+// post the record into every rank's mailbox over NVLink, spin until every rank's record has arrived; exchange.cuh)
+// and the fold that follows it.  A joint metering update is then 2 launches instead of 8 (phase 1, post, wait, bounds
+// fold, phase 2, post, wait, finalize), with no launch gap between a reduction and its exchange.
+template <class Sampler>
+__global__ void __launch_bounds__(256) meter_phase1x_kernel(const Sampler smp, long long n, float alpha, const float* __restrict__ prev,
+                                                            Workspace* ws, float* __restrict__ cache, const PeerXchg xc) {
+  __shared__ float smem[8 * 2];
+  __shared__ float s_rec[2];
+  __shared__ float s_g[kXchgRanks * 2];
+  float v[2] = {INFINITY, -INFINITY};
+  for_each_sample(smp, n, [&](long long i, const float (&rgb)[3]) {
+    if (cache) { const unsigned o = 3u * (unsigned)i; cache[o] = rgb[0]; cache[o + 1] = rgb[1]; cache[o + 2] = rgb[2]; }
+    v[0] = fminf(v[0], fminf(rgb[0], fminf(rgb[1], rgb[2])));
+    v[1] = fmaxf(v[1], fmaxf(rgb[0], fmaxf(rgb[1], rgb[2])));
+  });
+  const int op[2] = {0, 1};
+  block_fold<2>(v, op, smem);
+  if (threadIdx.x == 0) {
+    ws->partials[blockIdx.x * kPartialStride + 0] = v[0];
+    ws->partials[blockIdx.x * kPartialStride + 1] = v[1];
+  }
+  if (last_block_ticket(&ws->counter[0])) {
+    float f[2] = {INFINITY, -INFINITY};
+    for (int b = threadIdx.x; b < (int)gridDim.x; b += blockDim.x) {
+      f[0] = fminf(f[0], __ldcg(&ws->partials[b * kPartialStride + 0]));
+      f[1] = fmaxf(f[1], __ldcg(&ws->partials[b * kPartialStride + 1]));
+    }
+    block_fold<2>(f, op, smem);
+    if (threadIdx.x == 0) { s_rec[0] = f[0]; s_rec[1] = f[1]; }
+    __syncthreads();
+    if (threadIdx.x < 32) {
+      const uint32_t seq = mailbox_post_warp(xc.p, xc.world, xc.rank, 0, s_rec, B200ISP_REC1);
+      mailbox_wait_warp(xc.p[xc.rank], xc.world, 0, seq, s_g, B200ISP_REC1);
+      if (threadIdx.x == 0) fold_bounds(s_g, xc.world, alpha, prev, ws->bounds[0], ws->bounds[1]);     // identical on every rank
+    }
+  }
+}
+
+template <class Sampler>
+__global__ void __launch_bounds__(256) meter_phase2x_kernel(const Sampler smp, long long n, float alpha, const float* prev,
+                                                            float* metrics /* out; may alias prev */, Workspace* ws, const PeerXchg xc) {
+  __shared__ float smem[8 * 7];
+  __shared__ float s_rec[8];
+  __shared__ float s_g[kXchgRanks * 8];
+  const float bmin = __ldcg(&ws->bounds[0]), bmax = __ldcg(&ws->bounds[1]);
+  const float inv_den = __fdiv_rn(1.0f, __fadd_rn(__fsub_rn(bmax, bmin), 1e-6f));
+  float v[7] = {INFINITY, -INFINITY, 0.f, 0.f, 0.f, 0.f, 0.f};
+  for_each_sample(smp, n, [&](long long, const float (&rgb)[3]) { meter_accum(rgb, bmin, inv_den, v); });
+  const int op[7] = {0, 1, 2, 2, 2, 2, 2};
+  block_fold<7>(v, op, smem);
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int k = 0; k < 7; ++k) ws->partials[blockIdx.x * kPartialStride + k] = v[k];
+  }
+  if (last_block_ticket(&ws->counter[0])) {
+    float f[7] = {INFINITY, -INFINITY, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int b = threadIdx.x; b < (int)gridDim.x; b += blockDim.x) {
+      f[0] = fminf(f[0], __ldcg(&ws->partials[b * kPartialStride + 0]));
+      f[1] = fmaxf(f[1], __ldcg(&ws->partials[b * kPartialStride + 1]));
+#pragma unroll
+      for (int k = 2; k < 7; ++k) f[k] += __ldcg(&ws->partials[b * kPartialStride + k]);
+    }
+    block_fold<7>(f, op, smem);
+    if (threadIdx.x == 0) {
+#pragma unroll
+      for (int k = 0; k < 7; ++k) s_rec[k] = f[k];
+      s_rec[7] = (float)n;
+    }
+    __syncthreads();
+    if (threadIdx.x < 32) {
+      const uint32_t seq = mailbox_post_warp(xc.p, xc.world, xc.rank, 1, s_rec, B200ISP_REC2);
+      mailbox_wait_warp(xc.p[xc.rank], xc.world, 1, seq, s_g, B200ISP_REC2);
+      if (threadIdx.x == 0) {                                             // meter_finalize_kernel with the blended bounds at hand
+        float g[8] = {INFINITY, -INFINITY, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        for (int r = 0; r < xc.world; ++r) {
+          g[0] = fminf(g[0], s_g[8 * r]);
+          g[1] = fmaxf(g[1], s_g[8 * r + 1]);
+          for (int k = 2; k < 8; ++k) g[k] += s_g[8 * r + k];
+        }
+        const float fn = g[7];                                            // camera_isp.py:131-134 with n = all ranks' samples
+        const float stats[9] = {bmin, bmax, g[0], g[1], __fdiv_rn(g[2], fn), __fdiv_rn(g[3], fn),
+                                __fdiv_rn(g[4], fn), __fdiv_rn(g[5], fn), __fdiv_rn(g[6], fn)};
+        for (int k = 0; k < 9; ++k) {                                     // camera_isp.py:165-166
+          const float p = prev[k];
+          metrics[k] = __fadd_rn(stats[k], __fmul_rn(alpha, __fsub_rn(p, stats[k])));
+        }
+      }
+    }
+  }
+}
+
 // samples cached by phase 1 (3 floats each), read back coalesced by phase 2
 struct CachedSampler {
   const float* cache;
@@ -369,6 +463,19 @@ inline int launch_metering_phase2(const Sampler& smp, long long n, const float* 
   if (cache) meter_phase2_kernel<CachedSampler><<<grid, 256, 0, s>>>(CachedSampler{cache}, n, alpha, nullptr, nullptr, ws, rec2);
   else meter_phase2_kernel<Sampler><<<grid, 256, 0, s>>>(smp, n, alpha, nullptr, nullptr, ws, rec2);
   return cuda_status(cudaPeekAtLastError(), "meter_phase2_kernel");
+}
+
+// joint metering update of all ranks in two launches (the exchange runs inside the kernels' last block)
+template <class Sampler>
+inline int launch_metering_shared(const Sampler& smp, long long n, float alpha, const float* prev, float* metrics, Workspace* ws,
+                                  cudaStream_t s, float* cache, const PeerXchg& xc) {
+  const int grid = meter_grid(n);
+  meter_phase1x_kernel<Sampler><<<grid, 256, 0, s>>>(smp, n, alpha, prev, ws, cache, xc);
+  int st = cuda_status(cudaPeekAtLastError(), "meter_phase1x_kernel");
+  if (st) return st;
+  if (cache) meter_phase2x_kernel<CachedSampler><<<grid, 256, 0, s>>>(CachedSampler{cache}, n, alpha, prev, metrics, ws, xc);
+  else meter_phase2x_kernel<Sampler><<<grid, 256, 0, s>>>(smp, n, alpha, prev, metrics, ws, xc);
+  return cuda_status(cudaPeekAtLastError(), "meter_phase2x_kernel");
 }
 
 // Sampler over materialised (H, W, 3) images of the ISP dtype (camera_isp.py:168-170)

@@ -151,6 +151,11 @@ def shared_metering(backend, source, group=None, alpha: Optional[float] = None, 
     ``peer``: exchange through NVLink mailboxes instead of ``torch.distributed`` all-gathers."""
     if alpha is None:
         alpha = backend.begin()
+    source = list(source)
+    if peer is not None and isinstance(backend, CudaMeteringBackend) and source[0].dtype == torch.uint8 and source[0].ndim == 2:
+        # packed12 frames + NVLink mailboxes: the two exchanges run inside the metering kernels (2 launches, csrc/metering.cuh)
+        backend.isp.meter_packed12_shared(source, alpha, peer, out)
+        return
     ex = (lambda rec, kind: peer(rec, kind)) if peer is not None else (lambda rec, kind: exchange(rec, group))
     g1 = ex(backend.phase1(source), 1)
     g2 = ex(backend.phase2(source, g1, alpha), 2)

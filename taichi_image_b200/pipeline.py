@@ -18,10 +18,10 @@ from .dtypes import as_dtype, u8
 
 
 class _Slot:
-    def __init__(self, n, h, w, out_dtype, device):
+    def __init__(self, n, h, w, out_shape, out_dtype, device):
         self.d_in = [torch.empty((h, w * 3 // 2), dtype=torch.uint8, device=device) for _ in range(n)]
-        self.d_out = [torch.empty((h, w, 3), dtype=out_dtype.torch, device=device) for _ in range(n)]
-        self.h_out = [torch.empty((h, w, 3), dtype=out_dtype.torch, pin_memory=True) for _ in range(n)]
+        self.d_out = [torch.empty(out_shape, dtype=out_dtype.torch, device=device) for _ in range(n)]
+        self.h_out = [torch.empty(out_shape, dtype=out_dtype.torch, pin_memory=True) for _ in range(n)]
         self.copied_in = torch.cuda.Event()
         self.computed = torch.cuda.Event()
         self.copied_out = torch.cuda.Event()
@@ -30,17 +30,26 @@ class _Slot:
 
 class RigPipeline:
     def __init__(self, isp, n_frames: int, height: int, width: int, tonemap: str = "reinhard", dtype=u8,
-                 depth: int = 2, **tonemap_args):
+                 depth: int = 2, yuv420: bool = False, **tonemap_args):
+        """``isp`` may resize (outputs are then the resized images) and ``yuv420=True`` selects the planar YUV 4:2:0
+        output of ``process_packed12`` (1.5 instead of 3 bytes per pixel over PCIe).  A rotating / flipping ISP is not
+        supported here: the transformed copies would not land in the pinned output slots."""
         assert width % 8 == 0 and height % 2 == 0, "fused path needs width % 8 == 0 and even height"
+        base = getattr(isp, "isp", isp)
+        assert base.transform.value == "none", "RigPipeline writes straight into its slots: no transform"
         self.isp, self.n, self.h, self.w = isp, n_frames, height, width
         self.tonemap, self.out_dtype, self.tm = tonemap, as_dtype(dtype), tonemap_args
+        self.yuv420 = bool(yuv420)
         self.device = isp.device
+        plan = base._resize_plan(height, width)
+        ho, wo = (height, width) if plan is None else (plan[0][1], plan[0][0])
+        self.out_shape = (ho * 3 // 2, wo) if self.yuv420 else (ho, wo, 3)
         with torch.cuda.device(self.device):
             self.s_in, self.s_isp, self.s_out = (torch.cuda.Stream(self.device) for _ in range(3))
-            self.slots = [_Slot(n_frames, height, width, self.out_dtype, self.device) for _ in range(depth)]
+            self.slots = [_Slot(n_frames, height, width, self.out_shape, self.out_dtype, self.device) for _ in range(depth)]
         self._next = 0
         self.h2d_bytes_per_step = n_frames * height * width * 3 // 2
-        self.d2h_bytes_per_step = n_frames * height * width * 3 * self.out_dtype.itemsize
+        self.d2h_bytes_per_step = n_frames * int(np.prod(self.out_shape)) * self.out_dtype.itemsize
 
     @staticmethod
     def pin(frames: Sequence[np.ndarray]) -> List[torch.Tensor]:
@@ -64,7 +73,8 @@ class RigPipeline:
                 slot.copied_in.record(self.s_in)
             with torch.cuda.stream(self.s_isp):
                 self.s_isp.wait_event(slot.copied_in)
-                self.isp.process_packed12(slot.d_in, tonemap=self.tonemap, dtype=self.out_dtype, out=slot.d_out, **self.tm)
+                self.isp.process_packed12(slot.d_in, tonemap=self.tonemap, dtype=self.out_dtype, out=slot.d_out,
+                                          **(dict(yuv420=True) if self.yuv420 else {}), **self.tm)
                 slot.computed.record(self.s_isp)
             with torch.cuda.stream(self.s_out):
                 self.s_out.wait_event(slot.computed)

@@ -105,3 +105,52 @@ def test_peer_exchange_world1_and_emulated_ranks(cuda):
             assert _lib.lib.b200isp_mailbox_error(boxes[r], world, st) == 0
     for b in boxes:
         _lib.check(_lib.lib.b200isp_mailbox_close(b, 1), "close")
+
+
+class _FakePeer:
+    """the part of distributed.PeerExchange that meter_packed12_shared uses: mailbox table, world, rank"""
+
+    def __init__(self, peers, world, rank):
+        self._peers, self.world, self.rank = peers, world, rank
+
+
+@pytest.mark.parametrize("dt", ["f16", "f32"])
+@pytest.mark.parametrize("world", [2, 3])
+def test_in_kernel_exchange_emulated_ranks(cuda, dt, world):
+    """b200isp_meter_packed12_shared (the record exchanges run INSIDE the two metering kernels): `world` ranks emulated on
+    one GPU -- one mailbox, one ISP and one stream per rank, so that a rank's spinning last block really waits for the
+    other ranks' kernels.  All ranks must end with bit-identical metrics, identical to the split phase1 / phase2 /
+    finalize chain, and equal to the joint single-call metering of all cameras (reduction order aside)."""
+    import ctypes as C
+    from taichi_image_b200 import _lib
+    r = rng(90 + world)
+    n_cam = 5
+    boxes = []
+    for _ in range(world):
+        p, h = C.c_void_p(), (C.c_ubyte * 64)()
+        _lib.check(_lib.lib.b200isp_mailbox_create(world, C.byref(p), h), "create")
+        boxes.append(p)
+    table = (C.c_void_p * world)(*[b.value for b in boxes])
+    peers = [_FakePeer(table, world, k) for k in range(world)]
+    streams = [torch.cuda.Stream() for _ in range(world)]
+    isps = [make_isp(dt, moving_alpha=0.1) for _ in range(world)]
+    chain = EmulatedRanks([make_isp(dt, moving_alpha=0.1) for _ in range(world)])
+    joint = make_isp(dt, moving_alpha=0.1)
+    for step in range(4):
+        cu = [to_cuda(f) for f in frames(r, n_cam, 40, 56)]
+        shards = [[cu[i] for i in shard_cameras(n_cam, world, k)] for k in range(world)]
+        torch.cuda.synchronize()
+        for k in range(world):
+            alpha = isps[k]._metrics_and_alpha()
+            with torch.cuda.stream(streams[k]):
+                isps[k].meter_packed12_shared(shards[k], alpha, peers[k])
+        torch.cuda.synchronize()
+        chain.step(shards)
+        joint.process_packed12(cu, tonemap="linear")
+        for k in range(world):
+            assert _lib.lib.b200isp_mailbox_error(boxes[k], world, _lib.stream_ptr(torch.device("cuda", 0))) == 0
+            np.testing.assert_array_equal(to_np(isps[k].metrics), to_np(isps[0].metrics))
+            np.testing.assert_array_equal(to_np(isps[k].metrics), to_np(chain.isps[0].metrics))
+            np.testing.assert_allclose(to_np(isps[k].metrics), to_np(joint.metrics), rtol=5e-6, atol=1e-6)
+    for b in boxes:
+        _lib.check(_lib.lib.b200isp_mailbox_close(b, 1), "close")
