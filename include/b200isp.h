@@ -183,6 +183,9 @@ typedef struct {
                                    :371-373; interpolate.py:59-66) fused into the pass: outputs are (out_height, out_width, 3) */
   float scale_r, scale_c;       /* source position of output (ro, co) = (ro / scale_r, co / scale_c) in f32, interpolate.py:60 */
   int resize_gather;            /* 1: force the per-output-pixel gather instead of the resizing sweep (testing / profiling) */
+  int out_pitch;                /* elements per OUTPUT row; 0 = dense (3 * width).  Larger: every output frame is a tile of a bigger
+                                   image (the rig's camera grid, scripts/tonemap_scan.py:91-100) -- the sweep writes the tile in place */
+  int reserved0;                /* keeps the pointers below 8-byte aligned; must be 0 */
   void* profile_start;          /* optional cudaEvent_t pair recorded on `stream` immediately before / after */
   void* profile_stop;           /*   the dominant streaming kernel (bench.py's live roofline timing); NULL = off */
   void* meter_cache;            /* optional device scratch: >= n_frames*ceil(H/stride)*ceil(W/stride)*12 bytes; the second */

@@ -479,9 +479,17 @@ def camera_isp(name: str, dtype=f32):
             if out is None:
                 out = [torch.empty(oshape, dtype=out_dtype.torch, device=self.device) for _ in frames]
             else:
+                # dense frames, or equally pitched tiles of a larger image (rig.GridOutput: the camera grid of
+                # scripts/tonemap_scan.py:91-100 written in place by the sweep)
                 assert len(out) == len(frames)
+                pitch = out[0].stride(0) if out[0].ndim == 3 else 0
                 for o in out:
-                    assert tuple(o.shape) == oshape and o.dtype == out_dtype.torch and o.is_contiguous() and o.is_cuda
+                    assert tuple(o.shape) == oshape and o.dtype == out_dtype.torch and o.is_cuda
+                    assert o.is_contiguous() or (o.ndim == 3 and o.stride() == (pitch, 3, 1) and pitch >= 3 * w), \
+                        "outputs must be contiguous or row-pitched (H, W, 3) views"
+                if not out[0].is_contiguous():
+                    assert plan is None and not yuv420, "pitched outputs need the plain RGB sweep (no resize, no YUV)"
+                    p.out_pitch = int(pitch)
             metrics_ptr = 0 if self.metrics is None else self.metrics.data_ptr()
             with torch.cuda.device(self.device):
                 _lib.check(_lib.lib.b200isp_process_packed12(

@@ -119,7 +119,7 @@ __device__ __forceinline__ void store_px8(OutT* dst /* at (row, 8*tcol, 0) */, c
 // ---------------------------------------------------------------- demosaic epilogue
 // bayer.py:150-155, :132-134:  c = sum / (in_scale * 16); [c = M c]; clamp(c,0,1); cast(c*out_scale).
 // Integer planes without CCM take clamp(floor(sum/16), 0, scale), which equals the float chain for
-// every reachable sum (exhaustively checked in tests/test_oracle.py).
+// every reachable sum (exhaustively checked in tests/test_host_cpu.py::test_integer_demosaic_equals_floor_division).
 template <typename T>
 struct EpiDemosaic {
   T* out;

@@ -7,12 +7,16 @@
 // Rounding points of the ISP dtype are reproduced: Camera16 rounds the CFA,
 // the demosaiced RGB and the Reinhard intermediate through f16; Camera32 keeps f32.
 //
-// Launch plan per call (all on one stream, no host sync):
-//   [metering]  meter_phase1 -> meter_phase2   sparse per-pixel sampler straight from the packed bytes
-//   linear      stream<EpiLinear>  + border kernel
-//   reinhard    stream<EpiReinhardMax> + border   (frame-global max of the mapped values)
-//               stream<EpiReinhard>    + border   (second sweep re-reads the packed frame from L2)
-//   none        stream<EpiRgb> + border           (load_packed12 only: float RGB out)
+// Launch plan per call (all on one stream, no host sync; the 2-pixel image frame is renormalised INSIDE the sweep,
+// border_fix.cuh -- there is no border kernel):
+//   [metering]  meter_fused_kernel (one cooperative launch) or meter_phase1 -> meter_phase2; sampler straight from the packed bytes
+//   linear      stream2<EpiLinear2>                          one sweep
+//   reinhard    Camera32: stream2<EpiReinhardMax2> (frame-global max of the mapped values) -> stream2<EpiReinhard2>
+//                         (the write sweep recomputes the map), one pair of launches for all frames of the call
+//               Camera16: stream2<EpiReinhardMax2, STORE> (writes the f16 map the reference stores back anyway)
+//                         -> reinhard_scratch_out_kernel (element-wise normalise / gamma / quantise)
+//   none        stream2<EpiRgb2>                             load_packed12 only: float RGB out
+//   resizing ISP: csrc/resize_sweep.cuh (stream2_resize_kernel + orphan columns [+ normalise pass])
 #pragma once
 #include <algorithm>
 #include "stream2.cuh"
@@ -146,6 +150,7 @@ struct IspConsts {
   Workspace* ws;
   int frame0;
   int kbase;                 // 0: Malvar-He-Cutler, kBilinearBase: bilinear demosaic (offset into c_taps / c_border)
+  int orow;                  // elements per OUTPUT row: 3 W for dense frames, more when the frames are tiles of a grid image
 };
 
 // literal front end for one pixel (bayer.py:137-155 + ISP dtype rounding), used off the hot path
@@ -235,12 +240,12 @@ template <> struct Quant<float> {
 
 // quantised row of 8 pixels -> packed words -> warp-cooperative contiguous store (stream_engine.cuh)
 template <typename OutT, bool FULL = false>
-__device__ __forceinline__ void store_row8(const WarpCtx& wc, OutT* warp_out /* frame + 24 * tcol0 */, int W, int row,
-                                           const uint32_t (&v)[24]) {
+__device__ __forceinline__ void store_row8(const WarpCtx& wc, OutT* warp_out /* frame + 24 * tcol0 */, int orow /* elements per output row */,
+                                           int row, const uint32_t (&v)[24]) {
   constexpr int NW = Quant<OutT>::kWords;
   uint32_t w[NW];
   Quant<OutT>::pack(v, w);
-  warp_store_row<NW, FULL>(wc, warp_out + (size_t)((unsigned)row * (unsigned)W) * 3, w);
+  warp_store_row<NW, FULL>(wc, warp_out + (size_t)((unsigned)row * (unsigned)orow), w);
 }
 
 template <typename OutT> __device__ __forceinline__ void store_px(void* frame_out, int W, int row, int col, const float (&y)[3]) {
@@ -578,7 +583,7 @@ struct EpiRgb2 {      // load_packed12: ISP-dtype float RGB out
       raw_to_rgb<CAM16>(k, &x.v[3 * q], rgb);
       v[3 * q] = __float_as_uint(rgb[0]); v[3 * q + 1] = __float_as_uint(rgb[1]); v[3 * q + 2] = __float_as_uint(rgb[2]);
     }
-    store_row8<OutT>(st.wc, st.out, k.W, row, v);
+    store_row8<OutT>(st.wc, st.out, k.orow, row, v);
   }
 };
 
@@ -617,7 +622,7 @@ struct EpiLinear2 {
       linear_px<GAMMA>(st.c, rgb, y);
       v[3 * q] = Quant<OutT>::q(y[0]); v[3 * q + 1] = Quant<OutT>::q(y[1]); v[3 * q + 2] = Quant<OutT>::q(y[2]);
     }
-    store_row8<OutT>(st.wc, st.out, k.W, row, v);
+    store_row8<OutT>(st.wc, st.out, k.orow, row, v);
   }
   template <bool BROW, bool GFIRST, int KIND>
   __device__ __forceinline__ void emit_generic(const State& st, int row, const f2 (&R)[4], const f2 (&G)[4], const f2 (&B)[4]) const {
@@ -683,7 +688,7 @@ struct EpiLinear2 {
           }
         }
       }
-      store_row8<OutT, KIND == K_CORE>(st.wc, st.out, k.W, row, v);
+      store_row8<OutT, KIND == K_CORE>(st.wc, st.out, k.orow, row, v);
     }
   }
 };
@@ -722,7 +727,7 @@ struct EpiReinhardMax2 {      // pass 1: frame-global max of the mapped values (
       v[3 * q] = __float_as_uint(p[0]); v[3 * q + 1] = __float_as_uint(p[1]); v[3 * q + 2] = __float_as_uint(p[2]);
     }
     st.mx = mx;
-    if constexpr (STORE) store_row8<__half>(st.wc, st.out, k.W, row, v);
+    if constexpr (STORE) store_row8<__half>(st.wc, st.out, k.W * 3, row, v);
   }
   template <bool BROW, bool GFIRST, int KIND>
   __device__ __forceinline__ void emit(State& st, int row, const f2 (&R)[4], const f2 (&G)[4], const f2 (&B)[4]) const {
@@ -747,7 +752,7 @@ struct EpiReinhardMax2 {      // pass 1: frame-global max of the mapped values (
             v[3 * (j + 4) + ch] = __float_as_uint(hi);
           }
         }
-        store_row8<__half>(st.wc, st.out, k.W, row, v);
+        store_row8<__half>(st.wc, st.out, k.W * 3, row, v);
       } else {
         float dmin = 0.f;
 #pragma unroll
@@ -808,7 +813,7 @@ struct EpiReinhard2 {         // pass 2 recomputed from the packed frame: map, n
       reinhard_out<CAM16, GAMMA>(st.c, p, y);
       v[3 * q] = Quant<OutT>::q(y[0]); v[3 * q + 1] = Quant<OutT>::q(y[1]); v[3 * q + 2] = Quant<OutT>::q(y[2]);
     }
-    store_row8<OutT>(st.wc, st.out, k.W, row, v);
+    store_row8<OutT>(st.wc, st.out, k.orow, row, v);
   }
   __device__ __forceinline__ bool fast_kinds_ok(const State&) const { return true; }
   // packed path: color_adapt == 0, any gamma (kernel-uniform)
@@ -850,7 +855,7 @@ struct EpiReinhard2 {         // pass 2 recomputed from the packed frame: map, n
         }
       }
     }
-    store_row8<OutT, KIND == K_CORE>(st.wc, st.out, k.W, row, v);
+    store_row8<OutT, KIND == K_CORE>(st.wc, st.out, k.orow, row, v);
   }
 
   template <bool BROW, bool GFIRST, int KIND>
@@ -1266,9 +1271,10 @@ int run_fused(const FramePtrs& fp, int n_frames, const b200isp_fused_params& p, 
     if (st) return st;
     if constexpr (CAM16) {
       // Camera16: the reference stores the map as f16 anyway -> one sweep writes it to the caller's scratch, a light
-      // element-wise pass normalises it (no second sweep, no L2 grouping)
+      // element-wise pass normalises it (no second sweep, no L2 grouping); dense outputs only (the normalise pass
+      // indexes the output flat), pitched outputs take the two-sweep form below
       const size_t need = (size_t)n_frames * k.H * k.W * 3 * sizeof(__half);
-      if (p.reinhard_scratch && p.reinhard_scratch_bytes >= need) {
+      if (p.reinhard_scratch && p.reinhard_scratch_bytes >= need && k.orow == 3 * k.W) {
         FramePtrs sc = fp;
         for (int f = 0; f < n_frames; ++f) sc.out[f] = (char*)p.reinhard_scratch + (size_t)f * k.H * k.W * 3 * sizeof(__half);
         st = run_rstore<true>(sc, k, n_frames, rpt, s, p.profile_start, p.profile_stop);

@@ -23,9 +23,11 @@
 // Rows are addressed through incrementally advanced pointers; rows outside the image are never zero-filled by
 // predicated loads: the load is clamped to a valid row and the DECODE mask of that row is 0, which yields
 // the "zero sample" (biased 1.0f for Camera32, 0 for Camera16) the border arithmetic needs.  The same trick
-// masks the halo columns of the first / last thread column.  Six full-row buffers rotate with a period of
-// three steps (the loop body is unrolled three times), so no window row is ever copied; the compiler frees
-// the dead pairs of the two oldest rows by itself.
+// masks the halo columns of the first / last thread column.  Six full pair rows form the window.  The shipped
+// loop is ONE copy of the two-row step that slides the window with register moves (+4 MOV per pixel): rotating the
+// rows by unrolling the step three times needs no moves but triples the hot code, and the sweep is instruction-cache
+// bound before it is move bound (3x unrolled 171 us vs single step 162 us on cfg2).  The unrolled forms
+// remain behind Epi::kCompactLoop == false / ISP_S2_COMPACT_UNROLL (experiments, see experiments.cuh).
 #pragma once
 #include "stream_engine.cuh"
 
