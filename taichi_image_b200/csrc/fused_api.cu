@@ -41,7 +41,7 @@ static int fused_setup(const char* what, const uint8_t* const* packed_host, void
   k.metrics = metrics; k.ws = (Workspace*)workspace; k.frame0 = 0;
   k.kbase = p.demosaic == B200ISP_DEMOSAIC_BILINEAR ? kBilinearBase : 0;
   k.orow = p.out_pitch > 0 ? p.out_pitch : 3 * p.width;
-  ISP_REQUIRE(k.orow >= 3 * p.width && (k.orow * (int)dtype_size(p.out_dtype)) % 16 == 0, B200ISP_E_ALIGN,
+  ISP_REQUIRE(p.out_pitch <= 0 || (k.orow >= 3 * p.width && (k.orow * (int)dtype_size(p.out_dtype)) % 16 == 0), B200ISP_E_ALIGN,
               "%s: out_pitch must be >= 3 * width elements and a multiple of 16 bytes", what);
   ISP_REQUIRE(p.out_pitch <= 0 || (!resizes(p) && !p.out_yuv420), B200ISP_E_ARG, "%s: out_pitch needs the plain RGB sweep (no resize, no YUV)", what);
   return B200ISP_OK;
