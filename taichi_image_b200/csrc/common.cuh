@@ -98,6 +98,14 @@ __device__ __forceinline__ float warp_sum(float v) {
   return v;
 }
 
+// (shifted & mask) | one in ONE LOP3 (the compiler splits the two immediates into two): drops an integer field into the
+// mantissa of the float `one` -- the conversion-free sample decode of the sweeps
+__device__ __forceinline__ float biased_from_shifted(uint32_t shifted, uint32_t mask, uint32_t one) {
+  uint32_t r;
+  asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"(r) : "r"(shifted), "r"(mask), "r"(one));
+  return __uint_as_float(r);
+}
+
 // dispatch helpers -------------------------------------------------------------------------
 #define ISP_DISPATCH_DTYPE(dt, T, ...)                                   \
   switch (dt) {                                                          \

@@ -42,12 +42,7 @@ struct FramePtrs {
 // come out as 16 + S/4096 exactly and the bias folds into the epilogue's FMA.
 // Camera16: the reference stores cfa = f16(v * f32(1/4095)); the same value is produced with one FMA
 // (exact product, single rounding) and a packed f32->f16->f32 round trip.
-// (x & 0x007FF800) | 0x3F800000 in ONE LOP3 (the compiler splits the two immediates into two)
-__device__ __forceinline__ float biased_from_shifted(uint32_t shifted, uint32_t mask, uint32_t one) {
-  uint32_t r;
-  asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"(r) : "r"(shifted), "r"(mask), "r"(one));
-  return __uint_as_float(r);
-}
+// (biased_from_shifted: common.cuh)
 
 // ---------------------------------------------------------------- packed12 row loader of the pair engine (stream2.cuh)
 // Same words and the same one-LOP3 decode as Packed12Loader, but: the decode mask is a register (0 for rows

@@ -1,27 +1,16 @@
-// Register-window streaming engine for the Malvar-He-Cutler demosaic (reference: bayer.py:114-177).
+// Shared pieces of the streaming sweeps (stream2.cuh): task geometry, the scalar per-site Malvar-He-Cutler formulas
+// (used by the metering samplers), the warp-cooperative row store and the pattern dispatch.
 //
-// B200 mapping: one thread owns 8 consecutive pixel columns and walks DOWN the image keeping a
-// 6-row window of the CFA in registers (8 own columns + 2 halo columns per side), so
-// every CFA sample is fetched from memory once per row-chunk and decoded once; no shared memory, no
-// block barriers.  A warp covers a 256-pixel strip (coalesced 384-byte packed12 rows / 256..1024
-// byte typed rows), a "task" is (frame, row-chunk, strip) and tasks are laid out so that the warps
-// of a block sit on adjacent strips of the same rows (halo words hit L1).  The grid has one warp
-// per task; rows_per_task sizes it to several waves over the 148 SMs.  Rows are fetched one step
-// (two rows) ahead of their use, so the global-load latency is covered by a whole step of math.
+// History: this file used to hold the first, scalar register-window engine (41 instructions per pixel, r01); every
+// sweep now runs on the packed-f32x2 pair engine of stream2.cuh, the scalar kernel is gone.
 //
-// The 13-tap filters are evaluated through shared partial sums:
+// Partial sums of the 13-tap filters (SURVEY 7.3 H1, tables of bayer.py:30-55 x16):
 //   NS(c) = v[r-1][c]+v[r+1][c]   EW = v[r][c-1]+v[r][c+1]   NNSS = v[r-2][c]+v[r+2][c]
 //   EEWW = v[r][c-2]+v[r][c+2]    D = NS(c-1)+NS(c+1)
 //   R/B site:  own = 16C   G = 8C+4(NS+EW)-2(NNSS+EEWW)   opposite = 12C+4D-3(NNSS+EEWW)
 //   G site:    G = 16C     colour with horizontal neighbours = 10C+8EW-2D-2EEWW+NNSS
 //                          colour with vertical neighbours   = 10C+8NS-2D-2NNSS+EEWW
-// which are the tables of bayer.py:30-55 (x16).  To save multiplies the engine hands the epilogue
-// SCALED sums (own/16, G/2, opposite/4, G-site colours/2; see SiteScale) -- the epilogue folds the
-// power-of-two factor into the normalisation constant it multiplies with anyway.  The sums are exact
-// for integer-valued inputs (|sum| < 2^24), so the evaluation order does not matter there.
-// Out-of-image taps read as 0 and the streaming kernel normalises every pixel by 16; the 2-pixel
-// image frame, where the reference renormalises by the in-bounds weight sum (bayer.py:145-151), is
-// then rewritten by a per-pixel border kernel (pixel_ops.cuh) launched right after on the same stream.
+// The sums are exact for integer-valued inputs (|sum| < 2^24), so the evaluation order does not matter there.
 #pragma once
 #include "common.cuh"
 
@@ -72,77 +61,6 @@ __device__ __forceinline__ void malvar_gsite(float C, float NS, float EW, float 
   const float T = fmaf(5.f, C, -D);
   h2 = fmaf(0.5f, NNSS, fmaf(4.f, EW, T) - EEWW);
   v2 = fmaf(0.5f, EEWW, fmaf(4.f, NS, T) - NNSS);
-}
-
-// scale that turns the engine's value for (row type, pixel j, channel) back into the x16 filter sum
-template <bool BROW, bool GFIRST>
-struct SiteScale {
-  static __host__ __device__ constexpr bool gsite(int j) { return ((j & 1) == 0) == GFIRST; }
-  static __host__ __device__ constexpr float r(int j) { return gsite(j) ? 2.f : (BROW ? 4.f : 16.f); }
-  static __host__ __device__ constexpr float g(int j) { return gsite(j) ? 16.f : 2.f; }
-  static __host__ __device__ constexpr float b(int j) { return gsite(j) ? 2.f : (BROW ? 16.f : 4.f); }
-};
-
-// One output row of 8 pixels.  z / p1 / p2 are full 12-wide rows (column c0-2+i at index i); the two rows
-// above are passed as pointers with a compile-time column offset because the engine only carries the
-// columns that are still needed of them: m2[(j+2) + M2OFF] is column j+2 (NN tap), m1[(k+1) + M1OFF]
-// column k+1 (N / NW / NE taps).
-template <bool BROW, bool GFIRST, int M2OFF, int M1OFF>
-__device__ __forceinline__ void malvar_row(const float* __restrict__ m2, const float* __restrict__ m1,
-                                           const float (&z)[12], const float (&p1)[12], const float (&p2)[12],
-                                           float (&R)[8], float (&G)[8], float (&B)[8]) {
-  float ns[10];
-#pragma unroll
-  for (int k = 0; k < 10; ++k) ns[k] = m1[k + 1 + M1OFF] + p1[k + 1];
-#pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const float C = z[j + 2];
-    const float EW = z[j + 1] + z[j + 3];
-    const float EEWW = z[j] + z[j + 4];
-    const float NS = ns[j + 1];
-    const float D = ns[j] + ns[j + 2];
-    const float NNSS = m2[j + 2 + M2OFF] + p2[j + 2];
-    if (!SiteScale<BROW, GFIRST>::gsite(j)) {
-      float g2, opp4;
-      malvar_csite(C, NS, EW, NNSS, EEWW, D, g2, opp4);
-      G[j] = g2;
-      R[j] = BROW ? opp4 : C;
-      B[j] = BROW ? C : opp4;
-    } else {
-      float h2, v2;
-      malvar_gsite(C, NS, EW, NNSS, EEWW, D, h2, v2);
-      G[j] = C;
-      R[j] = BROW ? v2 : h2;
-      B[j] = BROW ? h2 : v2;
-    }
-  }
-}
-
-// One step = two output rows (row, row+1).  cA/cB are rows row / row+1, nA/nB receive rows row+2 / row+3
-// (fetched one step earlier), oA / oB hold what is still needed of rows row-2 (columns 2..9) and row-1
-// (columns 1..10).  The rows for the NEXT step are requested before the math so their latency is covered.
-template <bool BROW0, bool GFIRST0, class Loader, class Epi>
-__device__ __forceinline__ void stream_step(const Loader& ld, const Epi& epi, typename Epi::State& st,
-                                            const typename Loader::Cursor& cur, const StreamGeom& g, int row, int rend,
-                                            typename Loader::Raw& raw0, typename Loader::Raw& raw1,
-                                            float (&oA)[8], float (&oB)[10], const float (&cA)[12], const float (&cB)[12],
-                                            float (&nA)[12], float (&nB)[12]) {
-  ld.decode(raw0, nA);
-  ld.decode(raw1, nB);
-  // rows past the chunk halo or the image come back as zeros and are never used
-  ld.fetch(cur, row + 4 < rend + 2 ? row + 4 : -1, g, raw0);
-  ld.fetch(cur, row + 5 < rend + 2 ? row + 5 : -1, g, raw1);
-  ld.prefetch(cur, row + 8, g);
-  ld.prefetch(cur, row + 9, g);
-  float R[8], G[8], B[8];
-  malvar_row<BROW0, GFIRST0, -2, -1>(oA, oB, cA, cB, nA, R, G, B);
-  epi.template emit<BROW0, GFIRST0>(st, row, R, G, B);
-  malvar_row<!BROW0, !GFIRST0, -1, 0>(oB, cA, cB, nA, nB, R, G, B);
-  epi.template emit<!BROW0, !GFIRST0>(st, row + 1, R, G, B);
-#pragma unroll
-  for (int j = 0; j < 8; ++j) oA[j] = cA[j + 2];
-#pragma unroll
-  for (int j = 0; j < 10; ++j) oB[j] = cB[j + 1];
 }
 
 // ---------------------------------------------------------------- warp-cooperative row store
@@ -211,90 +129,6 @@ __device__ __forceinline__ void warp_store_row(const WarpCtx& wc, void* row_dst 
       if (FULL || idx < nchunks) st_out(d + idx, s[idx]);
     }
   }
-}
-
-// Loader concept:
-//   struct Raw;  struct Cursor;
-//   void open(Cursor&, int frame, int tcol, const StreamGeom&)           per-task base pointer / edge flags
-//   void fetch(const Cursor&, int row, const StreamGeom&, Raw&)          issue the global loads of one row (0 outside)
-//   void prefetch(const Cursor&, int row, const StreamGeom&)             optional L2 prefetch of a later row
-//   void decode(const Raw&, float (&v)[12])                              v[j] = CFA at column 8*tcol-2+j
-// Epilogue concept:
-//   static constexpr int kStageWords                                      per-warp staging words (0: stores nothing)
-//   struct State;  void init(State&, int frame, int tcol, const WarpCtx&);  void finish(State&, int frame, int lane, bool task_ok)
-//   template <bool BROW, bool GFIRST> void emit(State&, int row, R, G, B)   scaled filter sums, see SiteScale
-template <int PATTERN, class Loader, class Epi>
-__global__ void __launch_bounds__(256, 2) stream_kernel(const Loader ld, const Epi epi, const StreamGeom g) {
-  constexpr bool BROW0 = (PATTERN == B200ISP_GBRG || PATTERN == B200ISP_BGGR);
-  constexpr bool GFIRST0 = (PATTERN == B200ISP_GRBG || PATTERN == B200ISP_GBRG);
-  const int lane = threadIdx.x & 31;
-  long long task = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  const bool task_ok = task < g.total_tasks;
-  if (!task_ok) task = 0;
-  const int strip = (int)(task % g.warps_per_row);
-  const long long t2 = task / g.warps_per_row;
-  const int chunk = (int)(t2 % g.nchunks);
-  const int frame = (int)(t2 / g.nchunks);
-  const int tcol = min(strip * 32 + lane, g.ntcols - 1);   // lanes past the last column recompute it (never stored)
-
-  __shared__ __align__(16) uint32_t stage[8][Epi::kStageWords > 0 ? Epi::kStageWords : 1];
-  WarpCtx wc;
-  wc.lane = lane;
-  wc.tcol0 = strip * 32;
-  wc.nvalid = min(32, g.ntcols - strip * 32);
-  wc.stage = stage[threadIdx.x >> 5];
-
-  typename Epi::State st;
-  epi.init(st, frame, tcol, wc);
-
-  if (task_ok) {
-    const int r0 = chunk * g.rows_per_task;
-    const int rend = min(r0 + g.rows_per_task, g.H);
-    typename Loader::Cursor cur;
-    ld.open(cur, frame, tcol, g);
-
-    // The window: two 2-row buffers that alternate between "centre rows" and "incoming rows" (the loop is
-    // unrolled twice so no row is ever copied) plus the 18 values still needed of the two rows above.
-    float b0A[12], b0B[12], b1A[12], b1B[12], oA[8], oB[10];
-    typename Loader::Raw raw0, raw1;
-    {
-      float t[12];
-      ld.fetch(cur, r0 - 2, g, raw0);
-      ld.fetch(cur, r0 - 1, g, raw1);
-      ld.decode(raw0, t);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) oA[j] = t[j + 2];
-      ld.decode(raw1, t);
-#pragma unroll
-      for (int j = 0; j < 10; ++j) oB[j] = t[j + 1];
-    }
-    ld.fetch(cur, r0, g, raw0);
-    ld.fetch(cur, r0 + 1, g, raw1);
-    ld.decode(raw0, b0A);
-    ld.decode(raw1, b0B);
-    ld.fetch(cur, r0 + 2, g, raw0);
-    ld.fetch(cur, r0 + 3, g, raw1);
-    ld.prefetch(cur, r0 + 4, g); ld.prefetch(cur, r0 + 5, g);
-    ld.prefetch(cur, r0 + 6, g); ld.prefetch(cur, r0 + 7, g);
-
-#pragma unroll 1
-    for (int row = r0; row < rend; row += 4) {
-      stream_step<BROW0, GFIRST0>(ld, epi, st, cur, g, row, rend, raw0, raw1, oA, oB, b0A, b0B, b1A, b1B);
-      if (row + 2 < rend)
-        stream_step<BROW0, GFIRST0>(ld, epi, st, cur, g, row + 2, rend, raw0, raw1, oA, oB, b1A, b1B, b0A, b0B);
-      else
-        break;
-    }
-  }
-  epi.finish(st, frame, lane, task_ok);
-}
-
-template <int PATTERN, class Loader, class Epi>
-inline int launch_stream(const Loader& ld, const Epi& epi, const StreamGeom& g, cudaStream_t s, const char* what) {
-  if (g.total_tasks == 0) return B200ISP_OK;
-  const long long blocks = (g.total_tasks + 7) / 8;
-  stream_kernel<PATTERN, Loader, Epi><<<(unsigned)blocks, 256, 0, s>>>(ld, epi, g);
-  return cuda_status(cudaPeekAtLastError(), what);
 }
 
 #define ISP_DISPATCH_PATTERN(p, P, ...)                                        \
