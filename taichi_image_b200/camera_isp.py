@@ -463,6 +463,17 @@ def camera_isp(name: str, dtype=f32):
                 if sc is None or sc.numel() < need or sc.device != torch.device(self.device):
                     sc = self._reinhard_scratch = torch.empty(need, dtype=torch.uint8, device=self.device)
                 p.reinhard_scratch, p.reinhard_scratch_bytes = sc.data_ptr(), sc.numel()
+            elif (tonemap == "reinhard" and isp_dtype == f32 and ccm is None and float(tm.get("color_adapt", 0.0)) == 0.0
+                  and not yuv420 and os.environ.get("B200ISP_CAM32_ONE_SWEEP", "0") == "1"):
+                # EXPERIMENT, off by default (profiles/r02_reinhard_u16.txt: exact, but 8 % slower than the two sweeps):
+                # Camera32 without colour correction: scratch for the exact integer RGB (3 x u16 per pixel) + the f32 side
+                # table of the image-frame pixels -- one sweep + an element-wise pass (csrc/reinhard_u16.cuh)
+                a16 = lambda x: (x + 15) & ~15
+                need = len(frames) * (a16(h * w * 6) + a16((4 * w + 4 * (h - 4)) * 12))
+                sc = getattr(self, "_reinhard_scratch", None)
+                if sc is None or sc.numel() < need or sc.device != torch.device(self.device):
+                    sc = self._reinhard_scratch = torch.empty(need, dtype=torch.uint8, device=self.device)
+                p.reinhard_scratch, p.reinhard_scratch_bytes = sc.data_ptr(), sc.numel()
             if profile_events is not None:      # (start, stop) torch.cuda.Event pair, see bench.py
                 p.profile_start, p.profile_stop = profile_events[0].cuda_event, profile_events[1].cuda_event
             return p

@@ -1239,6 +1239,11 @@ int run_rmax(const FramePtrs& fp, IspConsts k, int frame0, int nframes, int rows
   return run_pass<CAM16, MODE_RMAX, uint8_t>(fp, k, frame0, nframes, rows_per_task, s);
 }
 
+// one-sweep Camera32 Reinhard (reinhard_u16.cuh / reinhard_u16.cu)
+size_t reinhard_u16_frame_bytes(int H, int W);
+template <typename OutT>
+int run_reinhard_u16(const FramePtrs& fp, int n_frames, const b200isp_fused_params& p, IspConsts k, cudaStream_t s);
+
 template <bool CAM16, typename OutT>
 int run_fused(const FramePtrs& fp, int n_frames, const b200isp_fused_params& p, IspConsts k, cudaStream_t s) {
   const int rpt = p.rows_per_task;
@@ -1284,6 +1289,13 @@ int run_fused(const FramePtrs& fp, int n_frames, const b200isp_fused_params& p, 
         reinhard_scratch_out_kernel<OutT><<<grid, 256, 0, s>>>(sc, fp, n_elems, k.gamma, k.ws);
         return cuda_status(cudaPeekAtLastError(), "reinhard_scratch_out_kernel");
       }
+    }
+    if constexpr (!CAM16) {
+      // Camera32 without colour correction, color_adapt == 0: ONE sweep that also stores the exact integer RGB (3 x u16 per
+      // pixel) + an element-wise map / normalise / quantise pass (reinhard_u16.cuh)
+      if (!k.ccm && k.ca == 0.f && !p.out_yuv420 && k.H >= 4 && k.W >= 8 && p.reinhard_scratch &&
+          p.reinhard_scratch_bytes >= (size_t)n_frames * reinhard_u16_frame_bytes(k.H, k.W))
+        return run_reinhard_u16<OutT>(fp, n_frames, p, k, s);
     }
     // Camera32 (or no scratch): max sweep, then the write sweep recomputes the map.  Both sweeps are bound by
     // instruction issue, not by DRAM, so the second read of the packed frames (1.5 B/px) is cheaper than cutting the
