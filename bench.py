@@ -587,8 +587,7 @@ def main():
                 # the metric's own dtype (RGB8) and the 1.5 B/px planar YUV 4:2:0 output end to end
                 e2e_variants = e2e_variants or []
                 e2e_variants.append(run_e2e(ctx, other, lv, args.e2e_steps))
-                if other == "cfg1_16":
-                    e2e_variants.append(run_e2e(ctx, other, lv, args.e2e_steps, yuv420=True))
+                e2e_variants.append(run_e2e(ctx, other, lv, args.e2e_steps, yuv420=True))
             configs.append(item)
             del lv
 

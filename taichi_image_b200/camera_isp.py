@@ -482,6 +482,12 @@ def camera_isp(name: str, dtype=f32):
                        profile_events=None, yuv420=False):
             h, w3 = frames[0].shape
             w = w3 * 2 // 3
+            if yuv420 and not (isp_dtype == f16 and tonemap == "reinhard" and not self._resizes):
+                # no YUV epilogue for this path: RGB8 into a persistent scratch, then the stand-alone RGB -> planar YUV 4:2:0
+                # kernel (csrc/yuv420.cu) on the device -- bit-identical to color.rgb_yuv420_image of the RGB result; the
+                # host only ever sees 1.5 bytes per pixel
+                return self._run_fused_yuv_two_step(frames, tonemap, out_dtype, out, tm, update_metering, alpha, rows_per_task,
+                                                    profile_events)
             p = self._fused_params(frames, tonemap, out_dtype, tm, update_metering, alpha, rows_per_task, profile_events, yuv420)
             plan = self._resize_plan(h, w)
             if plan is not None:
@@ -508,6 +514,27 @@ def camera_isp(name: str, dtype=f32):
                     _lib.workspace(self.device).data_ptr(), _lib.stream_ptr(self.device)), "process_packed12")
             return out
 
+        def _run_fused_yuv_two_step(self, frames, tonemap, out_dtype, out, tm, update_metering, alpha, rows_per_task, profile_events):
+            from .color.yuv_420 import YCrCb_T_bgr, _mat9
+            assert out_dtype == u8, "yuv420 output is u8"
+            h, w = frames[0].shape[0], frames[0].shape[1] * 2 // 3
+            plan = self._resize_plan(h, w)
+            ho, wo = (h, w) if plan is None else (plan[0][1], plan[0][0])
+            assert ho % 2 == 0 and wo % 2 == 0, "yuv420 output needs even output dimensions"
+            rgb = getattr(self, "_yuv_rgb_scratch", None)
+            if rgb is None or len(rgb) < len(frames) or tuple(rgb[0].shape) != (ho, wo, 3) or rgb[0].device != torch.device(self.device):
+                rgb = self._yuv_rgb_scratch = [torch.empty((ho, wo, 3), dtype=torch.uint8, device=self.device) for _ in frames]
+            rgb = self._run_fused(frames, tonemap, out_dtype, rgb[:len(frames)], tm, update_metering, alpha, rows_per_task, profile_events)
+            if out is None:
+                out = [torch.empty((ho * 3 // 2, wo), dtype=torch.uint8, device=self.device) for _ in frames]
+            mat = _mat9(YCrCb_T_bgr)
+            with torch.cuda.device(self.device):
+                for r, o in zip(rgb, out):
+                    assert tuple(o.shape) == (ho * 3 // 2, wo) and o.dtype == torch.uint8 and o.is_contiguous() and o.is_cuda
+                    _lib.check(_lib.lib.b200isp_rgb_yuv420(r.data_ptr(), u8.code, o.data_ptr(), u8.code, ho, wo, mat,
+                                                           _lib.stream_ptr(self.device)), "rgb_yuv420")
+            return out
+
         def process_packed12(self, frames: Sequence[torch.Tensor], tonemap: str = "reinhard", gamma: float = 1.0,
                              intensity: float = 1.0, light_adapt: float = 1.0, color_adapt: float = 0.0,
                              dtype=u8, ids_format: bool = False, out: Optional[list] = None,
@@ -527,14 +554,14 @@ def camera_isp(name: str, dtype=f32):
             announced tensors must not be modified before that call.  Results are identical to calling without it.
             ``meter_fn(frames, alpha, out, cooperative)``: replaces the local metering (distributed.SharedExposure).
 
-            ``yuv420=True`` (Camera16 + Reinhard + u8, fused frames only): every output is the planar YUV 4:2:0 image
-            ``color.rgb_yuv420_image`` would make of the RGB8 result -- ``(3H/2, W)`` u8, bit-identical -- written
-            directly by the normalise pass (1.5 instead of 3 bytes per pixel, no second kernel)."""
+            ``yuv420=True`` (u8, fused frames only): every output is the planar YUV 4:2:0 image
+            ``color.rgb_yuv420_image`` would make of the RGB8 result -- ``(3H/2, W)`` u8, bit-identical.  Camera16 +
+            Reinhard writes it directly from the normalise pass (no RGB image at all); every other path runs the RGB8
+            sweep into a device scratch followed by the stand-alone conversion kernel -- the host sees 1.5 B/px either way."""
             assert tonemap in ("linear", "reinhard")
             out_dtype = as_dtype(dtype)
             if yuv420:
-                assert isp_dtype == f16 and tonemap == "reinhard" and out_dtype == u8, \
-                    "yuv420 output is implemented for Camera16 + Reinhard + u8"
+                assert out_dtype == u8, "yuv420 output is u8"
                 assert self.transform == interpolate.ImageTransform.none, "yuv420 output cannot be transformed"
             frames = [f.to(self.device) for f in frames]
             assert 1 <= len(frames) <= _lib.MAX_FRAMES, f"1..{_lib.MAX_FRAMES} frames per call"
@@ -545,7 +572,7 @@ def camera_isp(name: str, dtype=f32):
                 frames, ids_format, lookahead = self._ids_to_standard(frames), False, None
                 self._lookahead = None
             fused = all(self._fused_ok(f, ids_format) for f in frames)
-            assert (fused and not self._resizes) or not yuv420, "yuv420 output needs frames the fused sweep accepts (no resize, width % 8 == 0)"
+            assert fused or not yuv420, "yuv420 output needs frames the fused sweep accepts (width % 8 == 0)"
             if not fused:
                 images = [self.load_packed12(f, ids_format) for f in frames]
                 if meter_fn is not None and update_metering:      # distributed.SharedExposure: joint metering of all ranks

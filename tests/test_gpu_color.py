@@ -3,6 +3,7 @@ import os
 
 import numpy as np
 import pytest
+import torch
 
 from oracle import isp_oracle as O
 from tests.util import rng, random_plane, to_cuda, to_np
@@ -93,14 +94,32 @@ def test_fused_yuv420_output(cuda, pattern, gamma, shape):
             assert_close_int(to_np(g), e, 1, "rgb behind the yuv")
 
 
+@pytest.mark.parametrize("dt,tonemap,kw", [("f32", "reinhard", dict()), ("f32", "linear", dict()), ("f16", "linear", dict()),
+                                           ("f32", "reinhard", dict(resize_width=48)), ("f16", "reinhard", dict(resize_width=48))])
+def test_yuv420_output_on_every_fused_path(cuda, dt, tonemap, kw):
+    """yuv420=True where no YUV epilogue exists (Camera32, linear, resizing ISPs): RGB8 sweep into a device scratch + the
+    stand-alone conversion kernel -- still bit-identical to rgb_yuv420_image of the RGB result, metrics unchanged"""
+    from taichi_image_b200 import bayer, camera_isp, color
+    from tests.util import packed_frame
+    cls = camera_isp.Camera16 if dt == "f16" else camera_isp.Camera32
+    a, b = cls(bayer.BayerPattern.RGGB, **kw), cls(bayer.BayerPattern.RGGB, **kw)
+    r = rng(84)
+    for step in range(2):
+        cu = [to_cuda(packed_frame(r, 64, 96)) for _ in range(2)]
+        yuv = a.process_packed12(cu, tonemap=tonemap, gamma=0.9, yuv420=True)
+        rgb = b.process_packed12(cu, tonemap=tonemap, gamma=0.9)
+        for y, g in zip(yuv, rgb):
+            assert tuple(y.shape) == (g.shape[0] * 3 // 2, g.shape[1]) and y.dtype == torch.uint8
+            assert np.array_equal(to_np(y), to_np(color.rgb_yuv420_image(g))), f"step {step}"
+        assert torch.equal(a.metrics, b.metrics)
+
+
 def test_fused_yuv420_unsupported_configurations_fail(cuda):
     from taichi_image_b200 import bayer, camera_isp
     from tests.util import packed_frame
     fr = [to_cuda(packed_frame(rng(83), 16, 32))]
     with pytest.raises(AssertionError):
-        camera_isp.Camera32(bayer.BayerPattern.RGGB).process_packed12(fr, tonemap="reinhard", yuv420=True)
-    with pytest.raises(AssertionError):
-        camera_isp.Camera16(bayer.BayerPattern.RGGB).process_packed12(fr, tonemap="linear", yuv420=True)
+        camera_isp.Camera32(bayer.BayerPattern.RGGB).process_packed12(fr, tonemap="reinhard", yuv420=True, dtype="u16")
     # the C layer refuses as well (no silent RGB output into a YUV-sized buffer)
     from taichi_image_b200 import _lib
     import torch

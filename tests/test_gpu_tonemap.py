@@ -95,3 +95,36 @@ def test_resize_area_matches_box_filter(cuda):
     assert_close_float(got, ref, rtol=1e-5, atol=1e-6)
     got = to_np(interpolate.resize_area(to_cuda(np.full((30, 50, 3), 0.25, np.float32)), (19, 7)))
     assert_close_float(got, np.full((7, 19, 3), 0.25, np.float32), rtol=1e-5, atol=1e-6)
+
+
+def _area_ref(img, wd, hd):
+    """exact box filter in float64: output (i, j) = coverage-weighted mean of the source over
+    [i hs/hd, (i+1) hs/hd) x [j ws/wd, (j+1) ws/wd)  (separable coverage weights)"""
+    hs, ws = img.shape[:2]
+
+    def weights(n_src, n_dst):
+        m = np.zeros((n_dst, n_src))
+        f = n_src / n_dst
+        for o in range(n_dst):
+            a, b = o * f, min((o + 1) * f, n_src)
+            for s in range(int(np.floor(a)), min(int(np.ceil(b)), n_src)):
+                m[o, s] = max(0.0, min(b, s + 1) - max(a, s))
+        return m / m.sum(axis=1, keepdims=True)
+
+    wr, wc = weights(hs, hd), weights(ws, wd)
+    return np.einsum("ir,jc,rck->ijk", wr, wc, img.astype(np.float64))
+
+
+@pytest.mark.parametrize("size", [(19, 7), (37, 23), (50, 30), (64, 48), (70, 41)])
+def test_resize_area_fractional_coverage(cuda, size):
+    """EXTENSION: the fractional-coverage branch of area_kernel (csrc/resize.cu) on a RANDOM image: non-integer shrink
+    factors in both axes, a factor of exactly 1 and an enlargement, against an exact float64 box filter"""
+    from taichi_image_b200 import interpolate
+    img = random_plane(rng(26), (30, 50, 3), "f32")
+    wd, hd = size
+    got = to_np(interpolate.resize_area(to_cuda(img), (wd, hd)))
+    assert got.shape == (hd, wd, 3)
+    assert_close_float(got, _area_ref(img, wd, hd).astype(np.float32), rtol=2e-5, atol=2e-6)
+    u8 = random_plane(rng(27), (30, 50, 3), "u8")
+    got8 = to_np(interpolate.resize_area(to_cuda(u8), (wd, hd)))
+    assert np.abs(got8.astype(np.int64) - np.trunc(_area_ref(u8, wd, hd) + 1e-9).astype(np.int64)).max() <= 1
