@@ -185,7 +185,11 @@ typedef struct {
   int resize_gather;            /* 1: force the per-output-pixel gather instead of the resizing sweep (testing / profiling) */
   int out_pitch;                /* elements per OUTPUT row; 0 = dense (3 * width).  Larger: every output frame is a tile of a bigger
                                    image (the rig's camera grid, scripts/tonemap_scan.py:91-100) -- the sweep writes the tile in place */
+  int flip;                     /* ISP transform applied by the sweep's store (interpolate.py:36-56): bit 0 = flip_horiz, bit 1 = flip_vert,
+                                   3 = rotate_180; the transposing transforms stay with b200isp_transform */
   int reserved0;                /* keeps the pointers below 8-byte aligned; must be 0 */
+  int ids_layout;               /* packed layout of the input frames: 0 = standard (packed.py:23-31), 1 = IDS (packed.py:36-44),
+                                   decoded inside the row loader (4 instead of 2 instructions per sample, no re-pack pass) */
   void* profile_start;          /* optional cudaEvent_t pair recorded on `stream` immediately before / after */
   void* profile_stop;           /*   the dominant streaming kernel (bench.py's live roofline timing); NULL = off */
   void* meter_cache;            /* optional device scratch: >= n_frames*ceil(H/stride)*ceil(W/stride)*12 bytes; the second */

@@ -123,6 +123,7 @@ def camera_isp(name: str, dtype=f32):
             self.dtype = isp_dtype
             # look-ahead metering state (process_packed12(lookahead=...)): second metrics buffer, side stream,
             # the pending update for the announced next batch, completion event of the previous sweep
+            self._ids_layout = False          # packed layout of the frames of the current process_packed12 call (metering included)
             self._metrics_alt = None
             self._side_stream = None
             self._lookahead = None
@@ -211,9 +212,11 @@ def camera_isp(name: str, dtype=f32):
             return self._convert(image, 2)
 
         def _fused_ok(self, image_data, ids_format) -> bool:
+            """frames the fused sweep takes: even height >= 4, width % 8 == 0, contiguous, 4-byte aligned.  The IDS layout is
+            decoded inside the sweep's row loader (csrc/fused_isp.cuh ids_sample) except by the resizing sweep."""
             h, w3 = image_data.shape
             w = w3 * 2 // 3
-            return (not ids_format and h >= 4 and h % 2 == 0 and w >= 8 and w % 8 == 0
+            return (not (ids_format and (self._resizes or self.demosaic != "malvar")) and h >= 4 and h % 2 == 0 and w >= 8 and w % 8 == 0
                     and image_data.is_contiguous() and image_data.data_ptr() % 4 == 0)
 
         def _ids_to_standard(self, frames):
@@ -229,10 +232,10 @@ def camera_isp(name: str, dtype=f32):
             """camera_isp.py:333-340: decode12(scaled) + demosaic (+CCM) (+resize) -> float RGB of the ISP dtype"""
             assert image_data.dtype == torch.uint8 and image_data.ndim == 2
             image_data = image_data.to(self.device)
-            if ids_format and self._fused_ok(image_data, False):
-                image_data, ids_format = self._ids_to_standard([image_data])[0], False
+            if ids_format and not self._fused_ok(image_data, True) and self._fused_ok(image_data, False):
+                image_data, ids_format = self._ids_to_standard([image_data])[0], False     # resizing / bilinear sweep: standard layout only
             if self._fused_ok(image_data, ids_format):
-                return self._run_fused([image_data], "none", isp_dtype, None, {})[0]      # resize included (resize_isp.cuh)
+                return self._run_fused([image_data], "none", isp_dtype, None, {}, ids_format=ids_format)[0]   # resize included
             w, h = (image_data.shape[1] * 2 // 3, image_data.shape[0])
             cfa = torch.empty(h, w, dtype=torch_dtype, device=self.device)
             packed.decode12_kernel(isp_dtype, scaled=True, ids_format=ids_format)(image_data.contiguous().view(-1), cfa.view(-1))
@@ -419,7 +422,7 @@ def camera_isp(name: str, dtype=f32):
 
         # ------------------------------------------------------------ fused path
         def _fused_params(self, frames, tonemap, out_dtype, tm, update_metering=False, alpha=0.0, rows_per_task=0,
-                          profile_events=None, yuv420=False):
+                          profile_events=None, yuv420=False, ids_format=None, flip=0):
             """b200isp_fused_params for a list of same-shape packed12 frames (include/b200isp.h)"""
             h, w3 = frames[0].shape
             w = w3 * 2 // 3
@@ -438,6 +441,8 @@ def camera_isp(name: str, dtype=f32):
             p.update_metering, p.rows_per_task = int(update_metering), int(rows_per_task)
             p.demosaic = 1 if self.demosaic == "bilinear" else 0
             p.out_yuv420 = int(bool(yuv420))
+            p.ids_layout = int(bool(self._ids_layout if ids_format is None else ids_format))
+            p.flip = int(flip)
             p.reinhard_group = int(os.environ.get("B200ISP_REINHARD_GROUP", "0"))      # tuning knob (0 = library default)
             plan = self._resize_plan(h, w)
             ho, wo = h, w
@@ -479,7 +484,7 @@ def camera_isp(name: str, dtype=f32):
             return p
 
         def _run_fused(self, frames, tonemap, out_dtype, out, tm, update_metering=False, alpha=0.0, rows_per_task=0,
-                       profile_events=None, yuv420=False):
+                       profile_events=None, yuv420=False, ids_format=None, flip=0):
             h, w3 = frames[0].shape
             w = w3 * 2 // 3
             if yuv420 and not (isp_dtype == f16 and tonemap == "reinhard" and not self._resizes):
@@ -488,7 +493,8 @@ def camera_isp(name: str, dtype=f32):
                 # host only ever sees 1.5 bytes per pixel
                 return self._run_fused_yuv_two_step(frames, tonemap, out_dtype, out, tm, update_metering, alpha, rows_per_task,
                                                     profile_events)
-            p = self._fused_params(frames, tonemap, out_dtype, tm, update_metering, alpha, rows_per_task, profile_events, yuv420)
+            p = self._fused_params(frames, tonemap, out_dtype, tm, update_metering, alpha, rows_per_task, profile_events, yuv420,
+                                   ids_format, flip)
             plan = self._resize_plan(h, w)
             if plan is not None:
                 w, h = plan[0]
@@ -567,11 +573,12 @@ def camera_isp(name: str, dtype=f32):
             assert 1 <= len(frames) <= _lib.MAX_FRAMES, f"1..{_lib.MAX_FRAMES} frames per call"
             shape = frames[0].shape
             assert all(f.shape == shape and f.dtype == torch.uint8 and f.ndim == 2 for f in frames)
-            if ids_format and all(self._fused_ok(f, False) for f in frames):
-                # IDS layout: re-pack into the standard layout (scratch reused by every call, hence no look-ahead)
+            if ids_format and not all(self._fused_ok(f, True) for f in frames) and all(self._fused_ok(f, False) for f in frames):
+                # IDS layout + resizing / bilinear sweep: re-pack into the standard layout (scratch reused by every call, hence no look-ahead)
                 frames, ids_format, lookahead = self._ids_to_standard(frames), False, None
                 self._lookahead = None
             fused = all(self._fused_ok(f, ids_format) for f in frames)
+            self._ids_layout = bool(ids_format) and fused      # every _fused_params of this call (sweep, metering) decodes IDS
             assert fused or not yuv420, "yuv420 output needs frames the fused sweep accepts (width % 8 == 0)"
             if not fused:
                 images = [self.load_packed12(f, ids_format) for f in frames]
@@ -592,13 +599,20 @@ def camera_isp(name: str, dtype=f32):
                     return list(out)
                 return res
             tm = dict(gamma=gamma, intensity=intensity, light_adapt=light_adapt, color_adapt=color_adapt)
+            # flip_horiz / flip_vert / rotate_180 are applied by the sweep's store (no extra pass); the transposing transforms
+            # run the tiled transform kernel on the results
+            flip = 0
+            if not self._resizes and not yuv420 and self.demosaic == "malvar":
+                flip = {interpolate.ImageTransform.flip_horiz: 1, interpolate.ImageTransform.flip_vert: 2,
+                        interpolate.ImageTransform.rotate_180: 3}.get(self.transform, 0)
+            finish = (lambda outs: outs) if (yuv420 or flip) else (lambda outs: [interpolate.transform(o, self.transform) for o in outs])
             pipelined = update_metering and (lookahead is not None or self._lookahead is not None or meter_fn is not None)
             if not pipelined:
                 alpha = self._metrics_and_alpha() if update_metering else 0.0
                 assert self.metrics is not None, "update_metering=False needs metrics from an earlier call"
                 outputs = self._run_fused(frames, tonemap, out_dtype, out, tm, update_metering=update_metering, alpha=alpha,
-                                          rows_per_task=rows_per_task, profile_events=profile_events, yuv420=yuv420)
-                return outputs if yuv420 else [interpolate.transform(o, self.transform) for o in outputs]
+                                          rows_per_task=rows_per_task, profile_events=profile_events, yuv420=yuv420, flip=flip)
+                return finish(outputs)
 
             # ---- look-ahead pipeline: metering(k+1) on the side stream under sweep(k)
             meter = meter_fn if meter_fn is not None else self.meter_packed12
@@ -629,7 +643,7 @@ def camera_isp(name: str, dtype=f32):
                 ready = torch.cuda.Event()
                 ready.record(main)
             outputs = self._run_fused(frames, tonemap, out_dtype, out, tm, update_metering=False,
-                                      rows_per_task=rows_per_task, profile_events=profile_events, yuv420=yuv420)
+                                      rows_per_task=rows_per_task, profile_events=profile_events, yuv420=yuv420, flip=flip)
             ev_sweep = torch.cuda.Event()
             ev_sweep.record(main)
             if lookahead is not None:
@@ -646,7 +660,7 @@ def camera_isp(name: str, dtype=f32):
                             done.record(side)
                     self._lookahead = dict(key=key(nxt), event=done, out=self._metrics_alt, frames=nxt)
             self._ev_prev_sweep = ev_sweep
-            return outputs if yuv420 else [interpolate.transform(o, self.transform) for o in outputs]
+            return finish(outputs)
 
     ISP.reinhard_kernel = staticmethod(_reinhard_kernel)     # camera_isp.py:415-416
     ISP.linear_kernel = staticmethod(_linear_kernel)

@@ -40,6 +40,10 @@ static int fused_setup(const char* what, const uint8_t* const* packed_host, void
               "%s: unknown demosaic %d", what, p.demosaic);
   k.metrics = metrics; k.ws = (Workspace*)workspace; k.frame0 = 0;
   k.kbase = p.demosaic == B200ISP_DEMOSAIC_BILINEAR ? kBilinearBase : 0;
+  k.flip = p.flip & 3;
+  ISP_REQUIRE(!(k.flip && (resizes(p) || p.out_yuv420)), B200ISP_E_ARG, "%s: flips in the store need the plain RGB sweep (no resize, no YUV)", what);
+  k.ids = p.ids_layout ? 1 : 0;
+  ISP_REQUIRE(!(k.ids && resizes(p)), B200ISP_E_ARG, "%s: the IDS layout is not available with the fused resize (re-pack first)", what);
   k.orow = p.out_pitch > 0 ? p.out_pitch : 3 * p.width;
   ISP_REQUIRE(p.out_pitch <= 0 || (k.orow >= 3 * p.width && (k.orow * (int)dtype_size(p.out_dtype)) % 16 == 0), B200ISP_E_ALIGN,
               "%s: out_pitch must be >= 3 * width elements and a multiple of 16 bytes", what);
@@ -64,11 +68,11 @@ static int with_packed12_sampler(const FramePtrs& fp, const b200isp_fused_params
   const long long n = (long long)n_frames * hs * wsamp;
   float* cache = (p.meter_cache && p.meter_cache_bytes >= (size_t)n * 3 * sizeof(float)) ? (float*)p.meter_cache : nullptr;
   if (stride % 8 == 0) {
-    if (cam16) return f(Packed12FastSampler<true>{Packed12Src<true>{fp, p.width * 3 / 2}, k, stride, hs, wsamp, p.width * 3 / 8}, n, cache);
-    return f(Packed12FastSampler<false>{Packed12Src<false>{fp, p.width * 3 / 2}, k, stride, hs, wsamp, p.width * 3 / 8}, n, cache);
+    if (cam16) return f(Packed12FastSampler<true>{Packed12Src<true>{fp, p.width * 3 / 2, k.ids}, k, stride, hs, wsamp, p.width * 3 / 8}, n, cache);
+    return f(Packed12FastSampler<false>{Packed12Src<false>{fp, p.width * 3 / 2, k.ids}, k, stride, hs, wsamp, p.width * 3 / 8}, n, cache);
   }
-  if (cam16) return f(Packed12Sampler<true>{Packed12Src<true>{fp, p.width * 3 / 2}, k, stride, hs, wsamp}, n, cache);
-  return f(Packed12Sampler<false>{Packed12Src<false>{fp, p.width * 3 / 2}, k, stride, hs, wsamp}, n, cache);
+  if (cam16) return f(Packed12Sampler<true>{Packed12Src<true>{fp, p.width * 3 / 2, k.ids}, k, stride, hs, wsamp}, n, cache);
+  return f(Packed12Sampler<false>{Packed12Src<false>{fp, p.width * 3 / 2, k.ids}, k, stride, hs, wsamp}, n, cache);
 }
 
 extern "C" int b200isp_meter_packed12_phase1(const uint8_t* const* packed_host, int n_frames, const b200isp_fused_params* params,

@@ -49,11 +49,25 @@ struct FramePtrs {
 // outside the image and for the halo columns of the first / last thread column -> "zero sample"), the halo
 // loads are predicated on per-thread constants instead of being zero-filled, and the row is delivered as the
 // eight pairs (v[k], v[k+4]).
-template <bool CAM16>
+// IDS layout (packed.py:36-44): a pixel pair is the bytes (b0, b1, b2) with p0 = b0 << 4 | (b2 & 0xF), p1 = b1 << 4 | b2 >> 4,
+// so a sample's twelve bits are a byte plus a nibble from another byte.  Given the two shifted copies of the word(s) that
+// bring the byte to mantissa bits 15..22 (a) and the nibble to bits 11..14 (b), the biased sample 1 + v/4096 is two LOP3:
+// a bit select and the usual mask-or -- 4 instead of 2 instructions per sample, still no conversion and no re-pack pass.
+__device__ __forceinline__ float ids_sample(uint32_t a, uint32_t b) {
+  uint32_t t;
+  asm("lop3.b32 %0, %1, %2, %3, 0xE4;" : "=r"(t) : "r"(a), "r"(b), "r"(0x007F8000u));      // (a & m) | (b & ~m)
+  return biased_from_shifted(t, 0x007FF800u, 0x3F800000u);
+}
+
+// EXT: the "extended" instantiation that also decodes the IDS layout (run-time flag `ids`).  The lean instantiation carries
+// none of that code: the sweep is so sensitive to the size of its hot loop that the run-time branch alone cost the cfg2
+// kernel 5 % (160.7 -> 168.8 us) -- measured, profiles/r02_ids_flip.txt.
+template <bool CAM16, bool EXT = false>
 struct Packed12Loader2 {
   FramePtrs fp;
   int pitch_words;       // W * 3 / 8
   int frame0;
+  int ids;               // 0: standard layout (packed.py:23-31), 1: IDS layout (packed.py:36-44), kernel-uniform
   static constexpr uint32_t kRowMask = 0x007FF800u;
 #ifndef ISP_S2_RING
 #define ISP_S2_RING 0      // measured on cfg2 (see stream2.cuh): register fetch 172 us; ring + 3x unroll 229 us; ring + 1 step 185 us
@@ -95,6 +109,31 @@ struct Packed12Loader2 {
     if (KIND != K_GENERAL) m = kRowMask;                     // immediates: one LOP3 per pixel
     const uint32_t mL = KIND == K_CORE ? kRowMask : (m & c.mL), mR = KIND == K_CORE ? kRowMask : (m & c.mR);
     float v[12];
+    if (EXT && ids) {
+      // pairs = byte triples: (-2,-1) = bytes 1..3 of w0; (0,1) = bytes 0..2 of w1; (2,3) = byte 3 of w1 + bytes 0..1 of w2;
+      // (4,5) = bytes 2..3 of w2 + byte 0 of w3; (6,7) = bytes 1..3 of w3; (8,9) = bytes 0..2 of w4
+      v[0] = ids_sample(w0 << 7, w0 >> 13);
+      v[1] = ids_sample(w0 >> 1, w0 >> 17);
+      v[2] = ids_sample(w1 << 15, w1 >> 5);
+      v[3] = ids_sample(w1 << 7, w1 >> 9);
+      v[4] = ids_sample(__funnelshift_r(w1, w2, 9), __funnelshift_r(w1, w2, 29));
+      v[5] = ids_sample(__funnelshift_r(w1, w2, 17), w2 >> 1);
+      v[6] = ids_sample(w2 >> 1, __funnelshift_r(w2, w3, 21));
+      v[7] = ids_sample(__funnelshift_r(w2, w3, 9), __funnelshift_r(w2, w3, 25));
+      v[8] = ids_sample(w3 << 7, w3 >> 13);
+      v[9] = ids_sample(w3 >> 1, w3 >> 17);
+      v[10] = ids_sample(w4 << 15, w4 >> 5);
+      v[11] = ids_sample(w4 << 7, w4 >> 9);
+      if (KIND != K_CORE) {                  // zero samples: rows outside the image, halo columns of the first / last thread column
+        const float z = __uint_as_float(one);
+        if (mL == 0u) { v[0] = z; v[1] = z; }
+        if (mR == 0u) { v[10] = z; v[11] = z; }
+        if (m == 0u) {
+#pragma unroll
+          for (int j = 2; j < 10; ++j) v[j] = z;
+        }
+      }
+    } else {
     v[0] = biased_from_shifted(w0 << 3, mL, one);                      // pixel -2: bits 8..19 of w0
     v[1] = biased_from_shifted(w0 >> 9, mL, one);                      // pixel -1: bits 20..31 of w0
     v[2] = biased_from_shifted(w1 << 11, m, one);                      // pixel 0 : bits 0..11 of w1
@@ -107,6 +146,7 @@ struct Packed12Loader2 {
     v[9] = biased_from_shifted(w3 >> 9, m, one);                       // pixel 7 : bits 20..31 of w3
     v[10] = biased_from_shifted(w4 << 11, mR, one);                    // pixel 8
     v[11] = biased_from_shifted(w4 >> 1, mR, one);                     // pixel 9
+    }
     if constexpr (CAM16) {
       constexpr float k = 4096.f * kInv4095;         // (b - 1) * 4096 * f32(1/4095), one rounding, then through f16
 #pragma unroll
@@ -126,10 +166,12 @@ template <bool CAM16>
 struct Packed12Src {
   FramePtrs fp;
   int pitch;             // bytes per packed row
+  int ids = 0;           // 1: IDS layout (packed.py:36-44)
   __device__ __forceinline__ float at(int frame, int r, int c) const {
     const uint8_t* p = fp.in[frame] + (size_t)r * pitch + 3 * (c >> 1);
     const uint32_t b1 = p[1];
-    const uint32_t v = (c & 1) ? ((uint32_t)p[2] << 4) | (b1 >> 4) : ((b1 & 0xFu) << 8) | p[0];
+    uint32_t v = (c & 1) ? ((uint32_t)p[2] << 4) | (b1 >> 4) : ((b1 & 0xFu) << 8) | p[0];
+    if (ids) v = (c & 1) ? (b1 << 4) | ((uint32_t)p[2] >> 4) : ((uint32_t)p[0] << 4) | ((uint32_t)p[2] & 0xFu);
     return round_isp<CAM16>(__fmul_rn((float)v, kInv4095));
   }
 };
@@ -145,6 +187,8 @@ struct IspConsts {
   Workspace* ws;
   int frame0;
   int kbase;                 // 0: Malvar-He-Cutler, kBilinearBase: bilinear demosaic (offset into c_taps / c_border)
+  int ids;                   // packed layout of the input frames: 0 standard, 1 IDS
+  int flip;                  // flips applied by the store: bit 0 horizontal, bit 1 vertical (rotate_180 = 3)
   int orow;                  // elements per OUTPUT row: 3 W for dense frames, more when the frames are tiles of a grid image
 };
 
@@ -241,6 +285,33 @@ __device__ __forceinline__ void store_row8(const WarpCtx& wc, OutT* warp_out /* 
   uint32_t w[NW];
   Quant<OutT>::pack(v, w);
   warp_store_row<NW, FULL>(wc, warp_out + (size_t)((unsigned)row * (unsigned)orow), w);
+}
+
+// The same with the ISP's flip transforms applied in the store (interpolate.py:36-56: flip_vert = row H-1-r, flip_horiz =
+// column W-1-c, rotate_180 = both): a flipped row is the row's pixels in reverse order, so the warp's strip lands mirrored
+// (lane order reversed in the stage, the lane's eight pixels reversed before packing) -- no extra pass over the image.
+// k.flip: bit 0 = horizontal, bit 1 = vertical; kernel-uniform, 0 on the hot path.
+// EXT: only the extended instantiations carry the flip code (see Packed12Loader2).
+template <typename OutT, bool FULL = false, bool EXT = false>
+__device__ __forceinline__ void store_out(const WarpCtx& wc, OutT* warp_out /* frame + 24 * tcol0 */, const IspConsts& k, int row,
+                                          const uint32_t (&v)[24]) {
+  if (!EXT || k.flip == 0) {
+    store_row8<OutT, FULL>(wc, warp_out, k.orow, row, v);
+    return;
+  }
+  const int orow_idx = (k.flip & 2) ? k.H - 1 - row : row;
+  if (!(k.flip & 1)) {
+    store_row8<OutT, false>(wc, warp_out, k.orow, orow_idx, v);
+    return;
+  }
+  uint32_t r[24];
+#pragma unroll
+  for (int q = 0; q < 8; ++q) { r[3 * q] = v[3 * (7 - q)]; r[3 * q + 1] = v[3 * (7 - q) + 1]; r[3 * q + 2] = v[3 * (7 - q) + 2]; }
+  constexpr int NW = Quant<OutT>::kWords;
+  uint32_t w[NW];
+  Quant<OutT>::pack(r, w);
+  OutT* base = warp_out - 24 * wc.tcol0 + 3 * (k.W - 8 * (wc.tcol0 + wc.nvalid));        // mirrored strip start
+  warp_store_row<NW, false>(wc, base + (size_t)((unsigned)orow_idx * (unsigned)k.orow), w, wc.lane < wc.nvalid ? wc.nvalid - 1 - wc.lane : wc.lane);
 }
 
 template <typename OutT> __device__ __forceinline__ void store_px(void* frame_out, int W, int row, int col, const float (&y)[3]) {
@@ -552,7 +623,7 @@ __device__ __forceinline__ f2 reinhard_pmax2(const ReinhardConsts& c, const f2 (
   return mul2(sm, pk(fast_rcp(dl), fast_rcp(dh)));
 }
 
-template <bool CAM16, typename OutT>
+template <bool CAM16, typename OutT, bool EXT = false>
 struct EpiRgb2 {      // load_packed12: ISP-dtype float RGB out
   FramePtrs fp;
   IspConsts k;
@@ -578,12 +649,12 @@ struct EpiRgb2 {      // load_packed12: ISP-dtype float RGB out
       raw_to_rgb<CAM16>(k, &x.v[3 * q], rgb);
       v[3 * q] = __float_as_uint(rgb[0]); v[3 * q + 1] = __float_as_uint(rgb[1]); v[3 * q + 2] = __float_as_uint(rgb[2]);
     }
-    store_row8<OutT>(st.wc, st.out, k.orow, row, v);
+    store_out<OutT, false, EXT>(st.wc, st.out, k, row, v);
   }
 };
 
 // FAST: Camera32, no CCM, gamma 1 -- the configuration the roofline is quoted on; everything stays in pairs.
-template <bool CAM16, typename OutT, bool FAST>
+template <bool CAM16, typename OutT, bool FAST, bool EXT = false>
 struct EpiLinear2 {
   static_assert(!(FAST && CAM16), "the packed fast path is Camera32 only");
   FramePtrs fp;
@@ -617,7 +688,7 @@ struct EpiLinear2 {
       linear_px<GAMMA>(st.c, rgb, y);
       v[3 * q] = Quant<OutT>::q(y[0]); v[3 * q + 1] = Quant<OutT>::q(y[1]); v[3 * q + 2] = Quant<OutT>::q(y[2]);
     }
-    store_row8<OutT>(st.wc, st.out, k.orow, row, v);
+    store_out<OutT, false, EXT>(st.wc, st.out, k, row, v);
   }
   template <bool BROW, bool GFIRST, int KIND>
   __device__ __forceinline__ void emit_generic(const State& st, int row, const f2 (&R)[4], const f2 (&G)[4], const f2 (&B)[4]) const {
@@ -683,7 +754,7 @@ struct EpiLinear2 {
           }
         }
       }
-      store_row8<OutT, KIND == K_CORE>(st.wc, st.out, k.orow, row, v);
+      store_out<OutT, KIND == K_CORE, EXT>(st.wc, st.out, k, row, v);
     }
   }
 };
@@ -783,7 +854,7 @@ struct EpiReinhardMax2 {      // pass 1: frame-global max of the mapped values (
   }
 };
 
-template <bool CAM16, typename OutT, bool CA0, bool GAMMA>
+template <bool CAM16, typename OutT, bool CA0, bool GAMMA, bool EXT = false>
 struct EpiReinhard2 {         // pass 2 recomputed from the packed frame: map, normalise by the max, gamma, quantise
   FramePtrs fp;
   IspConsts k;
@@ -808,7 +879,7 @@ struct EpiReinhard2 {         // pass 2 recomputed from the packed frame: map, n
       reinhard_out<CAM16, GAMMA>(st.c, p, y);
       v[3 * q] = Quant<OutT>::q(y[0]); v[3 * q + 1] = Quant<OutT>::q(y[1]); v[3 * q + 2] = Quant<OutT>::q(y[2]);
     }
-    store_row8<OutT>(st.wc, st.out, k.orow, row, v);
+    store_out<OutT, false, EXT>(st.wc, st.out, k, row, v);
   }
   __device__ __forceinline__ bool fast_kinds_ok(const State&) const { return true; }
   // packed path: color_adapt == 0, any gamma (kernel-uniform)
@@ -850,7 +921,7 @@ struct EpiReinhard2 {         // pass 2 recomputed from the packed frame: map, n
         }
       }
     }
-    store_row8<OutT, KIND == K_CORE>(st.wc, st.out, k.orow, row, v);
+    store_out<OutT, KIND == K_CORE, EXT>(st.wc, st.out, k, row, v);
   }
 
   template <bool BROW, bool GFIRST, int KIND>
@@ -924,18 +995,40 @@ struct Packed12FastSampler {
     }
   }
 
+  static __device__ __forceinline__ float idec(uint32_t a, uint32_t b) {      // IDS layout, see ids_sample
+    const float v = ids_sample(a, b);
+    if constexpr (CAM16) {
+      constexpr float kk = 4096.f * kInv4095;
+      return __half2float(__float2half_rn(fmaf(v, kk, -kk)));
+    } else {
+      return v;
+    }
+  }
+
   // the nine words of a sample -> scaled filter sums S (S * sc = x16 sum) of the three channels
   __device__ __forceinline__ void sums_from_words(uint32_t a0, uint32_t bm, uint32_t b0, uint32_t cm, uint32_t c0, uint32_t c1,
                                                   uint32_t dm, uint32_t d0, uint32_t e0, int row, float (&S)[3], float (&sc)[3],
                                                   bool& brow, bool& gsite) const {
     // pixel col-2 = bits 8..19 of word -1, col-1 = bits 20..31; col = bits 0..11 of word 0, col+1 = bits 12..23,
     // col+2 = bits 24..35 of (word 1 : word 0)
-    const float C = dec(c0 << 11);
-    const float EW = dec(cm >> 9) + dec(c0 >> 1);
-    const float EEWW = dec(cm << 3) + dec(__funnelshift_r(c0, c1, 13));
-    const float NS = dec(b0 << 11) + dec(d0 << 11);
-    const float D = (dec(bm >> 9) + dec(dm >> 9)) + (dec(b0 >> 1) + dec(d0 >> 1));
-    const float NNSS = dec(a0 << 11) + dec(e0 << 11);
+    float C, EW, EEWW, NS, D, NNSS;
+    if (src.ids) {
+      // IDS layout: pixel col = first sample of the triple in bytes 0..2 of the word, col+1 its second; col-2 / col-1 = the
+      // triple in bytes 1..3 of the previous word; col+2 = first sample of the triple that starts in byte 3
+      C = idec(c0 << 15, c0 >> 5);
+      EW = idec(cm >> 1, cm >> 17) + idec(c0 << 7, c0 >> 9);
+      EEWW = idec(cm << 7, cm >> 13) + idec(__funnelshift_r(c0, c1, 9), __funnelshift_r(c0, c1, 29));
+      NS = idec(b0 << 15, b0 >> 5) + idec(d0 << 15, d0 >> 5);
+      D = (idec(bm >> 1, bm >> 17) + idec(dm >> 1, dm >> 17)) + (idec(b0 << 7, b0 >> 9) + idec(d0 << 7, d0 >> 9));
+      NNSS = idec(a0 << 15, a0 >> 5) + idec(e0 << 15, e0 >> 5);
+    } else {
+      C = dec(c0 << 11);
+      EW = dec(cm >> 9) + dec(c0 >> 1);
+      EEWW = dec(cm << 3) + dec(__funnelshift_r(c0, c1, 13));
+      NS = dec(b0 << 11) + dec(d0 << 11);
+      D = (dec(bm >> 9) + dec(dm >> 9)) + (dec(b0 >> 1) + dec(d0 >> 1));
+      NNSS = dec(a0 << 11) + dec(e0 << 11);
+    }
     const bool brow0 = (k.pattern == B200ISP_GBRG || k.pattern == B200ISP_BGGR);
     const bool gfirst0 = (k.pattern == B200ISP_GRBG || k.pattern == B200ISP_GBRG);
     brow = brow0 != ((row & 1) != 0);
@@ -1070,43 +1163,56 @@ static inline void record_profile_event(void* ev, cudaStream_t s) {
 }
 
 // host dispatch of the Reinhard write sweep on (color_adapt == 0, gamma != 1)
-template <int P, bool CAM16, typename OutT>
-static int launch_reinhard(const Packed12Loader2<CAM16>& ld, const FramePtrs& fp, const IspConsts& k, const Stream2Geom& g, cudaStream_t s) {
-  const bool ca0 = k.ca == 0.f, gam = k.gamma != 1.0f;
-  if (ca0 && gam) { EpiReinhard2<CAM16, OutT, true, true> e{fp, k}; return launch_stream2<P>(ld, e, g, s, "isp_stream<reinhard>", k.kbase != 0); }
-  if (ca0) { EpiReinhard2<CAM16, OutT, true, false> e{fp, k}; return launch_stream2<P>(ld, e, g, s, "isp_stream<reinhard>", k.kbase != 0); }
-  if (gam) { EpiReinhard2<CAM16, OutT, false, true> e{fp, k}; return launch_stream2<P>(ld, e, g, s, "isp_stream<reinhard>", k.kbase != 0); }
-  EpiReinhard2<CAM16, OutT, false, false> e{fp, k};
-  return launch_stream2<P>(ld, e, g, s, "isp_stream<reinhard>", k.kbase != 0);
+template <int P, bool CAM16, typename OutT, bool EXT>
+static int launch_reinhard(const Packed12Loader2<CAM16, EXT>& ld, const FramePtrs& fp, const IspConsts& k, const Stream2Geom& g, cudaStream_t s) {
+  const bool ca0 = k.ca == 0.f, gam = k.gamma != 1.0f, bl = !EXT && k.kbase != 0;
+  if (ca0 && gam) { EpiReinhard2<CAM16, OutT, true, true, EXT> e{fp, k}; return launch_stream2<P>(ld, e, g, s, "isp_stream<reinhard>", bl); }
+  if (ca0) { EpiReinhard2<CAM16, OutT, true, false, EXT> e{fp, k}; return launch_stream2<P>(ld, e, g, s, "isp_stream<reinhard>", bl); }
+  if (gam) { EpiReinhard2<CAM16, OutT, false, true, EXT> e{fp, k}; return launch_stream2<P>(ld, e, g, s, "isp_stream<reinhard>", bl); }
+  EpiReinhard2<CAM16, OutT, false, false, EXT> e{fp, k};
+  return launch_stream2<P>(ld, e, g, s, "isp_stream<reinhard>", bl);
+}
+
+// EXT: the extended kernels (IDS layout in the row loader, flips in the store); Malvar only -- the host mirror routes
+// bilinear + IDS / flip through the re-pack pass / the transform kernel.
+template <bool CAM16, int MODE, typename OutT, bool EXT>
+static int run_pass_ext(const FramePtrs& fp, IspConsts k, int frame0, int nframes, int rows_per_task, cudaStream_t s,
+                        void* ev_start, void* ev_stop) {
+  k.frame0 = frame0;
+  const Stream2Geom g = make_geom2(k.H, k.W, nframes, rows_per_task);
+  const bool bl = !EXT && k.kbase != 0;
+  if (EXT && k.kbase != 0) { set_error("process_packed12: the IDS layout / flips are fused for the Malvar demosaic only"); return B200ISP_E_ARG; }
+  Packed12Loader2<CAM16, EXT> ld;
+  ld.fp = fp; ld.pitch_words = k.W * 3 / 8; ld.frame0 = frame0; ld.ids = k.ids;
+  int st = B200ISP_OK;
+  auto record = [&](void* ev) { record_profile_event(ev, s); };
+  if (ev_start) record(ev_start);
+  ISP_DISPATCH_PATTERN(k.pattern, P, {
+    if constexpr (MODE == MODE_RGB) { EpiRgb2<CAM16, OutT, EXT> e{fp, k}; st = launch_stream2<P>(ld, e, g, s, "isp_stream<rgb>", bl); }
+    else if constexpr (MODE == MODE_LINEAR) {
+      bool fast = false;
+      if constexpr (!CAM16) fast = !k.ccm && k.gamma == 1.0f;
+      if constexpr (!CAM16) { if (fast) { EpiLinear2<false, OutT, true, EXT> e{fp, k}; st = launch_stream2<P>(ld, e, g, s, "isp_stream<linear,fast>", bl); } }
+      if (!fast) { EpiLinear2<CAM16, OutT, false, EXT> e{fp, k}; st = launch_stream2<P>(ld, e, g, s, "isp_stream<linear>", bl); }
+    }
+    else if constexpr (MODE == MODE_RMAX) {
+      if (k.ca == 0.f) { EpiReinhardMax2<CAM16, true> e{fp, k}; st = launch_stream2<P>(ld, e, g, s, "isp_stream<reinhard_max>", bl); }
+      else { EpiReinhardMax2<CAM16, false> e{fp, k}; st = launch_stream2<P>(ld, e, g, s, "isp_stream<reinhard_max>", bl); }
+    } else {
+      st = launch_reinhard<P, CAM16, OutT, EXT>(ld, fp, k, g, s);
+    }
+  });
+  if (ev_stop) record(ev_stop);
+  return st;     // the 2-pixel image frame is renormalised inside the sweep (border_fix.cuh): no border kernel
 }
 
 template <bool CAM16, int MODE, typename OutT>
 static int run_pass(const FramePtrs& fp, IspConsts k, int frame0, int nframes, int rows_per_task, cudaStream_t s,
                     void* ev_start = nullptr, void* ev_stop = nullptr) {
-  k.frame0 = frame0;
-  const Stream2Geom g = make_geom2(k.H, k.W, nframes, rows_per_task);
-  Packed12Loader2<CAM16> ld;
-  ld.fp = fp; ld.pitch_words = k.W * 3 / 8; ld.frame0 = frame0;
-  int st = B200ISP_OK;
-  auto record = [&](void* ev) { record_profile_event(ev, s); };
-  if (ev_start) record(ev_start);
-  ISP_DISPATCH_PATTERN(k.pattern, P, {
-    if constexpr (MODE == MODE_RGB) { EpiRgb2<CAM16, OutT> e{fp, k}; st = launch_stream2<P>(ld, e, g, s, "isp_stream<rgb>", k.kbase != 0); }
-    else if constexpr (MODE == MODE_LINEAR) {
-      bool fast = false;
-      if constexpr (!CAM16) fast = !k.ccm && k.gamma == 1.0f;
-      if constexpr (!CAM16) { if (fast) { EpiLinear2<false, OutT, true> e{fp, k}; st = launch_stream2<P>(ld, e, g, s, "isp_stream<linear,fast>", k.kbase != 0); } }
-      if (!fast) { EpiLinear2<CAM16, OutT, false> e{fp, k}; st = launch_stream2<P>(ld, e, g, s, "isp_stream<linear>", k.kbase != 0); }
-    }
-    else if constexpr (MODE == MODE_RMAX) {
-      if (k.ca == 0.f) { EpiReinhardMax2<CAM16, true> e{fp, k}; st = launch_stream2<P>(ld, e, g, s, "isp_stream<reinhard_max>", k.kbase != 0); }
-      else { EpiReinhardMax2<CAM16, false> e{fp, k}; st = launch_stream2<P>(ld, e, g, s, "isp_stream<reinhard_max>", k.kbase != 0); }
-    } else {
-      st = launch_reinhard<P, CAM16, OutT>(ld, fp, k, g, s);
-    }
-  });
-  if (ev_stop) record(ev_stop);
-  return st;     // the 2-pixel image frame is renormalised inside the sweep (border_fix.cuh): no border kernel
+  // the max sweep stores nothing: it only needs the extended loader for IDS frames
+  const bool ext = k.ids != 0 || (MODE != MODE_RMAX && k.flip != 0);
+  if (ext) return run_pass_ext<CAM16, MODE, OutT, true>(fp, k, frame0, nframes, rows_per_task, s, ev_start, ev_stop);
+  return run_pass_ext<CAM16, MODE, OutT, false>(fp, k, frame0, nframes, rows_per_task, s, ev_start, ev_stop);
 }
 
 // ---------------------------------------------------------------- Camera16 Reinhard in ONE sweep + a light second pass
@@ -1219,14 +1325,22 @@ int run_rstore(const FramePtrs& fp_scratch, IspConsts k, int nframes, int rows_p
   } else {
     k.frame0 = 0;
     const Stream2Geom g = make_geom2(k.H, k.W, nframes, rows_per_task);
-    Packed12Loader2<true> ld;
-    ld.fp = fp_scratch; ld.pitch_words = k.W * 3 / 8; ld.frame0 = 0;
     int st = B200ISP_OK;
     if (ev_start) record_profile_event(ev_start, s);
-    ISP_DISPATCH_PATTERN(k.pattern, P, {
-      if (k.ca == 0.f) { EpiReinhardMax2<true, true, true> e{fp_scratch, k}; st = launch_stream2<P>(ld, e, g, s, "isp_stream<reinhard_store>", k.kbase != 0); }
-      else { EpiReinhardMax2<true, false, true> e{fp_scratch, k}; st = launch_stream2<P>(ld, e, g, s, "isp_stream<reinhard_store>", k.kbase != 0); }
-    });
+    auto launch = [&](auto ld, bool bl) -> int {
+      ld.fp = fp_scratch; ld.pitch_words = k.W * 3 / 8; ld.frame0 = 0; ld.ids = k.ids;
+      ISP_DISPATCH_PATTERN(k.pattern, P, {
+        if (k.ca == 0.f) { EpiReinhardMax2<true, true, true> e{fp_scratch, k}; st = launch_stream2<P>(ld, e, g, s, "isp_stream<reinhard_store>", bl); }
+        else { EpiReinhardMax2<true, false, true> e{fp_scratch, k}; st = launch_stream2<P>(ld, e, g, s, "isp_stream<reinhard_store>", bl); }
+      });
+      return st;
+    };
+    if (k.ids) {
+      if (k.kbase != 0) { set_error("process_packed12: the IDS layout is fused for the Malvar demosaic only"); return B200ISP_E_ARG; }
+      st = launch(Packed12Loader2<true, true>{}, false);
+    } else {
+      st = launch(Packed12Loader2<true, false>{}, k.kbase != 0);
+    }
     if (ev_stop) record_profile_event(ev_stop, s);
     return st;
   }
@@ -1274,7 +1388,7 @@ int run_fused(const FramePtrs& fp, int n_frames, const b200isp_fused_params& p, 
       // element-wise pass normalises it (no second sweep, no L2 grouping); dense outputs only (the normalise pass
       // indexes the output flat), pitched outputs take the two-sweep form below
       const size_t need = (size_t)n_frames * k.H * k.W * 3 * sizeof(__half);
-      if (p.reinhard_scratch && p.reinhard_scratch_bytes >= need && k.orow == 3 * k.W) {
+      if (p.reinhard_scratch && p.reinhard_scratch_bytes >= need && k.orow == 3 * k.W && k.flip == 0) {
         FramePtrs sc = fp;
         for (int f = 0; f < n_frames; ++f) sc.out[f] = (char*)p.reinhard_scratch + (size_t)f * k.H * k.W * 3 * sizeof(__half);
         st = run_rstore<true>(sc, k, n_frames, rpt, s, p.profile_start, p.profile_stop);
@@ -1293,7 +1407,7 @@ int run_fused(const FramePtrs& fp, int n_frames, const b200isp_fused_params& p, 
     if constexpr (!CAM16) {
       // Camera32 without colour correction, color_adapt == 0: ONE sweep that also stores the exact integer RGB (3 x u16 per
       // pixel) + an element-wise map / normalise / quantise pass (reinhard_u16.cuh)
-      if (!k.ccm && k.ca == 0.f && !p.out_yuv420 && k.H >= 4 && k.W >= 8 && p.reinhard_scratch &&
+      if (!k.ccm && k.ca == 0.f && !p.out_yuv420 && k.flip == 0 && k.ids == 0 && k.H >= 4 && k.W >= 8 && p.reinhard_scratch &&
           p.reinhard_scratch_bytes >= (size_t)n_frames * reinhard_u16_frame_bytes(k.H, k.W))
         return run_reinhard_u16<OutT>(fp, n_frames, p, k, s);
     }

@@ -58,7 +58,7 @@ int run_resize_pass_impl(const FramePtrs& io, const IspConsts& k0, const b200isp
   }
   const ResizeTasks rt = make_resize_tasks(k.H, k.W, n_frames, p.out_height, p.scale_r, p.rows_per_task);
   Packed12Loader2<CAM16> ld;
-  ld.fp = io; ld.pitch_words = k.W * 3 / 8; ld.frame0 = 0;
+  ld.fp = io; ld.pitch_words = k.W * 3 / 8; ld.frame0 = 0; ld.ids = 0;
   const EpiResize2<CAM16, MODE, OutT> epi{io, k, p.out_height, p.out_width, p.scale_r, p.scale_c};
   const long long blocks = (rt.total_tasks + kS2Warps - 1) / kS2Warps;
   ISP_DISPATCH_PATTERN(k.pattern, P, {

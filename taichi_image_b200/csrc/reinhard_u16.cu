@@ -8,7 +8,7 @@ size_t reinhard_u16_frame_bytes(int H, int W) { return reinhard_u16_frame_bytes_
 static int run_pass_a(const U16Scratch& sc, const FramePtrs& fp, const IspConsts& k, int n_frames, int rpt, cudaStream_t s) {
   const Stream2Geom g = make_geom2(k.H, k.W, n_frames, rpt);
   Packed12Loader2<false> ld;
-  ld.fp = fp; ld.pitch_words = k.W * 3 / 8; ld.frame0 = 0;
+  ld.fp = fp; ld.pitch_words = k.W * 3 / 8; ld.frame0 = 0; ld.ids = k.ids;
   const EpiReinhardMaxU16<true> e{sc, k};
   int st = B200ISP_OK;
   ISP_DISPATCH_PATTERN(k.pattern, P, { st = launch_stream2<P>(ld, e, g, s, "isp_stream<reinhard_u16>", k.kbase != 0); });

@@ -101,15 +101,16 @@ __device__ __forceinline__ void st_out(uint2* p, const uint2& v) {
 
 template <int NW, bool FULL = false>       // FULL: all 32 lanes map to real thread columns (no store predicates)
 __device__ __forceinline__ void warp_store_row(const WarpCtx& wc, void* row_dst /* warp's first byte of the row */,
-                                               const uint32_t (&w)[NW]) {
+                                               const uint32_t (&w)[NW], int slot = -1 /* staging slot; default: the lane */) {
   constexpr int CW = (NW % 4 == 0) ? 4 : 2;     // words per chunk
   constexpr int PER_LANE = NW / CW;
   const int nchunks = wc.nvalid * PER_LANE;
+  if (slot < 0) slot = wc.lane;
   __syncwarp();
   if constexpr (CW == 4) {
     uint4* s = reinterpret_cast<uint4*>(wc.stage);
 #pragma unroll
-    for (int i = 0; i < PER_LANE; ++i) s[PER_LANE * wc.lane + i] = make_uint4(w[4 * i], w[4 * i + 1], w[4 * i + 2], w[4 * i + 3]);
+    for (int i = 0; i < PER_LANE; ++i) s[PER_LANE * slot + i] = make_uint4(w[4 * i], w[4 * i + 1], w[4 * i + 2], w[4 * i + 3]);
     __syncwarp();
     uint4* d = reinterpret_cast<uint4*>(row_dst);
 #pragma unroll
@@ -120,7 +121,7 @@ __device__ __forceinline__ void warp_store_row(const WarpCtx& wc, void* row_dst 
   } else {
     uint2* s = reinterpret_cast<uint2*>(wc.stage);
 #pragma unroll
-    for (int i = 0; i < PER_LANE; ++i) s[PER_LANE * wc.lane + i] = make_uint2(w[2 * i], w[2 * i + 1]);
+    for (int i = 0; i < PER_LANE; ++i) s[PER_LANE * slot + i] = make_uint2(w[2 * i], w[2 * i + 1]);
     __syncwarp();
     uint2* d = reinterpret_cast<uint2*>(row_dst);
 #pragma unroll

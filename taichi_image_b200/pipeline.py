@@ -33,10 +33,12 @@ class RigPipeline:
                  depth: int = 2, yuv420: bool = False, **tonemap_args):
         """``isp`` may resize (outputs are then the resized images) and ``yuv420=True`` selects the planar YUV 4:2:0
         output of ``process_packed12`` (1.5 instead of 3 bytes per pixel over PCIe).  A rotating / flipping ISP is not
-        supported here: the transformed copies would not land in the pinned output slots."""
+        supported here only for flip_horiz / flip_vert / rotate_180 (applied by the sweep's store, so the result still lands in
+        the slot); the transposing transforms would return copies."""
         assert width % 8 == 0 and height % 2 == 0, "fused path needs width % 8 == 0 and even height"
         base = getattr(isp, "isp", isp)
-        assert base.transform.value == "none", "RigPipeline writes straight into its slots: no transform"
+        assert base.transform.value in ("none", "flip_horiz", "flip_vert", "rotate_180") and not (
+            base.transform.value != "none" and (base._resizes or yuv420)), "RigPipeline writes straight into its slots"
         self.isp, self.n, self.h, self.w = isp, n_frames, height, width
         self.tonemap, self.out_dtype, self.tm = tonemap, as_dtype(dtype), tonemap_args
         self.yuv420 = bool(yuv420)

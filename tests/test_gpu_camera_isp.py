@@ -362,3 +362,58 @@ def test_fused_ids_format(cuda, dt, tonemap):
     one = O.encode12(O.rgb_to_bayer(smooth_rgb(r, 36, 72), "GBRG"), scaled=True, ids_format=True)
     assert_close_float(to_np(isp.load_packed12(to_cuda(one), ids_format=True)), ref.load_packed12(one, ids_format=True),
                        rtol=1e-3, atol=1e-3 if dt == "f16" else 2e-6)
+
+
+@pytest.mark.parametrize("dt", ["f16", "f32"])
+@pytest.mark.parametrize("pattern", ["RGGB", "GBRG"])
+def test_ids_layout_in_the_row_loader_equals_repack(cuda, dt, pattern):
+    """IDS frames decoded inside the sweep's row loader and the metering sampler (csrc/fused_isp.cuh ids_sample) give bit for
+    bit the outputs and metrics of the same frames re-packed into the standard layout first -- at a width with interior
+    strips (K_CORE), a partial last strip and several row chunks"""
+    from taichi_image_b200 import packed
+    r = rng(96)
+    h, w = 44, 1032
+    a, b = make_isp(dt, bayer_pattern=pattern), make_isp(dt, bayer_pattern=pattern)
+    for step in range(2):
+        ids = [to_cuda(O.encode12(r.integers(0, 4096, size=(h, w)).astype(np.uint16), ids_format=True)) for _ in range(2)]
+        std = [packed.repack12_ids(f) for f in ids]
+        for tm, out in (("linear", "u16"), ("reinhard", "u8")):
+            ya = a.process_packed12(ids, tonemap=tm, dtype=out, gamma=0.9, ids_format=True, rows_per_task=6)
+            yb = b.process_packed12(std, tonemap=tm, dtype=out, gamma=0.9, rows_per_task=6)
+            assert torch.equal(a.metrics, b.metrics), f"{tm} step {step}: metrics"
+            for x, y in zip(ya, yb):
+                assert torch.equal(x, y), f"{tm} step {step}"
+    assert torch.equal(a.load_packed12(ids[0], ids_format=True), b.load_packed12(std[0]))
+
+
+@pytest.mark.parametrize("dt", ["f16", "f32"])
+@pytest.mark.parametrize("tname", ["flip_horiz", "flip_vert", "rotate_180"])
+@pytest.mark.parametrize("shape", [(40, 64), (44, 1032), (36, 776)])
+def test_flips_in_the_store(cuda, dt, tname, shape):
+    """flip_horiz / flip_vert / rotate_180 applied by the sweep's store (interpolate.py:36-56 without the extra pass): bit for
+    bit interpolate.transform of the untransformed result, for every epilogue family, with full and partial last strips;
+    `out=` then holds the transformed images"""
+    from taichi_image_b200.interpolate import ImageTransform, transform
+    r = rng(97)
+    h, w = shape
+    t = ImageTransform[tname]
+    cu = [to_cuda(f) for f in frames(r, 2, h, w)]
+    for tm, out, kw in (("linear", "u16", dict()), ("linear", "u8", dict(gamma=0.8)), ("reinhard", "u8", dict(gamma=0.9, intensity=2.0)),
+                        ("reinhard", "f16", dict())):
+        plain, flipped = make_isp(dt), make_isp(dt, transform=t)
+        exp = [transform(o, t) for o in plain.process_packed12(cu, tonemap=tm, dtype=out, rows_per_task=6, **kw)]
+        bufs = [torch.empty_like(e) for e in exp]
+        got = flipped.process_packed12(cu, tonemap=tm, dtype=out, rows_per_task=6, out=bufs, **kw)
+        assert got[0].data_ptr() == bufs[0].data_ptr()
+        for g, e in zip(got, exp):
+            if dt == "f16" and tm == "reinhard":
+                # Camera16 Reinhard with a flip takes the two-sweep form instead of the f16-scratch form: max_out comes from a
+                # different (equally valid) evaluation order, so the two differ in the last bit of a few values
+                assert float((g.float() - e.float()).abs().max()) <= (1.0 if out == "u8" else 2e-3), f"{dt} {tname} {tm}->{out} {shape}"
+            elif dt == "f32" and tm == "linear" and not kw:
+                # the unflipped reference ran the packed fast epilogue (frame columns renormalised by a reciprocal multiply),
+                # the flipped one the generic epilogue (IEEE division): the image-frame pixels may differ in the last bit
+                d = (g.int() - e.int()).abs()
+                assert int(d.max()) <= 1 and int((d != 0).sum()) <= 8 * (h + w), f"{dt} {tname} {tm}->{out} {shape}"
+            else:
+                assert torch.equal(g, e), f"{dt} {tname} {tm}->{out} {shape}"

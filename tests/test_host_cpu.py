@@ -27,8 +27,8 @@ def test_library_loads_and_exports_every_declared_symbol():
 
 def test_fused_params_struct_matches_header():
     from taichi_image_b200 import _lib
-    # 7 ints, 9 floats, 4 floats, int, float, 7 ints, 2 floats, 3 ints (34 x 4 bytes, no padding) + 4 pointers + 2 size_t
-    assert ctypes.sizeof(_lib.FusedParams) == 4 * (7 + 9 + 4 + 1 + 1 + 7 + 2 + 3) + 6 * ctypes.sizeof(ctypes.c_void_p)
+    # 7 ints, 9 floats, 4 floats, int, float, 7 ints, 2 floats, 5 ints (36 x 4 bytes, no padding) + 4 pointers + 2 size_t
+    assert ctypes.sizeof(_lib.FusedParams) == 4 * (7 + 9 + 4 + 1 + 1 + 7 + 2 + 5) + 6 * ctypes.sizeof(ctypes.c_void_p)
     header = open(os.path.join(ROOT, "include", "b200isp.h")).read()
     body = header[header.index("typedef struct {"):header.index("} b200isp_fused_params;")]
     names = re.findall(r"\b(?:int|float|void\*|size_t)\s+([a-z_0-9, \[\]]+);", body)
