@@ -12,6 +12,7 @@
 #pragma once
 #include "common.cuh"
 #include "exchange.cuh"
+#include <stdlib.h>
 
 namespace isp {
 
@@ -417,6 +418,19 @@ inline int meter_grid(long long n) {
   return (int)b;
 }
 
+// Grid of the two-launch (look-ahead / shared) form, which runs on a high-priority side stream UNDER the previous batch's
+// sweep: its CTAs take SM slots away from the sweep for as long as they live, so a latency-bound sampler should not
+// flood the GPU.  Samplers may define kSideGridCap (CTAs); B200ISP_METER_GRID_CAP overrides it (tuning knob).
+template <class Sampler, class = void> struct side_grid_cap { static constexpr int value = 4 * kNumSMs; };
+template <class Sampler> struct side_grid_cap<Sampler, std::enable_if_t<(Sampler::kSideGridCap > 0)>> { static constexpr int value = Sampler::kSideGridCap; };
+template <class Sampler>
+inline int meter_side_grid(long long n) {
+  int cap = side_grid_cap<Sampler>::value;
+  if (const char* e = getenv("B200ISP_METER_GRID_CAP")) { const int v = atoi(e); if (v > 0) cap = v; }
+  const int g = meter_grid(n);
+  return g < cap ? g : cap;
+}
+
 // cache: optional device scratch of n*3 floats -- phase 2 then re-reads the phase-1 samples instead of
 // recomputing them (the samples are identical either way).
 // prev: metrics before this update (read), metrics: updated metrics (written; may be the same buffer).
@@ -440,7 +454,7 @@ inline int launch_metering(const Sampler& smp, long long n, float alpha, const f
     if (e == cudaSuccess) return B200ISP_OK;
     (void)cudaGetLastError();         // fall through to the two-launch form
   }
-  const int grid = meter_grid(n);
+  const int grid = cooperative ? meter_grid(n) : meter_side_grid<Sampler>(n);
   meter_phase1_kernel<Sampler><<<grid, 256, 0, s>>>(smp, n, alpha, prev, ws, cache);
   int st = cuda_status(cudaPeekAtLastError(), "meter_phase1_kernel");
   if (st) return st;
@@ -469,7 +483,7 @@ inline int launch_metering_phase2(const Sampler& smp, long long n, const float* 
 template <class Sampler>
 inline int launch_metering_shared(const Sampler& smp, long long n, float alpha, const float* prev, float* metrics, Workspace* ws,
                                   cudaStream_t s, float* cache, const PeerXchg& xc) {
-  const int grid = meter_grid(n);
+  const int grid = meter_side_grid<Sampler>(n);
   meter_phase1x_kernel<Sampler><<<grid, 256, 0, s>>>(smp, n, alpha, prev, ws, cache, xc);
   int st = cuda_status(cudaPeekAtLastError(), "meter_phase1x_kernel");
   if (st) return st;

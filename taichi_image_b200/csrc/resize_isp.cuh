@@ -160,6 +160,9 @@ template <bool CAM16>
 struct ResizedSampler {
   ResizeSrc<CAM16> src;
   int stride, hs, ws_;
+  // look-ahead / shared form under the previous sweep: this sampler is latency-bound (a 6 x 6 window per sample); 592 CTAs of
+  // it displace the sweep for their whole 79 us, 296 CTAs cost 6.6 % less per step on cfg5 (profiles/r02_meter_grid_cap.txt)
+  static constexpr int kSideGridCap = 2 * kNumSMs;
   __device__ __forceinline__ void sample(long long idx, float (&rgb)[3]) const {
     const int j = (int)(idx % ws_);
     const long long q = idx / ws_;
