@@ -74,6 +74,31 @@ struct ResizeTone {
   }
 };
 
+// two resized pixels at once (f32x2 lanes = output columns co and co + 32 of one lane): the Reinhard map of the common
+// case (color_adapt == 0) stays packed; `b_ok` = the second pixel exists
+template <bool CAM16, int MODE, typename OutT>
+__device__ __forceinline__ float resize_tone2(const ResizeTone<CAM16, MODE, OutT>& t, const f2 (&rgb)[3], OutT* dst_a, OutT* dst_b, bool b_ok) {
+  if constexpr (MODE == RZ_RSTORE) {
+    if (t.rc.ca0) {
+      f2 n[3], r;
+      reinhard_nr2(t.rc, rgb, bc(1.0f), n, r);
+      float pa[3], pb[3];
+#pragma unroll
+      for (int c = 0; c < 3; ++c) upk(mul2(n[c], r), pa[c], pb[c]);
+      store3<OutT>(dst_a, pa);
+      float m = fmaxf(pa[0], fmaxf(pa[1], pa[2]));
+      if (b_ok) { store3<OutT>(dst_b, pb); m = fmaxf(m, fmaxf(pb[0], fmaxf(pb[1], pb[2]))); }
+      return m;
+    }
+  }
+  float a[3], b[3];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) upk(rgb[c], a[c], b[c]);
+  float m = t.apply(a, dst_a);
+  if (b_ok) m = fmaxf(m, t.apply(b, dst_b));
+  return m;
+}
+
 template <bool CAM16, int MODE, typename OutT>
 struct EpiResize2 {
   FramePtrs fp;              // .out = output (RZ_RSTORE: scratch) frames, (Ho, Wo, 3) OutT
@@ -134,18 +159,36 @@ struct EpiResize2 {
     OutT* orow = st.out + (size_t)ro * Wo * 3;
     float mx = st.mx;
     const int2* tab = reinterpret_cast<const int2*>(st.ring + 2 * kRowWords);
-    for (int co = st.co0 + st.lane; co < st.co1; co += 32) {
-      const int2 e = tab[co - st.co0];
-      const float fc = __int_as_float(e.y), gc = __fsub_rn(1.0f, fc);
-      const int ia = e.x & 0xFFFF, ib = ia + (e.x >> 16);
-      float rgb[3];
+    // two output pixels per iteration (columns co and co + 32): the mixes stay SCALAR __fmul_rn / __fadd_rn -- ptxas contracts
+    // mul.rn.f32x2 + add.rn.f32x2 into FFMA2 (the rounding modifier is mandatory on the packed forms, so it does not protect
+    // them), which breaks the reference's per-operation rounding (interpolate.py:62-66; caught by the bit-exactness test) --
+    // and the tone map that follows runs packed on the pair
+    for (int co = st.co0 + st.lane; co < st.co1; co += 64) {
+      const bool b_ok = co + 32 < st.co1;
+      const int2 e2[2] = {tab[co - st.co0], tab[(b_ok ? co + 32 : co) - st.co0]};
+      float px[2][3];
 #pragma unroll
-      for (int c = 0; c < 3; ++c) {       // mix along dim 0 first, then dim 1; every operation rounded (interpolate.py:62-66)
-        const float y1 = __fadd_rn(__fmul_rn(A[ia + c], gr), __fmul_rn(B[ia + c], fr));
-        const float y2 = __fadd_rn(__fmul_rn(A[ib + c], gr), __fmul_rn(B[ib + c], fr));
-        rgb[c] = round_isp<CAM16>(__fadd_rn(__fmul_rn(y1, gc), __fmul_rn(y2, fc)));
+      for (int l = 0; l < 2; ++l) {
+        const float fc = __int_as_float(e2[l].y), gc = __fsub_rn(1.0f, fc);
+        const int ia = e2[l].x & 0xFFFF, ib = ia + (e2[l].x >> 16);
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {     // mix along dim 0 first, then dim 1; every operation rounded
+          const float y1 = __fadd_rn(__fmul_rn(A[ia + c], gr), __fmul_rn(B[ia + c], fr));
+          const float y2 = __fadd_rn(__fmul_rn(A[ib + c], gr), __fmul_rn(B[ib + c], fr));
+          px[l][c] = __fadd_rn(__fmul_rn(y1, gc), __fmul_rn(y2, fc));
+        }
       }
-      mx = fmaxf(mx, st.tone.apply(rgb, orow + (size_t)co * 3));
+      f2 rgb[3];
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {       // cast to the ISP dtype
+        if constexpr (CAM16) {
+          const __half2 h = __floats2half2_rn(px[0][c], px[1][c]);
+          rgb[c] = pk(__low2float(h), __high2float(h));
+        } else {
+          rgb[c] = pk(px[0][c], px[1][c]);
+        }
+      }
+      mx = fmaxf(mx, resize_tone2<CAM16, MODE, OutT>(st.tone, rgb, orow + (size_t)co * 3, orow + (size_t)(co + 32) * 3, b_ok));
     }
     st.mx = mx;
   }
