@@ -28,7 +28,7 @@ from .dtypes import as_dtype, u8
 class GraphedStream:
     def __init__(self, isp, frames: Sequence[torch.Tensor], outs: Sequence[torch.Tensor], tonemap: str = "reinhard",
                  dtype=u8, next_frames: Optional[Sequence[torch.Tensor]] = None, rows_per_task: int = 0,
-                 next_outs: Optional[Sequence[torch.Tensor]] = None, **tonemap_args):
+                 next_outs: Optional[Sequence[torch.Tensor]] = None, ids_format: bool = False, **tonemap_args):
         """isp: Camera16 / Camera32 or a distributed.SharedExposure around one.  frames / outs: the device buffers of
         the even steps (batch 0 must already be in ``frames``).  next_frames / next_outs: the buffers of the odd steps
         (double-buffered ingest / egress); ``next_outs`` defaults to ``outs``, ``next_frames=None`` selects the
@@ -37,10 +37,12 @@ class GraphedStream:
         base = isp.isp if self.wrapper is not None else isp
         self.isp = base
         self.double_buffered = next_frames is not None
+        self.ids_format = bool(ids_format)        # packed layout of the stream's frames (decoded in the sweep's row loader)
         self.F = [list(frames), list(next_frames) if next_frames is not None else list(frames)]
         self.O = [list(outs), list(next_outs) if next_outs is not None else list(outs)]
-        assert all(base._fused_ok(f, False) for f in self.F[0] + self.F[1]), \
-            "GraphedStream needs frames the fused sweep accepts (standard layout, width % 8 == 0)"
+        assert all(base._fused_ok(f, self.ids_format) for f in self.F[0] + self.F[1]), \
+            "GraphedStream needs frames the fused sweep accepts (width % 8 == 0; IDS layout: Malvar, no resize)"
+        base._ids_layout = self.ids_format        # read by every parameter block built during warm-up and capture
         self.tonemap, self.out_dtype, self.tm = tonemap, as_dtype(dtype), dict(tonemap_args)
         self.rows_per_task = rows_per_task
         dev = base.device

@@ -30,7 +30,7 @@ class _Slot:
 
 class RigPipeline:
     def __init__(self, isp, n_frames: int, height: int, width: int, tonemap: str = "reinhard", dtype=u8,
-                 depth: int = 2, yuv420: bool = False, **tonemap_args):
+                 depth: int = 2, yuv420: bool = False, ids_format: bool = False, **tonemap_args):
         """``isp`` may resize (outputs are then the resized images) and ``yuv420=True`` selects the planar YUV 4:2:0
         output of ``process_packed12`` (1.5 instead of 3 bytes per pixel over PCIe).  A rotating / flipping ISP is not
         supported here only for flip_horiz / flip_vert / rotate_180 (applied by the sweep's store, so the result still lands in
@@ -42,6 +42,7 @@ class RigPipeline:
         self.isp, self.n, self.h, self.w = isp, n_frames, height, width
         self.tonemap, self.out_dtype, self.tm = tonemap, as_dtype(dtype), tonemap_args
         self.yuv420 = bool(yuv420)
+        self.ids_format = bool(ids_format)
         self.device = isp.device
         plan = base._resize_plan(height, width)
         ho, wo = (height, width) if plan is None else (plan[0][1], plan[0][0])
@@ -76,7 +77,8 @@ class RigPipeline:
             with torch.cuda.stream(self.s_isp):
                 self.s_isp.wait_event(slot.copied_in)
                 self.isp.process_packed12(slot.d_in, tonemap=self.tonemap, dtype=self.out_dtype, out=slot.d_out,
-                                          **(dict(yuv420=True) if self.yuv420 else {}), **self.tm)
+                                          **(dict(yuv420=True) if self.yuv420 else {}),
+                                          **(dict(ids_format=True) if self.ids_format else {}), **self.tm)
                 slot.computed.record(self.s_isp)
             with torch.cuda.stream(self.s_out):
                 self.s_out.wait_event(slot.computed)

@@ -417,3 +417,25 @@ def test_flips_in_the_store(cuda, dt, tname, shape):
                 assert int(d.max()) <= 1 and int((d != 0).sum()) <= 8 * (h + w), f"{dt} {tname} {tm}->{out} {shape}"
             else:
                 assert torch.equal(g, e), f"{dt} {tname} {tm}->{out} {shape}"
+
+
+def test_graphed_stream_and_pipeline_with_ids_frames(cuda):
+    """IDS frames through the CUDA-graph stream and the host-buffer pipeline == eager calls on the same frames"""
+    from taichi_image_b200.graphed import GraphedStream
+    from taichi_image_b200.pipeline import RigPipeline
+    r = rng(98)
+    h, w, n = 40, 64, 2
+    ids = [O.encode12(r.integers(0, 4096, size=(h, w)).astype(np.uint16), ids_format=True) for _ in range(n)]
+    cu = [to_cuda(f) for f in ids]
+    outs = [torch.empty((h, w, 3), dtype=torch.uint8, device="cuda") for _ in range(n)]
+    eager, gisp, pisp = make_isp("f32", moving_alpha=0.2), make_isp("f32", moving_alpha=0.2), make_isp("f32", moving_alpha=0.2)
+    gs = GraphedStream(gisp, cu, outs, tonemap="reinhard", ids_format=True, gamma=0.9)
+    pipe = RigPipeline(pisp, n, h, w, tonemap="reinhard", ids_format=True, gamma=0.9)
+    for k in range(3):
+        exp = eager.process_packed12(cu, tonemap="reinhard", gamma=0.9, ids_format=True)
+        got = [o.clone() for o in gs.step()]
+        host = pipe.process(RigPipeline.pin(ids))
+        torch.cuda.synchronize()
+        for x, y, z in zip(exp, got, host):
+            assert_close_int(to_np(x), to_np(y), 1, f"graphed ids step {k}")
+            assert np.array_equal(to_np(x), z.numpy()), f"pipeline ids step {k}"
