@@ -185,8 +185,9 @@ typedef struct {
   int resize_gather;            /* 1: force the per-output-pixel gather instead of the resizing sweep (testing / profiling) */
   int out_pitch;                /* elements per OUTPUT row; 0 = dense (3 * width).  Larger: every output frame is a tile of a bigger
                                    image (the rig's camera grid, scripts/tonemap_scan.py:91-100) -- the sweep writes the tile in place */
-  int flip;                     /* ISP transform applied by the sweep's store (interpolate.py:36-56): bit 0 = flip_horiz, bit 1 = flip_vert,
-                                   3 = rotate_180; the transposing transforms stay with b200isp_transform */
+  int flip;                     /* ISP transform applied by the sweep's store (interpolate.py:36-56): bit 0 = mirror columns, bit 1 = mirror
+                                   rows, bit 2 = transpose (output (W, H), out_pitch counts elements of ITS rows; needs height % 8 == 0):
+                                   flip_horiz 1, flip_vert 2, rotate_180 3, transpose 4, rotate_270 5, rotate_90 6, transverse 7 */
   int reserved0;                /* keeps the pointers below 8-byte aligned; must be 0 */
   int ids_layout;               /* packed layout of the input frames: 0 = standard (packed.py:23-31), 1 = IDS (packed.py:36-44),
                                    decoded inside the row loader (4 instead of 2 instructions per sample, no re-pack pass) */

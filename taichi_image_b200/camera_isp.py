@@ -499,6 +499,8 @@ def camera_isp(name: str, dtype=f32):
             if plan is not None:
                 w, h = plan[0]
             oshape = (h * 3 // 2, w) if yuv420 else (h, w, 3)       # planar YUV 4:2:0: color/yuv_420.py:95-118
+            if flip & 4:
+                oshape = (w, h, 3)                                  # transposing transform applied by the store
             if out is None:
                 out = [torch.empty(oshape, dtype=out_dtype.torch, device=self.device) for _ in frames]
             else:
@@ -508,7 +510,7 @@ def camera_isp(name: str, dtype=f32):
                 pitch = out[0].stride(0) if out[0].ndim == 3 else 0
                 for o in out:
                     assert tuple(o.shape) == oshape and o.dtype == out_dtype.torch and o.is_cuda
-                    assert o.is_contiguous() or (o.ndim == 3 and o.stride() == (pitch, 3, 1) and pitch >= 3 * w), \
+                    assert o.is_contiguous() or (o.ndim == 3 and o.stride() == (pitch, 3, 1) and pitch >= 3 * oshape[1]), \
                         "outputs must be contiguous or row-pitched (H, W, 3) views"
                 if not out[0].is_contiguous():
                     assert plan is None and not yuv420, "pitched outputs need the plain RGB sweep (no resize, no YUV)"
@@ -599,13 +601,29 @@ def camera_isp(name: str, dtype=f32):
                     return list(out)
                 return res
             tm = dict(gamma=gamma, intensity=intensity, light_adapt=light_adapt, color_adapt=color_adapt)
-            # flip_horiz / flip_vert / rotate_180 are applied by the sweep's store (no extra pass); the transposing transforms
-            # run the tiled transform kernel on the results
+            # every transform of interpolate.py:36-56 is applied by the sweep's store (no extra pass; csrc/fused_isp.cuh
+            # store_out): bit 0 mirrors the columns, bit 1 the rows, bit 2 transposes (needs height % 8 == 0, otherwise the
+            # tiled transform kernel runs on the results)
             flip = 0
             if not self._resizes and not yuv420 and self.demosaic == "malvar":
-                flip = {interpolate.ImageTransform.flip_horiz: 1, interpolate.ImageTransform.flip_vert: 2,
-                        interpolate.ImageTransform.rotate_180: 3}.get(self.transform, 0)
-            finish = (lambda outs: outs) if (yuv420 or flip) else (lambda outs: [interpolate.transform(o, self.transform) for o in outs])
+                T = interpolate.ImageTransform
+                flip = {T.flip_horiz: 1, T.flip_vert: 2, T.rotate_180: 3, T.transpose: 4, T.rotate_270: 5, T.rotate_90: 6,
+                        T.transverse: 7}.get(self.transform, 0)
+                if flip & 4 and not (shape[0] % 8 == 0 and shape[0] >= 16):
+                    flip = 0
+            if yuv420 or flip or self.transform == interpolate.ImageTransform.none:
+                finish = lambda outs: outs
+            elif out is None:
+                finish = lambda outs: [interpolate.transform(o, self.transform) for o in outs]
+            else:                          # transform kernel after the sweep, results into the caller's (transformed-shape) buffers
+                user_out, out = list(out), None
+                def finish(outs):
+                    res = [interpolate.transform(o, self.transform) for o in outs]
+                    assert len(res) == len(user_out) and all(u.shape == r.shape and u.dtype == r.dtype for u, r in zip(user_out, res)), \
+                        "out= buffers must have the shape / dtype of the transformed results"
+                    for u, r in zip(user_out, res):
+                        u.copy_(r)
+                    return user_out
             pipelined = update_metering and (lookahead is not None or self._lookahead is not None or meter_fn is not None)
             if not pipelined:
                 alpha = self._metrics_and_alpha() if update_metering else 0.0

@@ -40,13 +40,16 @@ static int fused_setup(const char* what, const uint8_t* const* packed_host, void
               "%s: unknown demosaic %d", what, p.demosaic);
   k.metrics = metrics; k.ws = (Workspace*)workspace; k.frame0 = 0;
   k.kbase = p.demosaic == B200ISP_DEMOSAIC_BILINEAR ? kBilinearBase : 0;
-  k.flip = p.flip & 3;
+  k.flip = p.flip & 7;
   ISP_REQUIRE(!(k.flip && (resizes(p) || p.out_yuv420)), B200ISP_E_ARG, "%s: flips in the store need the plain RGB sweep (no resize, no YUV)", what);
+  ISP_REQUIRE(!(k.flip & 4) || (p.height % 8 == 0 && p.height >= 16), B200ISP_E_SHAPE,
+              "%s: the transposing transforms in the store need height %% 8 == 0 and height >= 16, got %dx%d", what, p.height, p.width);
   k.ids = p.ids_layout ? 1 : 0;
   ISP_REQUIRE(!(k.ids && resizes(p)), B200ISP_E_ARG, "%s: the IDS layout is not available with the fused resize (re-pack first)", what);
-  k.orow = p.out_pitch > 0 ? p.out_pitch : 3 * p.width;
-  ISP_REQUIRE(p.out_pitch <= 0 || (k.orow >= 3 * p.width && (k.orow * (int)dtype_size(p.out_dtype)) % 16 == 0), B200ISP_E_ALIGN,
-              "%s: out_pitch must be >= 3 * width elements and a multiple of 16 bytes", what);
+  const int out_cols = (k.flip & 4) ? p.height : p.width;        // the transposing transforms write (W, H) images
+  k.orow = p.out_pitch > 0 ? p.out_pitch : 3 * out_cols;
+  ISP_REQUIRE(p.out_pitch <= 0 || (k.orow >= 3 * out_cols && (k.orow * (int)dtype_size(p.out_dtype)) % 16 == 0), B200ISP_E_ALIGN,
+              "%s: out_pitch must be >= 3 * (output width) elements and a multiple of 16 bytes", what);
   ISP_REQUIRE(p.out_pitch <= 0 || (!resizes(p) && !p.out_yuv420), B200ISP_E_ARG, "%s: out_pitch needs the plain RGB sweep (no resize, no YUV)", what);
   return B200ISP_OK;
 }

@@ -188,7 +188,7 @@ struct IspConsts {
   int frame0;
   int kbase;                 // 0: Malvar-He-Cutler, kBilinearBase: bilinear demosaic (offset into c_taps / c_border)
   int ids;                   // packed layout of the input frames: 0 standard, 1 IDS
-  int flip;                  // flips applied by the store: bit 0 horizontal, bit 1 vertical (rotate_180 = 3)
+  int flip;                  // transform applied by the store: bit 0 horizontal, bit 1 vertical (rotate_180 = 3), bit 2 transposed
   int orow;                  // elements per OUTPUT row: 3 W for dense frames, more when the frames are tiles of a grid image
 };
 
@@ -292,11 +292,59 @@ __device__ __forceinline__ void store_row8(const WarpCtx& wc, OutT* warp_out /* 
 // (lane order reversed in the stage, the lane's eight pixels reversed before packing) -- no extra pass over the image.
 // k.flip: bit 0 = horizontal, bit 1 = vertical; kernel-uniform, 0 on the hot path.
 // EXT: only the extended instantiations carry the flip code (see Packed12Loader2).
+// The TRANSPOSING transforms (k.flip bit 2; interpolate.py:36-56: rotate_90 / rotate_270 / transpose / transverse) turn an
+// image row into an output column: output (i, j) = source (r, c) with i = c or W-1-c (bit 0) and j = r or H-1-r (bit 1),
+// output shape (W, H).  A lane owns its eight source columns for the whole task, so the pixels that are contiguous in an
+// output row -- the same column of consecutive source rows -- all come from the same lane: it collects 24 bytes per column
+// (kTileRows rows) in a private piece of the warp's stage (layout [pixel][lane], pitch 7 words: conflict-free) and then
+// writes each as three 8-byte stores.  The 24-byte pieces of one task are adjacent in the output row, so L2 merges them
+// into whole sectors before they reach DRAM (default write policy, not evict-first).  Tasks start on tile boundaries
+// (Stream2Geom::border = 8, rows_per_task % 8 == 0, H % 8 == 0: checked on the host).
+constexpr int kTransposeStageWords = 8 * 32 * 7;
+template <typename OutT>
+__device__ __forceinline__ void store_transposed(const WarpCtx& wc, OutT* frame_out, const IspConsts& k, int row, const uint32_t (&v)[24]) {
+  constexpr int ES = (int)sizeof(OutT);
+  constexpr int TR = 8 / ES;                      // rows per tile: 8 (u8), 4 (u16 / f16), 2 (f32)
+  const int s = row & (TR - 1);
+  const int slot = (k.flip & 2) ? TR - 1 - s : s;
+  OutT* mine = reinterpret_cast<OutT*>(wc.stage + 7 * wc.lane) + 3 * slot;
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    OutT* p = mine + q * (32 * 28 / ES);
+#pragma unroll
+    for (int ch = 0; ch < 3; ++ch) {
+      if constexpr (std::is_same<OutT, __half>::value) p[ch] = __float2half_rn(__uint_as_float(v[3 * q + ch]));
+      else if constexpr (std::is_same<OutT, float>::value) p[ch] = __uint_as_float(v[3 * q + ch]);
+      else p[ch] = (OutT)v[3 * q + ch];
+    }
+  }
+  if (s != TR - 1) return;
+  const int rt = row - (TR - 1);
+  const int j0 = (k.flip & 2) ? k.H - TR - rt : rt;                 // first output column of the pieces
+  const size_t opitch = (size_t)k.orow * ES;                        // bytes per output row (dense: 3 * H elements)
+  const int c0 = 8 * (wc.tcol0 + wc.lane);
+  if (wc.lane >= wc.nvalid) return;
+  char* obase = reinterpret_cast<char*>(frame_out) + (size_t)j0 * 3 * ES;
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    const uint32_t* sp = wc.stage + 7 * (q * 32 + wc.lane);
+    const int c = c0 + q;                                           // < W: the width is a multiple of 8
+    uint2* d = reinterpret_cast<uint2*>(obase + (size_t)((k.flip & 1) ? k.W - 1 - c : c) * opitch);
+    d[0] = make_uint2(sp[0], sp[1]);
+    d[1] = make_uint2(sp[2], sp[3]);
+    d[2] = make_uint2(sp[4], sp[5]);
+  }
+}
+
 template <typename OutT, bool FULL = false, bool EXT = false>
 __device__ __forceinline__ void store_out(const WarpCtx& wc, OutT* warp_out /* frame + 24 * tcol0 */, const IspConsts& k, int row,
                                           const uint32_t (&v)[24]) {
   if (!EXT || k.flip == 0) {
     store_row8<OutT, FULL>(wc, warp_out, k.orow, row, v);
+    return;
+  }
+  if (k.flip & 4) {
+    store_transposed<OutT>(wc, warp_out - 24 * wc.tcol0, k, row, v);
     return;
   }
   const int orow_idx = (k.flip & 2) ? k.H - 1 - row : row;
@@ -627,7 +675,7 @@ template <bool CAM16, typename OutT, bool EXT = false>
 struct EpiRgb2 {      // load_packed12: ISP-dtype float RGB out
   FramePtrs fp;
   IspConsts k;
-  static constexpr int kStageWords = 32 * Quant<OutT>::kWords;
+  static constexpr int kStageWords = EXT ? kTransposeStageWords : 32 * Quant<OutT>::kWords;
   struct State { OutT* out; WarpCtx wc; int edge; };
   __device__ __forceinline__ void init(State& st, int frame, int tcol, const WarpCtx& wc) const {
     st.out = reinterpret_cast<OutT*>(fp.out[k.frame0 + frame]) + 24 * wc.tcol0;
@@ -659,7 +707,7 @@ struct EpiLinear2 {
   static_assert(!(FAST && CAM16), "the packed fast path is Camera32 only");
   FramePtrs fp;
   IspConsts k;
-  static constexpr int kStageWords = 32 * Quant<OutT>::kWords;
+  static constexpr int kStageWords = EXT ? kTransposeStageWords : 32 * Quant<OutT>::kWords;
   struct State { LinearConsts c; OutT* out; WarpCtx wc; int edge; bool inside; };
   __device__ __forceinline__ void init(State& st, int frame, int tcol, const WarpCtx& wc) const {
     st.c = linear_consts(k.metrics, k.gamma);
@@ -858,7 +906,7 @@ template <bool CAM16, typename OutT, bool CA0, bool GAMMA, bool EXT = false>
 struct EpiReinhard2 {         // pass 2 recomputed from the packed frame: map, normalise by the max, gamma, quantise
   FramePtrs fp;
   IspConsts k;
-  static constexpr int kStageWords = 32 * Quant<OutT>::kWords;
+  static constexpr int kStageWords = EXT ? kTransposeStageWords : 32 * Quant<OutT>::kWords;
   struct State { ReinhardConsts c; OutT* out; WarpCtx wc; int edge; };
   __device__ __forceinline__ void init(State& st, int frame, int tcol, const WarpCtx& wc) const {
     st.c = reinhard_consts(k, frame, true);
@@ -1179,7 +1227,7 @@ template <bool CAM16, int MODE, typename OutT, bool EXT>
 static int run_pass_ext(const FramePtrs& fp, IspConsts k, int frame0, int nframes, int rows_per_task, cudaStream_t s,
                         void* ev_start, void* ev_stop) {
   k.frame0 = frame0;
-  const Stream2Geom g = make_geom2(k.H, k.W, nframes, rows_per_task);
+  const Stream2Geom g = make_geom2(k.H, k.W, nframes, rows_per_task, (EXT && MODE != MODE_RMAX && (k.flip & 4)) ? 8 : 2);
   const bool bl = !EXT && k.kbase != 0;
   if (EXT && k.kbase != 0) { set_error("process_packed12: the IDS layout / flips are fused for the Malvar demosaic only"); return B200ISP_E_ARG; }
   Packed12Loader2<CAM16, EXT> ld;

@@ -149,9 +149,11 @@ enum { K_CORE = 0, K_EDGE = 1, K_GENERAL = 2 };
 //       the frame pixels its KIND can contain (border_fix.cuh).
 
 struct Stream2Geom {
-  StreamGeom g;             // rows_per_task / nchunks describe the INTERIOR rows 2 .. H-3
+  StreamGeom g;             // rows_per_task / nchunks describe the INTERIOR rows border .. H-border-1
   long long interior_tasks; // nframes * nchunks * warps_per_row
   long long total_tasks;    // + nframes * 2 * warps_per_row
+  int border;               // rows of the top / bottom border tasks (K_GENERAL): 2, or 8 for the transposing stores whose
+                            // 8-row tiles must not straddle a task
 };
 
 // rows_per_task <= 0: 24 rows per task (4 halo rows = 17 % extra loads, all L2 hits), shrunk for small jobs until
@@ -168,12 +170,15 @@ inline int auto_rows_per_task2(int H, int W, int nframes) {
   return rpt;
 }
 
-inline Stream2Geom make_geom2(int H, int W, int nframes, int rows_per_task) {
+inline Stream2Geom make_geom2(int H, int W, int nframes, int rows_per_task, int border = 2) {
   Stream2Geom s;
+  s.border = border;
   if (rows_per_task <= 0) rows_per_task = auto_rows_per_task2(H, W, nframes);
-  s.g = make_geom(H - 4 > 0 ? H - 4 : 0, W, nframes, rows_per_task);      // chunking of the interior rows
+  if (border > 2) rows_per_task = (rows_per_task + border - 1) / border * border;      // tasks start on tile boundaries
+  const int interior = H - 2 * border;
+  s.g = make_geom(interior > 0 ? interior : 0, W, nframes, rows_per_task);      // chunking of the interior rows
   s.g.H = H;
-  s.interior_tasks = (H > 4) ? s.g.total_tasks : 0;
+  s.interior_tasks = (interior > 0) ? s.g.total_tasks : 0;
   s.total_tasks = s.interior_tasks + (long long)nframes * 2 * s.g.warps_per_row;
   return s;
 }
@@ -330,15 +335,15 @@ __global__ void __launch_bounds__(ISP_S2_THREADS, ISP_S2_MINBLOCKS) stream2_kern
     const long long t2 = task / g.warps_per_row;
     const int chunk = (int)(t2 % g.nchunks);
     frame = (int)(t2 / g.nchunks);
-    r0 = 2 + chunk * g.rows_per_task;
-    rend = min(r0 + g.rows_per_task, g.H - 2);
+    r0 = sg.border + chunk * g.rows_per_task;
+    rend = min(r0 + g.rows_per_task, g.H - sg.border);
   } else {
     const long long t = task - sg.interior_tasks;
     strip = (int)(t % g.warps_per_row);
     const long long t2 = t / g.warps_per_row;
     frame = (int)(t2 >> 1);
-    r0 = (t2 & 1) ? g.H - 2 : 0;
-    rend = r0 + 2;
+    r0 = (t2 & 1) ? g.H - sg.border : 0;
+    rend = r0 + sg.border;
   }
   const int tcol = min(strip * 32 + lane, g.ntcols - 1);   // lanes past the last column recompute it (never stored)
 

@@ -32,13 +32,16 @@ class RigPipeline:
     def __init__(self, isp, n_frames: int, height: int, width: int, tonemap: str = "reinhard", dtype=u8,
                  depth: int = 2, yuv420: bool = False, ids_format: bool = False, **tonemap_args):
         """``isp`` may resize (outputs are then the resized images) and ``yuv420=True`` selects the planar YUV 4:2:0
-        output of ``process_packed12`` (1.5 instead of 3 bytes per pixel over PCIe).  A rotating / flipping ISP is not
-        supported here only for flip_horiz / flip_vert / rotate_180 (applied by the sweep's store, so the result still lands in
-        the slot); the transposing transforms would return copies."""
+        output of ``process_packed12`` (1.5 instead of 3 bytes per pixel over PCIe).  The ISP's transform is applied by the
+        sweep's store, so the result still lands in the slot: every transform for plain Malvar ISPs (the transposing ones --
+        rotate_90, the rig script's default -- need height % 8 == 0), none with resize / YUV."""
         assert width % 8 == 0 and height % 2 == 0, "fused path needs width % 8 == 0 and even height"
         base = getattr(isp, "isp", isp)
-        assert base.transform.value in ("none", "flip_horiz", "flip_vert", "rotate_180") and not (
-            base.transform.value != "none" and (base._resizes or yuv420)), "RigPipeline writes straight into its slots"
+        tname = base.transform.value
+        transposing = tname in ("rotate_90", "rotate_270", "transpose", "transverse")
+        assert tname == "none" or not (base._resizes or yuv420 or base.demosaic != "malvar"), \
+            "RigPipeline writes straight into its slots: transforms need the plain Malvar RGB sweep"
+        assert not transposing or (height % 8 == 0 and height >= 16), "transposing transforms in the store need height % 8 == 0"
         self.isp, self.n, self.h, self.w = isp, n_frames, height, width
         self.tonemap, self.out_dtype, self.tm = tonemap, as_dtype(dtype), tonemap_args
         self.yuv420 = bool(yuv420)
@@ -46,7 +49,7 @@ class RigPipeline:
         self.device = isp.device
         plan = base._resize_plan(height, width)
         ho, wo = (height, width) if plan is None else (plan[0][1], plan[0][0])
-        self.out_shape = (ho * 3 // 2, wo) if self.yuv420 else (ho, wo, 3)
+        self.out_shape = (ho * 3 // 2, wo) if self.yuv420 else ((wo, ho, 3) if transposing else (ho, wo, 3))
         with torch.cuda.device(self.device):
             self.s_in, self.s_isp, self.s_out = (torch.cuda.Stream(self.device) for _ in range(3))
             self.slots = [_Slot(n_frames, height, width, self.out_shape, self.out_dtype, self.device) for _ in range(depth)]

@@ -419,6 +419,60 @@ def test_flips_in_the_store(cuda, dt, tname, shape):
                 assert torch.equal(g, e), f"{dt} {tname} {tm}->{out} {shape}"
 
 
+@pytest.mark.parametrize("dt", ["f16", "f32"])
+@pytest.mark.parametrize("tname", ["rotate_90", "rotate_270", "transpose", "transverse"])
+@pytest.mark.parametrize("shape", [(40, 64), (48, 1032), (16, 776), (64, 264), (44, 72)])
+def test_transposing_transforms_in_the_store(cuda, dt, tname, shape):
+    """rotate_90 (the rig script's default) / rotate_270 / transpose / transverse applied by the sweep's store: each lane
+    collects 24-byte column pieces and writes them as output rows (csrc/fused_isp.cuh store_transposed) -- bit for bit
+    interpolate.transform of the untransformed result for every output dtype (8 / 4 / 2 rows per piece), tasks of 8 and of
+    24 rows; a height that is not a multiple of 8 falls back to the transform kernel behind the sweep (same results)"""
+    from taichi_image_b200.interpolate import ImageTransform, transform
+    r = rng(99)
+    h, w = shape
+    t = ImageTransform[tname]
+    cu = [to_cuda(f) for f in frames(r, 2, h, w)]
+    for tm, out, kw in (("linear", "u16", dict()), ("linear", "u8", dict(gamma=0.8)), ("reinhard", "u8", dict(gamma=0.9, intensity=2.0)),
+                        ("reinhard", "f16", dict()), ("linear", "f16", dict(gamma=0.7))):
+        for rpt in (0, 8):
+            plain, turned = make_isp(dt), make_isp(dt, transform=t)
+            exp = [transform(o, t) for o in plain.process_packed12(cu, tonemap=tm, dtype=out, rows_per_task=rpt, **kw)]
+            assert tuple(exp[0].shape) == (w, h, 3)
+            bufs = [torch.empty_like(e) for e in exp]
+            got = turned.process_packed12(cu, tonemap=tm, dtype=out, rows_per_task=rpt, out=bufs, **kw)
+            assert got[0].data_ptr() == bufs[0].data_ptr()
+            for g, e in zip(got, exp):
+                what = f"{dt} {tname} {tm}->{out} {shape} rpt {rpt}"
+                if dt == "f16" and tm == "reinhard":      # two-sweep form vs the f16-scratch form, see test_flips_in_the_store
+                    assert float((g.float() - e.float()).abs().max()) <= (1.0 if out == "u8" else 2e-3), what
+                elif dt == "f32" and tm == "linear" and not kw:   # packed fast epilogue vs generic epilogue at the image frame
+                    d = (g.int() - e.int()).abs()
+                    assert int(d.max()) <= 1 and int((d != 0).sum()) <= 8 * (h + w), what
+                elif tm == "reinhard" and h % 8 == 0:
+                    # source rows 2..7 and H-8..H-3 belong to the 8-row border tasks here (general epilogue: IEEE division) and to
+                    # the fast epilogue (reciprocal product) in the untransformed sweep: a last-bit difference on a rare value
+                    d = (g.float() - e.float()).abs()
+                    assert float(d.max()) <= (1.0 if out == "u8" else 1e-3) and int((d != 0).sum()) <= 1 + 12 * w * 3 // 500, what
+                else:
+                    assert torch.equal(g, e), what
+
+
+def test_rotated_tiles_of_a_grid_image(cuda):
+    """rotate_90 straight into row-pitched tiles of one grid image (scripts/tonemap_scan.py:91-100 with its default transform)"""
+    from taichi_image_b200.interpolate import ImageTransform, transform
+    r = rng(100)
+    h, w, n = 48, 72, 3
+    cu = [to_cuda(f) for f in frames(r, n, h, w)]
+    plain, turned = make_isp("f32"), make_isp("f32", transform=ImageTransform.rotate_90)
+    exp = [transform(o, ImageTransform.rotate_90) for o in plain.process_packed12(cu, tonemap="reinhard", gamma=0.9)]
+    grid = torch.zeros((w, n * h + 16, 3), dtype=torch.uint8, device="cuda")        # n tiles of (w, h) side by side + padding
+    tiles = [grid[:, i * h:(i + 1) * h] for i in range(n)]
+    turned.process_packed12(cu, tonemap="reinhard", gamma=0.9, out=tiles)
+    for i in range(n):
+        assert int((grid[:, i * h:(i + 1) * h].int() - exp[i].int()).abs().max()) <= 1      # border-task rows: see above
+    assert int(grid[:, n * h:].max()) == 0
+
+
 def test_graphed_stream_and_pipeline_with_ids_frames(cuda):
     """IDS frames through the CUDA-graph stream and the host-buffer pipeline == eager calls on the same frames"""
     from taichi_image_b200.graphed import GraphedStream

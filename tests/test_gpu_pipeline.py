@@ -56,3 +56,23 @@ def test_rig_pipeline_metrics_trajectory(cuda):
         direct.process_packed12([to_cuda(f) for f in b], tonemap="reinhard")
         pipe.process(RigPipeline.pin(b))
         np.testing.assert_array_equal(to_np(piped.metrics), to_np(direct.metrics))
+
+
+@pytest.mark.parametrize("tname", ["rotate_90", "flip_vert"])
+def test_rig_pipeline_with_a_transforming_isp(cuda, tname):
+    """the rig script's default transform (rotate_90, scripts/tonemap_scan.py) through the host-buffer pipeline: the sweep's
+    store writes the turned image straight into the slot"""
+    from taichi_image_b200.interpolate import ImageTransform
+    from taichi_image_b200.pipeline import RigPipeline
+    r = rng(62)
+    n, h, w = 2, 48, 72
+    t = ImageTransform[tname]
+    direct, piped = make_isp("f32", moving_alpha=0.2, transform=t), make_isp("f32", moving_alpha=0.2, transform=t)
+    pipe = RigPipeline(piped, n, h, w, tonemap="reinhard", gamma=0.9)
+    for _ in range(3):
+        b = frames(r, n, h, w)
+        exp = direct.process_packed12([to_cuda(f) for f in b], tonemap="reinhard", gamma=0.9)
+        got = pipe.process(RigPipeline.pin(b))
+        for g, e in zip(got, exp):
+            assert tuple(g.shape) == ((w, h, 3) if tname == "rotate_90" else (h, w, 3))
+            assert np.array_equal(g.numpy(), to_np(e))
