@@ -605,11 +605,14 @@ def camera_isp(name: str, dtype=f32):
             # store_out): bit 0 mirrors the columns, bit 1 the rows, bit 2 transposes (needs height % 8 == 0, otherwise the
             # tiled transform kernel runs on the results)
             flip = 0
-            if not self._resizes and not yuv420 and self.demosaic == "malvar":
+            if not self._resizes and not yuv420 and self.demosaic == "malvar" and os.environ.get("B200ISP_NO_FUSED_TRANSFORM", "0") != "1":
                 T = interpolate.ImageTransform
                 flip = {T.flip_horiz: 1, T.flip_vert: 2, T.rotate_180: 3, T.transpose: 4, T.rotate_270: 5, T.rotate_90: 6,
                         T.transverse: 7}.get(self.transform, 0)
-                if flip & 4 and not (shape[0] % 8 == 0 and shape[0] >= 16):
+                # the transposing store is OPT-IN (B200ISP_FUSED_TRANSPOSE=1): its 24-byte column pieces are partial-sector
+                # writes, L2 fills every one of them from DRAM (profiles/r02_transpose_store.txt: RGB8 Reinhard 11 % faster
+                # than the transform kernel behind the sweep, RGB16 linear 2.2x SLOWER)
+                if flip & 4 and not (shape[0] % 8 == 0 and shape[0] >= 16 and os.environ.get("B200ISP_FUSED_TRANSPOSE", "0") == "1"):
                     flip = 0
             if yuv420 or flip or self.transform == interpolate.ImageTransform.none:
                 finish = lambda outs: outs

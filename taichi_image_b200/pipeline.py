@@ -32,16 +32,16 @@ class RigPipeline:
     def __init__(self, isp, n_frames: int, height: int, width: int, tonemap: str = "reinhard", dtype=u8,
                  depth: int = 2, yuv420: bool = False, ids_format: bool = False, **tonemap_args):
         """``isp`` may resize (outputs are then the resized images) and ``yuv420=True`` selects the planar YUV 4:2:0
-        output of ``process_packed12`` (1.5 instead of 3 bytes per pixel over PCIe).  The ISP's transform is applied by the
-        sweep's store, so the result still lands in the slot: every transform for plain Malvar ISPs (the transposing ones --
-        rotate_90, the rig script's default -- need height % 8 == 0), none with resize / YUV."""
+        output of ``process_packed12`` (1.5 instead of 3 bytes per pixel over PCIe).  The ISP's flips are applied by the sweep's
+        store, so the result still lands in the slot; the transposing transforms (rotate_90, the rig script's default) run the
+        transform kernel behind the sweep and copy into the slot, or -- opt-in, B200ISP_FUSED_TRANSPOSE=1 -- the transposing
+        store.  No transform with resize / YUV."""
         assert width % 8 == 0 and height % 2 == 0, "fused path needs width % 8 == 0 and even height"
         base = getattr(isp, "isp", isp)
         tname = base.transform.value
         transposing = tname in ("rotate_90", "rotate_270", "transpose", "transverse")
         assert tname == "none" or not (base._resizes or yuv420 or base.demosaic != "malvar"), \
             "RigPipeline writes straight into its slots: transforms need the plain Malvar RGB sweep"
-        assert not transposing or (height % 8 == 0 and height >= 16), "transposing transforms in the store need height % 8 == 0"
         self.isp, self.n, self.h, self.w = isp, n_frames, height, width
         self.tonemap, self.out_dtype, self.tm = tonemap, as_dtype(dtype), tonemap_args
         self.yuv420 = bool(yuv420)

@@ -422,12 +422,13 @@ def test_flips_in_the_store(cuda, dt, tname, shape):
 @pytest.mark.parametrize("dt", ["f16", "f32"])
 @pytest.mark.parametrize("tname", ["rotate_90", "rotate_270", "transpose", "transverse"])
 @pytest.mark.parametrize("shape", [(40, 64), (48, 1032), (16, 776), (64, 264), (44, 72)])
-def test_transposing_transforms_in_the_store(cuda, dt, tname, shape):
+def test_transposing_transforms_in_the_store(cuda, dt, tname, shape, monkeypatch):
     """rotate_90 (the rig script's default) / rotate_270 / transpose / transverse applied by the sweep's store: each lane
     collects 24-byte column pieces and writes them as output rows (csrc/fused_isp.cuh store_transposed) -- bit for bit
     interpolate.transform of the untransformed result for every output dtype (8 / 4 / 2 rows per piece), tasks of 8 and of
     24 rows; a height that is not a multiple of 8 falls back to the transform kernel behind the sweep (same results)"""
     from taichi_image_b200.interpolate import ImageTransform, transform
+    monkeypatch.setenv("B200ISP_FUSED_TRANSPOSE", "1")      # opt-in experiment (camera_isp.process_packed12)
     r = rng(99)
     h, w = shape
     t = ImageTransform[tname]
@@ -457,9 +458,11 @@ def test_transposing_transforms_in_the_store(cuda, dt, tname, shape):
                     assert torch.equal(g, e), what
 
 
-def test_rotated_tiles_of_a_grid_image(cuda):
+@pytest.mark.parametrize("fused", ["0", "1"])
+def test_rotated_tiles_of_a_grid_image(cuda, fused, monkeypatch):
     """rotate_90 straight into row-pitched tiles of one grid image (scripts/tonemap_scan.py:91-100 with its default transform)"""
     from taichi_image_b200.interpolate import ImageTransform, transform
+    monkeypatch.setenv("B200ISP_FUSED_TRANSPOSE", fused)
     r = rng(100)
     h, w, n = 48, 72, 3
     cu = [to_cuda(f) for f in frames(r, n, h, w)]
