@@ -82,9 +82,15 @@ def build_cuda(force=False, jobs=None, verbose=False, out: Path | None = None) -
     nvcc = nvcc_path()
     tus = translation_units()
 
+    headers = list(CSRC.glob("*.cuh")) + [ROOT / "include" / "b200isp.h"]
+
     def compile_one(tu):
         name, src, defs = tu
         obj = OBJ / f"{name}.o"
+        # per-unit stamp: a change to one .cu file recompiles that unit only (any header change recompiles everything)
+        tu_stamp, tu_stamp_file = _digest([Path(src)] + headers, " ".join([*NVCC_FLAGS, *defs])), OBJ / f"{name}.stamp"
+        if not force and not verbose and obj.exists() and tu_stamp_file.exists() and tu_stamp_file.read_text() == tu_stamp:
+            return obj
         cmd = [nvcc, *NVCC_FLAGS, *defs, "-c", str(src), "-o", str(obj)]
         if verbose:
             cmd += ["-Xptxas", "-v"]
@@ -93,6 +99,7 @@ def build_cuda(force=False, jobs=None, verbose=False, out: Path | None = None) -
             raise RuntimeError(f"nvcc failed for {name}:\n{r.stdout}\n{r.stderr}")
         if verbose:
             (OBJ / f"{name}.ptxas.log").write_text(r.stderr)
+        tu_stamp_file.write_text(tu_stamp)
         return obj
 
     with ThreadPoolExecutor(max_workers=jobs or min(8, os.cpu_count() or 1)) as ex:

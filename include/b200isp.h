@@ -105,8 +105,10 @@ int b200isp_bounds(const void* src, int dtype, int64_t n_elems, float* bounds_ou
 int b200isp_linear(const void* src, int in_dtype, void* dst, int out_dtype, int64_t n_elems,
                    const float* bounds, float gamma, b200isp_stream stream);
 /* tonemap.py:134-168 reinhard_kernel(in,out)(image,temp,dest,gamma,intensity,la,ca):
- * the five dependent passes of the stand-alone Reinhard operator.
- * temp: n_pixels*3 floats (device scratch owned by the caller, as in the reference). */
+ * the five dependent passes of the stand-alone Reinhard operator, run as four reads of `src` that recompute the
+ * normalised value / the map instead of keeping them in an f32 image (same arithmetic per value).
+ * temp: NULL, or n_pixels*3 floats that receive the un-normalised Reinhard map (what the reference leaves in its
+ * caller-owned temp image; costs one extra 12 B/px write). */
 int b200isp_reinhard_standalone(const void* src, int in_dtype, float* temp, void* dst, int out_dtype,
                                 int64_t n_pixels, float gamma, float intensity, float light_adapt,
                                 float color_adapt, void* workspace, b200isp_stream stream);

@@ -10,7 +10,7 @@
 
 namespace isp {
 
-static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+static __host__ __device__ inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 // ---------------------------------------------------------------- 4-element vector access
 template <typename T> __device__ __forceinline__ void load4(const T* p, float (&v)[4]) {
@@ -159,11 +159,26 @@ template <typename T> __device__ __forceinline__ void store24(T* p, const float 
 }
 
 // ---------------------------------------------------------------- stand-alone Reinhard (tonemap.py:134-168)
-// pass A: temp = clamp((src - min) / range, 0, 1) as f32 (linear_func gamma 1, scale 1) fused with
-//         metering_func(temp, Bounds(0,1)) (tonemap.py:77-103): log-gray min/max, sums.
+// The reference runs five dependent passes over an f32 temp image (normalise -> meter -> map in place -> bounds -> linear).
+// Every pass after the first needs a whole-image reduction of the one before, so the source must be read four times -- but
+// the temp image need not exist: each pass RECOMPUTES the normalised value (two roundings) and, from pass C on, the map
+// from the source dtype.  Same arithmetic per value as the temp form (the temp held exactly these f32 values), 4 reads of
+// the source + 1 write of the result instead of 1 + 4 x 12 B/px of f32 traffic (f32 -> u8: 51 instead of 75 B/px, u8 ->
+// u8: 15 instead of 57 B/px).
+template <typename T> __device__ __forceinline__ void store24_raw(T* p, const T (&v)[24]) {
+  if constexpr (sizeof(T) == 1) {
+#pragma unroll
+    for (int i = 0; i < 3; ++i) reinterpret_cast<uint2*>(p)[i] = reinterpret_cast<const uint2*>(v)[i];
+  } else {
+#pragma unroll
+    for (int i = 0; i < 24 * (int)sizeof(T) / 16; ++i) reinterpret_cast<uint4*>(p)[i] = reinterpret_cast<const uint4*>(v)[i];
+  }
+}
+
+// pass A: metering_func(clamp((src - min) / range, 0, 1), Bounds(0,1)) (tonemap.py:77-103, :147-149): log-gray min/max, sums.
 template <typename InT>
-__global__ void __launch_bounds__(256) sa_normalise_meter_kernel(const InT* __restrict__ src, float* __restrict__ temp,
-                                                                 long long n_px, const float* __restrict__ b, Workspace* ws) {
+__global__ void __launch_bounds__(256) sa_normalise_meter_kernel(const InT* __restrict__ src, long long n_px, const float* __restrict__ b,
+                                                                 Workspace* ws) {
   __shared__ float smem[8 * 7];
   const float bmin = b[0];
   const float inv_range = __fdiv_rn(1.0f, __fsub_rn(b[1], bmin));
@@ -174,25 +189,20 @@ __global__ void __launch_bounds__(256) sa_normalise_meter_kernel(const InT* __re
     v[0] = fminf(v[0], lg); v[1] = fmaxf(v[1], lg);
     v[2] += lg; v[3] += gray; v[4] += s[0]; v[5] += s[1]; v[6] += s[2];
   };
-  // eight pixels per thread with 16-byte accesses when both images allow it, the tail (and unaligned images) per pixel
-  const bool vec = ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(temp)) & 15u) == 0;
-  const long long n8 = vec ? n_px / 8 : 0;
+  // eight pixels per thread with 16-byte accesses when the image allows it, the tail (and unaligned images) per pixel
+  const long long n8 = aligned16(src) ? n_px / 8 : 0;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (long long)gridDim.x * blockDim.x) {
     float x[24];
     load24(src + 24 * i, x);
 #pragma unroll
     for (int e = 0; e < 24; ++e) x[e] = clamp01(__fmul_rn(__fsub_rn(x[e], bmin), inv_range));
-    store24(temp + 24 * i, x);
 #pragma unroll
     for (int q = 0; q < 8; ++q) accum(x + 3 * q);
   }
   for (long long i = 8 * n8 + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_px; i += (long long)gridDim.x * blockDim.x) {
     float s[3];
 #pragma unroll
-    for (int k = 0; k < 3; ++k) {
-      s[k] = clamp01(__fmul_rn(__fsub_rn(to_f32(src[3 * i + k]), bmin), inv_range));
-      temp[3 * i + k] = s[k];
-    }
+    for (int k = 0; k < 3; ++k) s[k] = clamp01(__fmul_rn(__fsub_rn(to_f32(src[3 * i + k]), bmin), inv_range));
     accum(s);
   }
   const int op[7] = {0, 1, 2, 2, 2, 2, 2};
@@ -223,51 +233,84 @@ __global__ void __launch_bounds__(256) sa_normalise_meter_kernel(const InT* __re
   }
 }
 
-// pass B: Reinhard in place on temp (tonemap.py:107-131) fused with bounds_func(temp) (:146)
-__global__ void __launch_bounds__(256) sa_reinhard_kernel(float* __restrict__ temp, long long n_px, float intensity,
-                                                          float la, float ca, Workspace* ws) {
+// pass B (WRITE = false): bounds_func of the Reinhard map (tonemap.py:107-131, :146) -- min / max only, nothing stored.
+// pass C (WRITE = true):  dst = linear_func(map, those bounds, gamma) (:154); `temp`, when the caller wants the reference's
+//                         side effect, receives the un-normalised map.
+template <typename InT, typename OutT, bool WRITE>
+__global__ void __launch_bounds__(256) sa_reinhard_kernel(const InT* __restrict__ src, OutT* __restrict__ dst, float* __restrict__ temp,
+                                                          long long n_px, const float* __restrict__ b, float intensity, float la, float ca,
+                                                          float gamma, Workspace* ws) {
   __shared__ float smem[8 * 2];
   const ReinhardParams p = reinhard_params(ws->scratch + 8, intensity, la, ca);
+  const float bmin = b[0];
+  const float inv_range = __fdiv_rn(1.0f, __fsub_rn(b[1], bmin));
+  const float omin = WRITE ? b[2] : 0.f;
+  const float oinv = WRITE ? __fdiv_rn(1.0f, __fsub_rn(b[3], omin)) : 0.f;
+  const float inv_gamma = __fdiv_rn(1.0f, gamma);
+  const bool has_gamma = gamma != 1.0f;
   float v[2] = {INFINITY, -INFINITY};
   const bool ca0 = ca == 0.f;
-  // bmin = 0, range = 1: the scaled value is x itself.  MUFU evaluation of the map like the ISP kernels below
-  // (relative error ~1e-6, inside the <= 1 LSB contract)
+  // bmin = 0, range = 1: the scaled value is the normalised value itself.  MUFU evaluation of the map like the ISP kernels
+  // below (relative error ~1e-6, inside the <= 1 LSB contract)
   auto map_px = [&](const float* x, float* o) {
-    const float sc[3] = {x[0], x[1], x[2]};
-    float r[3];
+    float sc[3], r[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) sc[k] = clamp01(__fmul_rn(__fsub_rn(x[k], bmin), inv_range));
     if (ca0) reinhard_map_fast<true>(p, sc, r); else reinhard_map_fast<false>(p, sc, r);
 #pragma unroll
     for (int k = 0; k < 3; ++k) { o[k] = r[k]; v[0] = fminf(v[0], r[k]); v[1] = fmaxf(v[1], r[k]); }
   };
-  const long long n8 = (reinterpret_cast<uintptr_t>(temp) & 15u) == 0 ? n_px / 8 : 0;
+  // linear_func of the map: the map already carries the ~1e-6 relative error of its MUFU evaluation, so the gamma power uses
+  // the same lg2 / ex2 pair (powf made this pass issue-bound: 122 us of the call's 205 us on 4096x3000 f32 -> u8)
+  auto out_value = [&](float r) -> OutT {
+    float y = __fmul_rn(__fsub_rn(r, omin), oinv);
+    if (has_gamma) y = fast_pow(y, inv_gamma);
+    return cast_from_f32<OutT>(__fmul_rn(clamp01(y), DT<OutT>::scale));      // NaN -> 0 through the saturating clamp
+  };
+  bool vec = aligned16(src);
+  if (WRITE) vec = vec && aligned16(dst) && (!temp || aligned16(temp));
+  const long long n8 = vec ? n_px / 8 : 0;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (long long)gridDim.x * blockDim.x) {
     float x[24], o[24];
-    load24(temp + 24 * i, x);
+    load24(src + 24 * i, x);
 #pragma unroll
     for (int q = 0; q < 8; ++q) map_px(x + 3 * q, o + 3 * q);
-    store24(temp + 24 * i, o);
+    if constexpr (WRITE) {
+      if (temp) store24(temp + 24 * i, o);
+      alignas(16) OutT y[24];
+#pragma unroll
+      for (int e = 0; e < 24; ++e) y[e] = out_value(o[e]);
+      store24_raw(dst + 24 * i, y);
+    }
   }
   for (long long i = 8 * n8 + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_px; i += (long long)gridDim.x * blockDim.x) {
-    const float x[3] = {temp[3 * i], temp[3 * i + 1], temp[3 * i + 2]};
+    const float x[3] = {to_f32(src[3 * i]), to_f32(src[3 * i + 1]), to_f32(src[3 * i + 2])};
     float o[3];
     map_px(x, o);
+    if constexpr (WRITE) {
 #pragma unroll
-    for (int k = 0; k < 3; ++k) temp[3 * i + k] = o[k];
-  }
-  const int op[2] = {0, 1};
-  block_fold<2>(v, op, smem);
-  if (threadIdx.x == 0) {
-    ws->partials[blockIdx.x * kPartialStride + 0] = v[0];
-    ws->partials[blockIdx.x * kPartialStride + 1] = v[1];
-  }
-  if (last_block_ticket(&ws->counter[0])) {
-    float f[2] = {INFINITY, -INFINITY};
-    for (int b = threadIdx.x; b < (int)gridDim.x; b += blockDim.x) {
-      f[0] = fminf(f[0], __ldcg(&ws->partials[b * kPartialStride + 0]));
-      f[1] = fmaxf(f[1], __ldcg(&ws->partials[b * kPartialStride + 1]));
+      for (int k = 0; k < 3; ++k) {
+        if (temp) temp[3 * i + k] = o[k];
+        dst[3 * i + k] = out_value(o[k]);
+      }
     }
-    block_fold<2>(f, op, smem);
-    if (threadIdx.x == 0) { ws->scratch[2] = f[0]; ws->scratch[3] = f[1]; }
+  }
+  if constexpr (!WRITE) {
+    const int op[2] = {0, 1};
+    block_fold<2>(v, op, smem);
+    if (threadIdx.x == 0) {
+      ws->partials[blockIdx.x * kPartialStride + 0] = v[0];
+      ws->partials[blockIdx.x * kPartialStride + 1] = v[1];
+    }
+    if (last_block_ticket(&ws->counter[0])) {
+      float f[2] = {INFINITY, -INFINITY};
+      for (int bk = threadIdx.x; bk < (int)gridDim.x; bk += blockDim.x) {
+        f[0] = fminf(f[0], __ldcg(&ws->partials[bk * kPartialStride + 0]));
+        f[1] = fmaxf(f[1], __ldcg(&ws->partials[bk * kPartialStride + 1]));
+      }
+      block_fold<2>(f, op, smem);
+      if (threadIdx.x == 0) { ws->scratch[2] = f[0]; ws->scratch[3] = f[1]; }
+    }
   }
 }
 
@@ -394,21 +437,28 @@ extern "C" int b200isp_linear(const void* src, int in_dtype, void* dst, int out_
 extern "C" int b200isp_reinhard_standalone(const void* src, int in_dtype, float* temp, void* dst, int out_dtype,
                                            int64_t n_pixels, float gamma, float intensity, float light_adapt,
                                            float color_adapt, void* workspace, b200isp_stream stream) {
-  ISP_REQUIRE(n_pixels > 0 && src && temp && dst && workspace, B200ISP_E_ARG, "reinhard_standalone: bad argument");
+  ISP_REQUIRE(n_pixels > 0 && src && dst && workspace, B200ISP_E_ARG, "reinhard_standalone: bad argument");
   ISP_REQUIRE(gamma > 0.f, B200ISP_E_ARG, "reinhard_standalone: gamma must be positive");
   Workspace* ws = (Workspace*)workspace;
   cudaStream_t s = (cudaStream_t)stream;
-  float* ws_bounds = reinterpret_cast<float*>(reinterpret_cast<char*>(ws) + offsetof(Workspace, scratch));
+  float* ws_bounds = reinterpret_cast<float*>(reinterpret_cast<char*>(ws) + offsetof(Workspace, scratch));   // [0:2] source, [2:4] map
   const int grid = meter_grid(n_pixels);
+  // pass C writes: 8 pixels per thread, enough CTAs for every pixel (no grid-stride tail of idle SMs)
+  const unsigned wgrid = (unsigned)std::max<long long>(1, std::min<long long>((n_pixels / 8 + 255) / 256, 1 << 30));
   ISP_DISPATCH_DTYPE(in_dtype, InT, {
     int st = launch_bounds_kernel<InT>((const InT*)src, n_pixels * 3, ws_bounds, ws, s);       // tonemap.py:146
     if (st) return st;
-    sa_normalise_meter_kernel<InT><<<grid, 256, 0, s>>>((const InT*)src, temp, n_pixels, ws_bounds, ws);   // :147-149
+    sa_normalise_meter_kernel<InT><<<grid, 256, 0, s>>>((const InT*)src, n_pixels, ws_bounds, ws);   // :147-149
+    ISP_LAUNCH_CHECK("sa_normalise_meter_kernel");
+    sa_reinhard_kernel<InT, uint8_t, false><<<grid, 256, 0, s>>>((const InT*)src, nullptr, nullptr, n_pixels, ws_bounds, intensity,
+                                                                  light_adapt, color_adapt, gamma, ws);   // :150-153
+    ISP_LAUNCH_CHECK("sa_reinhard_kernel<bounds>");
+    ISP_DISPATCH_DTYPE(out_dtype, OutT, {
+      sa_reinhard_kernel<InT, OutT, true><<<wgrid, 256, 0, s>>>((const InT*)src, (OutT*)dst, temp, n_pixels, ws_bounds, intensity,
+                                                                 light_adapt, color_adapt, gamma, ws);     // :154
+    });
+    ISP_LAUNCH_CHECK("sa_reinhard_kernel<write>");
   });
-  ISP_LAUNCH_CHECK("sa_normalise_meter_kernel");
-  sa_reinhard_kernel<<<grid, 256, 0, s>>>(temp, n_pixels, intensity, light_adapt, color_adapt, ws);   // :150-153
-  ISP_LAUNCH_CHECK("sa_reinhard_kernel");
-  ISP_DISPATCH_DTYPE(out_dtype, OutT, return (launch_linear<float, OutT>(temp, (OutT*)dst, n_pixels * 3, ws_bounds + 2, gamma, s)));  // :154
   return B200ISP_OK;
 }
 

@@ -69,9 +69,9 @@ def tonemap_reinhard(src, gamma=1.0, intensity=1.0, light_adapt=1.0, color_adapt
     n_px = dev.shape[0] * dev.shape[1]
     if n_px:
         with torch.cuda.device(dev.device):
-            temp = torch.empty(dev.shape, dtype=torch.float32, device=dev.device)     # tonemap.py:163
+            # no temp image (tonemap.py:163): the passes recompute from the source (csrc/tonemap.cu)
             _lib.check(_lib.lib.b200isp_reinhard_standalone(
-                dev.data_ptr(), in_dtype.code, temp.data_ptr(), out.data_ptr(), dtype.code, n_px, float(gamma),
+                dev.data_ptr(), in_dtype.code, None, out.data_ptr(), dtype.code, n_px, float(gamma),
                 float(intensity), float(light_adapt), float(color_adapt), _lib.workspace(dev.device).data_ptr(),
                 _lib.stream_ptr(dev.device)), "tonemap_reinhard")
     return restore(out)
