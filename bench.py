@@ -57,7 +57,6 @@ OUT_BYTES = {"u8": 1, "u16": 2, "f16": 2, "f32": 4}
 # dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel per launch, from the ncu --set full captures
 # summarised under profiles/ (None where no capture exists); the source file is named next to the number
 TRAFFIC = {"cfg2": (843.8e6, "profiles/r01_stream2_kernel_ncu.txt (180.8 MB read + 663.0 MB written; the last ~56 MB of writes still in L2)"),
-           "cfg3": (282.1e6, "profiles/r02_reinhard_write_ncu.txt (111.1 MB read + 171.0 MB written)"),
            "cfg5": (243.2e6, "profiles/r02_resize_sweep_ncu.txt (148.4 MB read + 94.8 MB written)")}
 
 
@@ -268,12 +267,22 @@ class Ctx:
         return float(t.item())
 
 
-def launches_per_step(tonemap, isp_dt, resize, shared, lookahead):
+def uses_map16(isp_dt, out_dt, tm):
+    """Camera32 Reinhard -> u8 takes the one-sweep u16-map path (taichi_image_b200/camera_isp.py:_fused_params) unless
+    B200ISP_REINHARD_EXACT=1 keeps the exact max sweep + write sweep"""
+    return (isp_dt == "f32" and out_dt == "u8" and float(tm.get("color_adapt", 0.0)) == 0.0 and 0.3 <= float(tm.get("gamma", 1.0)) <= 1.0
+            and os.environ.get("B200ISP_REINHARD_EXACT", "0") != "1")
+
+
+def launches_per_step(tonemap, isp_dt, resize, shared, lookahead, map16=False):
     """launches of OUR kernels per step, counted from the launch plan:
-    sweep: linear 1; Reinhard Camera32 max sweep + write sweep = 2; Camera16 store sweep + normalise = 2;
+    sweep: linear 1; Reinhard Camera32 -> u8 map sweep + normalise + the two gated fallback sweeps = 4 (exact form: max sweep +
+    write sweep = 2); Camera16 store sweep + normalise = 2;
     resizing ISP: sweep + orphan columns (+ normalise for Reinhard) = 2 / 3;
     metering: cooperative 1; as look-ahead on the side stream 2; shared exposure 2 (exchange inside the kernels)"""
     sweep = (3 if tonemap == "reinhard" else 2) if resize else (2 if tonemap == "reinhard" else 1)
+    if map16:
+        sweep = 4
     return sweep + (2 if (shared or lookahead) else 1)
 
 
@@ -360,6 +369,8 @@ def run_workload(ctx: Ctx, name: str, steps: int, warmup: int, min_seconds: floa
                 px_per_step * 1.5 + n * ho * wo * 3 * (OUT_BYTES[isp_dt] if tonemap == "reinhard" else OUT_BYTES[out_dt])
         elif tonemap == "reinhard" and isp_dt == "f16":
             kern, kern_bytes = "isp::stream2_kernel<EpiReinhardMax2, STORE> (map sweep: packed in, f16 map out)", px_per_step * (1.5 + 6.0)
+        elif tonemap == "reinhard" and uses_map16(isp_dt, out_dt, tm):
+            kern, kern_bytes = "isp::stream2_kernel<EpiReinhardMax2<Camera32>, STORE> (map sweep: packed in, u16 fixed-point map out)", px_per_step * (1.5 + 6.0)
         elif tonemap == "reinhard":
             kern, kern_bytes = "isp::stream2_kernel<EpiReinhard2> (write sweep of the max + write pair)", alg_bytes
         else:
@@ -402,7 +413,8 @@ def run_workload(ctx: Ctx, name: str, steps: int, warmup: int, min_seconds: floa
                                                      "note": "the same isolated timing repeated right after the sustained window (power-capped clocks)"}
         res["step_gbps"] = alg_bytes / (res["ms_per_step"] * 1e-3) / 1e9
         res["step_frac_of_peak"] = res["step_gbps"] / ctx.peak
-    res["gpu_launches_per_step"] = launches_per_step(tonemap, isp_dt, bool(resize_w), shared, bool(args.lookahead))
+    res["gpu_launches_per_step"] = launches_per_step(tonemap, isp_dt, bool(resize_w), shared, bool(args.lookahead),
+                                                      map16=tonemap == "reinhard" and not resize_w and uses_map16(isp_dt, out_dt, tm))
     res["_live"] = dict(isp=isp, base=base, frames=frames, outs=outs, n=n, cam_ids=cam_ids, shared=shared, tm=tm)
     return res
 

@@ -190,7 +190,10 @@ typedef struct {
   int flip;                     /* ISP transform applied by the sweep's store (interpolate.py:36-56): bit 0 = mirror columns, bit 1 = mirror
                                    rows, bit 2 = transpose (output (W, H), out_pitch counts elements of ITS rows; needs height % 8 == 0):
                                    flip_horiz 1, flip_vert 2, rotate_180 3, transpose 4, rotate_270 5, rotate_90 6, transverse 7 */
-  int reserved0;                /* keeps the pointers below 8-byte aligned; must be 0 */
+  int reinhard_mode;            /* Camera32 Reinhard -> u8 with reinhard_scratch: 0 = one sweep that also stores the map as u16 fixed point
+                                   + a normalise pass (u8 within 1 LSB of the two-sweep result; color_adapt == 0, 0.3 <= gamma <= 1;
+                                   frames whose map leaves [0, 1) are redone exactly), 1 = always the exact max sweep + write sweep,
+                                   2 = experiment: exact integer-RGB scratch (csrc/reinhard_u16.cuh) */
   int ids_layout;               /* packed layout of the input frames: 0 = standard (packed.py:23-31), 1 = IDS (packed.py:36-44),
                                    decoded inside the row loader (4 instead of 2 instructions per sample, no re-pack pass) */
   void* profile_start;          /* optional cudaEvent_t pair recorded on `stream` immediately before / after */
@@ -198,7 +201,8 @@ typedef struct {
   void* meter_cache;            /* optional device scratch: >= n_frames*ceil(H/stride)*ceil(W/stride)*12 bytes; the second */
   size_t meter_cache_bytes;     /*   metering phase then re-reads the phase-1 samples instead of recomputing them */
   void* reinhard_scratch;       /* optional device scratch, >= n_frames*H*W*3*2 bytes: Camera16 Reinhard then runs ONE sweep that */
-  size_t reinhard_scratch_bytes;/*   stores the f16 map (camera_isp.py:211) + an element-wise normalise / quantise pass */
+  size_t reinhard_scratch_bytes;/*   stores the f16 map (camera_isp.py:211) + an element-wise normalise / quantise pass; Camera32 -> u8
+                                     likewise with a u16 fixed-point map (see reinhard_mode) */
 } b200isp_fused_params;
 
 /* camera_isp.py:333-340 load_packed12 + :376-385 update_metering + :394-413 tonemap_* over a

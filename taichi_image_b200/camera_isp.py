@@ -99,7 +99,8 @@ def camera_isp(name: str, dtype=f32):
                      device: torch.device = torch.device('cuda', 0),
                      metering_stride: int = 8,
                      demosaic: str = "malvar",
-                     resize_size: Optional[tuple] = None):
+                     resize_size: Optional[tuple] = None,
+                     reinhard_exact: Optional[bool] = None):
             """camera_isp.py:237-268.  ``demosaic="bilinear"`` (EXTENSION, north_star): 3x3 bilinear interpolation
             instead of Malvar-He-Cutler in every load / fused path of this object (``bayer_to_rgb(method=...)``)."""
             assert scale is None or resize_width == 0, "Cannot specify both scale and resize_width"
@@ -109,6 +110,9 @@ def camera_isp(name: str, dtype=f32):
             # (SURVEY Q9); the reference only knows the aspect-preserving ``scale`` / ``resize_width``
             self.resize_size = None if resize_size is None else (int(resize_size[0]), int(resize_size[1]))
             self.demosaic = demosaic
+            # EXTENSION: Camera32 Reinhard -> u8 runs one sweep + a u16 fixed-point map by default (u8 within 1 LSB of the exact
+            # form, csrc/fused_isp.cuh); True keeps the exact max sweep + write sweep (env default: B200ISP_REINHARD_EXACT=1)
+            self.reinhard_exact = (os.environ.get("B200ISP_REINHARD_EXACT", "0") == "1") if reinhard_exact is None else bool(reinhard_exact)
             self.bayer_pattern = bayer_pattern
             self.moving_alpha = moving_alpha
             self.scale = scale
@@ -479,6 +483,21 @@ def camera_isp(name: str, dtype=f32):
                 if sc is None or sc.numel() < need or sc.device != torch.device(self.device):
                     sc = self._reinhard_scratch = torch.empty(need, dtype=torch.uint8, device=self.device)
                 p.reinhard_scratch, p.reinhard_scratch_bytes = sc.data_ptr(), sc.numel()
+                p.reinhard_mode = 2
+            elif (tonemap == "reinhard" and isp_dtype == f32 and out_dtype.name == "u8" and not self.reinhard_exact
+                  and float(tm.get("color_adapt", 0.0)) == 0.0 and 0.3 <= float(tm.get("gamma", 1.0)) <= 1.0
+                  and not yuv420 and not flip and not p.ids_layout):
+                # Camera32 -> u8: ONE sweep that also stores the Reinhard map as u16 fixed point (6 B/px scratch) + a light
+                # normalise / gamma / quantise pass instead of the max sweep + write sweep (csrc/fused_isp.cuh, run_fused);
+                # the u8 result is within 1 LSB of the exact form, ISP(reinhard_exact=True) / B200ISP_REINHARD_EXACT=1 keep
+                # the two sweeps.  The library falls back to them on its own when the scratch does not apply (pitched outputs).
+                need = len(frames) * h * w * 6
+                sc = getattr(self, "_reinhard_scratch", None)
+                if sc is None or sc.numel() < need or sc.device != torch.device(self.device):
+                    sc = self._reinhard_scratch = torch.empty(need, dtype=torch.uint8, device=self.device)
+                p.reinhard_scratch, p.reinhard_scratch_bytes = sc.data_ptr(), sc.numel()
+            if tonemap == "reinhard" and self.reinhard_exact:
+                p.reinhard_mode = 1
             if profile_events is not None:      # (start, stop) torch.cuda.Event pair, see bench.py
                 p.profile_start, p.profile_stop = profile_events[0].cuda_event, profile_events[1].cuda_event
             return p

@@ -38,6 +38,7 @@ struct Workspace {
   unsigned int counter[8];        // last-block-done tickets
   float bounds[2];                // phase-1 min/max (blended) for the metering kernels
   float frame_max[B200ISP_MAX_FRAMES];   // Reinhard per-frame max (bit pattern of a non-negative float)
+  float frame_max2[B200ISP_MAX_FRAMES];  // the same for the frames the one-sweep u16 map declined (exact two-sweep fallback)
   float scratch[32];
   float partials[1];              // [kMaxPartialBlocks][kPartialStride] follows
 };

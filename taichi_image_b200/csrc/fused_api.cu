@@ -41,6 +41,7 @@ static int fused_setup(const char* what, const uint8_t* const* packed_host, void
   k.metrics = metrics; k.ws = (Workspace*)workspace; k.frame0 = 0;
   k.kbase = p.demosaic == B200ISP_DEMOSAIC_BILINEAR ? kBilinearBase : 0;
   k.flip = p.flip & 7;
+  k.gate = 0;
   ISP_REQUIRE(!(k.flip && (resizes(p) || p.out_yuv420)), B200ISP_E_ARG, "%s: flips in the store need the plain RGB sweep (no resize, no YUV)", what);
   ISP_REQUIRE(!(k.flip & 4) || (p.height % 8 == 0 && p.height >= 16), B200ISP_E_SHAPE,
               "%s: the transposing transforms in the store need height %% 8 == 0 and height >= 16, got %dx%d", what, p.height, p.width);

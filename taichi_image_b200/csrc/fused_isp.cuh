@@ -190,6 +190,8 @@ struct IspConsts {
   int ids;                   // packed layout of the input frames: 0 standard, 1 IDS
   int flip;                  // transform applied by the store: bit 0 horizontal, bit 1 vertical (rotate_180 = 3), bit 2 transposed
   int orow;                  // elements per OUTPUT row: 3 W for dense frames, more when the frames are tiles of a grid image
+  int gate;                  // 1: the sweep runs only on the frames the one-sweep u16 Reinhard map declined (reinhard_map16_declined),
+                             //    their max goes to / comes from ws->frame_max2; 0 everywhere else
 };
 
 // literal front end for one pixel (bayer.py:137-155 + ISP dtype rounding), used off the hot path
@@ -427,6 +429,16 @@ __device__ __forceinline__ void reinhard_out(const ReinhardConsts& c, const floa
   }
 }
 
+// One-sweep Camera32 Reinhard -> u8 (EpiReinhardMax2<false, CA0, STORE>): the map p = s / (adapt + s) is stored as
+// trunc(sat(p) * 65535) in a u16 scratch.  That is lossless enough for a u8 result only while every p lies in [0, 1) and the
+// frame maximum is not tiny: p >= 1 or inf (a channel far below the metered minimum makes its denominator <= 0; the
+// reference takes such a quotient into max_out, camera_isp.py:213) saturates to exactly 1.0, so a stored maximum of 1.0
+// means "something may have been clipped"; a maximum below 1/64 would magnify the 2^-17 quantisation step past 1/4 LSB of
+// u8 for the gammas the path accepts.  Such frames are declined: the normalise pass skips them and the gated max + write
+// sweeps (IspConsts::gate) redo them exactly.  Decided from ws->frame_max alone, so every kernel agrees without a flag.
+__device__ __forceinline__ bool reinhard_map16_declined(float mx) { return !(mx < 1.0f && mx >= 0.015625f); }
+constexpr float kMap16Scale = 65535.0f;
+
 __device__ __forceinline__ ReinhardConsts reinhard_consts(const IspConsts& k, int frame, bool with_max) {
   ReinhardConsts c;
   c.p = reinhard_params(k.metrics, k.intensity, k.la, k.ca);
@@ -439,7 +451,7 @@ __device__ __forceinline__ ReinhardConsts reinhard_consts(const IspConsts& k, in
   c.out_scale_inv_max = 0.f;
   c.max_out = 1.0f;
   if (with_max) {
-    c.max_out = fmaxf(1e-6f, __ldcg(&k.ws->frame_max[k.frame0 + frame]));      // camera_isp.py:190, :213
+    c.max_out = fmaxf(1e-6f, __ldcg(k.gate ? &k.ws->frame_max2[k.frame0 + frame] : &k.ws->frame_max[k.frame0 + frame]));      // camera_isp.py:190, :213
     c.out_scale_inv_max = __fdiv_rn(1.0f, c.max_out);
   }
   return c;
@@ -812,19 +824,24 @@ struct EpiLinear2 {
 // STORE (Camera16 only): also write the un-normalised map p, rounded through f16 exactly like the reference's in-place
 // write-back (camera_isp.py:211), to a scratch image -- the second pass then only normalises and quantises that
 // scratch (reinhard_scratch_out_kernel) instead of sweeping the packed frames again.
-template <bool CAM16, bool CA0, bool STORE = false>
+template <bool CAM16, bool CA0, bool STORE = false, bool GATED = false>
 struct EpiReinhardMax2 {      // pass 1: frame-global max of the mapped values (+ the map itself when STORE)
   FramePtrs fp;               // .out = scratch images (STORE only)
   IspConsts k;
-  static_assert(!STORE || CAM16, "the f16 scratch is exact only for Camera16");
-  static constexpr int kStageWords = STORE ? 32 * Quant<__half>::kWords : 0;
-  struct State { ReinhardConsts c; float mx; int edge; __half* out; WarpCtx wc; };
+  // STORE: Camera16 writes the f16 map the reference stores back (exact); Camera32 writes a u16 fixed-point map that is
+  // accurate enough for u8 outputs only (reinhard_map16_declined)
+  using ScratchT = std::conditional_t<CAM16, __half, uint16_t>;
+  static_assert(!(STORE && GATED), "the gated instantiation is the plain max sweep of the fallback");
+  static constexpr bool kGated = GATED;
+  static constexpr int kStageWords = STORE ? 32 * Quant<ScratchT>::kWords : 0;
+  struct State { ReinhardConsts c; float mx; int edge; ScratchT* out; WarpCtx wc; };
+  __device__ __forceinline__ bool enabled(int frame) const { return reinhard_map16_declined(__ldcg(&k.ws->frame_max[k.frame0 + frame])); }
   __device__ __forceinline__ void init(State& st, int frame, int tcol, const WarpCtx& wc) const {
     st.c = reinhard_consts(k, frame, false);
     st.mx = 0.f;
     st.edge = edge_bits(tcol, k.W);
     st.wc = wc;
-    st.out = STORE ? reinterpret_cast<__half*>(fp.out[k.frame0 + frame]) + 24 * wc.tcol0 : nullptr;
+    st.out = STORE ? reinterpret_cast<ScratchT*>(fp.out[k.frame0 + frame]) + 24 * wc.tcol0 : nullptr;
   }
   static constexpr bool kSplitEdge = false;     // measured: a separate K_CORE copy costs more (instruction cache) than its leaner code saves
   static constexpr bool kCompactLoop = true;
@@ -837,11 +854,20 @@ struct EpiReinhardMax2 {      // pass 1: frame-global max of the mapped values (
       float rgb[3], p[3];
       raw_to_rgb<CAM16>(k, &x.v[3 * q], rgb);
       reinhard_p<CAM16, CA0>(st.c, rgb, p);
-      mx = fmaxf(mx, fmaxf(p[0], fmaxf(p[1], p[2])));
-      v[3 * q] = __float_as_uint(p[0]); v[3 * q + 1] = __float_as_uint(p[1]); v[3 * q + 2] = __float_as_uint(p[2]);
+      if constexpr (STORE && !CAM16) {
+#pragma unroll
+        for (int ch = 0; ch < 3; ++ch) {
+          p[ch] = __saturatef(p[ch]);                   // NaN / negative -> 0, >= 1 -> 1.0 (declines the frame)
+          v[3 * q + ch] = __float_as_uint(__fmaf_rz(p[ch], kMap16Scale, 8388608.f));
+        }
+        mx = fmaxf(mx, fmaxf(p[0], fmaxf(p[1], p[2])));
+      } else {
+        mx = fmaxf(mx, fmaxf(p[0], fmaxf(p[1], p[2])));
+        v[3 * q] = __float_as_uint(p[0]); v[3 * q + 1] = __float_as_uint(p[1]); v[3 * q + 2] = __float_as_uint(p[2]);
+      }
     }
     st.mx = mx;
-    if constexpr (STORE) store_row8<__half>(st.wc, st.out, k.W * 3, row, v);
+    if constexpr (STORE) store_row8<ScratchT>(st.wc, st.out, k.W * 3, row, v);
   }
   template <bool BROW, bool GFIRST, int KIND>
   __device__ __forceinline__ void emit(State& st, int row, const f2 (&R)[4], const f2 (&G)[4], const f2 (&B)[4]) const {
@@ -850,7 +876,7 @@ struct EpiReinhardMax2 {      // pass 1: frame-global max of the mapped values (
       pairs_to_raw2<CAM16, BROW, GFIRST>(R, G, B, X);
       if (KIND == K_EDGE && st.edge) patch_cols_pairs<BROW, GFIRST>(X, st.edge, k.kbase);
       float mx = st.mx;
-      if constexpr (STORE) {
+      if constexpr (STORE && CAM16) {
         uint32_t v[24];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
@@ -867,6 +893,30 @@ struct EpiReinhardMax2 {      // pass 1: frame-global max of the mapped values (
           }
         }
         store_row8<__half>(st.wc, st.out, k.W * 3, row, v);
+      } else if constexpr (STORE) {
+        // Camera32: u16 fixed point.  The saturating product is the quotient itself (p = n * r), one FMUL.SAT per value;
+        // the quantiser is the packed RZ-FMA against 2^23 of the integer outputs.
+        uint32_t v[24];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          f2 rgb[3], n[3], r;
+          raw2_to_rgb2<CAM16>(k, X[j], rgb);
+          reinhard_nr2(st.c, rgb, bc(1.0f), n, r);
+          float rl, rh;
+          upk(r, rl, rh);
+#pragma unroll
+          for (int ch = 0; ch < 3; ++ch) {
+            float lo, hi, ql, qh;
+            upk(n[ch], lo, hi);
+            lo = __saturatef(lo * rl);
+            hi = __saturatef(hi * rh);
+            mx = fmaxf(mx, fmaxf(lo, hi));
+            upk(fma2_rz(pk(lo, hi), bc(kMap16Scale), bc(8388608.f)), ql, qh);
+            v[3 * j + ch] = __float_as_uint(ql);
+            v[3 * (j + 4) + ch] = __float_as_uint(qh);
+          }
+        }
+        store_row8<uint16_t, KIND == K_CORE>(st.wc, st.out, k.W * 3, row, v);
       } else {
         float dmin = 0.f;
 #pragma unroll
@@ -898,14 +948,17 @@ struct EpiReinhardMax2 {      // pass 1: frame-global max of the mapped values (
   __device__ __forceinline__ void finish(State& st, int frame, int lane, bool task_ok) const {
     const float m = warp_max(st.mx);
     if (lane == 0 && task_ok && m > 0.f)
-      atomicMax(reinterpret_cast<unsigned int*>(&k.ws->frame_max[k.frame0 + frame]), __float_as_uint(m));
+      atomicMax(reinterpret_cast<unsigned int*>(GATED ? &k.ws->frame_max2[k.frame0 + frame] : &k.ws->frame_max[k.frame0 + frame]),
+                __float_as_uint(m));
   }
 };
 
-template <bool CAM16, typename OutT, bool CA0, bool GAMMA, bool EXT = false>
+template <bool CAM16, typename OutT, bool CA0, bool GAMMA, bool EXT = false, bool GATED = false>
 struct EpiReinhard2 {         // pass 2 recomputed from the packed frame: map, normalise by the max, gamma, quantise
   FramePtrs fp;
-  IspConsts k;
+  IspConsts k;                // GATED (k.gate == 1): only the frames the one-sweep u16 map declined, max from ws->frame_max2
+  static constexpr bool kGated = GATED;
+  __device__ __forceinline__ bool enabled(int frame) const { return reinhard_map16_declined(__ldcg(&k.ws->frame_max[k.frame0 + frame])); }
   static constexpr int kStageWords = EXT ? kTransposeStageWords : 32 * Quant<OutT>::kWords;
   struct State { ReinhardConsts c; OutT* out; WarpCtx wc; int edge; };
   __device__ __forceinline__ void init(State& st, int frame, int tcol, const WarpCtx& wc) const {
@@ -1303,6 +1356,71 @@ __global__ void __launch_bounds__(256) reinhard_scratch_out_kernel(const FramePt
   }
 }
 
+// pass B of the one-sweep Camera32 Reinhard -> u8 path: out = trunc(255 * ((v + 0.5) / 65535 / max)^(1/gamma)) for the u16
+// map v of EpiReinhardMax2<false, CA0, STORE>; frames the map declined are skipped (the gated sweeps write them).
+// u16 -> f32 by dropping the halves into the mantissa of 2^23 (PRMT) and one exact packed subtraction -- no conversion
+// instruction, packed arithmetic throughout.  Dense outputs: 16 values per thread and iteration (two 16-byte loads, one
+// 16-byte store); PITCHED (the outputs are tiles of a grid image, orow > 3 W): 8 values, row / column from the chunk index.
+__device__ __forceinline__ void map16_pair(uint32_t w, f2 a2, f2 h2, f2 ig2, bool gamma, uint32_t& v0, uint32_t& v1) {
+  const f2 t = add2(pk(__uint_as_float(__byte_perm(w, 0x4B000000u, 0x7610)), __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7632))),
+                    bc(-8388608.f));
+  f2 q = fma2(t, a2, h2);
+  if (gamma) {
+    float lo, hi, l0, l1;
+    upk(q, lo, hi);
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l0) : "f"(lo));
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l1) : "f"(hi));
+    upk(mul2(pk(l0, l1), ig2), lo, hi);
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(l0) : "f"(lo));
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(l1) : "f"(hi));
+    q = pk(l0, l1);
+  }
+  float ql, qh;
+  upk(fma2_rz(q, bc(255.f), bc(8388608.f)), ql, qh);
+  v0 = __float_as_uint(ql);
+  v1 = __float_as_uint(qh);
+}
+__device__ __forceinline__ uint32_t pack4_u8(uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  return __byte_perm(__byte_perm(a, b, 0x0040), __byte_perm(c, d, 0x0040), 0x5410);
+}
+
+template <bool GAMMA, bool PITCHED>
+__global__ void __launch_bounds__(256) reinhard_map16_out_kernel(const FramePtrs scratch /* .out = u16 maps */, const FramePtrs fp,
+                                                                 int H, int W, int orow, float gamma, const Workspace* ws) {
+  const int frame = blockIdx.y;
+  const float mx = __ldcg(&ws->frame_max[frame]);
+  if (reinhard_map16_declined(mx)) return;
+  const uint4* src = reinterpret_cast<const uint4*>(scratch.out[frame]);
+  const float a = __fdiv_rn(__fdiv_rn(1.0f, mx), kMap16Scale);
+  const f2 a2 = bc(a), h2 = bc(0.5f * a), ig2 = bc((float)(1.0 / (double)gamma));
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  if constexpr (!PITCHED) {
+    uint4* dst = reinterpret_cast<uint4*>(fp.out[frame]);
+    const long long n16 = (long long)H * W * 3 / 16;                   // H even, W % 8 == 0
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += stride) {
+      const uint4 w0 = __ldcs(src + 2 * i), w1 = __ldcs(src + 2 * i + 1);
+      const uint32_t w[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+      uint32_t v[16];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) map16_pair(w[j], a2, h2, ig2, GAMMA, v[2 * j], v[2 * j + 1]);
+      __stcs(dst + i, make_uint4(pack4_u8(v[0], v[1], v[2], v[3]), pack4_u8(v[4], v[5], v[6], v[7]), pack4_u8(v[8], v[9], v[10], v[11]),
+                                 pack4_u8(v[12], v[13], v[14], v[15])));
+    }
+  } else {
+    uint8_t* dst = reinterpret_cast<uint8_t*>(fp.out[frame]);
+    const int cpr = W * 3 / 8;                                         // 8-value chunks per row
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < (long long)H * cpr; i += stride) {
+      const int row = (int)(i / cpr), c = (int)(i - (long long)row * cpr);
+      const uint4 w0 = __ldcs(src + i);
+      const uint32_t w[4] = {w0.x, w0.y, w0.z, w0.w};
+      uint32_t v[8];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) map16_pair(w[j], a2, h2, ig2, GAMMA, v[2 * j], v[2 * j + 1]);
+      __stcs(reinterpret_cast<uint2*>(dst + (size_t)row * orow + 8 * c), make_uint2(pack4_u8(v[0], v[1], v[2], v[3]), pack4_u8(v[4], v[5], v[6], v[7])));
+    }
+  }
+}
+
 // pass B with planar YUV 4:2:0 output (for video encoders): the u8 RGB of reinhard_scratch_out_kernel
 // is formed in registers and converted with the arithmetic of color/yuv_420.py:47-64 (csrc/yuv420.cu: x / 255, the
 // BT.601 matrix applied to the BGR-swizzled pixel, chroma = mean of the 2x2 quad, one-sided clamp) -- bit-identical
@@ -1365,34 +1483,37 @@ static __global__ void __launch_bounds__(128) reinhard_scratch_yuv_kernel(const 
   st_bytes<4>(planes + idx, cv4);
 }
 
-// pass A for frames [0, nframes): instantiated once (fused_inst.cu with ISP_INST_RMAX, Camera16)
+// pass A for frames [0, nframes): instantiated once per ISP dtype (fused_inst.cu with ISP_INST_RMAX); Camera16 stores the f16
+// map (any color_adapt), Camera32 the u16 fixed-point map (color_adapt == 0 only: the caller checks)
 template <bool CAM16>
 int run_rstore(const FramePtrs& fp_scratch, IspConsts k, int nframes, int rows_per_task, cudaStream_t s, void* ev_start, void* ev_stop) {
-  if constexpr (!CAM16) {
-    return B200ISP_E_DTYPE;
-  } else {
-    k.frame0 = 0;
-    const Stream2Geom g = make_geom2(k.H, k.W, nframes, rows_per_task);
-    int st = B200ISP_OK;
-    if (ev_start) record_profile_event(ev_start, s);
-    auto launch = [&](auto ld, bool bl) -> int {
-      ld.fp = fp_scratch; ld.pitch_words = k.W * 3 / 8; ld.frame0 = 0; ld.ids = k.ids;
-      ISP_DISPATCH_PATTERN(k.pattern, P, {
-        if (k.ca == 0.f) { EpiReinhardMax2<true, true, true> e{fp_scratch, k}; st = launch_stream2<P>(ld, e, g, s, "isp_stream<reinhard_store>", bl); }
-        else { EpiReinhardMax2<true, false, true> e{fp_scratch, k}; st = launch_stream2<P>(ld, e, g, s, "isp_stream<reinhard_store>", bl); }
-      });
-      return st;
-    };
-    if (k.ids) {
-      if (k.kbase != 0) { set_error("process_packed12: the IDS layout is fused for the Malvar demosaic only"); return B200ISP_E_ARG; }
-      st = launch(Packed12Loader2<true, true>{}, false);
-    } else {
-      st = launch(Packed12Loader2<true, false>{}, k.kbase != 0);
-    }
-    if (ev_stop) record_profile_event(ev_stop, s);
+  k.frame0 = 0;
+  const Stream2Geom g = make_geom2(k.H, k.W, nframes, rows_per_task);
+  int st = B200ISP_OK;
+  if (ev_start) record_profile_event(ev_start, s);
+  auto launch = [&](auto ld, bool bl) -> int {
+    ld.fp = fp_scratch; ld.pitch_words = k.W * 3 / 8; ld.frame0 = 0; ld.ids = k.ids;
+    ISP_DISPATCH_PATTERN(k.pattern, P, {
+      if (k.ca == 0.f) { EpiReinhardMax2<CAM16, true, true> e{fp_scratch, k}; st = launch_stream2<P>(ld, e, g, s, "isp_stream<reinhard_store>", bl); }
+      else if constexpr (CAM16) { EpiReinhardMax2<true, false, true> e{fp_scratch, k}; st = launch_stream2<P>(ld, e, g, s, "isp_stream<reinhard_store>", bl); }
+      else { set_error("process_packed12: the one-sweep Camera32 Reinhard map needs color_adapt == 0"); return B200ISP_E_ARG; }
+    });
     return st;
+  };
+  if (k.ids) {
+    if (k.kbase != 0) { set_error("process_packed12: the IDS layout is fused for the Malvar demosaic only"); return B200ISP_E_ARG; }
+    st = launch(Packed12Loader2<CAM16, true>{}, false);
+  } else {
+    st = launch(Packed12Loader2<CAM16, false>{}, k.kbase != 0);
   }
+  if (ev_stop) record_profile_event(ev_stop, s);
+  return st;
 }
+
+// The gated exact fallback of the one-sweep Camera32 path (color_adapt == 0, standard layout): max sweep into ws->frame_max2
+// + write sweep, both over all frames, every warp leaving at once unless its frame was declined -- in the usual case two
+// launches of CTAs that exit immediately.
+int run_rmax_gated(const FramePtrs& fp, IspConsts k, int nframes, int rows_per_task, cudaStream_t s);
 
 // frame-global Reinhard max for frames [frame0, frame0 + nframes): independent of the output dtype,
 // instantiated once per ISP dtype (fused_inst.cu with ISP_INST_RMAX)
@@ -1401,7 +1522,9 @@ int run_rmax(const FramePtrs& fp, IspConsts k, int frame0, int nframes, int rows
   return run_pass<CAM16, MODE_RMAX, uint8_t>(fp, k, frame0, nframes, rows_per_task, s);
 }
 
-// one-sweep Camera32 Reinhard (reinhard_u16.cuh / reinhard_u16.cu)
+int run_write_gated(const FramePtrs& fp, IspConsts k, int nframes, int rows_per_task, cudaStream_t s);
+
+// one-sweep Camera32 Reinhard, exact-integer experiment (reinhard_u16.cuh / reinhard_u16.cu)
 size_t reinhard_u16_frame_bytes(int H, int W);
 template <typename OutT>
 int run_reinhard_u16(const FramePtrs& fp, int n_frames, const b200isp_fused_params& p, IspConsts k, cudaStream_t s);
@@ -1452,10 +1575,41 @@ int run_fused(const FramePtrs& fp, int n_frames, const b200isp_fused_params& p, 
         return cuda_status(cudaPeekAtLastError(), "reinhard_scratch_out_kernel");
       }
     }
+    if constexpr (!CAM16 && std::is_same<OutT, uint8_t>::value) {
+      // Camera32 -> u8, color_adapt == 0, gamma in [0.3, 1]: ONE sweep that also stores the map as u16 fixed point
+      // (6 B/px scratch) + an element-wise normalise / gamma / quantise pass.  The second demosaic of the two-sweep form
+      // (66 of its 106 instructions per pixel) disappears; the u8 result is within 1 LSB of the two-sweep result
+      // (measured: profiles/r02_reinhard_map16.txt).  Frames whose map does not fit [0, 1) (reinhard_map16_declined) are
+      // redone exactly by the gated sweeps.  reinhard_mode 1 forces the exact two-sweep form.
+      const size_t need = (size_t)n_frames * k.H * k.W * 3 * sizeof(uint16_t);
+      if (p.reinhard_mode == 0 && k.ca == 0.f && k.gamma <= 1.0f && k.gamma >= 0.3f && !p.out_yuv420 && k.flip == 0 && k.ids == 0 &&
+          p.reinhard_scratch && p.reinhard_scratch_bytes >= need && p.reinhard_group <= 0) {
+        FramePtrs sc = fp;
+        for (int f = 0; f < n_frames; ++f) sc.out[f] = (char*)p.reinhard_scratch + (size_t)f * k.H * k.W * 3 * sizeof(uint16_t);
+        st = cuda_status(cudaMemsetAsync(k.ws->frame_max2, 0, sizeof(float) * B200ISP_MAX_FRAMES, s), "memset frame_max2");
+        if (st) return st;
+        st = run_rstore<false>(sc, k, n_frames, rpt, s, p.profile_start, p.profile_stop);
+        if (st) return st;
+        const long long n_elems = (long long)k.H * k.W * 3;
+        const dim3 grid((unsigned)std::min<long long>((n_elems / 16 + 255) / 256, (8 * kNumSMs + n_frames - 1) / n_frames), (unsigned)n_frames);
+        const bool gam = k.gamma != 1.0f, pitched = k.orow != 3 * k.W;
+        if (gam && pitched) reinhard_map16_out_kernel<true, true><<<grid, 256, 0, s>>>(sc, fp, k.H, k.W, k.orow, k.gamma, k.ws);
+        else if (gam) reinhard_map16_out_kernel<true, false><<<grid, 256, 0, s>>>(sc, fp, k.H, k.W, k.orow, k.gamma, k.ws);
+        else if (pitched) reinhard_map16_out_kernel<false, true><<<grid, 256, 0, s>>>(sc, fp, k.H, k.W, k.orow, k.gamma, k.ws);
+        else reinhard_map16_out_kernel<false, false><<<grid, 256, 0, s>>>(sc, fp, k.H, k.W, k.orow, k.gamma, k.ws);
+        st = cuda_status(cudaPeekAtLastError(), "reinhard_map16_out_kernel");
+        if (st) return st;
+        IspConsts kg = k;
+        kg.gate = 1;
+        st = run_rmax_gated(fp, kg, n_frames, rpt, s);
+        if (st) return st;
+        return run_write_gated(fp, kg, n_frames, rpt, s);
+      }
+    }
     if constexpr (!CAM16) {
-      // Camera32 without colour correction, color_adapt == 0: ONE sweep that also stores the exact integer RGB (3 x u16 per
-      // pixel) + an element-wise map / normalise / quantise pass (reinhard_u16.cuh)
-      if (!k.ccm && k.ca == 0.f && !p.out_yuv420 && k.flip == 0 && k.ids == 0 && k.H >= 4 && k.W >= 8 && p.reinhard_scratch &&
+      // EXPERIMENT (reinhard_mode 2): Camera32 without colour correction, color_adapt == 0: ONE sweep that also stores the exact
+      // integer RGB (3 x u16 per pixel) + an element-wise map / normalise / quantise pass (reinhard_u16.cuh)
+      if (p.reinhard_mode == 2 && !k.ccm && k.ca == 0.f && !p.out_yuv420 && k.flip == 0 && k.ids == 0 && k.H >= 4 && k.W >= 8 && p.reinhard_scratch &&
           p.reinhard_scratch_bytes >= (size_t)n_frames * reinhard_u16_frame_bytes(k.H, k.W))
         return run_reinhard_u16<OutT>(fp, n_frames, p, k, s);
     }
@@ -1475,6 +1629,7 @@ int run_fused(const FramePtrs& fp, int n_frames, const b200isp_fused_params& p, 
 }
 
 extern template int run_rstore<true>(const FramePtrs&, IspConsts, int, int, cudaStream_t, void*, void*);
+extern template int run_rstore<false>(const FramePtrs&, IspConsts, int, int, cudaStream_t, void*, void*);
 extern template int run_rmax<true>(const FramePtrs&, IspConsts, int, int, int, cudaStream_t);
 extern template int run_rmax<false>(const FramePtrs&, IspConsts, int, int, int, cudaStream_t);
 

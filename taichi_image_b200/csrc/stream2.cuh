@@ -263,19 +263,31 @@ __device__ __forceinline__ void stream2_rows(const Loader& ld, const Epi& epi, t
     epi.template emit<!BROW0, !GFIRST0, KIND>(st, row_ + 1, R_, G_, B_);                                        \
   }
 
+#ifndef ISP_S2_SLIDE_FADD2
+#define ISP_S2_SLIDE_FADD2 1
+#endif
 #ifndef ISP_S2_COMPACT_UNROLL
 #define ISP_S2_COMPACT_UNROLL 1     // measured: 1 step 607 / 147 Gpx/s (cfg2 / cfg3), 2 steps 585 / 120 -- code size beats moves
 #endif
   if constexpr (KIND == K_GENERAL || BL || (Epi::kCompactLoop && ISP_S2_COMPACT_UNROLL == 1)) {
     // cold kind, or an epilogue so large that three copies of the step overflow the instruction cache (Reinhard:
     // 51 KB hot, no_instruction 3.1 cycles per issue): one copy of the step, the window slides by register moves
+    // The slide as packed additions of -0.0 (exact identity for every float): one FADD2 moves a register PAIR, and because
+    // the result is a fresh value ptxas gives it the loop-carried register directly -- a plain copy costs two MOVs per pair
+    // (64 per step = 4 per pixel; ISP_S2_SLIDE_FADD2=0 restores them).  ptxas does not fold the addition away.
 #pragma unroll 1
     for (int row = r0; row < rend; row += 2) {
       ISP_STEP(0, row);
 #pragma unroll
       for (int k = 0; k < 4; ++k)
 #pragma unroll
-        for (int i = 0; i < 8; ++i) W[k][i] = W[k + 2][i];
+        for (int i = 0; i < 8; ++i) {
+#if ISP_S2_SLIDE_FADD2
+          W[k][i] = add2(W[k + 2][i], bc(-0.0f));
+#else
+          W[k][i] = W[k + 2][i];
+#endif
+        }
     }
   } else if constexpr (Epi::kCompactLoop) {
     // two copies of the step: half the register moves of the single-step form, two thirds of the unrolled code
@@ -314,18 +326,22 @@ constexpr int kRingStages = 1;
 constexpr int kRowSlotWords = 1;
 #endif
 
+// Epi::kGated: the epilogue can decline whole frames at run time (enabled(frame), warp-uniform) -- the gated fallback sweeps
+// of the one-sweep Reinhard path (fused_isp.cuh); every other epilogue has no such member and no such code.
+template <class Epi, class = void> struct has_gate { static constexpr bool value = false; };
+template <class Epi> struct has_gate<Epi, std::enable_if_t<Epi::kGated>> { static constexpr bool value = true; };
+
 template <class Loader, class = void> struct has_ring { static constexpr bool value = false; };
 template <class Loader> struct has_ring<Loader, std::enable_if_t<Loader::kRing>> { static constexpr bool value = true; };
 
 // BL: bilinear demosaic instead of Malvar-He-Cutler.  The bilinear kernels have no K_CORE copy of the loop and use
 // the single-step body (their binary stays small; the arithmetic saved is hidden behind the same DRAM traffic).
 template <int PATTERN, bool BL, class Loader, class Epi>
-__global__ void __launch_bounds__(ISP_S2_THREADS, ISP_S2_MINBLOCKS) stream2_kernel(const Loader ld, const Epi epi, const Stream2Geom sg) {
+__device__ __forceinline__ void stream2_task(const Loader& ld, const Epi& epi, const Stream2Geom& sg, long long task, uint32_t* stage_warp) {
   constexpr bool BROW0 = (PATTERN == B200ISP_GBRG || PATTERN == B200ISP_BGGR);
   constexpr bool GFIRST0 = (PATTERN == B200ISP_GRBG || PATTERN == B200ISP_GBRG);
   const StreamGeom& g = sg.g;
   const int lane = threadIdx.x & 31;
-  long long task = (long long)blockIdx.x * kS2Warps + (threadIdx.x >> 5);
   const bool task_ok = task < sg.total_tasks;
   if (!task_ok) task = 0;
   const bool border = task >= sg.interior_tasks;
@@ -346,13 +362,15 @@ __global__ void __launch_bounds__(ISP_S2_THREADS, ISP_S2_MINBLOCKS) stream2_kern
     rend = r0 + sg.border;
   }
   const int tcol = min(strip * 32 + lane, g.ntcols - 1);   // lanes past the last column recompute it (never stored)
+  if constexpr (has_gate<Epi>::value) {
+    if (!epi.enabled(frame)) return;                       // the whole warp works on one frame: uniform exit
+  }
 
-  __shared__ __align__(16) uint32_t stage[kS2Warps][Epi::kStageWords > 0 ? Epi::kStageWords : 1];
   WarpCtx wc;
   wc.lane = lane;
   wc.tcol0 = strip * 32;
   wc.nvalid = min(32, g.ntcols - strip * 32);
-  wc.stage = stage[threadIdx.x >> 5];
+  wc.stage = stage_warp;
 
   constexpr bool kSplit = Epi::kSplitEdge && !BL;
   constexpr bool kUseRing = has_ring<Loader>::value && kSplit;
@@ -383,11 +401,28 @@ __global__ void __launch_bounds__(ISP_S2_THREADS, ISP_S2_MINBLOCKS) stream2_kern
   epi.finish(st, frame, lane, task_ok);
 }
 
+
+// One warp per task, one launch of ceil(tasks / 4) CTAs.  Gated epilogues (has_gate: the exact fallback of the one-sweep
+// Reinhard path, which in the usual case has nothing to do) run a small persistent grid that strides over the tasks instead:
+// launching and retiring thousands of CTAs that exit at once costs 6.5 us per kernel, a few hundred cost 2.
+template <int PATTERN, bool BL, class Loader, class Epi>
+__global__ void __launch_bounds__(ISP_S2_THREADS, ISP_S2_MINBLOCKS) stream2_kernel(const Loader ld, const Epi epi, const Stream2Geom sg) {
+  __shared__ __align__(16) uint32_t stage[kS2Warps][Epi::kStageWords > 0 ? Epi::kStageWords : 1];
+  uint32_t* stage_warp = stage[threadIdx.x >> 5];
+  if constexpr (has_gate<Epi>::value) {
+    for (long long task = (long long)blockIdx.x * kS2Warps + (threadIdx.x >> 5); task < sg.total_tasks; task += (long long)gridDim.x * kS2Warps)
+      stream2_task<PATTERN, BL>(ld, epi, sg, task, stage_warp);
+  } else {
+    stream2_task<PATTERN, BL>(ld, epi, sg, (long long)blockIdx.x * kS2Warps + (threadIdx.x >> 5), stage_warp);
+  }
+}
+
 template <int PATTERN, class Loader, class Epi>
 inline int launch_stream2(const Loader& ld, const Epi& epi, const Stream2Geom& sg, cudaStream_t s, const char* what,
                           bool bilinear = false) {
   if (sg.total_tasks == 0) return B200ISP_OK;
-  const long long blocks = (sg.total_tasks + kS2Warps - 1) / kS2Warps;
+  long long blocks = (sg.total_tasks + kS2Warps - 1) / kS2Warps;
+  if (has_gate<Epi>::value && blocks > ISP_S2_MINBLOCKS * kNumSMs) blocks = ISP_S2_MINBLOCKS * kNumSMs;      // persistent (see stream2_kernel)
   if (bilinear) stream2_kernel<PATTERN, true, Loader, Epi><<<(unsigned)blocks, ISP_S2_THREADS, 0, s>>>(ld, epi, sg);
   else stream2_kernel<PATTERN, false, Loader, Epi><<<(unsigned)blocks, ISP_S2_THREADS, 0, s>>>(ld, epi, sg);
   return cuda_status(cudaPeekAtLastError(), what);

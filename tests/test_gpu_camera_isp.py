@@ -373,7 +373,8 @@ def test_ids_layout_in_the_row_loader_equals_repack(cuda, dt, pattern):
     from taichi_image_b200 import packed
     r = rng(96)
     h, w = 44, 1032
-    a, b = make_isp(dt, bayer_pattern=pattern), make_isp(dt, bayer_pattern=pattern)
+    # reinhard_exact: IDS frames always take the exact Reinhard sweeps, the standard layout would take the one-sweep u16 map
+    a, b = make_isp(dt, bayer_pattern=pattern, reinhard_exact=True), make_isp(dt, bayer_pattern=pattern, reinhard_exact=True)
     for step in range(2):
         ids = [to_cuda(O.encode12(r.integers(0, 4096, size=(h, w)).astype(np.uint16), ids_format=True)) for _ in range(2)]
         std = [packed.repack12_ids(f) for f in ids]
@@ -400,7 +401,7 @@ def test_flips_in_the_store(cuda, dt, tname, shape):
     cu = [to_cuda(f) for f in frames(r, 2, h, w)]
     for tm, out, kw in (("linear", "u16", dict()), ("linear", "u8", dict(gamma=0.8)), ("reinhard", "u8", dict(gamma=0.9, intensity=2.0)),
                         ("reinhard", "f16", dict())):
-        plain, flipped = make_isp(dt), make_isp(dt, transform=t)
+        plain, flipped = make_isp(dt, reinhard_exact=True), make_isp(dt, transform=t, reinhard_exact=True)      # like with like: the flips take the exact Reinhard sweeps
         exp = [transform(o, t) for o in plain.process_packed12(cu, tonemap=tm, dtype=out, rows_per_task=6, **kw)]
         bufs = [torch.empty_like(e) for e in exp]
         got = flipped.process_packed12(cu, tonemap=tm, dtype=out, rows_per_task=6, out=bufs, **kw)
@@ -436,7 +437,7 @@ def test_transposing_transforms_in_the_store(cuda, dt, tname, shape, monkeypatch
     for tm, out, kw in (("linear", "u16", dict()), ("linear", "u8", dict(gamma=0.8)), ("reinhard", "u8", dict(gamma=0.9, intensity=2.0)),
                         ("reinhard", "f16", dict()), ("linear", "f16", dict(gamma=0.7))):
         for rpt in (0, 8):
-            plain, turned = make_isp(dt), make_isp(dt, transform=t)
+            plain, turned = make_isp(dt, reinhard_exact=True), make_isp(dt, transform=t, reinhard_exact=True)      # like with like
             exp = [transform(o, t) for o in plain.process_packed12(cu, tonemap=tm, dtype=out, rows_per_task=rpt, **kw)]
             assert tuple(exp[0].shape) == (w, h, 3)
             bufs = [torch.empty_like(e) for e in exp]
