@@ -2,7 +2,7 @@
 """Benchmark of the camera-ISP hot path (BASELINE.json metric: Gpixel/s packed12 -> RGB8/RGB16 ISP at 1/2/4/8 B200,
 achieved HBM GB/s vs peak).
 
-    python bench.py --gpus N --steps K --warmup W [--impl reference] [--workload cfg2|cfg1|cfg1_16|cfg3|cfg5]
+    python bench.py --gpus N --steps K --warmup W [--impl reference] [--workload cfg2|cfg1|cfg1_16|cfg3|cfg5|cfg5_32]
                     [--cameras C]
 
 A step = one pass of the hot path over one batch of synthetic packed12 frames already resident in HBM: the fused
@@ -52,11 +52,15 @@ WORKLOADS = {
     "cfg5": (8, 3000, 4096, "f16", "reinhard", "f16", dict(gamma=0.9, intensity=3.0, light_adapt=0.9, color_adapt=0.0),
              "BASELINE configs[4] shard: 8 x 4096x3000 -> ISP + bilinear resize_width 1920 (fused into the sweep) -> Reinhard -> fp16"),
 }
-RESIZE_WIDTH = {"cfg5": 1920}
+# the same with the f32 ISP (Camera32): no f16 rounding of the intermediates to reproduce, fp16 only at the output
+WORKLOADS["cfg5_32"] = (8, 3000, 4096, "f32", "reinhard", "f16", dict(gamma=0.9, intensity=3.0, light_adapt=0.9, color_adapt=0.0),
+                        "BASELINE configs[4] shard with the f32 ISP: 8 x 4096x3000 -> Camera32 + bilinear resize_width 1920 (fused into the sweep) -> Reinhard -> fp16")
+RESIZE_WIDTH = {"cfg5": 1920, "cfg5_32": 1920}
 OUT_BYTES = {"u8": 1, "u16": 2, "f16": 2, "f32": 4}
 # dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel per launch, from the ncu --set full captures
 # summarised under profiles/ (None where no capture exists); the source file is named next to the number
-TRAFFIC = {"cfg2": (843.8e6, "profiles/r01_stream2_kernel_ncu.txt (180.8 MB read + 663.0 MB written; the last ~56 MB of writes still in L2)"),
+TRAFFIC = {"cfg2": (844.2e6, "profiles/r02_cfg2_sweep_fadd2_ncu.txt (181.0 MB read + 663.2 MB written; the last ~56 MB of writes still in L2)"),
+           "cfg3": (497.2e6, "profiles/r02_map16_sweep_ncu.txt (111.6 MB read + 385.7 MB written: packed frames in, u16 map out; the tail of the writes still in L2)"),
            "cfg5": (243.2e6, "profiles/r02_resize_sweep_ncu.txt (148.4 MB read + 94.8 MB written)")}
 
 

@@ -78,6 +78,14 @@ int b200isp_repack12_ids(const uint8_t* ids, uint8_t* standard, int64_t n_bytes,
 int b200isp_decode16(const uint8_t* encoded, int64_t n_values, void* out, int out_dtype,
                      int scaled, b200isp_stream stream);
 
+/* EXTENSION (SURVEY 8f-4 "10-bit packed"; the reference has no 10-bit format): MIPI CSI-2 RAW10, 5 bytes <-> 4 pixels --
+ * bytes 0..3 = bits 9..2 of pixels 0..3, byte 4 = their bits 1..0 (pixel 0 in the lowest bit pair).  Value conventions of
+ * packed.py:66-73 / :98-104 with 1023 in place of 4095.  n_values % 4 == 0; encoded has n_values*5/4 bytes. */
+int b200isp_decode10(const uint8_t* encoded, int64_t n_values, void* out, int out_dtype,
+                     int scaled, b200isp_stream stream);
+int b200isp_encode10(const void* values, int in_dtype, int64_t n_values, uint8_t* encoded,
+                     int scaled, b200isp_stream stream);
+
 /* ---- bayer.py ----------------------------------------------------------- */
 /* bayer.py:101-112 rgb_to_bayer_kernel(image, bayer, pixel_order). */
 int b200isp_rgb_to_bayer(const void* rgb, void* bayer, int dtype, int height, int width,

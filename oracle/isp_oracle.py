@@ -118,6 +118,37 @@ def decode16(enc: np.ndarray, dtype: str = "u16", scaled: bool = False) -> np.nd
     return out.reshape(shape[:-1] + (shape[-1] // 2,))
 
 
+# EXTENSION (SURVEY 8f-4 "10-bit packed"; the reference has no 10-bit format -> parity unpinned): MIPI CSI-2 RAW10,
+# 5 bytes <-> 4 pixels, bytes 0..3 = bits 9..2 of pixels 0..3, byte 4 = their bits 1..0 (pixel 0 in the lowest bit pair);
+# value conventions of packed.py:66-73 / :98-104 with 1023 in place of 4095.
+def encode10(values: np.ndarray, scaled: bool = False) -> np.ndarray:
+    shape = values.shape
+    assert shape[-1] % 4 == 0
+    flat = values.reshape(-1)
+    if scaled:
+        v = flat.astype(f32) * f32(1023.0 / SCALE[dtype_name(flat)])
+        p = round_half_away(v).astype(np.int64).astype(np.uint16)
+    else:
+        p = flat.astype(np.uint16)
+    p = (p & 0x3FF).reshape(-1, 4)
+    out = np.empty((p.shape[0], 5), np.uint8)
+    out[:, :4] = (p >> 2).astype(np.uint8)
+    out[:, 4] = ((p[:, 0] & 3) | ((p[:, 1] & 3) << 2) | ((p[:, 2] & 3) << 4) | ((p[:, 3] & 3) << 6)).astype(np.uint8)
+    return out.reshape(shape[:-1] + (shape[-1] * 5 // 4,))
+
+
+def decode10(enc: np.ndarray, dtype: str = "u16", scaled: bool = False) -> np.ndarray:
+    shape = enc.shape
+    assert enc.dtype == np.uint8 and shape[-1] % 5 == 0
+    b = enc.reshape(-1, 5).astype(np.uint16)
+    v = np.stack([(b[:, j] << 2) | ((b[:, 4] >> (2 * j)) & 3) for j in range(4)], -1).reshape(-1)
+    if scaled:
+        out = cast_to(v.astype(f32) * f32(SCALE[dtype] / 1023.0), dtype)
+    else:
+        out = v.astype(NP_DTYPE[dtype])
+    return out.reshape(shape[:-1] + (shape[-1] * 4 // 5,))
+
+
 # --------------------------------------------------------------------------
 # bayer.py
 # --------------------------------------------------------------------------
@@ -490,6 +521,9 @@ class ISP:
 
     def load_packed16(self, data):                       # camera_isp.py:342-347
         return self._process_image(decode16(data, self.dtype, scaled=True))
+
+    def load_packed10(self, data):                       # EXTENSION (MIPI RAW10), the path of load_packed16
+        return self._process_image(decode10(data, self.dtype, scaled=True))
 
     def load_16u(self, image):                           # camera_isp.py:82-87, :318-321
         return self._process_image((image.astype(f32) / f32(65535.0)).astype(NP_DTYPE[self.dtype]))

@@ -48,6 +48,8 @@ SIGNATURES = {
     "b200isp_decode12": [_vp, _i64, _vp, _i, _i, _i, _vp],
     "b200isp_repack12_ids": [_vp, _vp, _i64, _vp],
     "b200isp_decode16": [_vp, _i64, _vp, _i, _i, _vp],
+    "b200isp_decode10": [_vp, _i64, _vp, _i, _i, _vp],
+    "b200isp_encode10": [_vp, _i, _i64, _vp, _i, _vp],
     "b200isp_rgb_to_bayer": [_vp, _vp, _i, _i, _i, _i, _vp],
     "b200isp_bayer_to_rgb": [_vp, _i, _vp, _i, _i, _i, _i, C.POINTER(C.c_float), _vp],
     "b200isp_bayer_to_rgb_bilinear": [_vp, _i, _vp, _i, _i, _i, _i, C.POINTER(C.c_float), _vp],

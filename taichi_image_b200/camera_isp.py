@@ -254,6 +254,16 @@ def camera_isp(name: str, dtype=f32):
             packed.decode16_kernel(isp_dtype, scaled=True)(image_data.contiguous().view(-1), cfa.view(-1))
             return self._process_image(cfa)
 
+        def load_packed10(self, image_data):
+            """EXTENSION: MIPI RAW10 frames, (H, 5 W / 4) bytes -- decoded to the ISP dtype scaled by 1 / 1023
+            (``packed.decode10``), then the path of ``load_packed16``"""
+            assert image_data.dtype == torch.uint8 and image_data.ndim == 2 and image_data.shape[1] % 5 == 0
+            image_data = image_data.to(self.device)
+            w, h = (image_data.shape[1] * 4 // 5, image_data.shape[0])
+            cfa = torch.empty(h, w, dtype=torch_dtype, device=self.device)
+            packed.decode10_kernel(isp_dtype, scaled=True)(image_data.contiguous().view(-1), cfa.view(-1))
+            return self._process_image(cfa)
+
         def _process_image(self, cfa):
             """camera_isp.py:371-373 (with the configured pattern)"""
             rgb = bayer.bayer_to_rgb(cfa, self.bayer_pattern, correct_colors=self.color_correct_matrix, method=self.demosaic)
@@ -467,7 +477,8 @@ def camera_isp(name: str, dtype=f32):
             if tonemap == "reinhard" and (plan is not None or (isp_dtype == f16 and os.environ.get("B200ISP_CAM16_RECOMPUTE", "0") != "1")):
                 # scratch for the un-normalised Reinhard map in the ISP dtype: Camera16 (one sweep + a light normalise
                 # pass, csrc/fused_isp.cuh) and every resizing ISP (output resolution, csrc/fused_resize.cu)
-                need = len(frames) * ho * wo * 3 * isp_dtype.itemsize
+                # (+ 64 KB per frame: the table of the normalise pass, csrc/fused_isp.cuh run_lut_pass; unused by resizing ISPs)
+                need = len(frames) * ho * wo * 3 * isp_dtype.itemsize + len(frames) * 65536
                 sc = getattr(self, "_reinhard_scratch", None)
                 if sc is None or sc.numel() < need or sc.device != torch.device(self.device):
                     sc = self._reinhard_scratch = torch.empty(need, dtype=torch.uint8, device=self.device)
@@ -491,7 +502,7 @@ def camera_isp(name: str, dtype=f32):
                 # normalise / gamma / quantise pass instead of the max sweep + write sweep (csrc/fused_isp.cuh, run_fused);
                 # the u8 result is within 1 LSB of the exact form, ISP(reinhard_exact=True) / B200ISP_REINHARD_EXACT=1 keep
                 # the two sweeps.  The library falls back to them on its own when the scratch does not apply (pitched outputs).
-                need = len(frames) * h * w * 6
+                need = len(frames) * h * w * 6 + len(frames) * 65536          # maps + the 64 KB tables of the normalise pass
                 sc = getattr(self, "_reinhard_scratch", None)
                 if sc is None or sc.numel() < need or sc.device != torch.device(self.device):
                     sc = self._reinhard_scratch = torch.empty(need, dtype=torch.uint8, device=self.device)

@@ -597,10 +597,24 @@ __device__ __forceinline__ void patch_cols_pairs(f2 (&X)[4][3], int edge, int kb
 }
 
 // raw pair -> ISP RGB pair in [0,1]: CCM (kernel-uniform run-time flag), clamp (bayer.py:152-155), ISP dtype rounding
-template <bool CAM16>
+// colour matrix on the four pixel pairs of a row under ONE kernel-uniform branch (inside raw2_to_rgb2 it is taken once per
+// pair: 0.5 BRA per pixel in the Reinhard sweeps); callers then use raw2_to_rgb2<CAM16, false>
+__device__ __forceinline__ void ccm2_row(const IspConsts& k, f2 (&X)[4][3]) {
+  if (k.ccm) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const f2 x0 = X[j][0], x1 = X[j][1], x2 = X[j][2];
+#pragma unroll
+      for (int c = 0; c < 3; ++c)
+        X[j][c] = fma2(x2, bc(k.m[3 * c + 2]), fma2(x1, bc(k.m[3 * c + 1]), mul2(x0, bc(k.m[3 * c]))));
+    }
+  }
+}
+
+template <bool CAM16, bool DO_CCM = true>
 __device__ __forceinline__ void raw2_to_rgb2(const IspConsts& k, const f2 (&x)[3], f2 (&rgb)[3]) {
   f2 y[3] = {x[0], x[1], x[2]};
-  if (k.ccm) {
+  if (DO_CCM && k.ccm) {
 #pragma unroll
     for (int c = 0; c < 3; ++c)
       y[c] = fma2(x[2], bc(k.m[3 * c + 2]), fma2(x[1], bc(k.m[3 * c + 1]), mul2(x[0], bc(k.m[3 * c]))));
@@ -875,13 +889,14 @@ struct EpiReinhardMax2 {      // pass 1: frame-global max of the mapped values (
       f2 X[4][3];
       pairs_to_raw2<CAM16, BROW, GFIRST>(R, G, B, X);
       if (KIND == K_EDGE && st.edge) patch_cols_pairs<BROW, GFIRST>(X, st.edge, k.kbase);
+      ccm2_row(k, X);
       float mx = st.mx;
       if constexpr (STORE && CAM16) {
         uint32_t v[24];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           f2 rgb[3], p[3];
-          raw2_to_rgb2<CAM16>(k, X[j], rgb);
+          raw2_to_rgb2<CAM16, false>(k, X[j], rgb);
           reinhard_p2<CAM16>(st.c, rgb, p);
 #pragma unroll
           for (int ch = 0; ch < 3; ++ch) {
@@ -900,7 +915,7 @@ struct EpiReinhardMax2 {      // pass 1: frame-global max of the mapped values (
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           f2 rgb[3], n[3], r;
-          raw2_to_rgb2<CAM16>(k, X[j], rgb);
+          raw2_to_rgb2<CAM16, false>(k, X[j], rgb);
           reinhard_nr2(st.c, rgb, bc(1.0f), n, r);
           float rl, rh;
           upk(r, rl, rh);
@@ -922,7 +937,7 @@ struct EpiReinhardMax2 {      // pass 1: frame-global max of the mapped values (
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           f2 rgb[3];
-          raw2_to_rgb2<CAM16>(k, X[j], rgb);
+          raw2_to_rgb2<CAM16, false>(k, X[j], rgb);
           float lo, hi;
           upk(reinhard_pmax2(st.c, rgb, dmin), lo, hi);
           mx = fmaxf(mx, fmaxf(lo, hi));
@@ -931,7 +946,7 @@ struct EpiReinhardMax2 {      // pass 1: frame-global max of the mapped values (
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             f2 rgb[3], p[3];
-            raw2_to_rgb2<CAM16>(k, X[j], rgb);
+            raw2_to_rgb2<CAM16, false>(k, X[j], rgb);
             reinhard_p2<CAM16>(st.c, rgb, p);
 #pragma unroll
             for (int ch = 0; ch < 3; ++ch) mx = fmaxf(mx, fmaxf(lo_of(p[ch]), hi_of(p[ch])));
@@ -989,11 +1004,12 @@ struct EpiReinhard2 {         // pass 2 recomputed from the packed frame: map, n
     f2 X[4][3];
     pairs_to_raw2<CAM16, BROW, GFIRST>(R, G, B, X);
     if (KIND == K_EDGE && st.edge) patch_cols_pairs<BROW, GFIRST>(X, st.edge, k.kbase);
+    ccm2_row(k, X);
     uint32_t v[24];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       f2 rgb[3], n[3], r;
-      raw2_to_rgb2<CAM16>(k, X[j], rgb);
+      raw2_to_rgb2<CAM16, false>(k, X[j], rgb);
       // Camera32: q = p / max_out straight from the shared reciprocal; Camera16: p is rounded through f16 first
       reinhard_nr2(st.c, rgb, bc(CAM16 ? 1.0f : st.c.max_out), n, r);
       float rl, rh;
@@ -1322,7 +1338,7 @@ static int run_pass(const FramePtrs& fp, IspConsts k, int frame0, int nframes, i
 template <typename OutT>
 __global__ void __launch_bounds__(256) reinhard_scratch_out_kernel(const FramePtrs scratch /* .out = f16 maps */, const FramePtrs fp,
                                                                    long long n_elems /* per frame, % 8 == 0 */, float gamma, const Workspace* ws) {
-  const int frame = blockIdx.y;
+  const int frame = gridDim.y - 1 - blockIdx.y;       // last frame first: the sweep wrote it last, part of its map is still in L2
   const __half* src = reinterpret_cast<const __half*>(scratch.out[frame]);
   OutT* dst = reinterpret_cast<OutT*>(fp.out[frame]);
   const float inv_max = __fdiv_rn(1.0f, fmaxf(1e-6f, __ldcg(&ws->frame_max[frame])));
@@ -1387,7 +1403,7 @@ __device__ __forceinline__ uint32_t pack4_u8(uint32_t a, uint32_t b, uint32_t c,
 template <bool GAMMA, bool PITCHED>
 __global__ void __launch_bounds__(256) reinhard_map16_out_kernel(const FramePtrs scratch /* .out = u16 maps */, const FramePtrs fp,
                                                                  int H, int W, int orow, float gamma, const Workspace* ws) {
-  const int frame = blockIdx.y;
+  const int frame = gridDim.y - 1 - blockIdx.y;       // last frame first: the sweep wrote it last, part of its map is still in L2
   const float mx = __ldcg(&ws->frame_max[frame]);
   if (reinhard_map16_declined(mx)) return;
   const uint4* src = reinterpret_cast<const uint4*>(scratch.out[frame]);
@@ -1419,6 +1435,78 @@ __global__ void __launch_bounds__(256) reinhard_map16_out_kernel(const FramePtrs
       __stcs(reinterpret_cast<uint2*>(dst + (size_t)row * orow + 8 * c), make_uint2(pack4_u8(v[0], v[1], v[2], v[3]), pack4_u8(v[4], v[5], v[6], v[7])));
     }
   }
+}
+
+// pass B through a table (gamma != 1, dense u8 outputs): both 16-bit scratch formats -- the f16 map of Camera16 and the u16
+// fixed-point map of Camera32 -- have only 65 536 patterns, and the output is a pure function of the pattern and the frame
+// maximum.  reinhard_lut_build_kernel evaluates that function once per pattern and frame with exactly the arithmetic of
+// reinhard_scratch_out_kernel / map16_pair (so the result is bit-identical to them); reinhard_lut_out_kernel keeps the frame's
+// 64 KB table in shared memory and turns every value into one LDS.U8: no MUFU (the arithmetic pass needs 6 per pixel and sits
+// at 74 % of the MUFU pipe), 10 instead of 21 instructions per pixel -- the pass becomes a plain HBM stream.
+constexpr int kLutBytes = 65536;
+template <bool CAM16>
+__global__ void __launch_bounds__(256) reinhard_lut_build_kernel(uint8_t* lut /* n_frames x 65536 */, float gamma, const Workspace* ws) {
+  const int frame = blockIdx.y;
+  const uint32_t v = blockIdx.x * 256 + threadIdx.x;
+  const float mx = __ldcg(&ws->frame_max[frame]);
+  uint32_t out;
+  if constexpr (CAM16) {
+    const float inv_max = __fdiv_rn(1.0f, fmaxf(1e-6f, mx));
+    float q = __saturatef(__half2float(__ushort_as_half((unsigned short)v)) * inv_max);
+    if (gamma != 1.0f) q = fast_pow(q, (float)(1.0 / (double)gamma));
+    out = Quant<uint8_t>::q(q);
+  } else {
+    if (reinhard_map16_declined(mx)) return;
+    const float a = __fdiv_rn(__fdiv_rn(1.0f, mx), kMap16Scale);
+    uint32_t v1;
+    map16_pair(v | (v << 16), bc(a), bc(0.5f * a), bc((float)(1.0 / (double)gamma)), gamma != 1.0f, out, v1);
+  }
+  lut[(size_t)frame * kLutBytes + v] = (uint8_t)out;
+}
+
+template <bool CAM16>
+__global__ void __launch_bounds__(512) reinhard_lut_out_kernel(const FramePtrs scratch, const FramePtrs fp, long long n16 /* 16-value chunks per frame */,
+                                                               const uint8_t* __restrict__ lut, const Workspace* ws) {
+  extern __shared__ __align__(16) uint8_t s_lut[];
+  const int frame = gridDim.y - 1 - blockIdx.y;       // last frame first: the sweep wrote it last, part of its map is still in L2
+  if (!CAM16 && reinhard_map16_declined(__ldcg(&ws->frame_max[frame]))) return;
+  {
+    const uint4* g = reinterpret_cast<const uint4*>(lut + (size_t)frame * kLutBytes);
+    uint4* s4 = reinterpret_cast<uint4*>(s_lut);
+    for (int i = threadIdx.x; i < kLutBytes / 16; i += blockDim.x) s4[i] = __ldg(g + i);
+  }
+  __syncthreads();
+  const uint4* src = reinterpret_cast<const uint4*>(scratch.out[frame]);
+  uint4* dst = reinterpret_cast<uint4*>(fp.out[frame]);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (long long)gridDim.x * blockDim.x) {
+    const uint4 w0 = __ldcs(src + 2 * i), w1 = __ldcs(src + 2 * i + 1);
+    const uint32_t w[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+    uint32_t o[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const uint32_t a = s_lut[w[2 * j] & 0xFFFFu], b = s_lut[w[2 * j] >> 16], c = s_lut[w[2 * j + 1] & 0xFFFFu], d = s_lut[w[2 * j + 1] >> 16];
+      o[j] = a | (b << 8) | (c << 16) | (d << 24);
+    }
+    __stcs(dst + i, make_uint4(o[0], o[1], o[2], o[3]));
+  }
+}
+
+// launches the table form of pass B; lut = n_frames x 64 KB behind the maps in the caller's scratch
+template <bool CAM16>
+static int run_lut_pass(const FramePtrs& sc, const FramePtrs& fp, int n_frames, long long n_elems, uint8_t* lut, float gamma, const Workspace* ws,
+                        cudaStream_t s) {
+  reinhard_lut_build_kernel<CAM16><<<dim3(kLutBytes / 256, (unsigned)n_frames), 256, 0, s>>>(lut, gamma, ws);
+  int st = cuda_status(cudaPeekAtLastError(), "reinhard_lut_build_kernel");
+  if (st) return st;
+  static bool attr_set = false;          // per process and instantiation; the attribute belongs to the function, not to a device context
+  if (!attr_set) {
+    st = cuda_status(cudaFuncSetAttribute(reinhard_lut_out_kernel<CAM16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kLutBytes), "lut smem attribute");
+    if (st) return st;
+    attr_set = true;
+  }
+  const dim3 grid((unsigned)std::min<long long>((n_elems / 16 + 511) / 512, (3 * kNumSMs + n_frames - 1) / n_frames), (unsigned)n_frames);
+  reinhard_lut_out_kernel<CAM16><<<grid, 512, kLutBytes, s>>>(sc, fp, n_elems / 16, lut, ws);
+  return cuda_status(cudaPeekAtLastError(), "reinhard_lut_out_kernel");
 }
 
 // pass B with planar YUV 4:2:0 output (for video encoders): the u8 RGB of reinhard_scratch_out_kernel
@@ -1523,6 +1611,12 @@ int run_rmax(const FramePtrs& fp, IspConsts k, int frame0, int nframes, int rows
 }
 
 int run_write_gated(const FramePtrs& fp, IspConsts k, int nframes, int rows_per_task, cudaStream_t s);
+// B200ISP_REINHARD_LUT: 0 = arithmetic normalise pass everywhere, 1 (default) = table pass for Camera16, 2 = also for Camera32
+// (A/B measurements; the results are bit-identical)
+static inline int lut_pass_mode() {
+  static const int mode = [] { const char* e = getenv("B200ISP_REINHARD_LUT"); return e ? atoi(e) : 1; }();
+  return mode;
+}
 
 // one-sweep Camera32 Reinhard, exact-integer experiment (reinhard_u16.cuh / reinhard_u16.cu)
 size_t reinhard_u16_frame_bytes(int H, int W);
@@ -1570,6 +1664,10 @@ int run_fused(const FramePtrs& fp, int n_frames, const b200isp_fused_params& p, 
           return cuda_status(cudaPeekAtLastError(), "reinhard_scratch_yuv_kernel");
         }
         const long long n_elems = (long long)k.H * k.W * 3;
+        if constexpr (std::is_same<OutT, uint8_t>::value) {
+          if (k.gamma != 1.0f && p.reinhard_scratch_bytes >= need + (size_t)n_frames * kLutBytes && lut_pass_mode() >= 1)
+            return run_lut_pass<true>(sc, fp, n_frames, n_elems, (uint8_t*)p.reinhard_scratch + need, k.gamma, k.ws, s);
+        }
         const dim3 grid((unsigned)std::min<long long>((n_elems / 8 + 255) / 256, 4 * kNumSMs), (unsigned)n_frames);
         reinhard_scratch_out_kernel<OutT><<<grid, 256, 0, s>>>(sc, fp, n_elems, k.gamma, k.ws);
         return cuda_status(cudaPeekAtLastError(), "reinhard_scratch_out_kernel");
@@ -1593,7 +1691,11 @@ int run_fused(const FramePtrs& fp, int n_frames, const b200isp_fused_params& p, 
         const long long n_elems = (long long)k.H * k.W * 3;
         const dim3 grid((unsigned)std::min<long long>((n_elems / 16 + 255) / 256, (8 * kNumSMs + n_frames - 1) / n_frames), (unsigned)n_frames);
         const bool gam = k.gamma != 1.0f, pitched = k.orow != 3 * k.W;
-        if (gam && pitched) reinhard_map16_out_kernel<true, true><<<grid, 256, 0, s>>>(sc, fp, k.H, k.W, k.orow, k.gamma, k.ws);
+        // the table form of the pass (run_lut_pass) is opt-in here: measured 134.9 vs 131.5 us on cfg3 -- this pass is bound by
+        // its 2 : 1 read / write DRAM stream (4.75 TB/s), not by the MUFU pipe; Camera16 (scalar f16 arithmetic) gains 2 %
+        if (gam && !pitched && p.reinhard_scratch_bytes >= need + (size_t)n_frames * kLutBytes && lut_pass_mode() == 2)
+          st = run_lut_pass<false>(sc, fp, n_frames, n_elems, (uint8_t*)p.reinhard_scratch + need, k.gamma, k.ws, s);
+        else if (gam && pitched) reinhard_map16_out_kernel<true, true><<<grid, 256, 0, s>>>(sc, fp, k.H, k.W, k.orow, k.gamma, k.ws);
         else if (gam) reinhard_map16_out_kernel<true, false><<<grid, 256, 0, s>>>(sc, fp, k.H, k.W, k.orow, k.gamma, k.ws);
         else if (pitched) reinhard_map16_out_kernel<false, true><<<grid, 256, 0, s>>>(sc, fp, k.H, k.W, k.orow, k.gamma, k.ws);
         else reinhard_map16_out_kernel<false, false><<<grid, 256, 0, s>>>(sc, fp, k.H, k.W, k.orow, k.gamma, k.ws);

@@ -299,3 +299,139 @@ extern "C" int b200isp_decode16(const uint8_t* encoded, int64_t n_values, void* 
   ISP_LAUNCH_CHECK("decode16_kernel");
   return B200ISP_OK;
 }
+
+// ================================================================ 10-bit packed (EXTENSION; no reference counterpart)
+// MIPI CSI-2 RAW10: 5 bytes <-> 4 pixels; bytes 0..3 hold bits 9..2 of pixels 0..3, byte 4 their bits 1..0 (pixel 0 in the
+// lowest bit pair).  Value conventions are those of the 12-bit functions (packed.py:66-73, :98-104) with 1023 for 4095:
+// scaled decode = v * (scale_T / 1023), scaled encode = round(v * (1023 / scale_T)); the code is truncated to 10 bits.
+// Vector path: one thread converts 16 pixels = 20 packed bytes (five words; inputs 4-byte, outputs 16-byte aligned).
+namespace isp {
+
+__device__ __forceinline__ uint32_t byte_of(const uint32_t (&w)[5], int b) { return (w[b >> 2] >> (8 * (b & 3))) & 0xFFu; }
+
+template <typename T, bool SCALED>
+__global__ void __launch_bounds__(256) decode10_vec_kernel(const uint8_t* __restrict__ enc, T* __restrict__ out, int64_t n_groups, float k) {
+  const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= n_groups) return;
+  uint32_t w[5];
+#pragma unroll
+  for (int i = 0; i < 5; ++i) w[i] = __ldg(reinterpret_cast<const uint32_t*>(enc + g * 20) + i);
+  alignas(16) T v[16];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const uint32_t lsb = byte_of(w, 5 * q + 4);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) v[4 * q + j] = decoded_value<T, SCALED>((byte_of(w, 5 * q + j) << 2) | ((lsb >> (2 * j)) & 3u), k);
+  }
+  st_bytes<16 * (int)sizeof(T)>(out + g * 16, v);
+}
+
+template <typename T, bool SCALED>
+__global__ void __launch_bounds__(256) decode10_quad_kernel(const uint8_t* __restrict__ enc, T* __restrict__ out, int64_t quad_begin,
+                                                            int64_t n_quads, float k) {
+  const int64_t i = quad_begin + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_quads) return;
+  const uint8_t* b = enc + 5 * i;
+  const uint32_t lsb = b[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) out[4 * i + j] = decoded_value<T, SCALED>(((uint32_t)b[j] << 2) | ((lsb >> (2 * j)) & 3u), k);
+}
+
+template <typename T, bool SCALED>
+__global__ void __launch_bounds__(256) encode10_vec_kernel(const T* __restrict__ values, uint8_t* __restrict__ enc, int64_t n_groups, float k) {
+  const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= n_groups) return;
+  alignas(16) T v[16];
+  ld_bytes<16 * (int)sizeof(T)>(values + g * 16, v);
+  uint32_t w[5] = {0u, 0u, 0u, 0u, 0u};
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    uint32_t lsb = 0u;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const uint32_t p = value_to_u12<T, SCALED>(v[4 * q + j], k) & 0x3FFu;
+      const int b = 5 * q + j;
+      w[b >> 2] |= (p >> 2) << (8 * (b & 3));
+      lsb |= (p & 3u) << (2 * j);
+    }
+    const int b = 5 * q + 4;
+    w[b >> 2] |= lsb << (8 * (b & 3));
+  }
+#pragma unroll
+  for (int i = 0; i < 5; ++i) reinterpret_cast<uint32_t*>(enc + g * 20)[i] = w[i];
+}
+
+template <typename T, bool SCALED>
+__global__ void __launch_bounds__(256) encode10_quad_kernel(const T* __restrict__ values, uint8_t* __restrict__ enc, int64_t quad_begin,
+                                                            int64_t n_quads, float k) {
+  const int64_t i = quad_begin + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_quads) return;
+  uint32_t lsb = 0u;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const uint32_t p = value_to_u12<T, SCALED>(values[4 * i + j], k) & 0x3FFu;
+    enc[5 * i + j] = (uint8_t)(p >> 2);
+    lsb |= (p & 3u) << (2 * j);
+  }
+  enc[5 * i + 4] = (uint8_t)lsb;
+}
+
+template <typename T, bool SCALED>
+static int launch_decode10(const uint8_t* enc, T* out, int64_t n_values, float k, cudaStream_t s) {
+  const int64_t n_quads = n_values / 4;
+  const int64_t n_groups = ((reinterpret_cast<uintptr_t>(enc) & 3u) == 0 && aligned16(out)) ? n_values / 16 : 0;
+  if (n_groups > 0) {
+    decode10_vec_kernel<T, SCALED><<<(unsigned)((n_groups + 255) / 256), 256, 0, s>>>(enc, out, n_groups, k);
+    ISP_LAUNCH_CHECK("decode10_vec_kernel");
+  }
+  const int64_t rest = n_quads - 4 * n_groups;
+  if (rest > 0) {
+    decode10_quad_kernel<T, SCALED><<<(unsigned)((rest + 255) / 256), 256, 0, s>>>(enc, out, 4 * n_groups, n_quads, k);
+    ISP_LAUNCH_CHECK("decode10_quad_kernel");
+  }
+  return B200ISP_OK;
+}
+
+template <typename T, bool SCALED>
+static int launch_encode10(const T* values, uint8_t* enc, int64_t n_values, float k, cudaStream_t s) {
+  const int64_t n_quads = n_values / 4;
+  const int64_t n_groups = ((reinterpret_cast<uintptr_t>(enc) & 3u) == 0 && aligned16(values)) ? n_values / 16 : 0;
+  if (n_groups > 0) {
+    encode10_vec_kernel<T, SCALED><<<(unsigned)((n_groups + 255) / 256), 256, 0, s>>>(values, enc, n_groups, k);
+    ISP_LAUNCH_CHECK("encode10_vec_kernel");
+  }
+  const int64_t rest = n_quads - 4 * n_groups;
+  if (rest > 0) {
+    encode10_quad_kernel<T, SCALED><<<(unsigned)((rest + 255) / 256), 256, 0, s>>>(values, enc, 4 * n_groups, n_quads, k);
+    ISP_LAUNCH_CHECK("encode10_quad_kernel");
+  }
+  return B200ISP_OK;
+}
+
+}  // namespace isp
+
+extern "C" int b200isp_decode10(const uint8_t* encoded, int64_t n_values, void* out, int out_dtype, int scaled, b200isp_stream stream) {
+  ISP_REQUIRE(n_values >= 0 && n_values % 4 == 0, B200ISP_E_SHAPE, "decode10: n_values must be a multiple of 4, got %lld", (long long)n_values);
+  if (n_values == 0) return B200ISP_OK;
+  ISP_REQUIRE(encoded && out, B200ISP_E_ARG, "decode10: null pointer");
+  cudaStream_t s = (cudaStream_t)stream;
+  ISP_DISPATCH_DTYPE(out_dtype, T, {
+    const float k = (float)((double)DT<T>::scale / 1023.0);
+    if (scaled) return isp::launch_decode10<T, true>(encoded, (T*)out, n_values, k, s);
+    return isp::launch_decode10<T, false>(encoded, (T*)out, n_values, k, s);
+  });
+  return B200ISP_OK;
+}
+
+extern "C" int b200isp_encode10(const void* values, int in_dtype, int64_t n_values, uint8_t* encoded, int scaled, b200isp_stream stream) {
+  ISP_REQUIRE(n_values >= 0 && n_values % 4 == 0, B200ISP_E_SHAPE, "encode10: n_values must be a multiple of 4, got %lld", (long long)n_values);
+  if (n_values == 0) return B200ISP_OK;
+  ISP_REQUIRE(encoded && values, B200ISP_E_ARG, "encode10: null pointer");
+  cudaStream_t s = (cudaStream_t)stream;
+  ISP_DISPATCH_DTYPE(in_dtype, T, {
+    const float k = (float)(1023.0 / (double)DT<T>::scale);
+    if (scaled) return isp::launch_encode10<T, true>((const T*)values, encoded, n_values, k, s);
+    return isp::launch_encode10<T, false>((const T*)values, encoded, n_values, k, s);
+  });
+  return B200ISP_OK;
+}

@@ -1,4 +1,4 @@
-"""12-bit pack / unpack and raw-16 decode (reference: packed.py).
+"""12-bit pack / unpack and raw-16 decode (reference: packed.py), plus the 10-bit MIPI RAW10 extension.
 
 Same entry points as the reference: ``encode12``, ``decode12``, ``decode16`` on numpy arrays or torch
 tensors, and the kernel factories ``encode12_kernel`` / ``decode12_kernel`` / ``decode16_kernel``
@@ -125,3 +125,67 @@ def decode16(values, dtype=u16, scaled=False, ids_format=False):
     if flat.numel():
         decode16_kernel(dtype, scaled=scaled)(flat, decoded)
     return restore(decoded.reshape(shape[:-1] + (shape[-1] // 2,)))
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# EXTENSION (SURVEY 8f-4 "10-bit packed"; no reference counterpart): MIPI CSI-2 RAW10 -- 5 bytes <-> 4 pixels, bytes 0..3 =
+# bits 9..2 of pixels 0..3, byte 4 = their bits 1..0 (pixel 0 in the lowest bit pair).  Same calling conventions as the
+# 12-bit functions above, 1023 in place of 4095 (csrc/pack.cu: b200isp_decode10 / b200isp_encode10).
+@cache
+def encode10_kernel(in_type, scaled=False):
+    """returns f(values, encoded) on flat CUDA tensors (the shape of ``encode12_kernel``)"""
+    in_type = as_dtype(in_type)
+
+    def f(values: torch.Tensor, encoded: torch.Tensor):
+        _lib.require_cuda(values, "encode10")
+        _lib.require_cuda(encoded, "encode10")
+        assert as_dtype(values.dtype) is in_type and encoded.dtype == torch.uint8
+        assert values.is_contiguous() and encoded.is_contiguous()
+        n = values.numel()
+        assert encoded.numel() * 4 == n * 5, "encoded must hold 5 bytes per 4 values"
+        with torch.cuda.device(values.device):
+            _lib.check(_lib.lib.b200isp_encode10(values.data_ptr(), in_type.code, n, encoded.data_ptr(), int(scaled),
+                                                 _lib.stream_ptr(values.device)), "encode10")
+    return f
+
+
+@cache
+def decode10_kernel(out_type, scaled=False):
+    """returns k(encoded, out) on flat CUDA tensors (the shape of ``decode12_kernel``)"""
+    out_type = as_dtype(out_type)
+
+    def k(encoded: torch.Tensor, out: torch.Tensor):
+        _lib.require_cuda(encoded, "decode10")
+        _lib.require_cuda(out, "decode10")
+        assert encoded.dtype == torch.uint8 and as_dtype(out.dtype) is out_type
+        assert encoded.is_contiguous() and out.is_contiguous()
+        n = out.numel()
+        assert encoded.numel() * 4 == n * 5, "encoded must hold 5 bytes per 4 values"
+        with torch.cuda.device(out.device):
+            _lib.check(_lib.lib.b200isp_decode10(encoded.data_ptr(), n, out.data_ptr(), out_type.code, int(scaled),
+                                                 _lib.stream_ptr(out.device)), "decode10")
+    return k
+
+
+def encode10(values, scaled=False):
+    shape = tuple(values.shape)
+    assert shape[-1] % 4 == 0, f"last dimension must be a multiple of 4 for 10-bit encoding got: {shape}"
+    dev, restore = types.to_device(values)
+    flat = dev.reshape(-1)
+    encoded = torch.empty((flat.shape[0] * 5) // 4, dtype=torch.uint8, device=flat.device)
+    if flat.numel():
+        encode10_kernel(types.ti_type(values), scaled=scaled)(flat, encoded)
+    return restore(encoded.reshape(shape[:-1] + (shape[-1] * 5 // 4,)))
+
+
+def decode10(values, dtype=u16, scaled=False):
+    shape = tuple(values.shape)
+    assert types.ti_type(values) is u8
+    assert shape[-1] % 5 == 0, f"last dimension must be a factor of 5 for 10-bit decoding got: {shape}"
+    dtype = as_dtype(dtype)
+    dev, restore = types.to_device(values)
+    flat = dev.reshape(-1)
+    decoded = torch.empty((flat.shape[0] * 4) // 5, dtype=dtype.torch, device=flat.device)
+    if flat.numel():
+        decode10_kernel(dtype, scaled=scaled)(flat, decoded)
+    return restore(decoded.reshape(shape[:-1] + (shape[-1] * 4 // 5,)))
