@@ -576,6 +576,26 @@ __device__ __forceinline__ void pairs_to_raw2(const f2 (&R)[4], const f2 (&G)[4]
   }
 }
 
+// Camera32 without colour matrix, no frame column in this lane: demosaiced value and the clamp of bayer.py:152-155 as ONE
+// saturating scalar FMA per value (same product, same addend, same single rounding as the packed FMA of pairs_to_raw2, then
+// the clamp) -- two issue slots per value pair instead of three (packed FMA + two saturating moves)
+template <bool BROW, bool GFIRST>
+__device__ __forceinline__ void pairs_to_rgb2_sat(const f2 (&R)[4], const f2 (&G)[4], const f2 (&B)[4], f2 (&rgb)[4][3]) {
+  using SS = SiteScale2<BROW, GFIRST>;
+  constexpr float kn = 256.f * kInv4095;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const f2 in[3] = {R[j], G[j], B[j]};
+    const float sc[3] = {SS::r(j) * kn, SS::g(j) * kn, SS::b(j) * kn};
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      float lo, hi;
+      upk(in[c], lo, hi);
+      rgb[j][c] = pk(__saturatef(__fmaf_rn(sc[c], lo, -16.f * kn)), __saturatef(__fmaf_rn(sc[c], hi, -16.f * kn)));
+    }
+  }
+}
+
 // frame columns of an interior row on the raw pairs, exact (division) form; edge != 0 only in the first / last thread column
 template <bool BROW, bool GFIRST>
 __device__ __forceinline__ void patch_cols_pairs(f2 (&X)[4][3], int edge, int kbase) {
@@ -629,6 +649,24 @@ __device__ __forceinline__ void raw2_to_rgb2(const IspConsts& k, const f2 (&x)[3
       lo = __low2float(h); hi = __high2float(h);
     }
     rgb[c] = pk(lo, hi);
+  }
+}
+
+// ISP RGB pairs of a row for the packed Reinhard epilogues: the lean form (pairs_to_rgb2_sat) where it applies, else raw
+// pairs -> frame columns -> colour matrix -> clamp / ISP rounding
+template <bool CAM16, bool BROW, bool GFIRST, int KIND>
+__device__ __forceinline__ void row_rgb2(const IspConsts& k, int edge, const f2 (&R)[4], const f2 (&G)[4], const f2 (&B)[4], f2 (&rgb)[4][3]) {
+  bool lean = false;
+  if constexpr (!CAM16) lean = !k.ccm && !(KIND == K_EDGE && edge);
+  if (lean) {
+    if constexpr (!CAM16) pairs_to_rgb2_sat<BROW, GFIRST>(R, G, B, rgb);
+  } else {
+    f2 X[4][3];
+    pairs_to_raw2<CAM16, BROW, GFIRST>(R, G, B, X);
+    if (KIND == K_EDGE && edge) patch_cols_pairs<BROW, GFIRST>(X, edge, k.kbase);
+    ccm2_row(k, X);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) raw2_to_rgb2<CAM16, false>(k, X[j], rgb[j]);
   }
 }
 
@@ -886,18 +924,15 @@ struct EpiReinhardMax2 {      // pass 1: frame-global max of the mapped values (
   template <bool BROW, bool GFIRST, int KIND>
   __device__ __forceinline__ void emit(State& st, int row, const f2 (&R)[4], const f2 (&G)[4], const f2 (&B)[4]) const {
     if constexpr (KIND != K_GENERAL && CA0) {        // packed path
-      f2 X[4][3];
-      pairs_to_raw2<CAM16, BROW, GFIRST>(R, G, B, X);
-      if (KIND == K_EDGE && st.edge) patch_cols_pairs<BROW, GFIRST>(X, st.edge, k.kbase);
-      ccm2_row(k, X);
+      f2 P[4][3];
+      row_rgb2<CAM16, BROW, GFIRST, KIND>(k, st.edge, R, G, B, P);
       float mx = st.mx;
       if constexpr (STORE && CAM16) {
         uint32_t v[24];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          f2 rgb[3], p[3];
-          raw2_to_rgb2<CAM16, false>(k, X[j], rgb);
-          reinhard_p2<CAM16>(st.c, rgb, p);
+          f2 p[3];
+          reinhard_p2<CAM16>(st.c, P[j], p);
 #pragma unroll
           for (int ch = 0; ch < 3; ++ch) {
             float lo, hi;
@@ -914,9 +949,8 @@ struct EpiReinhardMax2 {      // pass 1: frame-global max of the mapped values (
         uint32_t v[24];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          f2 rgb[3], n[3], r;
-          raw2_to_rgb2<CAM16, false>(k, X[j], rgb);
-          reinhard_nr2(st.c, rgb, bc(1.0f), n, r);
+          f2 n[3], r;
+          reinhard_nr2(st.c, P[j], bc(1.0f), n, r);
           float rl, rh;
           upk(r, rl, rh);
 #pragma unroll
@@ -936,18 +970,15 @@ struct EpiReinhardMax2 {      // pass 1: frame-global max of the mapped values (
         float dmin = 0.f;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          f2 rgb[3];
-          raw2_to_rgb2<CAM16, false>(k, X[j], rgb);
           float lo, hi;
-          upk(reinhard_pmax2(st.c, rgb, dmin), lo, hi);
+          upk(reinhard_pmax2(st.c, P[j], dmin), lo, hi);
           mx = fmaxf(mx, fmaxf(lo, hi));
         }
         if (dmin < 0.f) {                      // some channel's denominator is negative: all three quotients, exactly
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
-            f2 rgb[3], p[3];
-            raw2_to_rgb2<CAM16, false>(k, X[j], rgb);
-            reinhard_p2<CAM16>(st.c, rgb, p);
+            f2 p[3];
+            reinhard_p2<CAM16>(st.c, P[j], p);
 #pragma unroll
             for (int ch = 0; ch < 3; ++ch) mx = fmaxf(mx, fmaxf(lo_of(p[ch]), hi_of(p[ch])));
           }
@@ -1001,17 +1032,14 @@ struct EpiReinhard2 {         // pass 2 recomputed from the packed frame: map, n
   // packed path: color_adapt == 0, any gamma (kernel-uniform)
   template <bool BROW, bool GFIRST, int KIND>
   __device__ __forceinline__ void emit_pairs(const State& st, int row, const f2 (&R)[4], const f2 (&G)[4], const f2 (&B)[4]) const {
-    f2 X[4][3];
-    pairs_to_raw2<CAM16, BROW, GFIRST>(R, G, B, X);
-    if (KIND == K_EDGE && st.edge) patch_cols_pairs<BROW, GFIRST>(X, st.edge, k.kbase);
-    ccm2_row(k, X);
+    f2 P[4][3];
+    row_rgb2<CAM16, BROW, GFIRST, KIND>(k, st.edge, R, G, B, P);
     uint32_t v[24];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      f2 rgb[3], n[3], r;
-      raw2_to_rgb2<CAM16, false>(k, X[j], rgb);
+      f2 n[3], r;
       // Camera32: q = p / max_out straight from the shared reciprocal; Camera16: p is rounded through f16 first
-      reinhard_nr2(st.c, rgb, bc(CAM16 ? 1.0f : st.c.max_out), n, r);
+      reinhard_nr2(st.c, P[j], bc(CAM16 ? 1.0f : st.c.max_out), n, r);
       float rl, rh;
       upk(r, rl, rh);
 #pragma unroll
@@ -1411,16 +1439,33 @@ __global__ void __launch_bounds__(256) reinhard_map16_out_kernel(const FramePtrs
   const f2 a2 = bc(a), h2 = bc(0.5f * a), ig2 = bc((float)(1.0 / (double)gamma));
   const long long stride = (long long)gridDim.x * blockDim.x;
   if constexpr (!PITCHED) {
+    // two 16-value chunks per iteration, the four 16-byte loads issued before the first use.  Measured on cfg3 (gamma 0.9):
+    // 8 CTAs per SM 131 us, 4: 155 us, 2: slower still -- unlike a plain copy this pass wants every thread slot
+    // (profiles/r02_reinhard_map16.txt); B200ISP_MAP16_CTAS overrides
     uint4* dst = reinterpret_cast<uint4*>(fp.out[frame]);
     const long long n16 = (long long)H * W * 3 / 16;                   // H even, W % 8 == 0
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += stride) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += 2 * stride) {
+      const long long i2 = i + stride;
+      const bool two = i2 < n16;
       const uint4 w0 = __ldcs(src + 2 * i), w1 = __ldcs(src + 2 * i + 1);
-      const uint32_t w[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
-      uint32_t v[16];
+      uint4 w2 = w0, w3 = w1;
+      if (two) { w2 = __ldcs(src + 2 * i2); w3 = __ldcs(src + 2 * i2 + 1); }
+      {
+        const uint32_t w[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+        uint32_t v[16];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) map16_pair(w[j], a2, h2, ig2, GAMMA, v[2 * j], v[2 * j + 1]);
-      __stcs(dst + i, make_uint4(pack4_u8(v[0], v[1], v[2], v[3]), pack4_u8(v[4], v[5], v[6], v[7]), pack4_u8(v[8], v[9], v[10], v[11]),
-                                 pack4_u8(v[12], v[13], v[14], v[15])));
+        for (int j = 0; j < 8; ++j) map16_pair(w[j], a2, h2, ig2, GAMMA, v[2 * j], v[2 * j + 1]);
+        __stcs(dst + i, make_uint4(pack4_u8(v[0], v[1], v[2], v[3]), pack4_u8(v[4], v[5], v[6], v[7]), pack4_u8(v[8], v[9], v[10], v[11]),
+                                   pack4_u8(v[12], v[13], v[14], v[15])));
+      }
+      if (two) {
+        const uint32_t w[8] = {w2.x, w2.y, w2.z, w2.w, w3.x, w3.y, w3.z, w3.w};
+        uint32_t v[16];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) map16_pair(w[j], a2, h2, ig2, GAMMA, v[2 * j], v[2 * j + 1]);
+        __stcs(dst + i2, make_uint4(pack4_u8(v[0], v[1], v[2], v[3]), pack4_u8(v[4], v[5], v[6], v[7]), pack4_u8(v[8], v[9], v[10], v[11]),
+                                    pack4_u8(v[12], v[13], v[14], v[15])));
+      }
     }
   } else {
     uint8_t* dst = reinterpret_cast<uint8_t*>(fp.out[frame]);
@@ -1689,7 +1734,8 @@ int run_fused(const FramePtrs& fp, int n_frames, const b200isp_fused_params& p, 
         st = run_rstore<false>(sc, k, n_frames, rpt, s, p.profile_start, p.profile_stop);
         if (st) return st;
         const long long n_elems = (long long)k.H * k.W * 3;
-        const dim3 grid((unsigned)std::min<long long>((n_elems / 16 + 255) / 256, (8 * kNumSMs + n_frames - 1) / n_frames), (unsigned)n_frames);
+        static const int ctas_per_sm = [] { const char* e = getenv("B200ISP_MAP16_CTAS"); const int v = e ? atoi(e) : 0; return v > 0 ? v : 8; }();
+        const dim3 grid((unsigned)std::min<long long>((n_elems / 16 + 255) / 256, (ctas_per_sm * kNumSMs + n_frames - 1) / n_frames), (unsigned)n_frames);
         const bool gam = k.gamma != 1.0f, pitched = k.orow != 3 * k.W;
         // the table form of the pass (run_lut_pass) is opt-in here: measured 134.9 vs 131.5 us on cfg3 -- this pass is bound by
         // its 2 : 1 read / write DRAM stream (4.75 TB/s), not by the MUFU pipe; Camera16 (scalar f16 arithmetic) gains 2 %
