@@ -6,7 +6,7 @@
 namespace isp {
 #ifdef ISP_INST_RMAX
 template int run_rmax<ISP_INST_CAM16 != 0>(const FramePtrs&, IspConsts, int, int, int, cudaStream_t);
-template int run_rstore<ISP_INST_CAM16 != 0>(const FramePtrs&, IspConsts, int, int, cudaStream_t, void*, void*);
+template int run_rstore<ISP_INST_CAM16 != 0>(const FramePtrs&, IspConsts, int, int, cudaStream_t, void*, void*, int);
 #else
 template int run_fused<ISP_INST_CAM16 != 0, ISP_INST_OUT>(const FramePtrs&, int, const b200isp_fused_params&, IspConsts, cudaStream_t);
 #endif

@@ -1430,8 +1430,8 @@ __device__ __forceinline__ uint32_t pack4_u8(uint32_t a, uint32_t b, uint32_t c,
 
 template <bool GAMMA, bool PITCHED>
 __global__ void __launch_bounds__(256) reinhard_map16_out_kernel(const FramePtrs scratch /* .out = u16 maps */, const FramePtrs fp,
-                                                                 int H, int W, int orow, float gamma, const Workspace* ws) {
-  const int frame = gridDim.y - 1 - blockIdx.y;       // last frame first: the sweep wrote it last, part of its map is still in L2
+                                                                 int H, int W, int orow, float gamma, const Workspace* ws, int frame0) {
+  const int frame = frame0 + gridDim.y - 1 - blockIdx.y;       // last frame first: the sweep wrote it last, part of its map is still in L2
   const float mx = __ldcg(&ws->frame_max[frame]);
   if (reinhard_map16_declined(mx)) return;
   const uint4* src = reinterpret_cast<const uint4*>(scratch.out[frame]);
@@ -1619,13 +1619,13 @@ static __global__ void __launch_bounds__(128) reinhard_scratch_yuv_kernel(const 
 // pass A for frames [0, nframes): instantiated once per ISP dtype (fused_inst.cu with ISP_INST_RMAX); Camera16 stores the f16
 // map (any color_adapt), Camera32 the u16 fixed-point map (color_adapt == 0 only: the caller checks)
 template <bool CAM16>
-int run_rstore(const FramePtrs& fp_scratch, IspConsts k, int nframes, int rows_per_task, cudaStream_t s, void* ev_start, void* ev_stop) {
-  k.frame0 = 0;
+int run_rstore(const FramePtrs& fp_scratch, IspConsts k, int nframes, int rows_per_task, cudaStream_t s, void* ev_start, void* ev_stop, int frame0) {
+  k.frame0 = frame0;
   const Stream2Geom g = make_geom2(k.H, k.W, nframes, rows_per_task);
   int st = B200ISP_OK;
   if (ev_start) record_profile_event(ev_start, s);
   auto launch = [&](auto ld, bool bl) -> int {
-    ld.fp = fp_scratch; ld.pitch_words = k.W * 3 / 8; ld.frame0 = 0; ld.ids = k.ids;
+    ld.fp = fp_scratch; ld.pitch_words = k.W * 3 / 8; ld.frame0 = frame0; ld.ids = k.ids;
     ISP_DISPATCH_PATTERN(k.pattern, P, {
       if (k.ca == 0.f) { EpiReinhardMax2<CAM16, true, true> e{fp_scratch, k}; st = launch_stream2<P>(ld, e, g, s, "isp_stream<reinhard_store>", bl); }
       else if constexpr (CAM16) { EpiReinhardMax2<true, false, true> e{fp_scratch, k}; st = launch_stream2<P>(ld, e, g, s, "isp_stream<reinhard_store>", bl); }
@@ -1656,6 +1656,20 @@ int run_rmax(const FramePtrs& fp, IspConsts k, int frame0, int nframes, int rows
 }
 
 int run_write_gated(const FramePtrs& fp, IspConsts k, int nframes, int rows_per_task, cudaStream_t s);
+// library-owned high-priority side stream + fork / join events, one set per device (created on first use, never destroyed)
+struct SideStream { cudaStream_t stream; cudaEvent_t ev[2 * B200ISP_MAX_FRAMES]; };
+SideStream* side_stream();
+// B200ISP_MAP16_OVERLAP: frame groups of the overlapped one-sweep Reinhard form (0 / 1 = off); B200ISP_MAP16_OVERLAP_CTAS: CTAs
+// per SM of the normalise pass while it runs under a sweep
+static inline int map16_overlap_groups(int n_frames) {
+  static const int want = [] { const char* e = getenv("B200ISP_MAP16_OVERLAP"); return e ? atoi(e) : 1; }();      // measured: does not pay
+  if (want <= 1 || n_frames < 4) return 1;
+  return std::min(want, n_frames / 2);
+}
+static inline int map16_overlap_ctas() {
+  static const int v = [] { const char* e = getenv("B200ISP_MAP16_OVERLAP_CTAS"); const int x = e ? atoi(e) : 0; return x > 0 ? x : 2; }();
+  return v;
+}
 // B200ISP_REINHARD_LUT: 0 = arithmetic normalise pass everywhere, 1 (default) = table pass for Camera16, 2 = also for Camera32
 // (A/B measurements; the results are bit-identical)
 static inline int lut_pass_mode() {
@@ -1701,7 +1715,7 @@ int run_fused(const FramePtrs& fp, int n_frames, const b200isp_fused_params& p, 
       if (p.reinhard_scratch && p.reinhard_scratch_bytes >= need && k.orow == 3 * k.W && k.flip == 0) {
         FramePtrs sc = fp;
         for (int f = 0; f < n_frames; ++f) sc.out[f] = (char*)p.reinhard_scratch + (size_t)f * k.H * k.W * 3 * sizeof(__half);
-        st = run_rstore<true>(sc, k, n_frames, rpt, s, p.profile_start, p.profile_stop);
+        st = run_rstore<true>(sc, k, n_frames, rpt, s, p.profile_start, p.profile_stop, 0);
         if (st) return st;
         if (p.out_yuv420) {
           const dim3 grid((unsigned)((k.W / 8 + 127) / 128), (unsigned)(k.H / 2), (unsigned)n_frames);
@@ -1731,22 +1745,57 @@ int run_fused(const FramePtrs& fp, int n_frames, const b200isp_fused_params& p, 
         for (int f = 0; f < n_frames; ++f) sc.out[f] = (char*)p.reinhard_scratch + (size_t)f * k.H * k.W * 3 * sizeof(uint16_t);
         st = cuda_status(cudaMemsetAsync(k.ws->frame_max2, 0, sizeof(float) * B200ISP_MAX_FRAMES, s), "memset frame_max2");
         if (st) return st;
-        st = run_rstore<false>(sc, k, n_frames, rpt, s, p.profile_start, p.profile_stop);
-        if (st) return st;
         const long long n_elems = (long long)k.H * k.W * 3;
         static const int ctas_per_sm = [] { const char* e = getenv("B200ISP_MAP16_CTAS"); const int v = e ? atoi(e) : 0; return v > 0 ? v : 8; }();
-        const dim3 grid((unsigned)std::min<long long>((n_elems / 16 + 255) / 256, (ctas_per_sm * kNumSMs + n_frames - 1) / n_frames), (unsigned)n_frames);
         const bool gam = k.gamma != 1.0f, pitched = k.orow != 3 * k.W;
-        // the table form of the pass (run_lut_pass) is opt-in here: measured 134.9 vs 131.5 us on cfg3 -- this pass is bound by
-        // its 2 : 1 read / write DRAM stream (4.75 TB/s), not by the MUFU pipe; Camera16 (scalar f16 arithmetic) gains 2 %
-        if (gam && !pitched && p.reinhard_scratch_bytes >= need + (size_t)n_frames * kLutBytes && lut_pass_mode() == 2)
-          st = run_lut_pass<false>(sc, fp, n_frames, n_elems, (uint8_t*)p.reinhard_scratch + need, k.gamma, k.ws, s);
-        else if (gam && pitched) reinhard_map16_out_kernel<true, true><<<grid, 256, 0, s>>>(sc, fp, k.H, k.W, k.orow, k.gamma, k.ws);
-        else if (gam) reinhard_map16_out_kernel<true, false><<<grid, 256, 0, s>>>(sc, fp, k.H, k.W, k.orow, k.gamma, k.ws);
-        else if (pitched) reinhard_map16_out_kernel<false, true><<<grid, 256, 0, s>>>(sc, fp, k.H, k.W, k.orow, k.gamma, k.ws);
-        else reinhard_map16_out_kernel<false, false><<<grid, 256, 0, s>>>(sc, fp, k.H, k.W, k.orow, k.gamma, k.ws);
-        st = cuda_status(cudaPeekAtLastError(), "reinhard_map16_out_kernel");
-        if (st) return st;
+        auto pass_b = [&](int f0, int nf, int per_sm, cudaStream_t ps) -> int {
+          const dim3 grid((unsigned)std::min<long long>((n_elems / 16 + 255) / 256, (per_sm * kNumSMs + nf - 1) / nf), (unsigned)nf);
+          if (gam && pitched) reinhard_map16_out_kernel<true, true><<<grid, 256, 0, ps>>>(sc, fp, k.H, k.W, k.orow, k.gamma, k.ws, f0);
+          else if (gam) reinhard_map16_out_kernel<true, false><<<grid, 256, 0, ps>>>(sc, fp, k.H, k.W, k.orow, k.gamma, k.ws, f0);
+          else if (pitched) reinhard_map16_out_kernel<false, true><<<grid, 256, 0, ps>>>(sc, fp, k.H, k.W, k.orow, k.gamma, k.ws, f0);
+          else reinhard_map16_out_kernel<false, false><<<grid, 256, 0, ps>>>(sc, fp, k.H, k.W, k.orow, k.gamma, k.ws, f0);
+          return cuda_status(cudaPeekAtLastError(), "reinhard_map16_out_kernel");
+        };
+        // Overlapped form -- EXPERIMENT, off by default (B200ISP_MAP16_OVERLAP=<groups>; profiles/r02_reinhard_map16.txt: cfg3
+        // 215 Gpixel/s serial, 212 / 208 / 203 / 186 with 2 or 3 groups and 1-3 CTAs of the pass per SM -- the pass takes the
+        // residency and the issue slots it uses away from the sweep, and the look-ahead metering already fills the idle ones).
+        // >= 4 frames, no profiling events: the frames are cut into groups; the normalise pass of group g runs
+        // on a high-priority side stream UNDER the map sweep of group g + 1 with a small grid (the sweep is bound by issue
+        // slots and fills the register file, the pass by MUFU / memory: a few of its CTAs per SM take one sweep CTA's place and
+        // use what the sweep leaves idle); the last group's pass runs alone with the full grid.  Fork / join through events,
+        // so the call stays one stream-ordered unit and is CUDA-graph capturable.
+        const int groups = (p.profile_start || p.profile_stop) ? 1 : map16_overlap_groups(n_frames);
+        if (groups > 1) {
+          SideStream* side = side_stream();
+          if (!side) return B200ISP_E_CUDA;
+          const int per = (n_frames + groups - 1) / groups;
+          int g = 0;
+          for (int f0 = 0; f0 < n_frames; f0 += per, ++g) {
+            const int nf = std::min(per, n_frames - f0);
+            st = run_rstore<false>(sc, k, nf, rpt, s, nullptr, nullptr, f0);
+            if (st) return st;
+            if (f0 + nf < n_frames) {
+              if ((st = cuda_status(cudaEventRecord(side->ev[2 * g], s), "event record"))) return st;
+              if ((st = cuda_status(cudaStreamWaitEvent(side->stream, side->ev[2 * g], 0), "stream wait"))) return st;
+              if ((st = pass_b(f0, nf, map16_overlap_ctas(), side->stream))) return st;
+              if ((st = cuda_status(cudaEventRecord(side->ev[2 * g + 1], side->stream), "event record"))) return st;
+            } else {
+              if ((st = pass_b(f0, nf, ctas_per_sm, s))) return st;
+            }
+          }
+          for (int j = 0; j + 1 < g; ++j)
+            if ((st = cuda_status(cudaStreamWaitEvent(s, side->ev[2 * j + 1], 0), "stream wait"))) return st;
+        } else {
+          st = run_rstore<false>(sc, k, n_frames, rpt, s, p.profile_start, p.profile_stop, 0);
+          if (st) return st;
+          // the table form of the pass (run_lut_pass) is opt-in here: measured 134.9 vs 131.5 us on cfg3 -- this pass is bound by
+          // its 2 : 1 read / write DRAM stream (4.75 TB/s), not by the MUFU pipe; Camera16 (scalar f16 arithmetic) gains 2 %
+          if (gam && !pitched && p.reinhard_scratch_bytes >= need + (size_t)n_frames * kLutBytes && lut_pass_mode() == 2)
+            st = run_lut_pass<false>(sc, fp, n_frames, n_elems, (uint8_t*)p.reinhard_scratch + need, k.gamma, k.ws, s);
+          else
+            st = pass_b(0, n_frames, ctas_per_sm, s);
+          if (st) return st;
+        }
         IspConsts kg = k;
         kg.gate = 1;
         st = run_rmax_gated(fp, kg, n_frames, rpt, s);
@@ -1776,8 +1825,8 @@ int run_fused(const FramePtrs& fp, int n_frames, const b200isp_fused_params& p, 
   }
 }
 
-extern template int run_rstore<true>(const FramePtrs&, IspConsts, int, int, cudaStream_t, void*, void*);
-extern template int run_rstore<false>(const FramePtrs&, IspConsts, int, int, cudaStream_t, void*, void*);
+extern template int run_rstore<true>(const FramePtrs&, IspConsts, int, int, cudaStream_t, void*, void*, int);
+extern template int run_rstore<false>(const FramePtrs&, IspConsts, int, int, cudaStream_t, void*, void*, int);
 extern template int run_rmax<true>(const FramePtrs&, IspConsts, int, int, int, cudaStream_t);
 extern template int run_rmax<false>(const FramePtrs&, IspConsts, int, int, int, cudaStream_t);
 

@@ -126,3 +126,45 @@ def test_map16_bilinear_demosaic_and_full_rows(cuda):
     b = exact.process_packed12(dev, tonemap="reinhard", gamma=0.8)
     for x, y in zip(a, b):
         assert_close_int(to_np(x), to_np(y), 1, "bilinear")
+
+
+@pytest.mark.parametrize("n", [4, 5, 7])
+def test_map16_overlapped_groups(cuda, n):
+    """>= 4 frames: the frames are cut into groups and the normalise pass of a group runs on a side stream under the next
+    group's map sweep (fork / join through events inside the call) -- same results, also back to back and with a declined frame"""
+    r = rng(76)
+    fast, exact, ref = make(False), make(True), O.ISP("f32")
+    tm = dict(gamma=0.9, intensity=3.0, light_adapt=0.9)
+    for step in range(3):
+        fr = [packed_frame(r, 30, 776) for _ in range(n)]
+        if step == 2:
+            fr[1] = packed_frame(r, 30, 776, smooth=False)          # pure noise: quotients beyond 1 -> declined -> gated exact sweeps
+        dev = [to_cuda(f) for f in fr]
+        got = fast.process_packed12(dev, tonemap="reinhard", **tm)
+        two = exact.process_packed12(dev, tonemap="reinhard", **tm)
+        exp = ref.tonemap_reinhard([ref.load_packed12(f) for f in fr], **tm)
+        for i, (g, t, e) in enumerate(zip(got, two, exp)):
+            assert_close_int(to_np(g), to_np(t), 1, f"exact form, step {step} frame {i}")
+            assert_close_int(to_np(g), e, 1, f"oracle, step {step} frame {i}")
+
+
+def test_map16_overlapped_form_in_a_subprocess(cuda):
+    """the experiment switch B200ISP_MAP16_OVERLAP is read once per process: run the overlapped form (2 groups, normalise pass of
+    group 0 on the library's side stream under the sweep of group 1) in a child process against the exact form"""
+    import os, subprocess, sys
+    code = (
+        "import numpy as np, torch\n"
+        "from tests.util import rng, packed_frame, to_cuda, to_np, assert_close_int\n"
+        "from tests.test_gpu_reinhard_map16 import make\n"
+        "r = rng(77); fast, exact = make(False), make(True)\n"
+        "for step in range(3):\n"
+        "    dev = [to_cuda(packed_frame(r, 44, 1032)) for _ in range(6)]\n"
+        "    a = fast.process_packed12(dev, tonemap='reinhard', gamma=0.9, intensity=3.0)\n"
+        "    b = exact.process_packed12(dev, tonemap='reinhard', gamma=0.9, intensity=3.0)\n"
+        "    fr = [assert_close_int(to_np(x), to_np(y), 1, 'overlapped') for x, y in zip(a, b)]\n"
+        "    assert max(fr) < 0.02\n"
+        "print('overlap ok')\n")
+    env = dict(os.environ, B200ISP_MAP16_OVERLAP="2", B200ISP_MAP16_OVERLAP_CTAS="2")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    res = subprocess.run([sys.executable, "-c", code], env=env, cwd=root, capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0 and "overlap ok" in res.stdout, res.stdout + res.stderr
