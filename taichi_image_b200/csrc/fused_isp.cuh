@@ -1705,7 +1705,9 @@ int run_fused(const FramePtrs& fp, int n_frames, const b200isp_fused_params& p, 
     if (p.tonemap == B200ISP_TM_LINEAR) return run_pass<CAM16, MODE_LINEAR, OutT>(fp, k, 0, n_frames, rpt, s, p.profile_start, p.profile_stop);
     // Reinhard: the second sweep should find the packed frames in L2 -> interleave max / write passes
     // per group of frames whose packed bytes stay well inside the 126 MB L2.
-    int st = cuda_status(cudaMemsetAsync(k.ws->frame_max, 0, sizeof(float) * B200ISP_MAX_FRAMES, s), "memset frame_max");
+    // frame_max and frame_max2 are adjacent in the workspace: one memset node
+    static_assert(offsetof(Workspace, frame_max2) == offsetof(Workspace, frame_max) + sizeof(float) * B200ISP_MAX_FRAMES, "adjacent");
+    int st = cuda_status(cudaMemsetAsync(k.ws->frame_max, 0, sizeof(float) * 2 * B200ISP_MAX_FRAMES, s), "memset frame_max");
     if (st) return st;
     if constexpr (CAM16) {
       // Camera16: the reference stores the map as f16 anyway -> one sweep writes it to the caller's scratch, a light
@@ -1743,8 +1745,6 @@ int run_fused(const FramePtrs& fp, int n_frames, const b200isp_fused_params& p, 
           p.reinhard_scratch && p.reinhard_scratch_bytes >= need && p.reinhard_group <= 0) {
         FramePtrs sc = fp;
         for (int f = 0; f < n_frames; ++f) sc.out[f] = (char*)p.reinhard_scratch + (size_t)f * k.H * k.W * 3 * sizeof(uint16_t);
-        st = cuda_status(cudaMemsetAsync(k.ws->frame_max2, 0, sizeof(float) * B200ISP_MAX_FRAMES, s), "memset frame_max2");
-        if (st) return st;
         const long long n_elems = (long long)k.H * k.W * 3;
         static const int ctas_per_sm = [] { const char* e = getenv("B200ISP_MAP16_CTAS"); const int v = e ? atoi(e) : 0; return v > 0 ? v : 8; }();
         const bool gam = k.gamma != 1.0f, pitched = k.orow != 3 * k.W;
