@@ -88,3 +88,21 @@ def test_isp_load_packed10(cuda, dt, pattern):
     assert_close_float(to_np(got).astype(np.float32), exp.astype(np.float32), rtol=1e-3, atol=1e-6 if dt == "f32" else 1e-3, what=f"load_packed10 {dt}")
     out = isp.tonemap_reinhard([got], gamma=0.8)
     assert out[0].dtype == torch.uint8 and tuple(out[0].shape) == (32, 48, 3)
+
+
+@pytest.mark.parametrize("n", [4, 16, 20, 36, 1028])
+def test_kernels_stay_inside_their_buffers(cuda, n):
+    """guard bands around the encode10 / decode10 outputs (vector kernel of 16 pixels + the 4-pixel tail kernel)"""
+    from taichi_image_b200 import packed, dtypes
+    x = rng(n).integers(0, 1024, size=n).astype(np.uint16)
+    xv = to_cuda(x)
+    ebuf = torch.full((n * 5 // 4 + 512,), 0xA5, dtype=torch.uint8, device="cuda")
+    enc = ebuf[256:256 + n * 5 // 4]
+    packed.encode10_kernel(dtypes.u16)(xv, enc)
+    dbuf = torch.full((n + 256,), 0x7777, dtype=torch.int16, device="cuda")
+    dec = dbuf.view(torch.uint16)[128:128 + n]
+    packed.decode10_kernel(dtypes.u16)(enc, dec)
+    torch.cuda.synchronize()
+    assert np.array_equal(to_np(enc), O.encode10(x)) and np.array_equal(to_np(dec), x)
+    assert bool((ebuf[:256] == 0xA5).all()) and bool((ebuf[256 + n * 5 // 4:] == 0xA5).all())
+    assert bool((dbuf[:128] == 0x7777).all()) and bool((dbuf[128 + n:] == 0x7777).all())

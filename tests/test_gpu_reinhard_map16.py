@@ -168,3 +168,30 @@ def test_map16_overlapped_form_in_a_subprocess(cuda):
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     res = subprocess.run([sys.executable, "-c", code], env=env, cwd=root, capture_output=True, text=True, timeout=600)
     assert res.returncode == 0 and "overlap ok" in res.stdout, res.stdout + res.stderr
+
+
+@pytest.mark.parametrize("cam,gamma", [("Camera32", 0.9), ("Camera32", 1.0), ("Camera16", 0.6)])
+def test_scratch_and_outputs_stay_inside_their_buffers(cuda, cam, gamma):
+    """guard bands (compute-sanitizer is not available on the GPU pool): the map scratch -- exactly the size the host mirror asks
+    for -- and the outputs are views into canary-filled buffers; the map sweep, the normalise passes (arithmetic, table, dense)
+    and the gated sweeps must leave every canary byte alone"""
+    from taichi_image_b200 import camera_isp, bayer
+    r = rng(78)
+    n, h, w = 5, 30, 776
+    isp = getattr(camera_isp, cam)(bayer.BayerPattern.RGGB)
+    dev = [to_cuda(packed_frame(r, h, w)) for _ in range(n)]
+    dev[3] = to_cuda(packed_frame(r, h, w, smooth=False))                 # a declined frame (Camera32): the gated sweeps run too
+    need = n * h * w * 6 + n * 65536
+    pad = 1 << 16
+    sbuf = torch.full((need + 2 * pad,), 0xA5, dtype=torch.uint8, device="cuda")
+    isp._reinhard_scratch = sbuf[pad:pad + need]
+    obuf = torch.full((n, h * w * 3 + pad), 0x5A, dtype=torch.uint8, device="cuda")
+    outs = [obuf[i, :h * w * 3].view(h, w, 3) for i in range(n)]
+    ref = getattr(camera_isp, cam)(bayer.BayerPattern.RGGB).process_packed12(dev, tonemap="reinhard", gamma=gamma)
+    got = isp.process_packed12(dev, tonemap="reinhard", gamma=gamma, out=outs)
+    torch.cuda.synchronize()
+    assert isp._reinhard_scratch.data_ptr() == sbuf[pad:].data_ptr(), "the preset scratch was replaced: its size no longer matches the host mirror"
+    assert bool((sbuf[:pad] == 0xA5).all()) and bool((sbuf[pad + need:] == 0xA5).all()), "write outside the map scratch"
+    assert bool((obuf[:, h * w * 3:] == 0x5A).all()), "write outside an output image"
+    for g, e in zip(got, ref):
+        assert torch.equal(g, e)
