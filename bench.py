@@ -60,7 +60,7 @@ OUT_BYTES = {"u8": 1, "u16": 2, "f16": 2, "f32": 4}
 # dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel per launch, from the ncu --set full captures
 # summarised under profiles/ (None where no capture exists); the source file is named next to the number
 TRAFFIC = {"cfg2": (844.2e6, "profiles/r02_cfg2_sweep_fadd2_ncu.txt (181.0 MB read + 663.2 MB written; the last ~56 MB of writes still in L2)"),
-           "cfg3": (497.2e6, "profiles/r02_map16_sweep_ncu.txt (111.6 MB read + 385.7 MB written: packed frames in, u16 map out; the tail of the writes still in L2)"),
+           "cfg3": (500.0e6, "profiles/r02_map16_sweep_ncu.txt (111.7 MB read + 388.3 MB written: packed frames in, u16 map out; the tail of the writes still in L2)"),
            "cfg5": (243.2e6, "profiles/r02_resize_sweep_ncu.txt (148.4 MB read + 94.8 MB written)")}
 
 
