@@ -2,7 +2,7 @@
 """Benchmark of the camera-ISP hot path (BASELINE.json metric: Gpixel/s packed12 -> RGB8/RGB16 ISP at 1/2/4/8 B200,
 achieved HBM GB/s vs peak).
 
-    python bench.py --gpus N --steps K --warmup W [--impl reference] [--workload cfg2|cfg1|cfg1_16|cfg3|cfg5|cfg5_32]
+    python bench.py --gpus N --steps K --warmup W [--impl reference] [--workload cfg2|cfg1|cfg1_16|cfg3|cfg3_rot90|cfg5|cfg5_32]
                     [--cameras C]
 
 A step = one pass of the hot path over one batch of synthetic packed12 frames already resident in HBM: the fused
@@ -55,6 +55,11 @@ WORKLOADS = {
 # the same with the f32 ISP (Camera32): no f16 rounding of the intermediates to reproduce, fp16 only at the output
 WORKLOADS["cfg5_32"] = (8, 3000, 4096, "f32", "reinhard", "f16", dict(gamma=0.9, intensity=3.0, light_adapt=0.9, color_adapt=0.0),
                         "BASELINE configs[4] shard with the f32 ISP: 8 x 4096x3000 -> Camera32 + bilinear resize_width 1920 (fused into the sweep) -> Reinhard -> fp16")
+# the rig script's default output orientation (scripts/tonemap_scan.py: transform rotate_90): cfg3 with the image turned by the
+# normalise pass of the one-sweep Reinhard form (csrc/fused_isp.cuh reinhard_out_transposed_kernel) -- outputs are (W, H, 3)
+WORKLOADS["cfg3_rot90"] = WORKLOADS["cfg3"][:7] + ("BASELINE configs[2] shard as the rig script runs it: 6 x 4096x3000 -> Reinhard -> RGB8, rotate_90 "
+                                                   "applied inside the call (Camera32)",)
+TRANSFORM = {"cfg3_rot90": "rotate_90"}
 RESIZE_WIDTH = {"cfg5": 1920, "cfg5_32": 1920}
 OUT_BYTES = {"u8": 1, "u16": 2, "f16": 2, "f32": 4}
 # dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel per launch, from the ncu --set full captures
@@ -310,7 +315,8 @@ def run_workload(ctx: Ctx, name: str, steps: int, warmup: int, min_seconds: floa
     shared = (world > 1) if shared is None else shared
     cam = tib.camera_isp.Camera16 if isp_dt == "f16" else tib.camera_isp.Camera32
     resize_w = RESIZE_WIDTH.get(name, 0)
-    base = cam(tib.bayer.BayerPattern.RGGB, moving_alpha=0.1, device=device, resize_width=resize_w, demosaic=args.demosaic)
+    base = cam(tib.bayer.BayerPattern.RGGB, moving_alpha=0.1, device=device, resize_width=resize_w, demosaic=args.demosaic,
+               transform=tib.interpolate.ImageTransform[TRANSFORM.get(name, "none")])
     isp = base
     if shared:
         from taichi_image_b200.distributed import SharedExposure
@@ -320,7 +326,10 @@ def run_workload(ctx: Ctx, name: str, steps: int, warmup: int, min_seconds: floa
     frames_b = [f.clone() for f in frames]                       # second ingest buffer set (double-buffered stream)
     plan = base._resize_plan(h, w)
     ho, wo = (h, w) if plan is None else (plan[0][1], plan[0][0])
-    outs = [torch.empty((ho, wo, 3), dtype=tib.as_dtype(out_dt).torch, device=device) for _ in range(n)]
+    flip = base._fused_flip(h, tonemap, tib.as_dtype(out_dt), tm.get("gamma", 1.0), tm.get("color_adapt", 0.0))
+    assert flip or name not in TRANSFORM, "the transform of this workload must be applied inside the fused call"
+    oshape = (wo, ho, 3) if flip & 4 else (ho, wo, 3)
+    outs = [torch.empty(oshape, dtype=tib.as_dtype(out_dt).torch, device=device) for _ in range(n)]
     px_per_step = n * h * w
     alg_bytes = px_per_step * 1.5 + n * ho * wo * 3 * OUT_BYTES[out_dt]
 
@@ -363,7 +372,7 @@ def run_workload(ctx: Ctx, name: str, steps: int, warmup: int, min_seconds: floa
         torch.cuda.synchronize()
         for a, b in iso:
             base._run_fused(frames, tonemap, tib.as_dtype(out_dt), outs, tm, update_metering=False,
-                            rows_per_task=args.rows_per_task, profile_events=(a, b))
+                            rows_per_task=args.rows_per_task, profile_events=(a, b), flip=flip)
         torch.cuda.synchronize()
         return sum(a.elapsed_time(b) for a, b in iso[2:]) / len(iso[2:])
 
@@ -590,7 +599,7 @@ def main():
     want_configs = (world == 1 and name == "cfg2" and not args.cameras) if args.configs < 0 else bool(args.configs)
     if want_configs:
         configs = []
-        for other in ("cfg1", "cfg3", "cfg1_16", "cfg5"):
+        for other in ("cfg1", "cfg3", "cfg3_rot90", "cfg1_16", "cfg5"):
             if other == name:
                 continue
             r = run_workload(ctx, other, 50, args.warmup, min_seconds=args.min_seconds)

@@ -497,7 +497,7 @@ def camera_isp(name: str, dtype=f32):
                 p.reinhard_mode = 2
             elif (tonemap == "reinhard" and isp_dtype == f32 and out_dtype.name == "u8" and not self.reinhard_exact
                   and float(tm.get("color_adapt", 0.0)) == 0.0 and 0.3 <= float(tm.get("gamma", 1.0)) <= 1.0
-                  and not yuv420 and not flip and not p.ids_layout):
+                  and not yuv420 and (not flip or flip & 4) and not p.ids_layout):
                 # Camera32 -> u8: ONE sweep that also stores the Reinhard map as u16 fixed point (6 B/px scratch) + a light
                 # normalise / gamma / quantise pass instead of the max sweep + write sweep (csrc/fused_isp.cuh, run_fused);
                 # the u8 result is within 1 LSB of the exact form, ISP(reinhard_exact=True) / B200ISP_REINHARD_EXACT=1 keep
@@ -512,6 +512,31 @@ def camera_isp(name: str, dtype=f32):
             if profile_events is not None:      # (start, stop) torch.cuda.Event pair, see bench.py
                 p.profile_start, p.profile_stop = profile_events[0].cuda_event, profile_events[1].cuda_event
             return p
+
+        def _fused_flip(self, height, tonemap, out_dtype, gamma, color_adapt, ids_format=False, yuv420=False):
+            """b200isp_fused_params.flip code of ``self.transform`` when the fused call applies the transform itself, else 0
+            (the tiled transform kernel then runs on the results)"""
+            shape = (height,)
+            flip = 0
+            if not self._resizes and not yuv420 and self.demosaic == "malvar" and os.environ.get("B200ISP_NO_FUSED_TRANSFORM", "0") != "1":
+                T = interpolate.ImageTransform
+                flip = {T.flip_horiz: 1, T.flip_vert: 2, T.rotate_180: 3, T.transpose: 4, T.rotate_270: 5, T.rotate_90: 6,
+                        T.transverse: 7}.get(self.transform, 0)
+                # Transposing transforms (rotate_90 is the rig script's default): the one-sweep Reinhard -> u8 forms turn the
+                # image in their element-wise normalise pass (csrc/fused_isp.cuh reinhard_out_transposed_kernel: shared-memory
+                # tile, 384-byte output pieces) -- no transform kernel, no extra 3 + 3 B/px.  Elsewhere the sweep's own
+                # transposing store stays OPT-IN (B200ISP_FUSED_TRANSPOSE=1): its 24-byte column pieces are partial-sector
+                # writes, L2 fills every one of them from DRAM (profiles/r02_transpose_store.txt: RGB16 linear 2.2x SLOWER)
+                if flip & 4:
+                    turn_ok = shape[0] % 8 == 0 and shape[0] >= 16
+                    in_pass = (turn_ok and tonemap == "reinhard" and out_dtype == u8 and not ids_format
+                               and os.environ.get("B200ISP_TURN_IN_PASS", "1") != "0"
+                               and ((isp_dtype == f16 and os.environ.get("B200ISP_CAM16_RECOMPUTE", "0") != "1")
+                                    or (isp_dtype == f32 and not self.reinhard_exact and float(color_adapt) == 0.0
+                                        and 0.3 <= float(gamma) <= 1.0 and os.environ.get("B200ISP_CAM32_ONE_SWEEP", "0") != "1")))
+                    if not (in_pass or (turn_ok and os.environ.get("B200ISP_FUSED_TRANSPOSE", "0") == "1")):
+                        flip = 0
+            return flip
 
         def _run_fused(self, frames, tonemap, out_dtype, out, tm, update_metering=False, alpha=0.0, rows_per_task=0,
                        profile_events=None, yuv420=False, ids_format=None, flip=0):
@@ -634,16 +659,7 @@ def camera_isp(name: str, dtype=f32):
             # every transform of interpolate.py:36-56 is applied by the sweep's store (no extra pass; csrc/fused_isp.cuh
             # store_out): bit 0 mirrors the columns, bit 1 the rows, bit 2 transposes (needs height % 8 == 0, otherwise the
             # tiled transform kernel runs on the results)
-            flip = 0
-            if not self._resizes and not yuv420 and self.demosaic == "malvar" and os.environ.get("B200ISP_NO_FUSED_TRANSFORM", "0") != "1":
-                T = interpolate.ImageTransform
-                flip = {T.flip_horiz: 1, T.flip_vert: 2, T.rotate_180: 3, T.transpose: 4, T.rotate_270: 5, T.rotate_90: 6,
-                        T.transverse: 7}.get(self.transform, 0)
-                # the transposing store is OPT-IN (B200ISP_FUSED_TRANSPOSE=1): its 24-byte column pieces are partial-sector
-                # writes, L2 fills every one of them from DRAM (profiles/r02_transpose_store.txt: RGB8 Reinhard 11 % faster
-                # than the transform kernel behind the sweep, RGB16 linear 2.2x SLOWER)
-                if flip & 4 and not (shape[0] % 8 == 0 and shape[0] >= 16 and os.environ.get("B200ISP_FUSED_TRANSPOSE", "0") == "1"):
-                    flip = 0
+            flip = self._fused_flip(shape[0], tonemap, out_dtype, gamma, color_adapt, ids_format, yuv420)
             if yuv420 or flip or self.transform == interpolate.ImageTransform.none:
                 finish = lambda outs: outs
             elif out is None:

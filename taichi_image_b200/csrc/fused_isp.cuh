@@ -1616,6 +1616,91 @@ static __global__ void __launch_bounds__(128) reinhard_scratch_yuv_kernel(const 
   st_bytes<4>(planes + idx, cv4);
 }
 
+// pass B with a TRANSPOSING transform (k.flip bit 2: transpose / rotate_90 / rotate_270 / transverse, interpolate.py:36-56 --
+// rotate_90 is the rig script's default, scripts/tonemap_scan.py) for both one-sweep Reinhard -> u8 forms: the element-wise
+// pass is the cheap place to turn the image, the sweep keeps its plain row stores and the separate transform kernel
+// (3 + 3 B/px) disappears.  Output (i, j) = source (r, c), i = c or W-1-c (bit 0), j = r or H-1-r (bit 1), shape (W, H).
+// CTA = a tile of 128 output columns (source rows) x 16 source columns.  Load phase: thread = 8 pixels of one source row
+// (3 x 16 bytes of the map; the tile's 96-byte row segments are whole sectors), normalise / gamma / quantise exactly like
+// the dense pass, one RGBx word per pixel into shared memory at [column][j + (j >> 3)] (row pitch 144 words).  Store phase:
+// thread = 8 consecutive pixels of one OUTPUT row (24 bytes, three 8-byte stores): a half warp writes 384 contiguous
+// bytes, and with that layout the 32 lanes of every LDS hit 32 different banks.  Default write policy: the two partial
+// sectors at the ends of a 384-byte piece meet their neighbours' (blockIdx.x runs along the output row) in L2.
+// Camera32: frames the u16 map declined were written as plain (H, W, 3) u8 into the frame's scratch by the gated write sweep
+// BEFORE this pass, which then only turns them.
+constexpr int kTpRows = 128, kTpCols = 16, kTpPitch = 144;
+template <bool CAM16, bool GAMMA>
+__global__ void __launch_bounds__(256) reinhard_out_transposed_kernel(const FramePtrs scratch, const FramePtrs fp, int H, int W, int orow, int flip,
+                                                                      float gamma, const Workspace* ws) {
+  __shared__ uint32_t tile[kTpCols * kTpPitch];
+  const int frame = gridDim.z - 1 - blockIdx.z;        // last frame first, like the dense pass
+  const int j0 = blockIdx.x * kTpRows, c0 = blockIdx.y * kTpCols;
+  const float mx = __ldcg(&ws->frame_max[frame]);
+  {
+    const int cg = threadIdx.x & 1, lr = threadIdx.x >> 1;
+    const int j = j0 + lr, c = c0 + 8 * cg;
+    if (j < H && c < W) {
+      const int r = (flip & 2) ? H - 1 - j : j;
+      const size_t px = (size_t)r * W + c;
+      uint32_t v[24];
+      if constexpr (CAM16) {
+        const uint4* src = reinterpret_cast<const uint4*>(reinterpret_cast<const __half*>(scratch.out[frame]) + px * 3);
+        const uint4 w3[3] = {__ldcs(src), __ldcs(src + 1), __ldcs(src + 2)};
+        const __half* t = reinterpret_cast<const __half*>(w3);
+        const float inv_max = __fdiv_rn(1.0f, fmaxf(1e-6f, mx));
+        const float inv_gamma = (float)(1.0 / (double)gamma);
+#pragma unroll
+        for (int e = 0; e < 24; ++e) {
+          float q = __saturatef(__half2float(t[e]) * inv_max);
+          if (GAMMA) q = fast_pow(q, inv_gamma);
+          v[e] = Quant<uint8_t>::q(q);
+        }
+      } else if (reinhard_map16_declined(mx)) {
+        const uint2* src = reinterpret_cast<const uint2*>(reinterpret_cast<const uint8_t*>(scratch.out[frame]) + px * 3);
+        const uint2 b3[3] = {__ldcs(src), __ldcs(src + 1), __ldcs(src + 2)};
+        const uint8_t* t = reinterpret_cast<const uint8_t*>(b3);
+#pragma unroll
+        for (int e = 0; e < 24; ++e) v[e] = t[e];
+      } else {
+        const uint4* src = reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(scratch.out[frame]) + px * 3);
+        const uint4 w3[3] = {__ldcs(src), __ldcs(src + 1), __ldcs(src + 2)};
+        const uint32_t* w = reinterpret_cast<const uint32_t*>(w3);
+        const float a = __fdiv_rn(__fdiv_rn(1.0f, mx), kMap16Scale);
+        const f2 a2 = bc(a), h2 = bc(0.5f * a), ig2 = bc((float)(1.0 / (double)gamma));
+#pragma unroll
+        for (int e = 0; e < 12; ++e) map16_pair(w[e], a2, h2, ig2, GAMMA, v[2 * e], v[2 * e + 1]);
+      }
+      uint32_t* col = tile + (8 * cg) * kTpPitch + lr + (lr >> 3);
+#pragma unroll
+      for (int q = 0; q < 8; ++q)      // the values' low bytes -> R | G << 8 | B << 16 (the top byte is never read)
+        col[q * kTpPitch] = __byte_perm(__byte_perm(v[3 * q], v[3 * q + 1], 0x0040), v[3 * q + 2], 0x0410);
+    }
+  }
+  __syncthreads();
+  {
+    const int rg = threadIdx.x & 15, lc = threadIdx.x >> 4;
+    const int j = j0 + 8 * rg, c = c0 + lc;
+    if (j < H && c < W) {                               // H % 8 == 0: the group is inside the row or entirely outside
+      const uint32_t* sp = tile + lc * kTpPitch + 9 * rg;
+      uint32_t p[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) p[q] = sp[q];
+      const int i = (flip & 1) ? W - 1 - c : c;
+      uint2* d = reinterpret_cast<uint2*>(reinterpret_cast<uint8_t*>(fp.out[frame]) + (size_t)i * orow + 3 * j);
+      d[0] = make_uint2(__byte_perm(p[0], p[1], 0x4210), __byte_perm(p[1], p[2], 0x5421));
+      d[1] = make_uint2(__byte_perm(p[2], p[3], 0x6542), __byte_perm(p[4], p[5], 0x4210));
+      d[2] = make_uint2(__byte_perm(p[5], p[6], 0x5421), __byte_perm(p[6], p[7], 0x6542));
+    }
+  }
+}
+template <bool CAM16>
+static int run_out_transposed(const FramePtrs& sc, const FramePtrs& fp, int n_frames, const IspConsts& k, cudaStream_t s) {
+  const dim3 grid((unsigned)((k.H + kTpRows - 1) / kTpRows), (unsigned)((k.W + kTpCols - 1) / kTpCols), (unsigned)n_frames);
+  if (k.gamma != 1.0f) reinhard_out_transposed_kernel<CAM16, true><<<grid, 256, 0, s>>>(sc, fp, k.H, k.W, k.orow, k.flip, k.gamma, k.ws);
+  else reinhard_out_transposed_kernel<CAM16, false><<<grid, 256, 0, s>>>(sc, fp, k.H, k.W, k.orow, k.flip, k.gamma, k.ws);
+  return cuda_status(cudaPeekAtLastError(), "reinhard_out_transposed_kernel");
+}
+
 // pass A for frames [0, nframes): instantiated once per ISP dtype (fused_inst.cu with ISP_INST_RMAX); Camera16 stores the f16
 // map (any color_adapt), Camera32 the u16 fixed-point map (color_adapt == 0 only: the caller checks)
 template <bool CAM16>
@@ -1714,11 +1799,16 @@ int run_fused(const FramePtrs& fp, int n_frames, const b200isp_fused_params& p, 
       // element-wise pass normalises it (no second sweep, no L2 grouping); dense outputs only (the normalise pass
       // indexes the output flat), pitched outputs take the two-sweep form below
       const size_t need = (size_t)n_frames * k.H * k.W * 3 * sizeof(__half);
-      if (p.reinhard_scratch && p.reinhard_scratch_bytes >= need && k.orow == 3 * k.W && k.flip == 0) {
+      const bool turned = (k.flip & 4) && std::is_same<OutT, uint8_t>::value && !p.out_yuv420 && k.orow % 8 == 0 && k.ids == 0;
+      if (p.reinhard_scratch && p.reinhard_scratch_bytes >= need && ((k.orow == 3 * k.W && k.flip == 0) || turned)) {
         FramePtrs sc = fp;
         for (int f = 0; f < n_frames; ++f) sc.out[f] = (char*)p.reinhard_scratch + (size_t)f * k.H * k.W * 3 * sizeof(__half);
-        st = run_rstore<true>(sc, k, n_frames, rpt, s, p.profile_start, p.profile_stop, 0);
+        IspConsts kp = k;            // the map is a plain dense (H, W, 3) image whatever the output looks like
+        kp.flip = 0;
+        kp.orow = 3 * k.W;
+        st = run_rstore<true>(sc, kp, n_frames, rpt, s, p.profile_start, p.profile_stop, 0);
         if (st) return st;
+        if (turned) return run_out_transposed<true>(sc, fp, n_frames, k, s);     // the normalise pass turns the image
         if (p.out_yuv420) {
           const dim3 grid((unsigned)((k.W / 8 + 127) / 128), (unsigned)(k.H / 2), (unsigned)n_frames);
           reinhard_scratch_yuv_kernel<<<grid, 128, 0, s>>>(sc, fp, k.H, k.W, k.gamma, k.ws);
@@ -1741,10 +1831,26 @@ int run_fused(const FramePtrs& fp, int n_frames, const b200isp_fused_params& p, 
       // (measured: profiles/r02_reinhard_map16.txt).  Frames whose map does not fit [0, 1) (reinhard_map16_declined) are
       // redone exactly by the gated sweeps.  reinhard_mode 1 forces the exact two-sweep form.
       const size_t need = (size_t)n_frames * k.H * k.W * 3 * sizeof(uint16_t);
-      if (p.reinhard_mode == 0 && k.ca == 0.f && k.gamma <= 1.0f && k.gamma >= 0.3f && !p.out_yuv420 && k.flip == 0 && k.ids == 0 &&
+      const bool turned = (k.flip & 4) && k.orow % 8 == 0;
+      if (p.reinhard_mode == 0 && k.ca == 0.f && k.gamma <= 1.0f && k.gamma >= 0.3f && !p.out_yuv420 && (k.flip == 0 || turned) && k.ids == 0 &&
           p.reinhard_scratch && p.reinhard_scratch_bytes >= need && p.reinhard_group <= 0) {
         FramePtrs sc = fp;
         for (int f = 0; f < n_frames; ++f) sc.out[f] = (char*)p.reinhard_scratch + (size_t)f * k.H * k.W * 3 * sizeof(uint16_t);
+        if (turned) {
+          // transposing transform: map sweep (plain row stores), then the gated exact sweeps leave the frames the map declined
+          // as plain (H, W, 3) u8 images in their scratch, then ONE pass normalises / turns every frame into the output
+          IspConsts kp = k;
+          kp.flip = 0;
+          kp.orow = 3 * k.W;
+          st = run_rstore<false>(sc, kp, n_frames, rpt, s, p.profile_start, p.profile_stop, 0);
+          if (st) return st;
+          kp.gate = 1;
+          st = run_rmax_gated(sc, kp, n_frames, rpt, s);
+          if (st) return st;
+          st = run_write_gated(sc, kp, n_frames, rpt, s);
+          if (st) return st;
+          return run_out_transposed<false>(sc, fp, n_frames, k, s);
+        }
         const long long n_elems = (long long)k.H * k.W * 3;
         static const int ctas_per_sm = [] { const char* e = getenv("B200ISP_MAP16_CTAS"); const int v = e ? atoi(e) : 0; return v > 0 ? v : 8; }();
         const bool gam = k.gamma != 1.0f, pitched = k.orow != 3 * k.W;

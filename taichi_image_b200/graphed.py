@@ -45,6 +45,13 @@ class GraphedStream:
         base._ids_layout = self.ids_format        # read by every parameter block built during warm-up and capture
         self.tonemap, self.out_dtype, self.tm = tonemap, as_dtype(dtype), dict(tonemap_args)
         self.rows_per_task = rows_per_task
+        # the ISP's transform is applied where the fused call applies it itself (flips in the sweep's store, transposing
+        # transforms in the normalise pass of the one-sweep Reinhard -> u8 forms); ``outs`` then have the transformed shape
+        self.flip = base._fused_flip(self.F[0][0].shape[0], tonemap, self.out_dtype, self.tm.get("gamma", 1.0),
+                                     self.tm.get("color_adapt", 0.0), self.ids_format)
+        from .interpolate import ImageTransform
+        assert self.flip or base.transform == ImageTransform.none, \
+            "GraphedStream: this ISP transform needs the separate transform kernel here -- use process_packed12"
         dev = base.device
         with torch.cuda.device(dev):
             self.main = torch.cuda.Stream(dev)
@@ -92,7 +99,7 @@ class GraphedStream:
         cur = torch.cuda.current_stream(isp.device)
         self.side.wait_stream(cur)
         isp._run_fused(self.F[p], self.tonemap, self.out_dtype, self.O[p], self.tm, update_metering=False,
-                       rows_per_task=self.rows_per_task)
+                       rows_per_task=self.rows_per_task, flip=self.flip)
         with torch.cuda.stream(self.side):
             self._meter(self.F[1 - p], 1.0 - float(isp.moving_alpha), metrics_next, cooperative=False)
         cur.wait_stream(self.side)
