@@ -195,7 +195,8 @@ typedef struct {
   int resize_gather;            /* 1: force the per-output-pixel gather instead of the resizing sweep (testing / profiling) */
   int out_pitch;                /* elements per OUTPUT row; 0 = dense (3 * width).  Larger: every output frame is a tile of a bigger
                                    image (the rig's camera grid, scripts/tonemap_scan.py:91-100) -- the sweep writes the tile in place */
-  int flip;                     /* ISP transform applied by the sweep's store (interpolate.py:36-56): bit 0 = mirror columns, bit 1 = mirror
+  int flip;                     /* ISP transform applied inside the call (interpolate.py:36-56; by the sweep's store, or -- transposing
+                                   transforms on the one-sweep Reinhard -> u8 forms -- by the normalise pass): bit 0 = mirror columns, bit 1 = mirror
                                    rows, bit 2 = transpose (output (W, H), out_pitch counts elements of ITS rows; needs height % 8 == 0):
                                    flip_horiz 1, flip_vert 2, rotate_180 3, transpose 4, rotate_270 5, rotate_90 6, transverse 7 */
   int reinhard_mode;            /* Camera32 Reinhard -> u8 with reinhard_scratch: 0 = one sweep that also stores the map as u16 fixed point
