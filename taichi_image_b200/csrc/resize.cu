@@ -1,5 +1,6 @@
 // Gather kernels: bilinear resize, area resize (extension) and the 8 rotate/flip transforms
 // (reference: interpolate.py:19-66 bilinear, :36-56 / :93-108 transform).
+#include <cstdlib>
 #include "common.cuh"
 
 namespace isp {
@@ -201,6 +202,107 @@ __global__ void __launch_bounds__(256) transform_words_kernel(const uint32_t* __
   }
 }
 
+// ---------------------------------------------------------------- transposing transforms of u8 / 16-bit RGB, the turned path
+// rotate_90 / rotate_270 / transpose / transverse of images whose height and width are multiples of 8 (every frame the fused
+// sweep accepts with H % 8 == 0): destination (i, j) = source (r, c), r = j or H-1-j (MR), c = i or W-1-i (MC).
+// CTA = 128 destination columns (source rows) x 32 destination rows (source columns).  A pixel travels through shared memory
+// as whole 32-bit words -- one word for 3-byte pixels (R | G << 8 | B << 16), two words in two planes for 6-byte pixels
+// (c0 | c1 << 16, c2) -- instead of byte granules: per pixel 1 / 2 STS + 1 / 2 LDS and two or three PRMT on each side.
+// Load phase: thread = 8 consecutive source pixels (24 / 48 bytes, 8- / 16-byte vectors), a warp covers 8 source rows x 32
+// columns; store phase: thread = 8 consecutive destination pixels, a half warp writes 384 / 768 contiguous bytes of one
+// destination row.  Layout [dest row li][lr + (lr >> 3)] with row pitch 144 words and 8 extra words per 8 rows: both the
+// stores of the load phase and the loads of the store phase are bank-conflict free.  blockIdx.x runs along the destination
+// row, so the partial sectors at the ends of a piece meet their neighbours' in L2 (default write policy).
+constexpr int kTurnRows = 128, kTurnCols = 32, kTurnPitch = 144, kTurnPlane = kTurnCols * kTurnPitch + 8 * (kTurnCols / 8 - 1);
+template <int PB>
+__global__ void __launch_bounds__(256) transform_turn_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, int H, int W,
+                                                             int mirror_r, int mirror_c) {
+  static_assert(PB == 3 || PB == 6, "u8 or 16-bit RGB");
+  constexpr int NP = PB / 3;                       // planes of words per pixel
+  constexpr int NW = 2 * PB;                       // 32-bit words of 8 pixels
+  __shared__ uint32_t tile[NP][kTurnPlane];
+  const int j0 = blockIdx.x * kTurnRows, i0 = blockIdx.y * kTurnCols;
+#pragma unroll
+  for (int it = 0; it < 2; ++it) {
+    const int id = threadIdx.x + 256 * it;
+    const int cg = id & 3, lr = id >> 2;
+    const int j = j0 + lr, ig = i0 + 8 * cg;       // first destination row of the group
+    if (j < H && ig < W) {
+      const int r = mirror_r ? H - 1 - j : j;
+      const int cs = mirror_c ? W - 8 - ig : ig;   // first SOURCE column of the eight
+      const uint8_t* sp = src + ((size_t)r * W + cs) * PB;
+      uint32_t w[NW];
+      if constexpr (PB == 3) {
+#pragma unroll
+        for (int v = 0; v < 3; ++v) { const uint2 x = __ldg(reinterpret_cast<const uint2*>(sp) + v); w[2 * v] = x.x; w[2 * v + 1] = x.y; }
+      } else {
+#pragma unroll
+        for (int v = 0; v < 3; ++v) { const uint4 x = __ldg(reinterpret_cast<const uint4*>(sp) + v); w[4 * v] = x.x; w[4 * v + 1] = x.y; w[4 * v + 2] = x.z; w[4 * v + 3] = x.w; }
+      }
+      uint32_t pa[8], pb[8];
+      if constexpr (PB == 3) {
+#pragma unroll
+        for (int g = 0; g < 2; ++g) {              // 4 pixels = 3 words; the top byte of a pixel word is never read
+          pa[4 * g] = w[3 * g];
+          pa[4 * g + 1] = __byte_perm(w[3 * g], w[3 * g + 1], 0x0543);
+          pa[4 * g + 2] = __byte_perm(w[3 * g + 1], w[3 * g + 2], 0x0432);
+          pa[4 * g + 3] = w[3 * g + 2] >> 8;
+        }
+      } else {
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {              // 2 pixels = 3 words; the top half of a plane-1 word is never read
+          pa[2 * g] = w[3 * g];
+          pb[2 * g] = w[3 * g + 1];
+          pa[2 * g + 1] = __byte_perm(w[3 * g + 1], w[3 * g + 2], 0x5432);
+          pb[2 * g + 1] = w[3 * g + 2] >> 16;
+        }
+      }
+      const int pos = lr + (lr >> 3);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const int li = 8 * cg + (mirror_c ? 7 - q : q);
+        const int at = li * kTurnPitch + 8 * cg + pos;
+        tile[0][at] = pa[q];
+        if constexpr (NP == 2) tile[1][at] = pb[q];
+      }
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int it = 0; it < 2; ++it) {
+    const int id = threadIdx.x + 256 * it;
+    const int rg = id & 15, li = id >> 4;
+    const int i = i0 + li, j = j0 + 8 * rg;
+    if (i < W && j < H) {
+      const int at = li * kTurnPitch + 8 * (li >> 3) + 9 * rg;
+      uint32_t pa[8], pb[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        pa[q] = tile[0][at + q];
+        if constexpr (NP == 2) pb[q] = tile[1][at + q];
+      }
+      uint8_t* dp = dst + ((size_t)i * H + j) * PB;
+      if constexpr (PB == 3) {
+        uint2* d = reinterpret_cast<uint2*>(dp);
+        d[0] = make_uint2(__byte_perm(pa[0], pa[1], 0x4210), __byte_perm(pa[1], pa[2], 0x5421));
+        d[1] = make_uint2(__byte_perm(pa[2], pa[3], 0x6542), __byte_perm(pa[4], pa[5], 0x4210));
+        d[2] = make_uint2(__byte_perm(pa[5], pa[6], 0x5421), __byte_perm(pa[6], pa[7], 0x6542));
+      } else {
+        uint32_t o[12];
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          o[3 * g] = pa[2 * g];
+          o[3 * g + 1] = __byte_perm(pb[2 * g], pa[2 * g + 1], 0x5410);
+          o[3 * g + 2] = __byte_perm(pa[2 * g + 1], pb[2 * g + 1], 0x5432);
+        }
+        uint4* d = reinterpret_cast<uint4*>(dp);
+#pragma unroll
+        for (int v = 0; v < 3; ++v) d[v] = make_uint4(o[4 * v], o[4 * v + 1], o[4 * v + 2], o[4 * v + 3]);
+      }
+    }
+  }
+}
+
 }  // namespace isp
 
 using namespace isp;
@@ -254,6 +356,20 @@ extern "C" int b200isp_transform(const void* src, void* dst, int dtype, int src_
   const int esz = dtype == B200ISP_U8 ? 1 : (dtype == B200ISP_F32 ? 4 : 2), pb = 3 * esz;
   const bool words = ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 3u) == 0 &&
                      ((size_t)src_w * pb) % 4 == 0 && ((size_t)wd * pb) % 4 == 0;
+  // 3- / 6-byte pixels, both extents multiples of 8, vector-aligned bases: whole-word pixel tiles (transform_turn_kernel)
+  if (swaps && (pb == 3 || pb == 6) && src_h % 8 == 0 && src_w % 8 == 0 &&
+      ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & (pb == 3 ? 7u : 15u)) == 0) {
+    static const bool off = [] { const char* e = getenv("B200ISP_TRANSFORM_TURN"); return e && atoi(e) == 0; }();   // A/B measurements
+    if (!off) {
+      const int mr = (transform == B200ISP_T_ROT90 || transform == B200ISP_T_TRANSVERSE) ? 1 : 0;
+      const int mc = (transform == B200ISP_T_ROT270 || transform == B200ISP_T_TRANSVERSE) ? 1 : 0;
+      const dim3 grid((src_h + kTurnRows - 1) / kTurnRows, (src_w + kTurnCols - 1) / kTurnCols);
+      if (pb == 3) transform_turn_kernel<3><<<grid, 256, 0, s>>>((const uint8_t*)src, (uint8_t*)dst, src_h, src_w, mr, mc);
+      else transform_turn_kernel<6><<<grid, 256, 0, s>>>((const uint8_t*)src, (uint8_t*)dst, src_h, src_w, mr, mc);
+      ISP_LAUNCH_CHECK("transform_turn_kernel");
+      return B200ISP_OK;
+    }
+  }
   if (words) {
     const uint32_t* sw = (const uint32_t*)src;
     uint32_t* dw = (uint32_t*)dst;

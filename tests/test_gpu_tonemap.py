@@ -75,7 +75,8 @@ def test_resize_width_and_per_axis(cuda):
 @pytest.mark.parametrize("name", ["u8", "u16", "f16", "f32"])
 @pytest.mark.parametrize("tname", O.TRANSFORMS)
 @pytest.mark.parametrize("shape", [(5, 9), (64, 33), (70, 130),                   # element-wise kernel (unaligned row pitch for u8)
-                                   (4, 4), (64, 128), (72, 132), (100, 260), (8, 68)])   # word kernel: full and partial tiles
+                                   (4, 4), (64, 128), (72, 132), (100, 260), (8, 68),    # word kernel: full and partial tiles
+                                   (8, 8), (128, 32), (136, 40), (264, 1032), (256, 72)])  # turned path (both extents % 8 == 0): 128 x 32 tiles
 def test_transform(cuda, name, tname, shape):
     import torch
     from taichi_image_b200 import interpolate
