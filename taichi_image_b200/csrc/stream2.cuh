@@ -410,6 +410,11 @@ __global__ void __launch_bounds__(ISP_S2_THREADS, ISP_S2_MINBLOCKS) stream2_kern
   __shared__ __align__(16) uint32_t stage[kS2Warps][Epi::kStageWords > 0 ? Epi::kStageWords : 1];
   uint32_t* stage_warp = stage[threadIdx.x >> 5];
   if constexpr (has_gate<Epi>::value) {
+    // the usual case -- no frame declined -- ends here after one look at the per-frame flags (a lane per frame) instead of
+    // one task decode (three 64-bit divisions) + flag load per task of the stride loop
+    bool any = false;
+    for (int f = threadIdx.x & 31; f < sg.g.nframes; f += 32) any |= epi.enabled(f);
+    if (!__any_sync(0xffffffffu, any)) return;
     for (long long task = (long long)blockIdx.x * kS2Warps + (threadIdx.x >> 5); task < sg.total_tasks; task += (long long)gridDim.x * kS2Warps)
       stream2_task<PATTERN, BL>(ld, epi, sg, task, stage_warp);
   } else {
