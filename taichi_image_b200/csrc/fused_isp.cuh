@@ -13,8 +13,13 @@
 //   linear      stream2<EpiLinear2>                          one sweep
 //   reinhard    Camera32: stream2<EpiReinhardMax2> (frame-global max of the mapped values) -> stream2<EpiReinhard2>
 //                         (the write sweep recomputes the map), one pair of launches for all frames of the call
+//               Camera32 -> u8 (color_adapt 0, gamma 0.3 .. 1): stream2<EpiReinhardMax2, STORE> (u16 fixed-point map)
+//                         -> reinhard_map16_out_kernel (normalise / gamma / quantise) -> the two gated exact sweeps
+//                         (they leave at once unless the map declined a frame)
 //               Camera16: stream2<EpiReinhardMax2, STORE> (writes the f16 map the reference stores back anyway)
 //                         -> reinhard_scratch_out_kernel (element-wise normalise / gamma / quantise)
+//               either one-sweep form -> u8 with a transposing ISP transform: the pass is reinhard_out_transposed_kernel
+//                         (same arithmetic, the image turned through a shared-memory tile; Camera32: after the gated sweeps)
 //   none        stream2<EpiRgb2>                             load_packed12 only: float RGB out
 //   resizing ISP: csrc/resize_sweep.cuh (stream2_resize_kernel + orphan columns [+ normalise pass])
 #pragma once
@@ -1628,9 +1633,12 @@ static __global__ void __launch_bounds__(128) reinhard_scratch_yuv_kernel(const 
 // sectors at the ends of a 384-byte piece meet their neighbours' (blockIdx.x runs along the output row) in L2.
 // Camera32: frames the u16 map declined were written as plain (H, W, 3) u8 into the frame's scratch by the gated write sweep
 // BEFORE this pass, which then only turns them.
+#ifndef ISP_TURNED_MINBLOCKS
+#define ISP_TURNED_MINBLOCKS 8     // like the dense pass (8 CTAs per SM measured best there): 32 registers per thread
+#endif
 constexpr int kTpRows = 128, kTpCols = 16, kTpPitch = 144;
 template <bool CAM16, bool GAMMA>
-__global__ void __launch_bounds__(256) reinhard_out_transposed_kernel(const FramePtrs scratch, const FramePtrs fp, int H, int W, int orow, int flip,
+__global__ void __launch_bounds__(256, ISP_TURNED_MINBLOCKS) reinhard_out_transposed_kernel(const FramePtrs scratch, const FramePtrs fp, int H, int W, int orow, int flip,
                                                                       float gamma, const Workspace* ws) {
   __shared__ uint32_t tile[kTpCols * kTpPitch];
   const int frame = gridDim.z - 1 - blockIdx.z;        // last frame first, like the dense pass
