@@ -1634,7 +1634,8 @@ static __global__ void __launch_bounds__(128) reinhard_scratch_yuv_kernel(const 
 // Camera32: frames the u16 map declined were written as plain (H, W, 3) u8 into the frame's scratch by the gated write sweep
 // BEFORE this pass, which then only turns them.
 #ifndef ISP_TURNED_MINBLOCKS
-#define ISP_TURNED_MINBLOCKS 8     // like the dense pass (8 CTAs per SM measured best there): 32 registers per thread
+#define ISP_TURNED_MINBLOCKS 6     // measured: 8 CTAs per SM (32 registers, no spills) gain 2 % on eager Camera32 calls but lose 1 % on
+                                   // Camera16 and 2 % on the graphed look-ahead step (cfg3_rot90 214 -> 207 Gpixel/s)
 #endif
 constexpr int kTpRows = 128, kTpCols = 16, kTpPitch = 144;
 template <bool CAM16, bool GAMMA>
