@@ -35,7 +35,9 @@ def test_turned_pass_equals_transform_of_the_plain_result(cuda, dt, tname, shape
     r = rng(311)
     h, w = shape
     cu = [to_cuda(packed_frame(r, h, w)) for _ in range(3)]
-    for kw in (dict(gamma=0.9, intensity=2.0), dict(), dict(gamma=0.45, light_adapt=0.8)):
+    # the last setting keeps Camera16 on the turned pass (any gamma / color_adapt) and sends Camera32 to the exact sweeps +
+    # transform kernel: equal to the transform of the plain result either way
+    for kw in (dict(gamma=0.9, intensity=2.0), dict(), dict(gamma=0.45, light_adapt=0.8), dict(gamma=1.2, color_adapt=0.5)):
         plain, turned = make(dt), make(dt, transform=t)
         exp = [transform(o, t) for o in plain.process_packed12(cu, tonemap="reinhard", **kw)]
         assert tuple(exp[0].shape) == (w, h, 3)

@@ -180,3 +180,39 @@ def test_c_abi_rejects_bad_arguments_without_touching_the_gpu():
     with pytest.raises(_lib.B200ISPError, match="bad shape"):
         _lib.check(E_SHAPE, "demo")
 
+
+
+def test_transform_routing_of_the_fused_call(monkeypatch):
+    """host logic of ISP._fused_flip (no GPU): which ISP transforms the fused call applies itself -- flips in the sweep's
+    store on every path, transposing transforms (interpolate.py:36-56) in the normalise pass of the one-sweep Reinhard -> u8
+    forms only; everything else returns 0 = the transform kernel runs behind the call"""
+    import torch
+    from taichi_image_b200 import camera_isp, bayer
+    from taichi_image_b200.dtypes import u8, u16, f16
+    from taichi_image_b200.interpolate import ImageTransform as T
+    for var in ("B200ISP_FUSED_TRANSPOSE", "B200ISP_TURN_IN_PASS", "B200ISP_NO_FUSED_TRANSFORM", "B200ISP_CAM16_RECOMPUTE",
+                "B200ISP_CAM32_ONE_SWEEP", "B200ISP_REINHARD_EXACT"):
+        monkeypatch.delenv(var, raising=False)
+    cpu = torch.device("cpu")
+    codes = {T.flip_horiz: 1, T.flip_vert: 2, T.rotate_180: 3, T.transpose: 4, T.rotate_270: 5, T.rotate_90: 6, T.transverse: 7}
+    for cam in (camera_isp.Camera16, camera_isp.Camera32):
+        for t, code in codes.items():
+            isp = cam(bayer.BayerPattern.RGGB, transform=t, device=cpu)
+            assert isp._fused_flip(3000, "reinhard", u8, 0.9, 0.0) == code
+            turning = code & 4
+            assert isp._fused_flip(3000, "linear", u16, 1.0, 0.0) == (0 if turning else code)        # the sweep writes the output itself
+            assert isp._fused_flip(3000, "reinhard", f16, 0.9, 0.0) == (0 if turning else code)
+            assert isp._fused_flip(3004, "reinhard", u8, 0.9, 0.0) == (0 if turning else code)       # height % 8 != 0
+            assert isp._fused_flip(3000, "reinhard", u8, 0.9, 0.0, ids_format=True) == (0 if turning else code)
+            assert isp._fused_flip(3000, "reinhard", u8, 0.9, 0.0, yuv420=True) == 0
+        assert cam(bayer.BayerPattern.RGGB, device=cpu)._fused_flip(3000, "reinhard", u8, 0.9, 0.0) == 0
+        assert cam(bayer.BayerPattern.RGGB, transform=T.rotate_90, resize_width=1920, device=cpu)._fused_flip(3000, "reinhard", u8, 0.9, 0.0) == 0
+    # Camera32: only where the one-sweep u16 map applies (color_adapt == 0, 0.3 <= gamma <= 1, not reinhard_exact)
+    isp = camera_isp.Camera32(bayer.BayerPattern.RGGB, transform=T.rotate_90, device=cpu)
+    assert isp._fused_flip(3000, "reinhard", u8, 1.2, 0.0) == 0 and isp._fused_flip(3000, "reinhard", u8, 0.9, 0.5) == 0
+    assert camera_isp.Camera32(bayer.BayerPattern.RGGB, transform=T.rotate_90, reinhard_exact=True, device=cpu)._fused_flip(3000, "reinhard", u8, 0.9, 0.0) == 0
+    assert camera_isp.Camera16(bayer.BayerPattern.RGGB, transform=T.rotate_90, device=cpu)._fused_flip(3000, "reinhard", u8, 1.2, 0.5) == 6
+    monkeypatch.setenv("B200ISP_TURN_IN_PASS", "0")
+    assert isp._fused_flip(3000, "reinhard", u8, 0.9, 0.0) == 0
+    monkeypatch.setenv("B200ISP_FUSED_TRANSPOSE", "1")                                               # the sweep's own transposing store (opt-in)
+    assert isp._fused_flip(3000, "linear", u16, 1.0, 0.0) == 6
